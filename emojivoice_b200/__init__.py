@@ -1,0 +1,8 @@
+"""emojivoice_b200: B200-native (sm_100a) synthesis hot path of rosielab/emojivoice behind the reference's own
+call surface.  See DESIGN.md / INTEGRATION.md."""
+from .config import EMOJI_MAPPING_FEMALE, EMOJI_MAPPING_MALE, HIFIGAN_V1, VCTK, AttrDict, MatchaConfig  # noqa: F401
+from .emoji_frontend import emoji_to_spk, intersperse  # noqa: F401
+from .hifigan import Denoiser, Generator, to_waveform  # noqa: F401
+from .matcha import MatchaTTS  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,146 @@
+"""ctypes binding of libemojivoice_b200.so (include/emojivoice_b200.h).  PyTorch only supplies device memory and the
+current CUDA stream; every kernel lives in the shared library.  There is NO fallback: if the library is missing or
+the device is not sm_100, the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libemojivoice_b200.so")
+
+PREC = {"fp32": 0, "float32": 0, torch.float32: 0, "bf16": 1, "bfloat16": 1, torch.bfloat16: 1}
+
+
+class EvTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class EvMatchaCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_vocab", "n_spks", "spk_emb_dim", "n_feats", "enc_channels", "enc_filter_channels",
+        "enc_filter_channels_dp", "enc_heads", "enc_layers", "enc_kernel", "enc_prenet", "dec_channels", "dec_heads",
+        "dec_head_dim", "dec_mid_blocks")] + [("mel_mean", C.c_float), ("mel_std", C.c_float)]
+
+
+class EvHifiganCfg(C.Structure):
+    _fields_ = [("num_mels", C.c_int32), ("upsample_initial_channel", C.c_int32), ("n_ups", C.c_int32),
+                ("n_kernels", C.c_int32), ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
+                ("resblock_kernel_sizes", C.c_int32 * 4), ("resblock_dilation_sizes", (C.c_int32 * 3) * 4)]
+
+
+_P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+# name -> (restype, argtypes); must list every symbol include/emojivoice_b200.h declares (tests check it)
+SIGNATURES = {
+    "ev_create": (_I, [C.POINTER(_P), _I]),
+    "ev_destroy": (_I, [_P]),
+    "ev_last_error": (C.c_char_p, [_P]),
+    "ev_version": (_I, []),
+    "ev_load_matcha": (_I, [_P, C.POINTER(EvTensor), _I, C.POINTER(EvMatchaCfg), _P]),
+    "ev_load_hifigan": (_I, [_P, C.POINTER(EvTensor), _I, C.POINTER(EvHifiganCfg), _P]),
+    "ev_encode_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "ev_encode": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ev_align": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "ev_decode_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "ev_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _SZ, _P]),
+    "ev_vocode_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "ev_vocode": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "ev_denoise_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "ev_denoiser_init": (_I, [_P, _P, _P, _SZ, _P]),
+    "ev_denoise": (_I, [_P, _P, _I, _I, _F, _P, _P, _SZ, _P]),
+    "ev_launch_count": (_I64, [_P, _I]),
+    "ev_test_conv1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ev_test_euler_schedule": (_I, [_I, C.POINTER(_F), C.POINTER(_F)]),
+    "ev_test_row_sum": (_I, [_P, _P, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- there is no python/CPU substitute."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build the CUDA library first (python -m emojivoice_b200.build). "
+                "emojivoice_b200 has no CPU or eager-PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Context:
+    """One ev_ctx per (process, device).  Owns the packed weights; hands out a growing scratch workspace."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("emojivoice_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"emojivoice_b200 runs on CUDA devices only, got {self.device}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = C.c_void_p()
+            rc = lib().ev_create(C.byref(h), self.device.index)
+        if rc != 0:
+            raise RuntimeError(f"ev_create failed ({rc}): {lib().ev_last_error(None).decode()}")
+        self.handle = h
+        self._ws = None
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {lib().ev_last_error(self.handle).decode()}")
+
+    def workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launch_count(self, reset=False) -> int:
+        return int(lib().ev_launch_count(self.handle, 1 if reset else 0))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib().ev_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def tensor_list(sd: dict, device):
+    """state_dict -> (ctypes array of EvTensor, keep-alive list).  Tensors are moved to `device` as contiguous fp32."""
+    keep, arr = [], (EvTensor * len(sd))()
+    for i, (k, v) in enumerate(sd.items()):
+        t = v.detach().to(device=device, dtype=torch.float32).contiguous()
+        name = k.encode()
+        keep.append((t, name))
+        arr[i].name = name
+        arr[i].data = t.data_ptr()
+        arr[i].ndim = min(t.dim(), 4)
+        for d in range(min(t.dim(), 4)):
+            arr[i].shape[d] = t.shape[d]
+        if t.dim() == 0:
+            arr[i].ndim, arr[i].shape[0] = 1, 1
+    return arr, keep

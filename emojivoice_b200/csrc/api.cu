@@ -1,0 +1,112 @@
+// Context lifetime, bookkeeping and the single-kernel unit-test hooks of the C ABI (include/emojivoice_b200.h).
+#include "ctx.cuh"
+
+using namespace ev;
+
+namespace {
+thread_local std::string g_create_error;
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+}  // namespace
+
+extern "C" int ev_version(void) { return 100; }
+
+extern "C" const char* ev_last_error(const ev_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ev_create(ev_ctx** out, int device) {
+  if (!out) return EV_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n);
+  if (ce != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(ce);
+    return EV_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device index out of range"; return EV_ERR_INVALID; }
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return EV_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = std::string("emojivoice_b200 needs an sm_100-class GPU (B200); found ") + prop.name + " sm_" +
+                     std::to_string(prop.major) + std::to_string(prop.minor) + " -- there is no fallback path";
+    return EV_ERR_NO_DEVICE;
+  }
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(ce); return EV_ERR_CUDA; }
+  std::string msg;
+  if (!conv_tc_init(&msg)) { g_create_error = msg; return EV_ERR_CUDA; }
+  ev_ctx* ctx = new ev_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return EV_OK;
+}
+
+extern "C" int ev_destroy(ev_ctx* ctx) {
+  if (!ctx) return EV_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (void* p : ctx->owned) cudaFree(p);
+  delete ctx;
+  return EV_OK;
+}
+
+extern "C" int64_t ev_launch_count(const ev_ctx* ctx, int reset) {
+  if (!ctx) return 0;
+  const int64_t v = ctx->launches;
+  if (reset) const_cast<ev_ctx*>(ctx)->launches = 0;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ test hooks
+extern "C" int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const float* bias, int B, int Cin, int T,
+                              int Cout, int K, int stride, int padding, int dilation, int transposed, int precision,
+                              float* y, void* stream) {
+  if (!ctx || !x || !w || !y) return EV_ERR_INVALID;
+  cudaStream_t s = as_stream(stream);
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t mark = ctx->owned.size();
+  auto release = [&]() {
+    cudaStreamSynchronize(s);
+    for (size_t i = mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+    ctx->owned.resize(mark);
+  };
+  ev_tensor tw{}, tb{};
+  tw.name = "w"; tw.data = w; tw.ndim = 3;
+  tw.shape[0] = transposed ? Cin : Cout; tw.shape[1] = transposed ? Cout : Cin; tw.shape[2] = K;
+  tb.name = "b"; tb.data = bias; tb.ndim = 1; tb.shape[0] = Cout;
+  ev_tensor list[2] = {tw, tb};
+  WeightStore ws(ctx, list, bias ? 2 : 1, s);
+  ConvWeights cw;
+  int rc = make_conv(ctx, ws, {"w"}, bias ? std::vector<std::string>{"b"} : std::vector<std::string>{}, Cout, Cin, K, stride,
+                     padding, dilation, transposed ? CONV_TRANSPOSED : CONV_NORMAL, true, &cw);
+  if (rc) { release(); return rc; }
+  ConvGeom g;
+  const int T_out = conv_geometry(cw, B, T, &g);
+  void *xa = nullptr, *yo = nullptr;
+  const size_t esz = precision == EV_PREC_BF16 ? 2 : 4;
+  if ((rc = device_alloc(ctx, (size_t)B * T * Cin * esz, &xa, false, s)) || (rc = device_alloc(ctx, (size_t)B * T_out * Cout * 4, &yo, false, s))) { release(); return rc; }
+  Epilogue e;
+  e.out_f32 = reinterpret_cast<float*>(yo); e.f32_ld = Cout; e.f32_bs = (long long)T_out * Cout;
+  const RowMask none{nullptr, 0};
+  cudaError_t ce;
+  if (precision == EV_PREC_BF16) {
+    ce = cf_to_cl<bf16>(x, B, Cin, T, reinterpret_cast<bf16*>(xa), Cin, (long long)T * Cin, 1.0f, none, s);
+    if (ce == cudaSuccess) rc = run_conv<bf16>(ctx, cw, reinterpret_cast<bf16*>(xa), Cin, (long long)T * Cin, B, T, e, s);
+  } else {
+    ce = cf_to_cl<float>(x, B, Cin, T, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, 1.0f, none, s);
+    if (ce == cudaSuccess) rc = run_conv<float>(ctx, cw, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, B, T, e, s);
+  }
+  if (ce != cudaSuccess) { release(); return cuda_fail(ctx, ce, "cf_to_cl"); }
+  if (rc) { release(); return rc; }
+  ce = cl_to_cf(reinterpret_cast<float*>(yo), Cout, (long long)T_out * Cout, B, Cout, T_out, y, 1.0f, 0.0f, s);
+  if (ce != cudaSuccess) { release(); return cuda_fail(ctx, ce, "cl_to_cf"); }
+  ce = cudaStreamSynchronize(s);
+  release();
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "ev_test_conv1d");
+  return EV_OK;
+}
+
+extern "C" int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream) {
+  if (!ctx || !x || !out) return EV_ERR_INVALID;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, row_sum_aten(x, B, Tx, out, as_stream(stream)));
+  return EV_OK;
+}

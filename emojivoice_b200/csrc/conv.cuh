@@ -1,0 +1,95 @@
+// Implicit-GEMM 1-D convolution: geometry, fused epilogue and weight layouts shared by the two back ends
+//   conv_simt.cu : fp32 CUDA-core kernel, fixed summation order (text encoder always; parity mode elsewhere)
+//   conv_tc.cu   : bf16 tcgen05/TMEM kernel fed by TMA (decoder + vocoder in EV_PREC_BF16)
+//
+// All activations are CHANNEL-LAST: element (b, t, c) of a tensor lives at  base + b*bs + t*ld + c.
+// One GEMM row = one output time step, K = taps x C_in, N = C_out.  Every reference op on the path maps onto it:
+//   nn.Conv1d(k, dilation d, "same")      taps=k,  t_in = t + j*d - pad
+//   nn.Conv1d(3, stride 2, pad 1)         taps=3,  t_in = 2t + j - 1                       (decoder.py:67)
+//   nn.ConvTranspose1d(k=2s, stride s, p) polyphase: GEMM row r holds outputs t = s*r + phase - p,
+//                                         N = s*C_out, taps=2 (t_in = r, r-1)               (decoder.py:144, hifigan/models.py:160)
+//   nn.Linear / 1x1 conv                  taps=1
+#pragma once
+#include "common.cuh"
+
+namespace ev {
+
+constexpr int kMaxTaps = 16;
+
+struct ConvGeom {
+  int B;            // batch items
+  int M;            // GEMM rows per batch item
+  int N;            // GEMM columns (C_out, or s*C_out for the polyphase transposed conv)
+  int C_in;         // channels reduced per tap
+  int taps;
+  int conv_stride;  // input rows advanced per GEMM row
+  int T_in;         // valid input rows per batch item (outside -> zero padding)
+  int tap_off[kMaxTaps];  // t_in = row*conv_stride + tap_off[j]
+};
+
+// out value  v = ((acc + bias) [*mask] * alpha + res + res2) / div
+// out_f32 <- v ;  out_act <- act(v) [*mask]
+struct Epilogue {
+  const float* bias = nullptr;      // [C_out]
+  const float* res = nullptr;       long long res_ld = 0, res_bs = 0;
+  const float* res2 = nullptr;      long long res2_ld = 0, res2_bs = 0;
+  float* out_f32 = nullptr;         long long f32_ld = 0, f32_bs = 0;
+  void* out_act = nullptr;          long long act_ld = 0, act_bs = 0;   // float (SIMT) or bf16 (TC)
+  RowMask mask = {nullptr, 0};
+  int mask_pre = 0, mask_act = 0;
+  float alpha = 1.0f, div = 1.0f;
+  int act = ACT_NONE;
+  float slope = 0.0f;
+  const float* snake_a = nullptr;     // exp(alpha)            [C_out]
+  const float* snake_invb = nullptr;  // 1/(exp(beta)+1e-9)    [C_out]
+  int phase_cout = 0;  // C_out per phase (== N for ordinary convs)
+  int up_s = 1, up_p = 0;
+  int T_out = 0;       // valid output rows per batch item
+};
+
+// (GEMM row r, GEMM column n) -> (output time t, output channel co); returns false when the slot is outside the output.
+__device__ __forceinline__ bool ep_coord(const Epilogue& e, int r, int n, int& t, int& co) {
+  int phase = n / e.phase_cout;
+  co = n - phase * e.phase_cout;
+  t = e.up_s * r + phase - e.up_p;
+  return t >= 0 && t < e.T_out;
+}
+
+__device__ __forceinline__ float ep_value(const Epilogue& e, int b, int t, int co, float acc, float maskv) {
+  float v = acc + (e.bias ? __ldg(e.bias + co) : 0.0f);
+  if (e.mask_pre) v *= maskv;
+  v *= e.alpha;
+  if (e.res) v += e.res[b * e.res_bs + (long long)t * e.res_ld + co];
+  if (e.res2) v += e.res2[b * e.res2_bs + (long long)t * e.res2_ld + co];
+  if (e.div != 1.0f) v = v / e.div;
+  return v;
+}
+
+__device__ __forceinline__ float ep_act(const Epilogue& e, int co, float v, float maskv) {
+  float sa = 0.0f, sb = 0.0f;
+  if (e.act == ACT_SNAKE) { sa = __ldg(e.snake_a + co); sb = __ldg(e.snake_invb + co); }
+  float w = apply_act(v, e.act, e.slope, sa, sb);
+  if (e.mask_act) w *= maskv;
+  return w;
+}
+
+// Packed weights of one convolution / linear layer, both layouts (owned by the context).
+struct ConvWeights {
+  float* w_f32 = nullptr;   // [taps][C_in][N_pad]      (N contiguous; SIMT B-operand)
+  bf16* w_bf16 = nullptr;   // [taps][N_pad128][K_pad]  (C_in contiguous, K-major; TMA/UMMA B-operand)
+  float* bias = nullptr;    // [C_out] or nullptr
+  int taps = 0, C_in = 0, N = 0, N_pad = 0, N_pad_tc = 0, K_pad = 0;
+  // geometry template
+  int conv_stride = 1, dilation = 1, pad = 0, transposed = 0, up_s = 1, up_p = 0, C_out = 0, ksize = 1;
+};
+
+// conv_simt.cu
+cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, long long x_bs, const ConvWeights& w,
+                             const Epilogue& e, cudaStream_t stream);
+// conv_tc.cu
+cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, long long x_bs, int x_rows_alloc,
+                           const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err);
+bool conv_tc_init(std::string* err);
+int conv_tc_pick_bn(int N);
+
+}  // namespace ev

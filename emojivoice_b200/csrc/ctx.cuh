@@ -1,0 +1,131 @@
+// Context, weight store and the conv dispatch shared by matcha.cu / hifigan.cu / api.cu.
+#pragma once
+#include <map>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/emojivoice_b200.h"
+#include "conv.cuh"
+#include "kernels.cuh"
+
+namespace ev {
+
+struct ResnetW {
+  ConvWeights conv1, conv2, res;
+  float *gn1_g = nullptr, *gn1_b = nullptr, *gn2_g = nullptr, *gn2_b = nullptr;
+  int c_in = 0;
+};
+struct TransformerW {
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln3_g = nullptr, *ln3_b = nullptr;
+  ConvWeights qkv, out, ff1, ff2;
+  float *snake_a = nullptr, *snake_invb = nullptr;
+};
+struct EncLayerW {
+  ConvWeights qkv, o, ffn1, ffn2;
+  float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+};
+
+struct MatchaW {
+  bool loaded = false;
+  ev_matcha_cfg cfg{};
+  float* spk_table = nullptr;
+  float* tok_emb = nullptr;
+  ConvWeights pre_conv[3], pre_proj;
+  float *pre_g[3] = {}, *pre_b[3] = {};
+  std::vector<EncLayerW> enc;
+  ConvWeights proj_m, dp_conv1, dp_conv2, dp_proj;
+  float *dp_g1 = nullptr, *dp_b1 = nullptr, *dp_g2 = nullptr, *dp_b2 = nullptr;
+  float *rope_cos = nullptr, *rope_sin = nullptr;
+  int rope_T = 0;
+  // estimator
+  ConvWeights time1, time2, temb_proj;  // temb_proj stacks the 6 resnet mlp.1 layers (N = 6*C)
+  ResnetW rn[6];                        // down0, down1, mid0, mid1, up0, up1
+  TransformerW tf[6];
+  ConvWeights down0, down1_conv, up0, up1_conv, final_conv, final_proj;
+  float *final_g = nullptr, *final_b = nullptr;
+};
+
+struct HifiganW {
+  bool loaded = false;
+  ev_hifigan_cfg cfg{};
+  ConvWeights conv_pre;
+  ConvWeights ups[8];
+  ConvWeights c1[8][4][3], c2[8][4][3];
+  float* post_w = nullptr;   // [7][C_last]
+  float* post_b = nullptr;
+  int c_last = 0, total_up = 1;
+  float* denoise_bias = nullptr;  // (n_fft/2+1) once ev_denoiser_init ran
+};
+
+}  // namespace ev
+
+struct ev_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::string err;
+  long long launches = 0;
+  std::vector<void*> owned;     // cudaMalloc'ed by this context
+  ev::MatchaW matcha;
+  ev::HifiganW hifigan;
+};
+
+namespace ev {
+
+int fail(ev_ctx* ctx, int code, const std::string& msg);
+int cuda_fail(ev_ctx* ctx, cudaError_t ce, const char* what);
+#define EV_CUDA(ctx, expr)                                          \
+  do {                                                              \
+    cudaError_t _ce = (expr);                                       \
+    if (_ce != cudaSuccess) return ev::cuda_fail(ctx, _ce, #expr);  \
+  } while (0)
+#define EV_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != 0) return _rc;   \
+  } while (0)
+
+// Bump allocator over the caller's workspace (256-byte granules).
+struct Workspace {
+  char* base;
+  size_t size, off = 0;
+  bool overflow = false;
+  Workspace(void* p, size_t n) : base(reinterpret_cast<char*>(p)), size(n) {}
+  template <typename T> T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T), 256);
+    if (base == nullptr) { off += bytes; return nullptr; }   // sizing pass
+    if (off + bytes > size) { overflow = true; return nullptr; }
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+// name -> tensor lookup over the caller's ev_tensor list
+struct WeightStore {
+  std::map<std::string, const ev_tensor*> by_name;
+  ev_ctx* ctx;
+  cudaStream_t stream;
+  WeightStore(ev_ctx* c, const ev_tensor* w, int n, cudaStream_t s);
+  const ev_tensor* get(const std::string& name, std::initializer_list<long long> shape);
+  bool has(const std::string& name) const { return by_name.count(name) != 0; }
+  // plain fp32 copy owned by the context
+  int copy_vec(const std::string& name, long long n, float** out);
+};
+
+enum ConvKind { CONV_NORMAL = 0, CONV_TRANSPOSED = 1 };
+// Allocate + pack one conv / linear layer.  `names` may list several tensors stacked along N (fused QKV, stacked mlps).
+int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weight_names, const std::vector<std::string>& bias_names,
+              int c_out_each, int c_in, int ksize, int stride, int pad, int dilation, ConvKind kind, bool want_bf16,
+              ConvWeights* out);
+int device_alloc(ev_ctx* ctx, size_t bytes, void** out, bool zero, cudaStream_t s);
+
+// Derive the GEMM geometry of `w` applied to B items of T_in rows; returns T_out.
+int conv_geometry(const ConvWeights& w, int B, int T_in, ConvGeom* g);
+
+// Launch `w` on x (ActT = float -> CUDA-core fp32, bf16 -> tcgen05); e carries the fused epilogue.
+template <typename ActT>
+int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, long long x_bs, int B, int T_in,
+             Epilogue e, cudaStream_t s);
+
+}  // namespace ev

@@ -1,0 +1,403 @@
+// Coalesced / vectorised / warp-shuffle kernels around the GEMMs: layout glue, embeddings, LayerNorm, GroupNorm,
+// Mish, the decoder input pack, the sinusoidal time embedding and HiFi-GAN's conv_post+tanh tail.
+#include "kernels.cuh"
+
+namespace ev {
+namespace {
+
+// ---------------------------------------------------------------------------------------------- transposes
+template <typename OutT>
+__global__ void cf_to_cl_kernel(const float* __restrict__ in, int C, int T, OutT* __restrict__ out, long long out_ld,
+                                long long out_bs, float scale, RowMask mask) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* inb = in + (long long)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? inb[(long long)c * T + t] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) out[b * out_bs + (long long)t * out_ld + c] = from_float<OutT>(tile[threadIdx.x][i] * scale * mask.at(b, t));
+  }
+}
+
+__global__ void cl_to_cf_kernel(const float* __restrict__ in, long long in_ld, long long in_bs, int C, int T,
+                                float* __restrict__ out, float mul, float add) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? in[b * in_bs + (long long)t * in_ld + c] : 0.0f;
+  }
+  __syncthreads();
+  float* outb = out + (long long)b * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) outb[(long long)c * T + t] = tile[threadIdx.x][i] * mul + add;
+  }
+}
+
+__global__ void i64_to_i32_kernel(const long long* in, int* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int)in[i];
+}
+
+struct Vals32 { float v[32]; };
+__global__ void upload_kernel(float* dst, Vals32 vals, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------- embeddings
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ emb, int Tx, int C,
+                                    int n_vocab, float scale, RowMask mask, float* __restrict__ out, long long out_ld) {
+  const int row = blockIdx.x, b = row / Tx, t = row - b * Tx;
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  const float m = mask.at(b, t);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)row * out_ld + c] = emb[id * C + c] * scale * m;
+}
+
+__global__ void embed_speakers_kernel(const long long* ids, const float* table, int dim, int n_spks, float* out) {
+  const int b = blockIdx.x;
+  long long id = ids[b];
+  id = id < 0 ? 0 : (id >= n_spks ? n_spks - 1 : id);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) out[b * dim + c] = table[id * dim + c];
+}
+
+__global__ void fill_speaker_kernel(const float* spk, int T, int dim, RowMask mask, float* buf, long long ld, int c0) {
+  const int row = blockIdx.x, b = row / T, t = row - b * T;
+  const float m = mask.at(b, t);
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) buf[(long long)row * ld + c0 + c] = spk[b * dim + c] * m;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
+template <typename ActT, int VPL>  // VPL = ceil(C/32) values per lane
+__global__ void __launch_bounds__(256) layer_norm_kernel(LnArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = a.B * a.T;
+  if (warp >= rows) return;
+  const int b = warp / a.T, t = warp - b * a.T;
+  const float* x = a.x + (long long)warp * a.x_ld;
+  const float* ad = a.add ? a.add + (long long)warp * a.add_ld : nullptr;
+  float v[VPL];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    float xv = 0.0f;
+    if (c < a.C) {
+      xv = x[c];
+      if (ad) xv += ad[c];
+      if (a.pre_relu) xv = fmaxf(xv, 0.0f);
+    }
+    v[i] = xv;
+    sum += xv;
+  }
+  const float mean = warp_sum(sum) / (float)a.C;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    const float d = (c < a.C) ? v[i] - mean : 0.0f;
+    sq += d * d;
+  }
+  const float var = warp_sum(sq) / (float)a.C;
+  const float rstd = 1.0f / sqrtf(var + a.eps);
+  const float m = a.mask.at(b, t);
+  ActT* oa = a.out_act ? reinterpret_cast<ActT*>(a.out_act) + (long long)warp * a.act_ld : nullptr;
+  float* of = a.out_f32 ? a.out_f32 + (long long)warp * a.f32_ld : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    if (c < a.C) {
+      float y = (v[i] - mean) * rstd * a.gamma[c] + a.beta[c];
+      if (a.post_relu) y = fmaxf(y, 0.0f);
+      y *= m;
+      if (of) of[c] = y;
+      if (oa) oa[c] = from_float<ActT>(y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- time embedding
+__global__ void time_sinusoid_kernel(const float* t_steps, int n, int dim, float* out) {
+  const int s = blockIdx.x, half = dim / 2;
+  // decoder.py:23-26: exp(arange(half) * -(log(1e4)/(half-1))), then (1000*t)*freq, all in float32
+  const float neg = (float)(-(log(10000.0) / (double)(half - 1)));
+  const float tt = __fmul_rn(1000.0f, t_steps[s]);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float freq = (float)exp((double)__fmul_rn((float)i, neg));
+    const float arg = __fmul_rn(tt, freq);
+    out[s * dim + i] = (float)sin((double)arg);
+    out[s * dim + half + i] = (float)cos((double)arg);
+  }
+}
+
+template <typename ActT>
+__global__ void decoder_pack_kernel(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ spk,
+                                    int F, int S, int T, float temperature, RowMask mask, float* __restrict__ x_state,
+                                    ActT* __restrict__ xin, long long xin_ld) {
+  // one block per (b, 32-frame tile): transposes z and mu through shared memory
+  extern __shared__ float sh[];  // [2][F][33]
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  float* zs = sh;
+  float* ms = sh + F * 33;
+  for (int idx = threadIdx.x; idx < F * 32; idx += blockDim.x) {
+    const int c = idx >> 5, tt = idx & 31, t = t0 + tt;
+    const long long g = ((long long)b * F + c) * T + t;
+    zs[c * 33 + tt] = t < T ? z[g] * temperature : 0.0f;
+    ms[c * 33 + tt] = t < T ? mu[g] : 0.0f;
+  }
+  __syncthreads();
+  const int C = 2 * F + S;
+  for (int idx = threadIdx.x; idx < 32 * C; idx += blockDim.x) {
+    const int tt = idx / C, c = idx - tt * C, t = t0 + tt;
+    if (t >= T) continue;
+    const float m = mask.at(b, t);
+    float v;
+    if (c < F) {
+      v = zs[c * 33 + tt];
+      x_state[((long long)b * T + t) * F + c] = v;
+    } else if (c < 2 * F) {
+      v = ms[(c - F) * 33 + tt];
+    } else {
+      v = spk[b * S + (c - 2 * F)];
+    }
+    xin[((long long)b * T + t) * xin_ld + c] = from_float<ActT>(v * m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm
+constexpr int GN_ROWS = 32;  // frames per statistics block
+// partial[b][chunk][group][2] (sum, sum of squares) in double; blockDim = C threads (C <= 1024, 32 ch per group)
+__global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int cpg, double* __restrict__ partial) {
+  const int b = blockIdx.y, chunk = blockIdx.x, c = threadIdx.x;
+  const int t0 = chunk * GN_ROWS, t1 = min(T, t0 + GN_ROWS);
+  float s = 0.0f, q = 0.0f;
+  const float* xb = x + ((long long)b * T) * C;
+  for (int t = t0; t < t1; ++t) {
+    const float v = xb[(long long)t * C + c];
+    s += v;
+    q += v * v;
+  }
+  // reduce over the cpg channels of the group (cpg is a power of two <= 32, groups are lane-aligned)
+  double ds = (double)s, dq = (double)q;
+  for (int o = cpg >> 1; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  if ((c % cpg) == 0) {
+    const int g = c / cpg, G = C / cpg;
+    double* p = partial + (((long long)b * gridDim.x + chunk) * G + g) * 2;
+    p[0] = ds;
+    p[1] = dq;
+  }
+}
+
+template <typename ActT, int VPL>
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
+  // warp per (b,t) row; lane owns channels lane + 32*i, which belong to group (lane + 32 i) / cpg
+  extern __shared__ float stat[];  // [G][2] mean, rstd for this block's batch item
+  const int b = blockIdx.y;
+  const int G = a.groups, cpg = a.C / G;
+  if ((int)threadIdx.x < G) {
+    double s = 0.0, q = 0.0;
+    for (int ch = 0; ch < a.n_chunks; ++ch) {
+      const double* p = a.partial + (((long long)b * a.n_chunks + ch) * G + threadIdx.x) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    const double n = (double)cpg * (double)a.T;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[2 * threadIdx.x] = (float)mean;
+    stat[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= a.T) return;
+  const long long row = (long long)b * a.T + t;
+  const float* x = a.x + row * a.C;
+  const float m = a.mask.at(b, t);
+  float y[VPL];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int c = lane + 32 * i;
+    float v = 0.0f;
+    if (c < a.C) {
+      const int g = c / cpg;
+      v = (x[c] - stat[2 * g]) * stat[2 * g + 1] * a.gamma[c] + a.beta[c];
+      v = mish_f(v) * m;                                   // Block1D: Mish then *mask (decoder.py:41-43)
+      if (a.temb) v = (v + a.temb[c]) * m;                 // h += mlp(t); next Block1D multiplies by mask again
+      if (a.res) v += a.res[row * a.res_ld + c];
+      if (a.out_f32) a.out_f32[row * a.f32_ld + c] = v;
+      if (a.out_act) reinterpret_cast<ActT*>(a.out_act)[row * a.act_ld + c] = from_float<ActT>(v);
+    }
+    y[i] = v;
+    sum += v;
+  }
+  if (a.out_ln) {  // fused pre-LN of the transformer block that follows (transformer.py:262), eps 1e-5
+    const float mean = warp_sum(sum) / (float)a.C;
+    float sq = 0.0f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float d = (lane + 32 * i < a.C) ? y[i] - mean : 0.0f;
+      sq += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)a.C + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int c = lane + 32 * i;
+      if (c < a.C)
+        reinterpret_cast<ActT*>(a.out_ln)[row * a.ln_ld + c] = from_float<ActT>((y[i] - mean) * rstd * a.ln_gamma[c] + a.ln_beta[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- vocoder tail
+template <int C>
+__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, int L, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ wav) {
+  // 256 output samples per block; the (256+6) x C input window is staged in shared memory with LeakyReLU(0.01) applied
+  __shared__ float xs[(256 + 6) * (C + 1)];
+  __shared__ float ws[7 * C];
+  const int b = blockIdx.y, t0 = blockIdx.x * 256;
+  for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
+  const float* xb = x + (long long)b * L * C;
+  for (int i = threadIdx.x; i < (256 + 6) * C; i += 256) {
+    const int r = i / C, c = i - r * C, t = t0 + r - 3;
+    float v = (t >= 0 && t < L) ? xb[(long long)t * C + c] : 0.0f;
+    xs[r * (C + 1) + c] = v > 0.0f ? v : v * 0.01f;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
+  float acc = bias[0];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const float* xr = xs + (threadIdx.x + j) * (C + 1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc = fmaf(ws[j * C + c], xr[c], acc);
+  }
+  float y = tanhf(acc);
+  y = fminf(fmaxf(y, -1.0f), 1.0f);
+  wav[(long long)b * L + t] = y;
+}
+
+}  // namespace
+
+// ================================================================================================ launchers
+template <typename OutT>
+cudaError_t cf_to_cl(const float* in, int B, int C, int T, OutT* out, long long out_ld, long long out_bs, float scale,
+                     RowMask mask, cudaStream_t s) {
+  dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B), block(32, 8);
+  cf_to_cl_kernel<OutT><<<grid, block, 0, s>>>(in, C, T, out, out_ld, out_bs, scale, mask);
+  return cudaGetLastError();
+}
+template cudaError_t cf_to_cl<float>(const float*, int, int, int, float*, long long, long long, float, RowMask, cudaStream_t);
+template cudaError_t cf_to_cl<bf16>(const float*, int, int, int, bf16*, long long, long long, float, RowMask, cudaStream_t);
+
+cudaError_t cl_to_cf(const float* in, long long in_ld, long long in_bs, int B, int C, int T, float* out, float mul,
+                     float add, cudaStream_t s) {
+  dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B), block(32, 8);
+  cl_to_cf_kernel<<<grid, block, 0, s>>>(in, in_ld, in_bs, C, T, out, mul, add);
+  return cudaGetLastError();
+}
+
+cudaError_t i64_to_i32(const long long* in, int* out, int n, cudaStream_t s) {
+  i64_to_i32_kernel<<<ceil_div(n, 256), 256, 0, s>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t upload_floats(float* dst, const float* vals_host, int n, cudaStream_t s) {
+  for (int off = 0; off < n; off += 32) {
+    Vals32 v;
+    const int m = n - off < 32 ? n - off : 32;
+    for (int i = 0; i < 32; ++i) v.v[i] = i < m ? vals_host[off + i] : 0.0f;
+    upload_kernel<<<1, 32, 0, s>>>(dst + off, v, m);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t embed_tokens(const long long* ids, const float* emb, int B, int Tx, int C, int n_vocab, float scale,
+                         RowMask mask, float* out, long long out_ld, cudaStream_t s) {
+  embed_tokens_kernel<<<B * Tx, 64, 0, s>>>(ids, emb, Tx, C, n_vocab, scale, mask, out, out_ld);
+  return cudaGetLastError();
+}
+cudaError_t embed_speakers(const long long* ids, const float* table, int B, int dim, int n_spks, float* out, cudaStream_t s) {
+  embed_speakers_kernel<<<B, 64, 0, s>>>(ids, table, dim, n_spks, out);
+  return cudaGetLastError();
+}
+cudaError_t fill_speaker_channels(const float* spk, int B, int T, int dim, RowMask mask, float* buf, long long ld, int c0,
+                                  cudaStream_t s) {
+  fill_speaker_kernel<<<B * T, 64, 0, s>>>(spk, T, dim, mask, buf, ld, c0);
+  return cudaGetLastError();
+}
+
+template <typename ActT>
+cudaError_t layer_norm_rows(const LnArgs& a, cudaStream_t s) {
+  const int rows = a.B * a.T;
+  const int blocks = ceil_div(rows, 8);
+  const int vpl = ceil_div(a.C, 32);
+  if (vpl <= 6) layer_norm_kernel<ActT, 6><<<blocks, 256, 0, s>>>(a);
+  else if (vpl <= 8) layer_norm_kernel<ActT, 8><<<blocks, 256, 0, s>>>(a);
+  else if (vpl <= 32) layer_norm_kernel<ActT, 32><<<blocks, 256, 0, s>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+template cudaError_t layer_norm_rows<float>(const LnArgs&, cudaStream_t);
+template cudaError_t layer_norm_rows<bf16>(const LnArgs&, cudaStream_t);
+
+cudaError_t time_sinusoid(const float* t_steps, int n, int dim, float* out, cudaStream_t s) {
+  time_sinusoid_kernel<<<n, 128, 0, s>>>(t_steps, n, dim, out);
+  return cudaGetLastError();
+}
+
+template <typename ActT>
+cudaError_t decoder_pack_input(const float* z_cf, const float* mu_cf, const float* spk, int B, int F, int S, int T,
+                               float temperature, RowMask mask, float* x_state, ActT* xin, long long xin_ld, cudaStream_t s) {
+  dim3 grid(ceil_div(T, 32), B);
+  const size_t sh = (size_t)2 * F * 33 * sizeof(float);
+  decoder_pack_kernel<ActT><<<grid, 256, sh, s>>>(z_cf, mu_cf, spk, F, S, T, temperature, mask, x_state, xin, xin_ld);
+  return cudaGetLastError();
+}
+template cudaError_t decoder_pack_input<float>(const float*, const float*, const float*, int, int, int, int, float, RowMask, float*, float*, long long, cudaStream_t);
+template cudaError_t decoder_pack_input<bf16>(const float*, const float*, const float*, int, int, int, int, float, RowMask, float*, bf16*, long long, cudaStream_t);
+
+cudaError_t group_norm_stats(const float* x, int B, int T, int C, int groups, double* partial, int* n_chunks_out,
+                             cudaStream_t s) {
+  const int cpg = C / groups;
+  if (C > 1024 || C % groups || cpg > 32 || (cpg & (cpg - 1)) || (C % 32)) return cudaErrorInvalidValue;
+  const int chunks = ceil_div(T, GN_ROWS);
+  *n_chunks_out = chunks;
+  gn_stats_kernel<<<dim3(chunks, B), C, 0, s>>>(x, T, C, cpg, partial);
+  return cudaGetLastError();
+}
+
+template <typename ActT>
+cudaError_t group_norm_apply(const GnApplyArgs& a, cudaStream_t s) {
+  const int vpl = ceil_div(a.C, 32);
+  dim3 grid(ceil_div(a.T, 8), a.B);
+  const size_t sh = (size_t)a.groups * 2 * sizeof(float);
+  if (vpl <= 8) gn_apply_kernel<ActT, 8><<<grid, 256, sh, s>>>(a);
+  else if (vpl <= 32) gn_apply_kernel<ActT, 32><<<grid, 256, sh, s>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+template cudaError_t group_norm_apply<float>(const GnApplyArgs&, cudaStream_t);
+template cudaError_t group_norm_apply<bf16>(const GnApplyArgs&, cudaStream_t);
+
+cudaError_t conv_post_tanh(const float* x, int B, int L, int C, const float* w, const float* bias, float* wav, cudaStream_t s) {
+  dim3 grid(ceil_div(L, 256), B);
+  if (C == 32) conv_post_kernel<32><<<grid, 256, 0, s>>>(x, L, w, bias, wav);
+  else if (C == 16) conv_post_kernel<16><<<grid, 256, 0, s>>>(x, L, w, bias, wav);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+}  // namespace ev

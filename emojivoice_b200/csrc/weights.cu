@@ -1,0 +1,187 @@
+// Weight packing (reference state_dict layouts -> kernel layouts, fp32 + bf16 twins) and the conv dispatch.
+#include "ctx.cuh"
+
+namespace ev {
+
+int fail(ev_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+int cuda_fail(ev_ctx* ctx, cudaError_t ce, const char* what) {
+  return fail(ctx, EV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+}
+
+int device_alloc(ev_ctx* ctx, size_t bytes, void** out, bool zero, cudaStream_t s) {
+  void* p = nullptr;
+  EV_CUDA(ctx, cudaMalloc(&p, bytes ? bytes : 16));
+  ctx->owned.push_back(p);
+  if (zero) EV_CUDA(ctx, cudaMemsetAsync(p, 0, bytes ? bytes : 16, s));
+  *out = p;
+  return 0;
+}
+
+WeightStore::WeightStore(ev_ctx* c, const ev_tensor* w, int n, cudaStream_t s) : ctx(c), stream(s) {
+  for (int i = 0; i < n; ++i)
+    if (w[i].name) by_name[w[i].name] = &w[i];
+}
+
+const ev_tensor* WeightStore::get(const std::string& name, std::initializer_list<long long> shape) {
+  auto it = by_name.find(name);
+  if (it == by_name.end()) { fail(ctx, EV_ERR_MISSING, "missing weight tensor: " + name); return nullptr; }
+  const ev_tensor* t = it->second;
+  long long want = 1, have = 1;
+  for (long long d : shape) want *= d;
+  for (int i = 0; i < t->ndim; ++i) have *= t->shape[i];
+  if (want != have || t->data == nullptr) {
+    fail(ctx, EV_ERR_INVALID, "weight tensor " + name + " has " + std::to_string(have) + " elements, expected " + std::to_string(want));
+    return nullptr;
+  }
+  return t;
+}
+
+int WeightStore::copy_vec(const std::string& name, long long n, float** out) {
+  const ev_tensor* t = get(name, {n});
+  if (!t) return ctx->err.find("missing") == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
+  void* p;
+  EV_TRY(device_alloc(ctx, (size_t)n * sizeof(float), &p, false, stream));
+  EV_CUDA(ctx, cudaMemcpyAsync(p, t->data, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  *out = reinterpret_cast<float*>(p);
+  return 0;
+}
+
+namespace {
+// src is (C_out, C_in, K) [nn.Conv1d / nn.Linear with K=1] or (C_in, C_out, K) [nn.ConvTranspose1d].
+// Ordinary conv:   GEMM column n = co,              tap j = kernel index j
+// Transposed conv: GEMM column n = phase*C_out + co, tap e in {0,1} holds kernel index m = phase + s*e   (k == 2s)
+__global__ void pack_conv_kernel(const float* __restrict__ src, int C_out, int C_in, int K, int transposed, int s,
+                                 int taps, int n_local, int n_off, float* __restrict__ dst_f32, int N_pad,
+                                 bf16* __restrict__ dst_bf16, int N_pad_tc, int K_pad) {
+  const long long total = (long long)taps * C_in * n_local;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % n_local);
+    const int ci = (int)((idx / n_local) % C_in);
+    const int tap = (int)(idx / ((long long)n_local * C_in));
+    float v;
+    if (!transposed) {
+      v = src[((long long)n * C_in + ci) * K + tap];
+    } else {
+      const int phase = n / C_out, co = n - phase * C_out;
+      v = src[((long long)ci * C_out + co) * K + phase + s * tap];
+    }
+    if (dst_f32) dst_f32[((long long)tap * C_in + ci) * N_pad + n_off + n] = v;
+    if (dst_bf16) dst_bf16[((long long)tap * N_pad_tc + n_off + n) * K_pad + ci] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace
+
+int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weight_names,
+              const std::vector<std::string>& bias_names, int c_out_each, int c_in, int ksize, int stride, int pad,
+              int dilation, ConvKind kind, bool want_bf16, ConvWeights* out) {
+  ConvWeights w;
+  const int parts = (int)weight_names.size();
+  w.transposed = kind == CONV_TRANSPOSED;
+  w.ksize = ksize;
+  w.C_in = c_in;
+  w.conv_stride = w.transposed ? 1 : stride;
+  w.dilation = dilation;
+  w.pad = pad;
+  int n_local;
+  if (w.transposed) {
+    if (ksize != 2 * stride || pad >= stride || parts != 1 || dilation != 1)
+      return fail(ctx, EV_ERR_INVALID, "transposed conv must have kernel == 2*stride and padding < stride: " + weight_names[0]);
+    w.taps = 2;
+    w.up_s = stride;
+    w.up_p = pad;
+    w.C_out = c_out_each;
+    n_local = stride * c_out_each;
+  } else {
+    if (ksize > kMaxTaps) return fail(ctx, EV_ERR_INVALID, "kernel too wide: " + weight_names[0]);
+    w.taps = ksize;
+    w.C_out = c_out_each * parts;
+    n_local = c_out_each;
+  }
+  w.N = n_local * parts;
+  w.N_pad = (w.N == 1) ? 4 : (int)align_up(w.N, 4);
+  const int bn = conv_tc_pick_bn(w.N);
+  w.N_pad_tc = (int)align_up(w.N, bn);
+  w.K_pad = (int)align_up(c_in, 64);
+  void* p;
+  EV_TRY(device_alloc(ctx, (size_t)w.taps * c_in * w.N_pad * sizeof(float), &p, true, ws.stream));
+  w.w_f32 = reinterpret_cast<float*>(p);
+  if (want_bf16) {
+    EV_TRY(device_alloc(ctx, (size_t)w.taps * w.N_pad_tc * w.K_pad * sizeof(bf16), &p, true, ws.stream));
+    w.w_bf16 = reinterpret_cast<bf16*>(p);
+  }
+  for (int i = 0; i < parts; ++i) {
+    const ev_tensor* t = ws.get(weight_names[i], {(long long)c_out_each, (long long)c_in, (long long)ksize});
+    if (!t) return ctx->err.rfind("missing", 0) == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
+    const long long total = (long long)w.taps * c_in * n_local;
+    const int blocks = (int)std::min<long long>(4096, ceil_div_ll(total, 256));
+    pack_conv_kernel<<<blocks, 256, 0, ws.stream>>>(t->data, c_out_each, c_in, ksize, w.transposed, stride, w.taps,
+                                                    n_local, i * n_local, w.w_f32, w.N_pad, w.w_bf16, w.N_pad_tc, w.K_pad);
+    EV_CUDA(ctx, cudaGetLastError());
+  }
+  if (!bias_names.empty()) {
+    if ((int)bias_names.size() != parts) return fail(ctx, EV_ERR_INVALID, "bias list does not match weight list");
+    EV_TRY(device_alloc(ctx, (size_t)align_up(w.C_out, 4) * sizeof(float), &p, true, ws.stream));
+    w.bias = reinterpret_cast<float*>(p);
+    for (int i = 0; i < parts; ++i) {
+      const ev_tensor* t = ws.get(bias_names[i], {(long long)c_out_each});
+      if (!t) return ctx->err.rfind("missing", 0) == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
+      EV_CUDA(ctx, cudaMemcpyAsync(w.bias + (size_t)i * c_out_each, t->data, (size_t)c_out_each * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, ws.stream));
+    }
+  }
+  *out = w;
+  return 0;
+}
+
+int conv_geometry(const ConvWeights& w, int B, int T_in, ConvGeom* g) {
+  g->B = B;
+  g->N = w.N;
+  g->C_in = w.C_in;
+  g->taps = w.taps;
+  g->T_in = T_in;
+  g->conv_stride = w.conv_stride;
+  int T_out;
+  if (w.transposed) {
+    // t_out + p = s*r + phase,  phase in [0,s);  tap e reads input row r - e  (weights.cu pack_conv_kernel)
+    g->tap_off[0] = 0;
+    g->tap_off[1] = -1;
+    g->M = T_in + 1;
+    T_out = (T_in - 1) * w.up_s - 2 * w.up_p + w.ksize;
+  } else {
+    for (int j = 0; j < w.taps; ++j) g->tap_off[j] = j * w.dilation - w.pad;
+    T_out = (T_in + 2 * w.pad - w.dilation * (w.ksize - 1) - 1) / w.conv_stride + 1;
+    g->M = T_out;
+  }
+  return T_out;
+}
+
+template <typename ActT>
+int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, long long x_bs, int B, int T_in, Epilogue e,
+             cudaStream_t s) {
+  ConvGeom g;
+  const int T_out = conv_geometry(w, B, T_in, &g);
+  e.bias = w.bias;
+  e.T_out = T_out;
+  e.phase_cout = w.transposed ? w.C_out : w.N;
+  e.up_s = w.transposed ? w.up_s : 1;
+  e.up_p = w.transposed ? w.up_p : 0;
+  cudaError_t ce;
+  if constexpr (std::is_same<ActT, float>::value) {
+    ce = conv_simt_launch(g, x, x_ld, x_bs, w, e, s);
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "conv_simt_launch");
+  } else {
+    if (!w.w_bf16) return fail(ctx, EV_ERR_STATE, "layer has no bf16 weights");
+    std::string msg;
+    ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg);
+    if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
+  }
+  ctx->launches++;
+  return 0;
+}
+template int run_conv<float>(ev_ctx*, const ConvWeights&, const float*, long long, long long, int, int, Epilogue, cudaStream_t);
+template int run_conv<bf16>(ev_ctx*, const ConvWeights&, const bf16*, long long, long long, int, int, Epilogue, cudaStream_t);
+
+}  // namespace ev

@@ -1,0 +1,153 @@
+/*
+ * emojivoice_b200 -- C ABI of the B200-native synthesis hot path.
+ *
+ * One shared library (libemojivoice_b200.so, sm_100a only) holds every CUDA kernel and the layer
+ * orchestration of the path   MatchaTTS.synthesise(...) -> vocoder(mel) [-> denoiser]   of
+ * rosielab/emojivoice.  The reference has no FFI for this path (it is plain PyTorch); the entry points below
+ * are therefore cut at the python calls a maintainer would rebind, and each one names the reference
+ * interface it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors use the reference's own layouts (channel-first, contiguous, fp32 / int64);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises, allocates
+ *     outputs, or spawns threads; scratch comes from the caller via the *_workspace_bytes() queries;
+ *   - every function returns 0 on success or a negative ev_status; ev_last_error() gives the message;
+ *     nothing throws across the boundary; a context is not re-entrant.
+ *   - there is no CPU fallback: on a machine without an sm_100 device ev_create() fails.
+ */
+#ifndef EMOJIVOICE_B200_H
+#define EMOJIVOICE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define EV_API __attribute__((visibility("default")))
+#else
+#define EV_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ev_ctx ev_ctx;
+
+typedef enum {
+  EV_OK = 0,
+  EV_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  EV_ERR_CUDA = -2,      /* a CUDA runtime or driver call failed */
+  EV_ERR_MISSING = -3,   /* a required weight tensor was not supplied */
+  EV_ERR_STATE = -4,     /* weights not loaded / workspace too small */
+  EV_ERR_NO_DEVICE = -5  /* no sm_100 device */
+} ev_status;
+
+/* Arithmetic of the dense contractions in the decoder and vocoder (the text encoder and the duration /
+ * alignment stage are always fp32 + integer so that durations stay bit-exact). */
+typedef enum {
+  EV_PREC_FP32 = 0, /* fp32 CUDA-core implicit GEMM, fixed summation order (parity mode, rel-L2 <= 1e-4) */
+  EV_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 TMEM accumulation, fp32 residual streams */
+} ev_precision;
+
+/* A named fp32 device tensor in the reference's state_dict layout (SURVEY.md 8a "weights contract"). */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} ev_tensor;
+
+/* Hyper-parameters of MatchaTTS.__init__ (Matcha-TTS/matcha/models/matcha_tts.py:27-76,
+ * configs/model/{matcha,encoder/default,decoder/default}.yaml). */
+typedef struct {
+  int32_t n_vocab, n_spks, spk_emb_dim, n_feats;
+  int32_t enc_channels, enc_filter_channels, enc_filter_channels_dp, enc_heads, enc_layers, enc_kernel, enc_prenet;
+  int32_t dec_channels, dec_heads, dec_head_dim, dec_mid_blocks;
+  float mel_mean, mel_std;
+} ev_matcha_cfg;
+
+/* HiFi-GAN generator hyper-parameters (Matcha-TTS/matcha/hifigan/config.py:1-28). */
+typedef struct {
+  int32_t num_mels, upsample_initial_channel, n_ups, n_kernels;
+  int32_t upsample_rates[8], upsample_kernel_sizes[8];
+  int32_t resblock_kernel_sizes[4], resblock_dilation_sizes[4][3];
+} ev_hifigan_cfg;
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+EV_API int ev_create(ev_ctx** out, int device);
+EV_API int ev_destroy(ev_ctx* ctx);
+EV_API const char* ev_last_error(const ev_ctx* ctx); /* also valid with ctx == NULL (last creation error) */
+EV_API int ev_version(void);
+
+/* ---- weights ---------------------------------------------------------------------------------------
+ * Replace MatchaTTS.load_state_dict / load_from_checkpoint (feel_me.py:156-159) and
+ * Generator.load_state_dict + remove_weight_norm (feel_me.py:161-167, hifigan/models.py:199-206).
+ * The library packs its own copies (kernel layouts, bf16 twins); the caller's tensors may be freed after
+ * the call returns (the call synchronises `stream`). */
+EV_API int ev_load_matcha(ev_ctx* ctx, const ev_tensor* weights, int n_weights, const ev_matcha_cfg* cfg, void* stream);
+EV_API int ev_load_hifigan(ev_ctx* ctx, const ev_tensor* weights, int n_weights, const ev_hifigan_cfg* cfg, void* stream);
+
+/* ---- text encoder + duration predictor + length stage ------------------------------------------------
+ * Replaces matcha_tts.py:116-124: spk_emb lookup, TextEncoder.forward (text_encoder.py:378-410),
+ * w = exp(logw)*mask, w_ceil = ceil(w)*length_scale, y_lengths = trunc(max(sum(w_ceil),1)).
+ *   x (B,Tx) int64, x_lengths (B) int64, spks (B) int64 (ignored when n_spks == 1)
+ *   out: spk_emb (B,spk_emb_dim), mu_x (B,n_feats,Tx), logw (B,1,Tx), w_ceil (B,1,Tx), y_lengths (B) int64 */
+EV_API size_t ev_encode_workspace_bytes(const ev_ctx* ctx, int B, int Tx);
+EV_API int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths, const int64_t* spks, int B, int Tx,
+              float length_scale, float* spk_emb, float* mu_x, float* logw, float* w_ceil, int64_t* y_lengths,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- alignment / length regulator (integer, bit-exact) -----------------------------------------------
+ * Replaces matcha_tts.py:129-135: sequence_mask, generate_path (utils/model.py:29-41) and
+ * mu_y = attn^T mu_x (a gather).  T_pad = fix_len_compatibility(max y_lengths) is computed by the caller
+ * (it fixes the output shapes; utils/model.py:14-20).
+ *   out: attn (B,Tx,T_pad) 0/1 fp32, mu_y (B,n_feats,T_pad), y_mask (B,1,T_pad) */
+EV_API int ev_align(ev_ctx* ctx, const float* w_ceil, const int64_t* x_lengths, const int64_t* y_lengths,
+             const float* mu_x, int B, int Tx, int T_pad, float* attn, float* mu_y, float* y_mask, void* stream);
+
+/* ---- flow-matching decoder -----------------------------------------------------------------------------
+ * Replaces CFM.forward + solve_euler + Decoder.forward + denormalize (flow_matching.py:32-85,
+ * decoder.py:363-443, utils/model.py:71-90): x0 = z*temperature, n_timesteps Euler steps of the U-Net
+ * estimator on the padded extent T_pad (a multiple of 4), mel = x*mel_std + mel_mean.
+ *   mu_y, z, out decoder_out, mel : (B,n_feats,T_pad);  spk_emb (B,spk_emb_dim) or NULL;  y_lengths (B) int64 */
+EV_API size_t ev_decode_workspace_bytes(const ev_ctx* ctx, int B, int T_pad, int n_timesteps);
+EV_API int ev_decode(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const float* z, const float* spk_emb,
+              int B, int T_pad, int n_timesteps, float temperature, int precision, float* decoder_out,
+              float* mel, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- HiFi-GAN generator ----------------------------------------------------------------------------------
+ * Replaces Generator.forward (hifigan/models.py:181-197) followed by the `.clamp(-1, 1)` of to_waveform
+ * (feel_me.py:181-187; a no-op after tanh, kept for the contract).  mel (B,num_mels,T) -> wav (B,1,T*prod(rates)). */
+EV_API size_t ev_vocode_workspace_bytes(const ev_ctx* ctx, int B, int T);
+EV_API int ev_vocode(ev_ctx* ctx, const float* mel, int B, int T, int precision, float* wav, void* workspace,
+              size_t workspace_bytes, void* stream);
+
+/* ---- bias denoiser -----------------------------------------------------------------------------------------
+ * Replaces Denoiser.forward (hifigan/denoiser.py:58-64): centred hann STFT(1024, hop 256) -> magnitude minus
+ * strength*bias_spec clamped at 0 -> inverse STFT with the original phase.  ev_denoiser_init computes
+ * bias_spec = |STFT(vocoder(zeros(1,80,88)))|[:, :, 0] (denoiser.py:17-56) with the loaded generator.
+ *   audio (B,L) -> out (B,L'), L' = hop*(L/hop) as torch.istft returns; bias_spec_out (n_fft/2+1) optional. */
+EV_API size_t ev_denoise_workspace_bytes(const ev_ctx* ctx, int B, int L);
+EV_API int ev_denoiser_init(ev_ctx* ctx, float* bias_spec_out, void* workspace, size_t workspace_bytes, void* stream);
+EV_API int ev_denoise(ev_ctx* ctx, const float* audio, int B, int L, float strength, float* out, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* ---- bookkeeping the bench reads: kernels launched by this context since the last reset ------------------- */
+EV_API int64_t ev_launch_count(const ev_ctx* ctx, int reset);
+
+/* ---- unit-test hooks (one kernel each; used by tests/ through the same ABI) -------------------------------
+ * conv1d: x (B,Cin,T) fp32, w (Cout,Cin,K) [or (Cin,Cout,K) when transposed!=0], bias (Cout) or NULL ->
+ * y (B,Cout,Tout); same arithmetic path as the models use (precision selects CUDA-core fp32 / tcgen05 bf16). */
+EV_API int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout,
+                   int K, int stride, int padding, int dilation, int transposed, int precision, float* y,
+                   void* stream);
+/* The float32 Euler times/steps of flow_matching.py:52,68-83 as the library computes them (pure host code). */
+EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
+/* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */
+EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOJIVOICE_B200_H */

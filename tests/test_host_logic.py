@@ -1,0 +1,90 @@
+"""CPU-side checks: the C ABI exports what the header declares, host-only helpers, emoji front-end, synthetic data."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import emojivoice_b200 as ev
+from emojivoice_b200 import _lib, synthetic
+from emojivoice_b200.config import VCTK
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "emojivoice_b200.h")).read()
+    declared = set(re.findall(r"EV_API\s+[\w\s\*]+?\b(ev_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.ev_version() >= 100
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.Context()
+    m = ev.MatchaTTS(**VCTK.constructor_kwargs())
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({})
+
+
+@pytest.mark.parametrize("n", [1, 2, 4, 10, 50])
+def test_euler_schedule_matches_torch_float32(n):
+    t = (C.c_float * n)()
+    d = (C.c_float * n)()
+    assert _lib.lib().ev_test_euler_schedule(n, t, d) == 0
+    # flow_matching.py:52,68-83
+    span = torch.linspace(0, 1, n + 1)
+    tt, dt = span[0], span[1] - span[0]
+    for step in range(1, n + 1):
+        assert float(tt) == t[step - 1] and float(dt) == d[step - 1], (step, float(tt), t[step - 1], float(dt), d[step - 1])
+        tt = tt + dt
+        if step < n:
+            dt = span[step + 1] - tt
+
+
+def test_emoji_front_end():
+    # feel_me.py:298-312: first emoji of the text that is in the map wins; emoji and brackets are stripped
+    assert ev.emoji_to_spk("wow \U0001F62E (so cool) \U0001F60D") == ("wow  so cool ", 54)
+    assert ev.emoji_to_spk("no emoji here") == ("no emoji here", 0)
+    assert ev.emoji_to_spk("unknown \U0001F984 then \U0001F923", default=0) == ("unknown  then ", 15)
+    # demo_story_script.py:177-182: mapping order, default 12
+    txt = "\U0001F923 first in text, \U0001F60D first in map"
+    assert ev.emoji_to_spk(txt, order="mapping", default=12)[1] == 107
+    assert ev.emoji_to_spk("plain", order="mapping", default=12)[1] == 12
+    assert ev.emoji_to_spk("x \U0001F60E", mapping=ev.EMOJI_MAPPING_MALE)[1] == 6
+    assert ev.intersperse([5, 6, 7]) == [0, 5, 0, 6, 0, 7, 0]
+
+
+def test_synthetic_inputs_are_blank_interspersed_and_in_range():
+    x, xl, spk = synthetic.phoneme_batch(6, 3, 20, seed=3)
+    assert x.shape[1] == int(xl.max()) and (xl % 2 == 1).all()
+    for b in range(6):
+        row = x[b, : xl[b]]
+        assert (row[0::2] == 0).all() and (row[1::2] > 0).all() and (row < 178).all()
+        assert (x[b, xl[b]:] == 0).all()
+    assert set(spk.tolist()) <= set(ev.EMOJI_MAPPING_FEMALE.values())
+    a = synthetic.matcha_state_dict(VCTK, seed=5)
+    b = synthetic.matcha_state_dict(VCTK, seed=5)
+    assert synthetic.checksum(a) == synthetic.checksum(b)
+    assert sum(v.numel() for k, v in a.items() if k not in ("mel_mean", "mel_std")) == 20_857_569
+
+
+def test_aten_sum_order_restatement_matches_torch():
+    """numpy restatement of SURVEY.md Appendix B (the order the CUDA length stage reproduces) vs torch.sum on CPU."""
+    from tests.aten_sum_ref import sum_f32
+
+    rng = np.random.default_rng(0)
+    for n in (1, 3, 7, 8, 9, 15, 16, 17, 33, 64, 151, 333, 511, 512, 513, 1100, 2100):
+        for ls in (0.8, 0.9, 1.1, 1.2):
+            w = (np.ceil(np.exp(rng.normal(0.9, 0.6, size=n))).astype(np.float32) * np.float32(ls)).astype(np.float32)
+            w[rng.integers(0, n + 1):] = 0.0
+            want = float(torch.sum(torch.from_numpy(w).view(1, 1, n), [1, 2])[0])
+            assert sum_f32(w) == want, (n, ls)
