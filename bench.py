@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds synthesised per second (22.05 kHz, mel + vocoder) on N x B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: MatchaTTS.synthesise(x, x_lengths, n_timesteps=10,
+temperature=0.667, spks=emoji ids, length_scale=0.8) followed by vocoder(mel).clamp(-1, 1), on BASELINE.json
+configs[1] (batch 32 emoji-tagged utterances of ~5 s, bf16, random-init VCTK Matcha-TTS + HiFi-GAN v1).
+For N > 1 the driver launches one rank per GPU with torch.distributed.run; utterances shard by batch, every
+rank synthesises its own 32 utterances (weak scaling), no collective on the data path.
+
+One JSON line is printed by rank 0 (see the task contract): `value` is measured with the inputs resident in HBM,
+`e2e` through the same public API with pinned HOST inputs and the waveform read back, `roofline` for the dominant
+kernel from a CUDA-event-instrumented step, `cpu_baseline` = the CPU oracle (a port of the reference's PyTorch
+path) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR, HOP = 22050, 256
+N_TIMESTEPS, TEMPERATURE, LENGTH_SCALE = 10, 0.667, 0.8      # feel_me.py:71-77 (the operating point of every app)
+BATCH, P_LO, P_HI = 32, 60, 90                                # Tx = 2P+1 in [121, 181]
+CPU_SAMPLE = 2                                                # utterances of the batch the CPU baseline synthesises
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=float(p["hbm_gbs"]), tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="MEASURED_PEAKS.json (sustained bf16, copy bandwidth)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback of B200_PROFILING.md")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def audio_seconds(mel_lengths) -> float:
+    return float(mel_lengths.sum()) * HOP / SR
+
+
+def cpu_oracle_rate(x, xl, spks, n_utts, repeats=2):
+    """The reference's CPU PyTorch path (restated in oracle/) on the first n_utts utterances, all host threads."""
+    from emojivoice_b200 import synthetic
+    from emojivoice_b200.config import HIFIGAN_V1, VCTK
+    from oracle import hifigan_oracle as ho
+    from oracle import matcha_oracle as mo
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synthetic.matcha_state_dict(VCTK, seed=1234)
+    hsd = synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321)
+    n = min(n_utts, x.shape[0])
+    xs, ls, ss = x[:n, : int(xl[:n].max())].contiguous(), xl[:n], spks[:n]
+
+    def once():
+        t0 = time.perf_counter()
+        out = mo.synthesise(sd, VCTK, xs, ls, N_TIMESTEPS, TEMPERATURE, ss, LENGTH_SCALE)
+        wav = ho.generator(hsd, HIFIGAN_V1, out["mel"]).clamp(-1, 1)
+        dt = time.perf_counter() - t0
+        return audio_seconds(out["mel_lengths"]), dt, wav
+
+    return once, n
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the python reference cannot
+    travel to the GPU box), all host threads, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from emojivoice_b200 import synthetic
+
+    x, xl, spks = synthetic.phoneme_batch(BATCH, P_LO, P_HI, seed=2000)
+    once, n = cpu_oracle_rate(x, xl, spks, CPU_SAMPLE)
+    for _ in range(args.warmup):
+        once()
+    t0 = time.perf_counter()
+    secs = 0.0
+    for _ in range(args.steps):
+        a, _, _ = once()
+        secs += a
+    dt = time.perf_counter() - t0
+    val = secs / dt
+    sample = f"first {n} utterances of the batch per step ({secs / args.steps:.1f} audio-s), fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "rtf": 1.0 / val}))
+
+
+def workload_config():
+    return {"workload": "BASELINE.json configs[1]: batch 32 emoji-tagged utterances (~5 s each), n_timesteps=10, "
+                        "Matcha-TTS VCTK arch + HiFi-GAN v1, random init, synthetic blank-interspersed phoneme ids",
+            "batch_per_gpu": BATCH, "n_timesteps": N_TIMESTEPS, "temperature": TEMPERATURE, "length_scale": LENGTH_SCALE,
+            "tokens_per_utt": f"2P+1, P~U[{P_LO},{P_HI}]", "speakers": "11 emoji voices (feel_me.py:84-96)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+
+    import emojivoice_b200 as ev
+    from emojivoice_b200 import synthetic
+    from emojivoice_b200.config import HIFIGAN_V1, VCTK
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = ev.MatchaTTS(**VCTK.constructor_kwargs(), device=dev, precision=args.precision).eval()
+    model.load_state_dict(synthetic.matcha_state_dict(VCTK, seed=1234))
+    voc = ev.Generator(HIFIGAN_V1, device=dev, precision=args.precision)
+    voc.load_state_dict(synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321))
+    voc.eval()
+    voc.remove_weight_norm()
+
+    # every rank synthesises its own batch (weak scaling); same distribution, different seed
+    x, xl, spks = synthetic.phoneme_batch(BATCH, P_LO, P_HI, seed=2000 + rank)
+    x_pin, xl_pin, spk_pin = x.pin_memory(), xl.pin_memory(), spks.pin_memory()
+    x_dev, xl_dev, spk_dev = x.to(dev), xl.to(dev), spks.to(dev)
+
+    def step_resident():
+        out = model.synthesise(x_dev, xl_dev, N_TIMESTEPS, TEMPERATURE, spk_dev, LENGTH_SCALE)
+        wav = voc(out["mel"]).clamp(-1, 1)                      # to_waveform, feel_me.py:183
+        return out, wav
+
+    wav_host = [None]
+    len_host = torch.empty(BATCH, dtype=torch.int64).pin_memory()
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)
+        ld = xl_pin.to(dev, non_blocking=True)
+        sd_ = spk_pin.to(dev, non_blocking=True)
+        out = model.synthesise(xd, ld, N_TIMESTEPS, TEMPERATURE, sd_, LENGTH_SCALE)
+        wav = voc(out["mel"]).clamp(-1, 1)
+        if wav_host[0] is None or wav_host[0].shape != wav.shape:
+            wav_host[0] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
+        wav_host[0].copy_(wav, non_blocking=True)               # .cpu() of to_waveform (feel_me.py:187)
+        len_host.copy_(out["mel_lengths"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out, wav
+
+    for _ in range(args.warmup):
+        out, wav = step_resident()
+    torch.cuda.synchronize()
+    secs_per_step = audio_seconds(out["mel_lengths"].cpu())
+    frames = int(out["mel_lengths"].sum())
+    t_pad = int(out["t_pad"])
+    ws_bytes = (model._ctx._ws.numel() if model._ctx._ws is not None else 0) + (voc._ctx._ws.numel() if voc._ctx._ws is not None else 0)
+
+    # ---------------- timed region: K steps, inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    model.launch_count(reset=True); voc.launch_count(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.launch_count() + voc.launch_count()
+    clocks = sampler.stop()
+
+    # ---------------- e2e: same steps through the public API with pinned host inputs and the waveform read back
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    tt = torch.tensor([ms, ms_e2e, -secs_per_step], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)                # slowest rank bounds the job
+        tot = torch.tensor([secs_per_step, float(launches)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_secs, launches = float(tot[0]), int(tot[1])
+    else:
+        total_secs = secs_per_step
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+    value = total_secs * args.steps / (ms / 1e3)
+    value_e2e = total_secs * args.steps / (ms_e2e / 1e3)
+    h2d = x.numel() * 8 + xl.numel() * 8 + spks.numel() * 8
+    d2h = int(wav.numel()) * 4 + BATCH * 8
+
+    # ---------------- roofline of the dominant kernel: one more step with CUDA events around every launch
+    peaks = load_peaks()
+    model._ctx.profile_begin(); voc._ctx.profile_begin()
+    step_resident()
+    stats = model._ctx.profile_end() + voc._ctx.profile_end()
+    agg = {}
+    for s in stats:
+        a = agg.setdefault(s["name"], dict(name=s["name"], launches=0, total_ms=0.0, flops=0.0, bytes=0.0))
+        for k in ("launches", "total_ms", "flops", "bytes"):
+            a[k] += s[k]
+    klist = sorted(agg.values(), key=lambda a: -a["total_ms"])
+    ksum = sum(a["total_ms"] for a in klist) or 1.0
+    table = []
+    for a in klist[:10]:
+        sec = a["total_ms"] / 1e3
+        table.append({"name": a["name"], "launches": a["launches"], "ms": round(a["total_ms"], 3),
+                      "share": round(a["total_ms"] / ksum, 4), "tflops": round(a["flops"] / sec / 1e12, 2) if sec else 0,
+                      "gbs": round(a["bytes"] / sec / 1e9, 1) if sec else 0})
+    top = klist[0]
+    sec = top["total_ms"] / 1e3
+    ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    ai = top["flops"] / max(top["bytes"], 1.0)
+    if top["flops"] > 0 and ai >= ridge:
+        ach, peak, unit, bound = top["flops"] / sec / 1e12, peaks["tflops"], "TFLOP/s", "tensor"
+    else:
+        ach, peak, unit, bound = top["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+    roofline = {"kernel": top["name"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
+                "frac": round(ach / peak, 4), "traffic": None, "launches": top["launches"],
+                "avg_launch_us": round(top["total_ms"] * 1e3 / max(top["launches"], 1), 2),
+                "share_of_step": round(top["total_ms"] / ksum, 4), "arith_intensity": round(ai, 1),
+                "peak_source": peaks["source"], "how": "CUDA events around every launch on the launching stream, one "
+                "instrumented step right after the timed region; algorithmic FLOPs/bytes (valid un-padded work)"}
+    # whole-path algorithmic FLOPs as a fraction of the tensor roofline
+    tx = xl.double()
+    flops_step = float((tx * (19309056 + 6144 * tx)).sum()) + 0.0
+    ml = out["mel_lengths"].double().cpu()
+    flops_step += float((N_TIMESTEPS * ml * (11116544 + 1536 * ml)).sum()) + float((ml * 614105088).sum())
+    path_tflops = flops_step * args.steps / (ms / 1e3) / 1e12 * (world if world > 1 else 1)
+
+    result = {
+        "metric": "audio_seconds_per_second", "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
+        "data": "synthetic",
+        "config": dict(workload_config(), audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames,
+                       t_pad=t_pad, l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
+                       "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9)),
+        "rtf": round(1.0 / value, 8), "x_realtime": round(value, 1),
+        "clocks": clocks,
+        "e2e": {"value": round(value_e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "path_tflops": round(path_tflops, 2), "path_frac_of_tensor_peak": round(path_tflops / (peaks["tflops"] * world), 4),
+        "kernels": table,
+    }
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        once, n = cpu_oracle_rate(x, xl, spks, CPU_SAMPLE)
+        once()
+        best = None
+        for _ in range(2):
+            a, dt, _ = once()
+            best = (a, dt) if best is None or dt < best[1] else best
+        result["cpu_baseline"] = {"value": round(best[0] / best[1], 3), "unit": "audio-s/s", "cores": torch.get_num_threads(),
+                                  "kind": "port", "sample": f"first {n} utterances of the batch ({best[0]:.1f} audio-s), fp32 "
+                                  f"torch CPU oracle, warm-up 1, best of 2, {os.cpu_count()} host cpus"}
+    elif rank == 0:
+        result["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,11 @@ class EvHifiganCfg(C.Structure):
                 ("resblock_kernel_sizes", C.c_int32 * 4), ("resblock_dilation_sizes", (C.c_int32 * 3) * 4)]
 
 
+class EvKernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("total_ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 _P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 # name -> (restype, argtypes); must list every symbol include/emojivoice_b200.h declares (tests check it)
 SIGNATURES = {
@@ -51,6 +56,8 @@ SIGNATURES = {
     "ev_denoiser_init": (_I, [_P, _P, _P, _SZ, _P]),
     "ev_denoise": (_I, [_P, _P, _I, _I, _F, _P, _P, _SZ, _P]),
     "ev_launch_count": (_I64, [_P, _I]),
+    "ev_profile_begin": (_I, [_P]),
+    "ev_profile_end": (_I, [_P, C.POINTER(EvKernelStat), _I, C.POINTER(_I)]),
     "ev_test_conv1d": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ev_test_euler_schedule": (_I, [_I, C.POINTER(_F), C.POINTER(_F)]),
     "ev_test_row_sum": (_I, [_P, _P, _I, _I, _P, _P]),
@@ -116,6 +123,17 @@ class Context:
 
     def launch_count(self, reset=False) -> int:
         return int(lib().ev_launch_count(self.handle, 1 if reset else 0))
+
+    def profile_begin(self):
+        self.check(lib().ev_profile_begin(self.handle), "ev_profile_begin")
+
+    def profile_end(self):
+        """-> list of dicts {name, launches, total_ms, flops, bytes}, one per kernel class launched since begin."""
+        arr = (EvKernelStat * 64)()
+        n = C.c_int(0)
+        self.check(lib().ev_profile_end(self.handle, arr, 64, C.byref(n)), "ev_profile_end")
+        return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
+                     flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n.value)]
 
     def close(self):
         if getattr(self, "handle", None):

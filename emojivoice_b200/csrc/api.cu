@@ -1,4 +1,6 @@
 // Context lifetime, bookkeeping and the single-kernel unit-test hooks of the C ABI (include/emojivoice_b200.h).
+#include <cstring>
+
 #include "ctx.cuh"
 
 using namespace ev;
@@ -53,6 +55,46 @@ extern "C" int64_t ev_launch_count(const ev_ctx* ctx, int reset) {
   const int64_t v = ctx->launches;
   if (reset) const_cast<ev_ctx*>(ctx)->launches = 0;
   return v;
+}
+
+extern "C" int ev_profile_begin(ev_ctx* ctx) {
+  if (!ctx) return EV_ERR_INVALID;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, cudaDeviceSynchronize());
+  for (auto& r : ctx->prof) { ctx->event_pool.push_back(r.e0); ctx->event_pool.push_back(r.e1); }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return EV_OK;
+}
+
+extern "C" int ev_profile_end(ev_ctx* ctx, ev_kernel_stat* out, int max_entries, int* n_out) {
+  if (!ctx || !out || !n_out) return EV_ERR_INVALID;
+  ctx->profiling = false;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, cudaDeviceSynchronize());
+  const int nk = (int)ctx->kernel_names.size();
+  std::vector<ev_kernel_stat> agg(nk);
+  for (int i = 0; i < nk; ++i) {
+    memset(&agg[i], 0, sizeof(ev_kernel_stat));
+    strncpy(agg[i].name, ctx->kernel_names[i].c_str(), sizeof(agg[i].name) - 1);
+  }
+  for (auto& r : ctx->prof) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+      agg[r.kid].launches++;
+      agg[r.kid].total_ms += ms;
+      agg[r.kid].flops += r.flops;
+      agg[r.kid].bytes += r.bytes;
+    }
+    ctx->event_pool.push_back(r.e0);
+    ctx->event_pool.push_back(r.e1);
+  }
+  ctx->prof.clear();
+  int n = 0;
+  for (int i = 0; i < nk && n < max_entries; ++i)
+    if (agg[i].launches > 0) out[n++] = agg[i];
+  *n_out = n;
+  return EV_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ test hooks

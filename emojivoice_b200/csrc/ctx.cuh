@@ -46,6 +46,12 @@ struct MatchaW {
   float *final_g = nullptr, *final_b = nullptr;
 };
 
+struct DenoiseBasis {          // windowed Fourier bases of the bias denoiser (denoiser.cu)
+  ConvWeights fwd, inv;
+  float* win_sq = nullptr;     // hann^2 [1024]
+  bool ready = false;
+};
+
 struct HifiganW {
   bool loaded = false;
   ev_hifigan_cfg cfg{};
@@ -56,9 +62,14 @@ struct HifiganW {
   float* post_b = nullptr;
   int c_last = 0, total_up = 1;
   float* denoise_bias = nullptr;  // (n_fft/2+1) once ev_denoiser_init ran
+  DenoiseBasis dn;
 };
 
 }  // namespace ev
+
+namespace ev {
+struct ProfRecord { int kid; double flops, bytes; cudaEvent_t e0, e1; };
+}
 
 struct ev_ctx {
   int device = 0;
@@ -68,6 +79,11 @@ struct ev_ctx {
   std::vector<void*> owned;     // cudaMalloc'ed by this context
   ev::MatchaW matcha;
   ev::HifiganW hifigan;
+  // optional per-launch CUDA-event timing (ev_profile_begin/end); off in normal operation
+  bool profiling = false;
+  std::vector<ev::ProfRecord> prof;
+  std::vector<std::string> kernel_names;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace ev {
@@ -83,6 +99,20 @@ int cuda_fail(ev_ctx* ctx, cudaError_t ce, const char* what);
   do {                          \
     int _rc = (expr);           \
     if (_rc != 0) return _rc;   \
+  } while (0)
+
+// Every kernel launch goes through one of these: counts the launch and, while profiling, brackets it with events
+// recorded on the launching stream.
+struct LaunchScope {
+  ev_ctx* ctx; cudaStream_t s; int idx;
+  LaunchScope(ev_ctx* c, cudaStream_t st, const char* name, double flops, double bytes);
+  ~LaunchScope();
+};
+#define EV_LAUNCH(ctx, s, name, flops, bytes, expr)                 \
+  do {                                                              \
+    cudaError_t _ce;                                                \
+    { ev::LaunchScope _ls(ctx, s, name, flops, bytes); _ce = (expr); } \
+    if (_ce != cudaSuccess) return ev::cuda_fail(ctx, _ce, name);   \
   } while (0)
 
 // Bump allocator over the caller's workspace (256-byte granules).

@@ -164,8 +164,8 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
   plan_vocode<ActT>(h, B, T, w, &v);
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_vocode: workspace too small");
   const RowMask none{nullptr, 0};
-  EV_CUDA(ctx, (cf_to_cl<ActT>(mel, B, c.num_mels, T, v.mel, c.num_mels, (long long)T * c.num_mels, 1.0f, none, s)));
-  ctx->launches++;
+  EV_LAUNCH(ctx, s, "cf_to_cl", 0, (double)B * T * c.num_mels * (4.0 + sizeof(ActT)),
+            (cf_to_cl<ActT>(mel, B, c.num_mels, T, v.mel, c.num_mels, (long long)T * c.num_mels, 1.0f, none, s)));
   int C = c.upsample_initial_channel;
   long long L = T;
   {  // x = conv_pre(mel); the loop's first leaky_relu is fused here
@@ -208,8 +208,8 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
       }
     }
   }
-  EV_CUDA(ctx, conv_post_tanh(v.sum, B, (int)L, C, h.post_w, h.post_b, wav, s));
-  ctx->launches++;
+  EV_LAUNCH(ctx, s, "conv_post_tanh", 2.0 * B * (double)L * C * 7, (double)B * L * (4.0 * C + 4.0),
+            conv_post_tanh(v.sum, B, (int)L, C, h.post_w, h.post_b, wav, s));
   return 0;
 }
 }  // namespace

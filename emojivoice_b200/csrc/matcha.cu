@@ -213,12 +213,14 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_encode: workspace too small");
   const int C = c.enc_channels, H = C + (c.n_spks > 1 ? c.spk_emb_dim : 0);
   const long long bsC = (long long)Tx * C, bsH = (long long)Tx * H;
-  EV_CUDA(ctx, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), e.xlen32, B, s));
+  const double R = (double)B * Tx;
+  EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), e.xlen32, B, s));
   const RowMask mask{e.xlen32, 0};
   if (c.n_spks > 1)
-    EV_CUDA(ctx, embed_speakers(reinterpret_cast<const long long*>(spks), m.spk_table, B, c.spk_emb_dim, c.n_spks, spk_emb, s));
-  EV_CUDA(ctx, embed_tokens(reinterpret_cast<const long long*>(x), m.tok_emb, B, Tx, C, c.n_vocab, sqrtf((float)C), mask, e.h0, C, s));
-  ctx->launches += 3;
+    EV_LAUNCH(ctx, s, "embed_speakers", 0, 8.0 * B * c.spk_emb_dim,
+              embed_speakers(reinterpret_cast<const long long*>(spks), m.spk_table, B, c.spk_emb_dim, c.n_spks, spk_emb, s));
+  EV_LAUNCH(ctx, s, "embed_tokens", 0, R * (8 + 8.0 * C),
+            embed_tokens(reinterpret_cast<const long long*>(x), m.tok_emb, B, Tx, C, c.n_vocab, sqrtf((float)C), mask, e.h0, C, s));
   if (c.enc_prenet) {
     // ConvReluNorm (text_encoder.py:60-67): 3 x [conv5(x*mask) -> LN -> ReLU], 1x1 proj, + x_org, * mask
     const float* cur = e.h0;
@@ -230,8 +232,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
       LnArgs ln;
       ln.x = e.tmp; ln.x_ld = C; ln.gamma = m.pre_g[i]; ln.beta = m.pre_b[i]; ln.eps = 1e-4f; ln.post_relu = 1; ln.mask = mask;
       ln.out_f32 = pp[i & 1]; ln.f32_ld = C; ln.B = B; ln.T = Tx; ln.C = C;
-      EV_CUDA(ctx, layer_norm_rows<float>(ln, s));
-      ctx->launches++;
+      EV_LAUNCH(ctx, s, "layer_norm", 0, R * C * 8.0, layer_norm_rows<float>(ln, s));
       cur = pp[i & 1];
     }
     Epilogue ep;
@@ -242,8 +243,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     EV_CUDA(ctx, cudaMemcpy2DAsync(e.X, (size_t)H * 4, e.h0, (size_t)C * 4, (size_t)C * 4, (size_t)B * Tx, cudaMemcpyDeviceToDevice, s));
   }
   if (c.n_spks > 1) {
-    EV_CUDA(ctx, fill_speaker_channels(spk_emb, B, Tx, c.spk_emb_dim, mask, e.X, H, C, s));
-    ctx->launches++;
+    EV_LAUNCH(ctx, s, "fill_speaker", 0, R * c.spk_emb_dim * 4.0, fill_speaker_channels(spk_emb, B, Tx, c.spk_emb_dim, mask, e.X, H, C, s));
   }
   // Encoder (text_encoder.py:314-325), post-LN blocks.  Every stream is kept masked: padded rows never reach a valid
   // row (conv inputs are masked, padded keys get -1e4), so zeroing them early changes nothing that is observable.
@@ -259,16 +259,14 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     at.lens = e.xlen32; at.len_shift = 0; at.mode = 0;
     at.rope_cos = m.rope_cos; at.rope_sin = m.rope_sin; at.rope_dim = hd / 2;
     at.out = e.att; at.out_ld = H; at.out_bs = bsH;
-    EV_CUDA(ctx, attention_rows<float>(at, s));
-    ctx->launches++;
+    EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
     Epilogue eo;  // x + y
     eo.res = e.X; eo.res_ld = H; eo.res_bs = bsH; eo.out_f32 = e.tmp; eo.f32_ld = H; eo.f32_bs = bsH;
     EV_TRY(run_conv<float>(ctx, L.o, e.att, H, bsH, B, Tx, eo, s));
     LnArgs l1;
     l1.x = e.tmp; l1.x_ld = H; l1.gamma = L.ln1_g; l1.beta = L.ln1_b; l1.eps = 1e-4f; l1.mask = mask;
     l1.out_f32 = e.X1; l1.f32_ld = H; l1.B = B; l1.T = Tx; l1.C = H;
-    EV_CUDA(ctx, layer_norm_rows<float>(l1, s));
-    ctx->launches++;
+    EV_LAUNCH(ctx, s, "layer_norm", 0, R * H * 8.0, layer_norm_rows<float>(l1, s));
     Epilogue e1;  // relu(conv_1(x*mask)) * mask
     e1.act = ACT_RELU; e1.mask = mask; e1.mask_act = 1;
     e1.out_act = e.F; e1.act_ld = c.enc_filter_channels; e1.act_bs = (long long)Tx * c.enc_filter_channels;
@@ -279,15 +277,13 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     EV_TRY(run_conv<float>(ctx, L.ffn2, e.F, c.enc_filter_channels, (long long)Tx * c.enc_filter_channels, B, Tx, e2, s));
     LnArgs l2 = l1;
     l2.gamma = L.ln2_g; l2.beta = L.ln2_b; l2.out_f32 = e.X;
-    EV_CUDA(ctx, layer_norm_rows<float>(l2, s));
-    ctx->launches++;
+    EV_LAUNCH(ctx, s, "layer_norm", 0, R * H * 8.0, layer_norm_rows<float>(l2, s));
   }
   {  // mu = proj_m(x) * mask  (text_encoder.py:405) -> channel-first output
     Epilogue ep;
     ep.mask = mask; ep.mask_pre = 1; ep.out_f32 = e.mu_cl; ep.f32_ld = c.n_feats; ep.f32_bs = (long long)Tx * c.n_feats;
     EV_TRY(run_conv<float>(ctx, m.proj_m, e.X, H, bsH, B, Tx, ep, s));
-    EV_CUDA(ctx, cl_to_cf(e.mu_cl, c.n_feats, (long long)Tx * c.n_feats, B, c.n_feats, Tx, mu_x, 1.0f, 0.0f, s));
-    ctx->launches++;
+    EV_LAUNCH(ctx, s, "cl_to_cf", 0, R * c.n_feats * 8.0, cl_to_cf(e.mu_cl, c.n_feats, (long long)Tx * c.n_feats, B, c.n_feats, Tx, mu_x, 1.0f, 0.0f, s));
   }
   {  // DurationPredictor (text_encoder.py:84-94): conv -> relu -> LN (x2), 1x1 proj, masks in between
     const int Fd = c.enc_filter_channels_dp;
@@ -298,15 +294,14 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     LnArgs ln;
     ln.x = e.tmp; ln.x_ld = Fd; ln.pre_relu = 1; ln.gamma = m.dp_g1; ln.beta = m.dp_b1; ln.eps = 1e-4f; ln.mask = mask;
     ln.out_f32 = e.D1; ln.f32_ld = Fd; ln.B = B; ln.T = Tx; ln.C = Fd;
-    EV_CUDA(ctx, layer_norm_rows<float>(ln, s));
+    EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
     EV_TRY(run_conv<float>(ctx, m.dp_conv2, e.D1, Fd, bsF, B, Tx, ep, s));
     ln.gamma = m.dp_g2; ln.beta = m.dp_b2; ln.out_f32 = e.D2;
-    EV_CUDA(ctx, layer_norm_rows<float>(ln, s));
+    EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
     Epilogue el;
     el.mask = mask; el.mask_pre = 1; el.out_f32 = logw; el.f32_ld = 1; el.f32_bs = Tx;
     EV_TRY(run_conv<float>(ctx, m.dp_proj, e.D2, Fd, bsF, B, Tx, el, s));
-    EV_CUDA(ctx, durations(logw, e.xlen32, B, Tx, length_scale, w_ceil, reinterpret_cast<long long*>(y_lengths), s));
-    ctx->launches += 3;
+    EV_LAUNCH(ctx, s, "durations", 0, R * 8.0, durations(logw, e.xlen32, B, Tx, length_scale, w_ceil, reinterpret_cast<long long*>(y_lengths), s));
   }
   return 0;
 }
@@ -325,12 +320,12 @@ extern "C" int ev_align(ev_ctx* ctx, const float* w_ceil, const int64_t* x_lengt
   const size_t n = (size_t)2 * B + (size_t)B * T_pad;
   EV_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&scratch), n * sizeof(int), s));
   int* xl = scratch; int* yl = scratch + B; int* tok = scratch + 2 * B;
-  EV_CUDA(ctx, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), xl, B, s));
-  EV_CUDA(ctx, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), yl, B, s));
-  EV_CUDA(ctx, generate_path(w_ceil, xl, yl, B, Tx, T_pad, attn, tok, s));
-  EV_CUDA(ctx, gather_mu(mu_x, tok, yl, B, ctx->matcha.cfg.n_feats, Tx, T_pad, mu_y, y_mask, s));
+  const int Fm = ctx->matcha.cfg.n_feats;
+  EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), xl, B, s));
+  EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), yl, B, s));
+  EV_LAUNCH(ctx, s, "generate_path", 0, 4.0 * B * (double)Tx * T_pad, generate_path(w_ceil, xl, yl, B, Tx, T_pad, attn, tok, s));
+  EV_LAUNCH(ctx, s, "gather_mu", 0, 8.0 * B * (double)Fm * T_pad, gather_mu(mu_x, tok, yl, B, Fm, Tx, T_pad, mu_y, y_mask, s));
   EV_CUDA(ctx, cudaFreeAsync(scratch, s));
-  ctx->launches += 4;
   return 0;
 }
 
@@ -409,21 +404,21 @@ struct Decoder {
     Epilogue e1; e1.out_f32 = d.h; e1.f32_ld = D; e1.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.conv1, in, in_ld, in_bs, B, Tl, e1, s));
     int chunks = 0;
-    EV_CUDA(ctx, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
+    const double RD = (double)B * Tl * D;
+    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g1;
     g1.x = d.h; g1.partial = d.gn_partial; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
     g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.out_act = d.a; g1.act_ld = D;
-    EV_CUDA(ctx, group_norm_apply<ActT>(g1, s));
+    EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
     EV_TRY(run_conv<ActT>(ctx, w.conv2, d.a, D, bsD, B, Tl, e1, s));
     Epilogue er; er.out_f32 = d.r; er.f32_ld = D; er.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.res, in, in_ld, in_bs, B, Tl, er, s));
-    EV_CUDA(ctx, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
+    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g2;
     g2.x = d.h; g2.partial = d.gn_partial; g2.n_chunks = chunks; g2.gamma = w.gn2_g; g2.beta = w.gn2_b;
     g2.B = B; g2.T = Tl; g2.C = D; g2.mask = mask; g2.res = d.r; g2.res_ld = D; g2.out_f32 = d.xr; g2.f32_ld = D;
     g2.ln_gamma = m.tf[k].ln1_g; g2.ln_beta = m.tf[k].ln1_b; g2.out_ln = d.n; g2.ln_ld = D;
-    EV_CUDA(ctx, group_norm_apply<ActT>(g2, s));
-    ctx->launches += 4;
+    EV_LAUNCH(ctx, s, "gn_apply_ln", 0, RD * (12.0 + sizeof(ActT)), group_norm_apply<ActT>(g2, s));
     return 0;
   }
 
@@ -439,20 +434,20 @@ struct Decoder {
     at.B = B; at.T = Tl; at.H = m.cfg.dec_heads; at.D = m.cfg.dec_head_dim; at.scale = 1.0f / sqrtf((float)m.cfg.dec_head_dim);
     at.lens = d.ylen32; at.len_shift = shift; at.mode = 1;
     at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
-    EV_CUDA(ctx, attention_rows<ActT>(at, s));
+    EV_LAUNCH(ctx, s, "attention_dec", 4.0 * B * m.cfg.dec_heads * (double)Tl * Tl * m.cfg.dec_head_dim,
+              (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s));
     LnArgs ln;
     ln.x = d.xr; ln.x_ld = D; ln.gamma = w.ln3_g; ln.beta = w.ln3_b; ln.eps = 1e-5f; ln.out_act = d.n; ln.act_ld = D;
     ln.B = B; ln.T = Tl; ln.C = D;
-    EV_CUDA(ctx, layer_norm_rows<ActT>(ln, s));
+    EV_LAUNCH(ctx, s, "layer_norm", 0, (double)B * Tl * D * (4.0 + sizeof(ActT)), layer_norm_rows<ActT>(ln, s));
     Epilogue e1; e1.act = ACT_SNAKE; e1.snake_a = w.snake_a; e1.snake_invb = w.snake_invb;
     e1.out_act = d.ff; e1.act_ld = 4 * D; e1.act_bs = (long long)Tl * 4 * D;
     EV_TRY(run_conv<ActT>(ctx, w.ff1, d.n, D, bsD, B, Tl, e1, s));
     Epilogue e2; e2.res = d.xr; e2.res_ld = D; e2.res_bs = bsD;
     e2.out_act = out; e2.act_ld = out_ld; e2.act_bs = (long long)Tl * out_ld; e2.mask = mask; e2.mask_act = 1;
     EV_TRY(run_conv<ActT>(ctx, w.ff2, d.ff, 4 * D, (long long)Tl * 4 * D, B, Tl, e2, s));
-    ctx->launches += 2;
     return 0;
   }
 
@@ -490,12 +485,12 @@ struct Decoder {
     { Epilogue e; e.out_f32 = d.h; e.f32_ld = D; e.f32_bs = (long long)T * D;
       EV_TRY(run_conv<ActT>(ctx, m.final_conv, d.n, D, (long long)T * D, B, T, e, s)); }
     int chunks = 0;
-    EV_CUDA(ctx, group_norm_stats(d.h, B, T, D, 8, d.gn_partial, &chunks, s));
+    const double RD = (double)B * T * D;
+    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, T, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g;
     g.x = d.h; g.partial = d.gn_partial; g.n_chunks = chunks; g.gamma = m.final_g; g.beta = m.final_b;
     g.B = B; g.T = T; g.C = D; g.mask = mask0; g.out_act = d.a; g.act_ld = D;
-    EV_CUDA(ctx, group_norm_apply<ActT>(g, s));
-    ctx->launches += 2;
+    EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g, s));
     const int F = m.cfg.n_feats;
     Epilogue e; e.mask = mask0; e.mask_pre = 1; e.alpha = dt;
     e.res = d.xstate; e.res_ld = F; e.res_bs = (long long)T * F;
@@ -517,27 +512,27 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
   plan_decode<ActT>(c, B, T, n_steps, w, &d);
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_decode: workspace too small");
   const int D = c.dec_channels, F = c.n_feats, S = c.n_spks > 1 ? c.spk_emb_dim : 0, dec_in = 2 * F + S;
-  EV_CUDA(ctx, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), d.ylen32, B, s));
+  EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), d.ylen32, B, s));
   const RowMask mask0{d.ylen32, 0};
   // time embeddings of all steps at once (they do not depend on the batch): sinusoid -> Linear -> SiLU -> Linear,
   // then Mish -> the six resnet mlp Linears stacked along N (decoder.py:381-382, :49,58)
   std::vector<float> ts, dts;
   euler_schedule(n_steps, &ts, &dts);
-  EV_CUDA(ctx, upload_floats(d.t_steps, ts.data(), n_steps, s));
-  EV_CUDA(ctx, time_sinusoid(d.t_steps, n_steps, dec_in, d.sinus, s));
+  EV_LAUNCH(ctx, s, "upload_floats", 0, 4.0 * n_steps, upload_floats(d.t_steps, ts.data(), n_steps, s));
+  ctx->launches += ceil_div(n_steps, 32) - 1;
+  EV_LAUNCH(ctx, s, "time_sinusoid", 0, 4.0 * n_steps * dec_in, time_sinusoid(d.t_steps, n_steps, dec_in, d.sinus, s));
   { Epilogue e; e.act = ACT_SILU; e.out_act = d.th1; e.act_ld = 4 * D; e.act_bs = 0;
     EV_TRY(run_conv<float>(ctx, m.time1, d.sinus, dec_in, 0, 1, n_steps, e, s)); }
   { Epilogue e; e.act = ACT_MISH; e.out_act = d.th2; e.act_ld = 4 * D; e.act_bs = 0;
     EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_steps, e, s)); }
   { Epilogue e; e.out_f32 = d.tproj; e.f32_ld = 6 * D; e.f32_bs = 0;
     EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_steps, e, s)); }
-  EV_CUDA(ctx, (decoder_pack_input<ActT>(z, mu_y, spk_emb, B, F, S, T, temperature, mask0, d.xstate, d.xin, dec_in, s)));
-  ctx->launches += 3 + ceil_div(n_steps, 32);
+  EV_LAUNCH(ctx, s, "decoder_pack_input", 0, (double)B * T * (12.0 * F + sizeof(ActT) * dec_in),
+            (decoder_pack_input<ActT>(z, mu_y, spk_emb, B, F, S, T, temperature, mask0, d.xstate, d.xin, dec_in, s)));
   Decoder<ActT> dec{ctx, m, d, B, T, s, D, c.dec_heads * c.dec_head_dim};
   for (int k = 0; k < n_steps; ++k) EV_TRY(dec.step(d.tproj + (size_t)k * 6 * D, dts[k]));
-  EV_CUDA(ctx, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, decoder_out, 1.0f, 0.0f, s));
-  if (mel) EV_CUDA(ctx, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, mel, c.mel_std, c.mel_mean, s));
-  ctx->launches += 2;
+  EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, decoder_out, 1.0f, 0.0f, s));
+  if (mel) EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, mel, c.mel_std, c.mel_mean, s));
   return 0;
 }
 

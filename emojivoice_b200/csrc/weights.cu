@@ -11,6 +11,26 @@ int cuda_fail(ev_ctx* ctx, cudaError_t ce, const char* what) {
   return fail(ctx, EV_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(ce));
 }
 
+LaunchScope::LaunchScope(ev_ctx* c, cudaStream_t st, const char* name, double flops, double bytes) : ctx(c), s(st), idx(-1) {
+  ctx->launches++;
+  if (!ctx->profiling) return;
+  int kid = -1;
+  for (size_t i = 0; i < ctx->kernel_names.size(); ++i)
+    if (ctx->kernel_names[i] == name) { kid = (int)i; break; }
+  if (kid < 0) { kid = (int)ctx->kernel_names.size(); ctx->kernel_names.push_back(name); }
+  ProfRecord r{kid, flops, bytes, nullptr, nullptr};
+  for (cudaEvent_t* e : {&r.e0, &r.e1}) {
+    if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else if (cudaEventCreate(e) != cudaSuccess) return;
+  }
+  cudaEventRecord(r.e0, s);
+  idx = (int)ctx->prof.size();
+  ctx->prof.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (idx >= 0) cudaEventRecord(ctx->prof[idx].e1, s);
+}
+
 int device_alloc(ev_ctx* ctx, size_t bytes, void** out, bool zero, cudaStream_t s) {
   void* p = nullptr;
   EV_CUDA(ctx, cudaMalloc(&p, bytes ? bytes : 16));
@@ -168,17 +188,28 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
   e.phase_cout = w.transposed ? w.C_out : w.N;
   e.up_s = w.transposed ? w.up_s : 1;
   e.up_p = w.transposed ? w.up_p : 0;
+  // algorithmic work of this launch: valid multiply-adds only (padding, polyphase zero taps excluded)
+  const double taps_eff = w.transposed ? (double)w.ksize / w.up_s : (double)w.taps;
+  const double flops = 2.0 * B * (double)T_out * w.C_out * taps_eff * w.C_in;
+  const double esz = sizeof(ActT);
+  double bytes = (double)B * T_in * w.C_in * esz + (double)w.taps * w.N * w.C_in * esz;
+  if (e.out_f32) bytes += 4.0 * B * T_out * w.C_out;
+  if (e.out_act) bytes += esz * B * T_out * w.C_out;
+  if (e.res) bytes += 4.0 * B * T_out * w.C_out;
+  if (e.res2) bytes += 4.0 * B * T_out * w.C_out;
   cudaError_t ce;
   if constexpr (std::is_same<ActT, float>::value) {
-    ce = conv_simt_launch(g, x, x_ld, x_bs, w, e, s);
+    { LaunchScope ls(ctx, s, "conv_simt_f32", flops, bytes); ce = conv_simt_launch(g, x, x_ld, x_bs, w, e, s); }
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "conv_simt_launch");
   } else {
     if (!w.w_bf16) return fail(ctx, EV_ERR_STATE, "layer has no bf16 weights");
     std::string msg;
-    ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg);
+    static const char* names[4] = {"conv_tc_bn32", "conv_tc_bn64", "conv_tc_bn128", "conv_tc_bn256"};
+    const int bn = conv_tc_pick_bn(w.N);
+    const char* nm = names[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3];
+    { LaunchScope ls(ctx, s, nm, flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg); }
     if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   }
-  ctx->launches++;
   return 0;
 }
 template int run_conv<float>(ev_ctx*, const ConvWeights&, const float*, long long, long long, int, int, Epilogue, cudaStream_t);

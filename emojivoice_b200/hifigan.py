@@ -113,8 +113,8 @@ class Denoiser:
         ctx, L = vocoder._ctx, _lib.lib()
         self.bias_spec = torch.empty(1, 513, 1, device=self.device)
         with torch.cuda.device(self.device):
-            ws = ctx.workspace(max(L.ev_denoise_workspace_bytes(ctx.handle, 1, 88 * vocoder.hop),
-                                   L.ev_vocode_workspace_bytes(ctx.handle, 1, 88)) + (1 << 20))
+            ws = ctx.workspace(L.ev_denoise_workspace_bytes(ctx.handle, 1, 88 * vocoder.hop) +
+                               L.ev_vocode_workspace_bytes(ctx.handle, 1, 88) + (1 << 20))
             ctx.check(L.ev_denoiser_init(ctx.handle, _lib.ptr(self.bias_spec), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                       "ev_denoiser_init")
 

@@ -136,6 +136,19 @@ EV_API int ev_denoise(ev_ctx* ctx, const float* audio, int B, int L, float stren
 /* ---- bookkeeping the bench reads: kernels launched by this context since the last reset ------------------- */
 EV_API int64_t ev_launch_count(const ev_ctx* ctx, int reset);
 
+/* ---- per-kernel timing for roofline reports (CUDA events on the launching stream around every launch) ----------
+ * ev_profile_begin switches recording on; ev_profile_end synchronises the device, aggregates per kernel class and
+ * switches it off.  `flops` / `bytes` are the ALGORITHMIC work of the launches (valid, un-padded work only). */
+typedef struct {
+  char name[48];
+  int64_t launches;
+  double total_ms;
+  double flops;
+  double bytes;
+} ev_kernel_stat;
+EV_API int ev_profile_begin(ev_ctx* ctx);
+EV_API int ev_profile_end(ev_ctx* ctx, ev_kernel_stat* out, int max_entries, int* n_out);
+
 /* ---- unit-test hooks (one kernel each; used by tests/ through the same ABI) -------------------------------
  * conv1d: x (B,Cin,T) fp32, w (Cout,Cin,K) [or (Cin,Cout,K) when transposed!=0], bias (Cout) or NULL ->
  * y (B,Cout,Tout); same arithmetic path as the models use (precision selects CUDA-core fp32 / tcgen05 bf16). */

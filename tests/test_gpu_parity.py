@@ -60,7 +60,7 @@ CONV_CASES = [
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv1d_kernel_matches_torch(ctx, case, prec):
     B, Cin, T, Cout, K, stride, pad, dil, transposed = case
-    g = torch.Generator().manual_seed(hash(case) % 1000)
+    g = torch.Generator().manual_seed(sum(int(v) * (i + 1) for i, v in enumerate(case)))
     x = torch.randn(B, Cin, T, generator=g)
     w = torch.randn((Cin, Cout, K) if transposed else (Cout, Cin, K), generator=g) / (Cin * K) ** 0.5
     b = torch.randn(Cout, generator=g)
@@ -71,7 +71,8 @@ def test_conv1d_kernel_matches_torch(ctx, case, prec):
     else:
         ref = F.conv1d(xr.double(), wr.double(), b.double(), stride=stride, padding=pad, dilation=dil)
     y = torch.empty(ref.shape, device="cuda")
-    rc = _lib.lib().ev_test_conv1d(ctx.handle, _lib.ptr(x.cuda()), _lib.ptr(w.cuda()), _lib.ptr(b.cuda()), B, Cin, T, Cout, K,
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()          # keep the device tensors alive across the call
+    rc = _lib.lib().ev_test_conv1d(ctx.handle, _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), B, Cin, T, Cout, K,
                                    stride, pad, dil, int(transposed), _lib.PREC[prec], _lib.ptr(y), _lib.stream_ptr())
     ctx.check(rc, "ev_test_conv1d")
     assert rel_l2(y.cpu(), ref) < 2e-6
@@ -83,7 +84,8 @@ def test_length_sum_follows_aten_cpu_order(ctx):
         for ls in (0.8, 0.9, 1.0, 1.1, 1.2):
             w = torch.from_numpy((np.ceil(np.exp(rng.normal(0.9, 0.6, size=(32, n)))) * ls).astype(np.float32))
             out = torch.empty(32, device="cuda")
-            ctx.check(_lib.lib().ev_test_row_sum(ctx.handle, _lib.ptr(w.cuda()), 32, n, _lib.ptr(out), _lib.stream_ptr()), "row_sum")
+            wd = w.cuda()
+            ctx.check(_lib.lib().ev_test_row_sum(ctx.handle, _lib.ptr(wd), 32, n, _lib.ptr(out), _lib.stream_ptr()), "row_sum")
             assert torch.equal(out.cpu(), torch.sum(w.view(32, 1, n), [1, 2])), (n, ls)      # bit-exact
 
 
