@@ -2,16 +2,25 @@
 // staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring.  sm_100a only.
 //
 // Tile: 128 output time steps (UMMA M = 128 = TMEM lanes) x BN output channels (UMMA N = BN TMEM columns),
-// reduced over taps x ceil(C_in/64) stages of K = 64 bf16 channels (4 x UMMA K=16 per stage).
-//   A (activations) : 3-D tensor map (channel, time, batch) over the channel-last bf16 tensor; the box
-//                     [64 ch x 128 rows] for tap j is fetched at row  m0 + tap_row[j]  -- rows outside [0,T) are
-//                     zero-filled by TMA, which IS the convolution's zero padding (no im2col, no halo copies);
-//                     the stride-2 conv reads a (T/2, 2*ld) view of the same memory (tap_col selects even/odd).
+// reduced over ceil(C_in/64) K-chunks x taps (4 x UMMA K=16 per weight tile).
+//   A (activations) : 3-D tensor map (channel, time, batch) over the channel-last bf16 tensor.  ONE haloed box
+//                     [64 ch x (128 + (taps-1)*dilation) rows] is fetched per K-chunk at row m0 - pad; every tap's MMA
+//                     reads the same smem tile through a descriptor whose start address is advanced by
+//                     tap*dilation rows (the 128B swizzle is a function of absolute smem address bits, so no
+//                     base-offset is needed -- verified on hardware).  Rows outside [0,T) are zero-filled by TMA,
+//                     which IS the convolution's zero padding (no im2col, no halo copies in HBM).
+//                     The stride-2 conv reads a (T/2, 2*ld) view of the same memory (tap_col selects even/odd rows).
 //   B (weights)     : 3-D tensor map (c_in, n, tap) over [taps][N_pad][K_pad] bf16, box [64 x BN].
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld 32x32b, fused bias / mask / Euler-or-residual / activation, vector stores).
+// PERSISTENT CTAs (one per SM) walk the tile list; TMEM holds two accumulators so the epilogue of tile i overlaps
+// the TMA/MMA main loop of tile i+1.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue: tcgen05.ld -> fp32 staging tile in smem -> row-wise coalesced pass with the fused
+// bias / mask / Euler-or-residual / MRF-mean / activation and vectorised fp32 + bf16 stores.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "conv.cuh"
 
@@ -21,16 +30,25 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int NUM_THREADS = 320;
+constexpr int EPI_THREADS = 256;
+constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 8;
+constexpr int kMaxGroups = kMaxTaps;
 
 struct TcParams {
   ConvGeom g;
   Epilogue e;
-  int tap_row[kMaxTaps];
-  int tap_col[kMaxTaps];
+  // taps are processed in groups that share one activation tile: with halo reuse all taps form one group whose
+  // tile covers rows [m0 + grp_row0, m0 + grp_row0 + a_rows); otherwise every tap is its own 128-row group.
+  int n_groups;
+  int grp_row0[kMaxGroups], grp_col0[kMaxGroups], grp_first[kMaxGroups], grp_count[kMaxGroups];
+  int tap_byte_off[kMaxTaps];   // byte offset of tap j's first row inside its group's tile (rows are 128 B)
+  int a_rows;                   // TMA box rows of the activation tile (128 + halo, multiple of 8)
+  int a_slot_bytes;             // a_rows*128 rounded up to 1024
+  int a_slots, b_slots;
   int kchunks;
   int vec_ok;
+  int m_tiles, n_tiles, total_tiles;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -41,6 +59,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -96,6 +117,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 // K-major operand tile, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row groups 1024 B apart (SBO), version 1.
+// The start address may sit any number of 128-B rows into a 1024-B aligned tile (tap offsets of a haloed tile).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -113,36 +135,37 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 template <int BN>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES = BN >= 256 ? 4 : 3;  // 1 CTA/SM at BN=256; 2-3 co-resident CTAs for the narrow tiles
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + slack for the 1024-B alignment
+  static constexpr int STAGE_LD = BN + 4;                         // floats per staged accumulator row
+  static constexpr int STAGING_BYTES = BM * STAGE_LD * 4;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators
 };
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS], b_full[MAX_B_SLOTS], b_empty[MAX_B_SLOTS];
+  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
 
-  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = tiles0, b_base = tiles0 + (uint32_t)(p.a_slots * p.a_slot_bytes);
+  float* stage = reinterpret_cast<float*>(smem_raw + (tiles0 - smem_u32(smem_raw)) + p.a_slots * p.a_slot_bytes + p.b_slots * C::B_TILE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
-  const int n_iters = p.g.taps * p.kchunks;
+  const int A_SLOTS = p.a_slots, B_SLOTS = p.b_slots;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)C::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -152,112 +175,199 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_expect_tx(&full_bar[s], (uint32_t)C::STAGE_BYTES);
-        const uint32_t sa = tiles + (uint32_t)s * C::STAGE_BYTES;
-        tma_load_3d(sa, &tmA, &full_bar[s], p.tap_col[tap] + kc * BK, m0 + p.tap_row[tap], b);
-        tma_load_3d(sa + A_TILE_BYTES, &tmB, &full_bar[s], kc * BK, n0, tap);
+      // ---------------- TMA producer: per tile, per K-chunk, per tap group: one (haloed) activation tile, then one
+      // weight tile per tap.  Ring positions run on across tiles, so the next tile's loads start while this one computes.
+      int ai = 0, bi = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
+        const int m0 = mt * BM, n0 = nt * BN;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < p.n_groups; ++g, ++ai) {
+            const int sa = ai % A_SLOTS;
+            mbar_wait(&a_empty[sa], ((uint32_t)(ai / A_SLOTS) & 1u) ^ 1u);
+            mbar_expect_tx(&a_full[sa], (uint32_t)(p.a_rows * BK * 2));
+            tma_load_3d(a_base + (uint32_t)(sa * p.a_slot_bytes), &tmA, &a_full[sa], p.grp_col0[g] + kc * BK, m0 + p.grp_row0[g], b);
+            for (int j = 0; j < p.grp_count[g]; ++j, ++bi) {
+              const int sb = bi % B_SLOTS;
+              mbar_wait(&b_empty[sb], ((uint32_t)(bi / B_SLOTS) & 1u) ^ 1u);
+              mbar_expect_tx(&b_full[sb], (uint32_t)C::B_TILE_BYTES);
+              tma_load_3d(b_base + (uint32_t)(sb * C::B_TILE_BYTES), &tmB, &b_full[sb], kc * BK, n0, p.grp_first[g] + j);
+            }
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
+      // ---------------- MMA issuer (single thread): every tap re-reads the same smem tile at a row offset
       constexpr uint32_t idesc = make_idesc(BM, BN);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % C::STAGES;
-        const uint32_t ph = (uint32_t)(it / C::STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      int ai = 0, bi = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t sa = tiles + (uint32_t)s * C::STAGE_BYTES;
-        const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+        uint32_t first = 1;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int g = 0; g < p.n_groups; ++g, ++ai) {
+            const int sa = ai % A_SLOTS;
+            mbar_wait(&a_full[sa], (uint32_t)(ai / A_SLOTS) & 1u);
+            const uint32_t a_tile = a_base + (uint32_t)(sa * p.a_slot_bytes);
+            for (int j = 0; j < p.grp_count[g]; ++j, ++bi) {
+              const int sb = bi % B_SLOTS;
+              mbar_wait(&b_full[sb], (uint32_t)(bi / B_SLOTS) & 1u);
+              tcgen05_fence_after();
+              const uint64_t da = make_smem_desc(a_tile + (uint32_t)p.tap_byte_off[p.grp_first[g] + j]);
+              const uint64_t db = make_smem_desc(b_base + (uint32_t)(sb * C::B_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B along K inside the swizzle atom = +2 in the (addr>>4) field
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((it | k) != 0));
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 B along K inside the swizzle atom = +2 in the (addr>>4) field
+                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
+            }
+            umma_commit(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
+          }
+        }
+        umma_commit(&acc_full[buf]);       // accumulator complete -> epilogue
       }
-      umma_commit(&accum_bar);       // accumulator complete
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: warp q = warp%4 owns TMEM lanes [32q, 32q+32) = GEMM rows m0+32q+lane
-    const int q = warp & 3;
-    const int r = m0 + q * 32 + lane;
+    // ---------------- epilogue (warps 2..9): (q, half) = TMEM lane quarter, column half
+    // phase 1: TMEM -> registers -> fp32 staging tile in smem (thread = accumulator row), then the accumulator is
+    //          handed back to the MMA warp;  phase 2: warps walk the staged tile row-wise: coalesced residual loads
+    //          issued ahead of the stores, fused epilogue arithmetic, coalesced fp32 + bf16 stores.
+    const int ew = warp - 2;
+    const int q = warp & 3, half = ew >> 2;
+    const int et = threadIdx.x - 64;
     const Epilogue& e = p.e;
-    mbar_wait(&accum_bar, 0);
-    tcgen05_fence_after();
     bf16* out_act = reinterpret_cast<bf16*>(e.out_act);
+    const bool has_res = e.res != nullptr, has_res2 = e.res2 != nullptr, has_f32 = e.out_f32 != nullptr, has_act = e.out_act != nullptr;
+    const bool use_div = e.div != 1.0f, snake = e.act == ACT_SNAKE;
+    const float slope = e.act == ACT_LRELU ? e.slope : (e.act == ACT_RELU ? 0.0f : 1.0f);
+    const float alpha = e.alpha;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
+      const int m0 = mt * BM, n0 = nt * BN;
+      const int buf = ti & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+      tcgen05_fence_after();
+      {
+        float* srow = stage + (q * 32 + lane) * C::STAGE_LD;
+        constexpr int CHUNKS = BN / 32;                      // 32-column chunks of the tile
+        constexpr int PER = CHUNKS >= 2 ? CHUNKS / 2 : 1;    // chunks per warp (BN=32: only half 0 works)
+        if (CHUNKS >= 2 || half == 0) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nb = n0 + c * 32;
-      if (nb >= p.g.N) break;  // warp-uniform
-      __syncwarp();            // tcgen05.ld is .sync.aligned: reconverge lanes that skipped the previous chunk
-      uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), raw);
-      if (r >= p.g.M) continue;
-      const int phase = nb / e.phase_cout;
-      const int co0 = nb - phase * e.phase_cout;
-      const bool one_phase = (co0 + 32 <= e.phase_cout) && (nb + 32 <= p.g.N);
-      if (one_phase && p.vec_ok) {
-        const int t = e.up_s * r + phase - e.up_p;
-        if (t < 0 || t >= e.T_out) continue;
-        const float mv = e.mask.at(b, t);
-        const float* bias = e.bias ? e.bias + co0 : nullptr;
-        const float* res = e.res ? e.res + b * e.res_bs + (long long)t * e.res_ld + co0 : nullptr;
-        const float* res2 = e.res2 ? e.res2 + b * e.res2_bs + (long long)t * e.res2_ld + co0 : nullptr;
-        float* of = e.out_f32 ? e.out_f32 + b * e.f32_bs + (long long)t * e.f32_ld + co0 : nullptr;
-        bf16* oa = out_act ? out_act + b * e.act_bs + (long long)t * e.act_ld + co0 : nullptr;
+          for (int ci = 0; ci < PER; ++ci) {
+            const int c = (CHUNKS >= 2 ? half * PER : 0) + ci;
+            uint32_t raw[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), raw);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float v[4] = {__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3])};
-          if (bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + j)); v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w; }
-          if (e.mask_pre) { v[0] *= mv; v[1] *= mv; v[2] *= mv; v[3] *= mv; }
-          v[0] *= e.alpha; v[1] *= e.alpha; v[2] *= e.alpha; v[3] *= e.alpha;
-          if (res) { const float4 t4 = *reinterpret_cast<const float4*>(res + j); v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w; }
-          if (res2) { const float4 t4 = *reinterpret_cast<const float4*>(res2 + j); v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w; }
-          if (e.div != 1.0f) { v[0] = v[0] / e.div; v[1] = v[1] / e.div; v[2] = v[2] / e.div; v[3] = v[3] / e.div; }
-          if (of) *reinterpret_cast<float4*>(of + j) = make_float4(v[0], v[1], v[2], v[3]);
-          if (oa) {
-            const float a0 = ep_act(e, co0 + j, v[0], mv), a1 = ep_act(e, co0 + j + 1, v[1], mv);
-            const float a2 = ep_act(e, co0 + j + 2, v[2], mv), a3 = ep_act(e, co0 + j + 3, v[3], mv);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(oa + j) = pk;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging complete, TMEM reads retired
+      if (et == 0) mbar_arrive(&acc_empty[buf]);
+      if (p.vec_ok) {
+        constexpr int G = (BN / 4) < 32 ? (BN / 4) : 32;   // lanes per staged row
+        constexpr int RPI = 32 / G;                        // rows per warp iteration
+        constexpr int ITERS = 16 / RPI;                    // iterations per warp (16 rows each)
+        constexpr int U = ITERS < 8 ? ITERS : 8;           // iterations whose loads are issued before any store
+        const int sub = lane / G, cl = (lane % G) * 4;
+        const int n = n0 + cl;
+        const bool n_ok = n < p.g.N;
+        int co = 0, phase = 0;
+        if (n_ok) { phase = n / e.phase_cout; co = n - phase * e.phase_cout; }
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
+        if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
+        if (n_ok && snake) {
+          sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
+          sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
+        }
+        const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
+        // per-lane base pointers of this tile (row term added per iteration)
+        const float* res_p = has_res ? e.res + b * e.res_bs + co : nullptr;
+        const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
+        float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
+        bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
+        const float* srow0 = stage + (ew * 16 + sub) * C::STAGE_LD + cl;
+        const int r_base = m0 + ew * 16 + sub;
+#pragma unroll 1
+        for (int it0 = 0; it0 < ITERS; it0 += U) {
+          float4 rres[U], rres2[U];
+          int tt[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int r = r_base + (it0 + u) * RPI;
+            int t = e.up_s * r + phase - e.up_p;
+            if (!n_ok || r >= p.g.M || t >= e.T_out) t = -1;
+            tt[u] = t;
+            if (has_res) rres[u] = t >= 0 ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_res2) rres2[u] = t >= 0 ? *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int t = tt[u];
+            if (t < 0) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(srow0 + (it0 + u) * RPI * C::STAGE_LD);
+            float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
+            const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
+            if (e.mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
+            v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha;
+            if (has_res) { v0 += rres[u].x; v1 += rres[u].y; v2 += rres[u].z; v3 += rres[u].w; }
+            if (has_res2) { v0 += rres2[u].x; v1 += rres2[u].y; v2 += rres2[u].z; v3 += rres2[u].w; }
+            if (use_div) { v0 = v0 / e.div; v1 = v1 / e.div; v2 = v2 / e.div; v3 = v3 / e.div; }
+            if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
+            if (has_act) {
+              float a0, a1, a2, a3;
+              if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
+                const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
+                a0 = fmaf(sb4.x, s0 * s0, v0); a1 = fmaf(sb4.y, s1 * s1, v1); a2 = fmaf(sb4.z, s2 * s2, v2); a3 = fmaf(sb4.w, s3 * s3, v3);
+              } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
+                a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
+              }
+              if (e.mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
+              __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+            }
           }
         }
       } else {
-#pragma unroll 1
-        for (int j = 0; j < 32; ++j) {
-          const int n = nb + j;
-          if (n >= p.g.N) break;
+        // generic scalar path (unaligned strides / channel counts that are not multiples of 4)
+        for (int idx = et; idx < BM * BN; idx += EPI_THREADS) {
+          const int rl = idx / BN, nl = idx - rl * BN;
+          const int r = m0 + rl, n = n0 + nl;
+          if (r >= p.g.M || n >= p.g.N) continue;
           int t, co;
           if (!ep_coord(e, r, n, t, co)) continue;
           const float mv = e.mask.at(b, t);
-          // dynamic register-array index: keep it simple, this path only serves ragged tails (e.g. N = 80)
-          float accv = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) accv = (jj == j) ? __uint_as_float(raw[jj]) : accv;
-          const float v = ep_value(e, b, t, co, accv, mv);
+          const float v = ep_value(e, b, t, co, stage[rl * C::STAGE_LD + nl], mv);
           if (e.out_f32) e.out_f32[b * e.f32_bs + (long long)t * e.f32_ld + co] = v;
           if (out_act) out_act[b * e.act_bs + (long long)t * e.act_ld + co] = __float2bfloat16_rn(ep_act(e, co, v, mv));
         }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging may be overwritten by the next tile
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+int g_halo_mode = -1;   // EV_TC_HALO=0 disables halo reuse (one activation tile per tap) for debugging
 
 bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                 uint64_t s2_bytes, uint32_t b0, uint32_t b1, std::string* err) {
@@ -281,29 +391,43 @@ bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, ui
   return true;
 }
 
+int g_sm_count = 0;
+
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t stream) {
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
+  // smem: 1 KiB alignment slack + activation ring + weight ring + fp32 staging tile (one persistent CTA per SM)
+  const int budget = 200 * 1024 - 1024 - C::STAGING_BYTES;
+  int a_slots = 3;
+  int b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES;
+  if (b_slots < 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES; }
+  if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
+  if (b_slots < 2) return cudaErrorInvalidConfiguration;
+  p.a_slots = a_slots;
+  p.b_slots = b_slots;
+  const int smem = 1024 + a_slots * p.a_slot_bytes + b_slots * C::B_TILE_BYTES + C::STAGING_BYTES;
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
-  dim3 grid(ceil_div(p.g.M, BM), ceil_div(p.g.N, BN), p.g.B);
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  p.m_tiles = ceil_div(p.g.M, BM);
+  p.n_tiles = ceil_div(p.g.N, BN);
+  p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
+  const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 int conv_tc_pick_bn(int N) {
-  if (N % 256 == 0) return 256;
+  // two CTAs stay resident per SM at BN = 128 (one drains its accumulator while the other feeds the tensor core)
   if (N % 128 == 0) return 128;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  return 256;
+  return 128;
 }
 
 bool conv_tc_init(std::string* err) {
@@ -316,6 +440,10 @@ bool conv_tc_init(std::string* err) {
     return false;
   }
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (g_sm_count <= 0) g_sm_count = 148;
   return true;
 }
 
@@ -327,31 +455,53 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
     if (err) *err = "conv_tc: activation tensor is not 16-byte aligned / strided";
     return cudaErrorInvalidValue;
   }
+  if (g_halo_mode < 0) {
+    const char* env = getenv("EV_TC_HALO");
+    g_halo_mode = env ? atoi(env) : 1;
+  }
   TcParams p;
   p.g = g;
   p.e = e;
   p.kchunks = ceil_div(g.C_in, BK);
+  int tap_row[kMaxTaps], tap_col[kMaxTaps];
   CUtensorMap tmA, tmB;
-  bool ok;
+  uint64_t d0, d1, s1;
   if (g.conv_stride == 1) {
-    for (int j = 0; j < g.taps; ++j) { p.tap_row[j] = g.tap_off[j]; p.tap_col[j] = 0; }
-    ok = encode_map(&tmA, x, (uint64_t)g.C_in, (uint64_t)g.T_in, (uint64_t)g.B, (uint64_t)x_ld * 2, (uint64_t)x_bs * 2,
-                    BK, BM, err);
+    for (int j = 0; j < g.taps; ++j) { tap_row[j] = g.tap_off[j]; tap_col[j] = 0; }
+    d0 = (uint64_t)g.C_in; d1 = (uint64_t)g.T_in; s1 = (uint64_t)x_ld * 2;
   } else if (g.conv_stride == 2) {
     // (T, ld) viewed as (T/2, 2*ld): time 2j+h is row j, columns [h*ld, h*ld + C_in)
     if (g.T_in & 1) { if (err) *err = "conv_tc: stride-2 conv needs an even input length"; return cudaErrorInvalidValue; }
     for (int j = 0; j < g.taps; ++j) {
       const int off = g.tap_off[j];
       const int h = ((off % 2) + 2) % 2;
-      p.tap_row[j] = (off - h) / 2;
-      p.tap_col[j] = h * (int)x_ld;
+      tap_row[j] = (off - h) / 2;
+      tap_col[j] = h * (int)x_ld;
     }
-    ok = encode_map(&tmA, x, (uint64_t)(x_ld + g.C_in), (uint64_t)(g.T_in / 2), (uint64_t)g.B, (uint64_t)x_ld * 4,
-                    (uint64_t)x_bs * 2, BK, BM, err);
+    d0 = (uint64_t)(x_ld + g.C_in); d1 = (uint64_t)(g.T_in / 2); s1 = (uint64_t)x_ld * 4;
   } else {
     if (err) *err = "conv_tc: unsupported stride";
     return cudaErrorInvalidValue;
   }
+  // halo reuse: all taps read one tile when they share the column origin and the row span fits a TMA box
+  int lo = tap_row[0], hi = tap_row[0];
+  bool same_col = true;
+  for (int j = 1; j < g.taps; ++j) { lo = std::min(lo, tap_row[j]); hi = std::max(hi, tap_row[j]); same_col &= tap_col[j] == tap_col[0]; }
+  const bool halo = g_halo_mode != 0 && g.taps > 1 && same_col && (BM + hi - lo) <= 256;
+  if (halo) {
+    p.n_groups = 1;
+    p.grp_row0[0] = lo; p.grp_col0[0] = tap_col[0]; p.grp_first[0] = 0; p.grp_count[0] = g.taps;
+    for (int j = 0; j < g.taps; ++j) p.tap_byte_off[j] = (tap_row[j] - lo) * BK * 2;
+    p.a_rows = (int)align_up(BM + hi - lo, 8);
+  } else {
+    p.n_groups = g.taps;
+    for (int j = 0; j < g.taps; ++j) {
+      p.grp_row0[j] = tap_row[j]; p.grp_col0[j] = tap_col[j]; p.grp_first[j] = j; p.grp_count[j] = 1; p.tap_byte_off[j] = 0;
+    }
+    p.a_rows = BM;
+  }
+  p.a_slot_bytes = (int)align_up((size_t)p.a_rows * BK * 2, 1024);
+  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * 2, BK, (uint32_t)p.a_rows, err);
   if (!ok) return cudaErrorInvalidValue;
   (void)x_rows;
   const int BN = conv_tc_pick_bn(g.N);
@@ -362,8 +512,12 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
   ok = encode_map(&tmB, w.w_bf16, (uint64_t)w.K_pad, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, (uint64_t)w.K_pad * 2,
                   (uint64_t)w.K_pad * w.N_pad_tc * 2, BK, (uint32_t)BN, err);
   if (!ok) return cudaErrorInvalidValue;
+  if (e.act != ACT_NONE && e.act != ACT_RELU && e.act != ACT_LRELU && e.act != ACT_SNAKE) {
+    if (err) *err = "conv_tc: the tensor-core epilogue implements identity / (leaky) ReLU / SnakeBeta only";
+    return cudaErrorInvalidValue;
+  }
   auto al4 = [](long long v) { return (v & 3) == 0; };
-  p.vec_ok = (e.phase_cout % 32 == 0) && al4(e.res_ld) && al4(e.res_bs) && al4(e.res2_ld) && al4(e.res2_bs) &&
+  p.vec_ok = (e.phase_cout % 4 == 0) && (g.N % 4 == 0) && al4(e.res_ld) && al4(e.res_bs) && al4(e.res2_ld) && al4(e.res2_bs) &&
              al4(e.f32_ld) && al4(e.f32_bs) && al4(e.act_ld) && al4(e.act_bs) &&
              ((reinterpret_cast<uintptr_t>(e.res) | reinterpret_cast<uintptr_t>(e.res2) |
                reinterpret_cast<uintptr_t>(e.out_f32) | reinterpret_cast<uintptr_t>(e.bias)) & 15) == 0 &&
@@ -371,8 +525,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream);
     case 64: return launch_bn<64>(tmA, tmB, p, stream);
-    case 128: return launch_bn<128>(tmA, tmB, p, stream);
-    default: return launch_bn<256>(tmA, tmB, p, stream);
+    default: return launch_bn<128>(tmA, tmB, p, stream);
   }
 }
 

@@ -163,6 +163,7 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
   VocBuffers<ActT> v;
   plan_vocode<ActT>(h, B, T, w, &v);
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_vocode: workspace too small");
+  ctx->prof_tag = "/voc";
   const RowMask none{nullptr, 0};
   EV_LAUNCH(ctx, s, "cf_to_cl", 0, (double)B * T * c.num_mels * (4.0 + sizeof(ActT)),
             (cf_to_cl<ActT>(mel, B, c.num_mels, T, v.mel, c.num_mels, (long long)T * c.num_mels, 1.0f, none, s)));

@@ -211,6 +211,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
   EncBuffers e;
   plan_encode(c, B, Tx, w, &e);
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_encode: workspace too small");
+  ctx->prof_tag = "/enc";
   const int C = c.enc_channels, H = C + (c.n_spks > 1 ? c.spk_emb_dim : 0);
   const long long bsC = (long long)Tx * C, bsH = (long long)Tx * H;
   const double R = (double)B * Tx;
@@ -511,6 +512,7 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
   DecBuffers<ActT> d;
   plan_decode<ActT>(c, B, T, n_steps, w, &d);
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_decode: workspace too small");
+  ctx->prof_tag = "/dec";
   const int D = c.dec_channels, F = c.n_feats, S = c.n_spks > 1 ? c.spk_emb_dim : 0, dec_in = 2 * F + S;
   EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), d.ylen32, B, s));
   const RowMask mask0{d.ylen32, 0};

@@ -199,15 +199,16 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
   if (e.res2) bytes += 4.0 * B * T_out * w.C_out;
   cudaError_t ce;
   if constexpr (std::is_same<ActT, float>::value) {
-    { LaunchScope ls(ctx, s, "conv_simt_f32", flops, bytes); ce = conv_simt_launch(g, x, x_ld, x_bs, w, e, s); }
+    const std::string nm = std::string("conv_simt_f32") + ctx->prof_tag;
+    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_simt_launch(g, x, x_ld, x_bs, w, e, s); }
     if (ce != cudaSuccess) return cuda_fail(ctx, ce, "conv_simt_launch");
   } else {
     if (!w.w_bf16) return fail(ctx, EV_ERR_STATE, "layer has no bf16 weights");
     std::string msg;
     static const char* names[4] = {"conv_tc_bn32", "conv_tc_bn64", "conv_tc_bn128", "conv_tc_bn256"};
     const int bn = conv_tc_pick_bn(w.N);
-    const char* nm = names[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3];
-    { LaunchScope ls(ctx, s, nm, flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg); }
+    const std::string nm = std::string(names[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3]) + ctx->prof_tag;
+    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg); }
     if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   }
   return 0;
