@@ -49,6 +49,7 @@ struct TcParams {
   int kchunks;
   int vec_ok;
   int m_tiles, n_tiles, total_tiles;
+  int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -159,8 +160,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < MAX_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -178,6 +179,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- TMA producer: per tile, per K-chunk, per tap group: one (haloed) activation tile, then one
       // weight tile per tap.  Ring positions run on across tiles, so the next tile's loads start while this one computes.
       int ai = 0, bi = 0;
+      if (p.resident) {   // narrow layers: every (K-chunk, tap) weight tile is fetched once and kept
+        const int n_w = p.kchunks * p.g.taps;
+        mbar_expect_tx(&b_full[0], (uint32_t)(n_w * C::B_TILE_BYTES));
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int j = 0; j < p.g.taps; ++j)
+            tma_load_3d(b_base + (uint32_t)((kc * p.g.taps + j) * C::B_TILE_BYTES), &tmB, &b_full[0], kc * BK, 0, j);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
         const int m0 = mt * BM, n0 = nt * BN;
@@ -187,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&a_empty[sa], ((uint32_t)(ai / A_SLOTS) & 1u) ^ 1u);
             mbar_expect_tx(&a_full[sa], (uint32_t)(p.a_rows * BK * 2));
             tma_load_3d(a_base + (uint32_t)(sa * p.a_slot_bytes), &tmA, &a_full[sa], p.grp_col0[g] + kc * BK, m0 + p.grp_row0[g], b);
+            if (p.resident) continue;
             for (int j = 0; j < p.grp_count[g]; ++j, ++bi) {
               const int sb = bi % B_SLOTS;
               mbar_wait(&b_empty[sb], ((uint32_t)(bi / B_SLOTS) & 1u) ^ 1u);
@@ -203,6 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- MMA issuer (single thread): every tap re-reads the same smem tile at a row offset
       constexpr uint32_t idesc = make_idesc(BM, BN);
       int ai = 0, bi = 0, ti = 0;
+      if (p.resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti & 1;
         mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -213,19 +223,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int g = 0; g < p.n_groups; ++g, ++ai) {
             const int sa = ai % A_SLOTS;
             mbar_wait(&a_full[sa], (uint32_t)(ai / A_SLOTS) & 1u);
+            tcgen05_fence_after();
             const uint32_t a_tile = a_base + (uint32_t)(sa * p.a_slot_bytes);
-            for (int j = 0; j < p.grp_count[g]; ++j, ++bi) {
-              const int sb = bi % B_SLOTS;
-              mbar_wait(&b_full[sb], (uint32_t)(bi / B_SLOTS) & 1u);
-              tcgen05_fence_after();
-              const uint64_t da = make_smem_desc(a_tile + (uint32_t)p.tap_byte_off[p.grp_first[g] + j]);
-              const uint64_t db = make_smem_desc(b_base + (uint32_t)(sb * C::B_TILE_BYTES));
+            for (int j = 0; j < p.grp_count[g]; ++j) {
+              const int tap = p.grp_first[g] + j;
+              uint32_t b_tile;
+              int sb = 0;
+              if (p.resident) {
+                b_tile = b_base + (uint32_t)((kc * p.g.taps + tap) * C::B_TILE_BYTES);
+              } else {
+                sb = bi % B_SLOTS;
+                mbar_wait(&b_full[sb], (uint32_t)(bi / B_SLOTS) & 1u);
+                tcgen05_fence_after();
+                b_tile = b_base + (uint32_t)(sb * C::B_TILE_BYTES);
+                ++bi;
+              }
+              const uint64_t da = make_smem_desc(a_tile + (uint32_t)p.tap_byte_off[tap]);
+              const uint64_t db = make_smem_desc(b_tile);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 B along K inside the swizzle atom = +2 in the (addr>>4) field
                 umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
                 first = 0;
               }
-              umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
+              if (!p.resident) umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
             }
             umma_commit(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
           }
@@ -248,6 +268,84 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool use_div = e.div != 1.0f, snake = e.act == ACT_SNAKE;
     const float slope = e.act == ACT_LRELU ? e.slope : (e.act == ACT_RELU ? 0.0f : 1.0f);
     const float alpha = e.alpha;
+    constexpr int G = (BN / 4) < 32 ? (BN / 4) : 32;   // lanes per staged row
+    constexpr int RPI = 32 / G;                        // rows per warp iteration
+    constexpr int ITERS = 16 / RPI;                    // iterations per warp (16 rows each)
+    constexpr int U = ITERS < 8 ? ITERS : 8;           // iterations per batch: loads of a batch are issued together
+    constexpr int NB = ITERS / U;                      // batches per tile (1 or 2)
+    const int sub = lane / G, cl = (lane % G) * 4;
+    const float* srow0 = stage + (ew * 16 + sub) * C::STAGE_LD + cl;
+
+    // residual loads of one batch of one tile (issued long before they are consumed; tt[u] < 0 marks an invalid row)
+    auto issue = [&](int tile, int it0, float4 (&rr)[U], float4 (&rr2)[U], int (&tt)[U]) {
+      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
+      const int n = nt * BN + cl;
+      const bool n_ok = n < p.g.N;
+      int co = 0, phase = 0;
+      if (n_ok) { phase = n / e.phase_cout; co = n - phase * e.phase_cout; }
+      const int r_base = mt * BM + ew * 16 + sub;
+      const float* res_p = has_res ? e.res + b * e.res_bs + co : nullptr;
+      const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r_base + (it0 + u) * RPI;
+        int t = e.up_s * r + phase - e.up_p;
+        if (!n_ok || r >= p.g.M || t >= e.T_out) t = -1;
+        tt[u] = t;
+        if (has_res) rr[u] = t >= 0 ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_res2) rr2[u] = t >= 0 ? *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    // fused epilogue arithmetic + coalesced stores of one batch
+    auto finish = [&](int tile, int it0, const float4 (&rr)[U], const float4 (&rr2)[U], const int (&tt)[U]) {
+      const int nt = tile % p.n_tiles, b = tile / (p.n_tiles * p.m_tiles);
+      const int n = nt * BN + cl;
+      const bool n_ok = n < p.g.N;
+      int co = 0;
+      if (n_ok) co = n - (n / e.phase_cout) * e.phase_cout;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
+      if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
+      if (n_ok && snake) {
+        sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
+        sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
+      }
+      const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
+      float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
+      bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = tt[u];
+        if (t < 0) continue;
+        const float4 a4 = *reinterpret_cast<const float4*>(srow0 + (it0 + u) * RPI * C::STAGE_LD);
+        float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
+        const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
+        if (e.mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
+        v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha;
+        if (has_res) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
+        if (has_res2) { v0 += rr2[u].x; v1 += rr2[u].y; v2 += rr2[u].z; v3 += rr2[u].w; }
+        if (use_div) { v0 = v0 / e.div; v1 = v1 / e.div; v2 = v2 / e.div; v3 = v3 / e.div; }
+        if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
+        if (has_act) {
+          float a0, a1, a2, a3;
+          if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
+            const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
+            a0 = fmaf(sb4.x, s0 * s0, v0); a1 = fmaf(sb4.y, s1 * s1, v1); a2 = fmaf(sb4.z, s2 * s2, v2); a3 = fmaf(sb4.w, s3 * s3, v3);
+          } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
+            a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
+          }
+          if (e.mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+        }
+      }
+    };
+
+    float4 P[U], P2[U];
+    int Pt[U];
+    if (p.vec_ok && (int)blockIdx.x < p.total_tiles) issue((int)blockIdx.x, 0, P, P2, Pt);   // first tile's residuals
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
       const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
@@ -275,71 +373,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("bar.sync 1, 256;" ::: "memory");           // staging complete, TMEM reads retired
       if (et == 0) mbar_arrive(&acc_empty[buf]);
       if (p.vec_ok) {
-        constexpr int G = (BN / 4) < 32 ? (BN / 4) : 32;   // lanes per staged row
-        constexpr int RPI = 32 / G;                        // rows per warp iteration
-        constexpr int ITERS = 16 / RPI;                    // iterations per warp (16 rows each)
-        constexpr int U = ITERS < 8 ? ITERS : 8;           // iterations whose loads are issued before any store
-        const int sub = lane / G, cl = (lane % G) * 4;
-        const int n = n0 + cl;
-        const bool n_ok = n < p.g.N;
-        int co = 0, phase = 0;
-        if (n_ok) { phase = n / e.phase_cout; co = n - phase * e.phase_cout; }
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
-        if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
-        if (n_ok && snake) {
-          sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
-          sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
-        }
-        const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
-        // per-lane base pointers of this tile (row term added per iteration)
-        const float* res_p = has_res ? e.res + b * e.res_bs + co : nullptr;
-        const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
-        float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
-        bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
-        const float* srow0 = stage + (ew * 16 + sub) * C::STAGE_LD + cl;
-        const int r_base = m0 + ew * 16 + sub;
-#pragma unroll 1
-        for (int it0 = 0; it0 < ITERS; it0 += U) {
-          float4 rres[U], rres2[U];
-          int tt[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int r = r_base + (it0 + u) * RPI;
-            int t = e.up_s * r + phase - e.up_p;
-            if (!n_ok || r >= p.g.M || t >= e.T_out) t = -1;
-            tt[u] = t;
-            if (has_res) rres[u] = t >= 0 ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_res2) rres2[u] = t >= 0 ? *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int t = tt[u];
-            if (t < 0) continue;
-            const float4 a4 = *reinterpret_cast<const float4*>(srow0 + (it0 + u) * RPI * C::STAGE_LD);
-            float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
-            const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
-            if (e.mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
-            v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha;
-            if (has_res) { v0 += rres[u].x; v1 += rres[u].y; v2 += rres[u].z; v3 += rres[u].w; }
-            if (has_res2) { v0 += rres2[u].x; v1 += rres2[u].y; v2 += rres2[u].z; v3 += rres2[u].w; }
-            if (use_div) { v0 = v0 / e.div; v1 = v1 / e.div; v2 = v2 / e.div; v3 = v3 / e.div; }
-            if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
-            if (has_act) {
-              float a0, a1, a2, a3;
-              if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
-                const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
-                a0 = fmaf(sb4.x, s0 * s0, v0); a1 = fmaf(sb4.y, s1 * s1, v1); a2 = fmaf(sb4.z, s2 * s2, v2); a3 = fmaf(sb4.w, s3 * s3, v3);
-              } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
-                a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
-              }
-              if (e.mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
-              __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
-            }
-          }
+        const int next = tile + (int)gridDim.x;
+        if (NB == 2) {
+          float4 Q[U], Q2[U];
+          int Qt[U];
+          issue(tile, U, Q, Q2, Qt);         // second half's residuals fly while the first half is finished
+          finish(tile, 0, P, P2, Pt);
+          if (next < p.total_tiles) issue(next, 0, P, P2, Pt);
+          finish(tile, U, Q, Q2, Qt);
+        } else {
+          finish(tile, 0, P, P2, Pt);
+          if (next < p.total_tiles) issue(next, 0, P, P2, Pt);   // next tile's residuals fly during its main loop
         }
       } else {
         // generic scalar path (unaligned strides / channel counts that are not multiples of 4)
@@ -392,17 +436,31 @@ bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, ui
 }
 
 int g_sm_count = 0;
+int g_resident_mode = 1;   // EV_TC_RESIDENT=0 disables the weights-resident variant (debugging)
 
 template <int BN>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
-  // smem: 1 KiB alignment slack + activation ring + weight ring + fp32 staging tile (one persistent CTA per SM)
+  // smem: 1 KiB alignment slack + activation ring + weight ring (or all weights) + fp32 staging tile
   const int budget = 200 * 1024 - 1024 - C::STAGING_BYTES;
-  int a_slots = 3;
-  int b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES;
-  if (b_slots < 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES; }
-  if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
-  if (b_slots < 2) return cudaErrorInvalidConfiguration;
+  p.m_tiles = ceil_div(p.g.M, BM);
+  p.n_tiles = ceil_div(p.g.N, BN);
+  p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
+  const int w_tiles = p.kchunks * p.g.taps;
+  int a_slots, b_slots;
+  p.resident = (g_resident_mode != 0) && p.n_tiles == 1 && p.total_tiles >= 2 * g_sm_count &&
+               (w_tiles * C::B_TILE_BYTES + 2 * p.a_slot_bytes <= budget);
+  if (p.resident) {
+    b_slots = w_tiles;
+    a_slots = (budget - w_tiles * C::B_TILE_BYTES) / p.a_slot_bytes;
+    if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
+  } else {
+    a_slots = 3;
+    b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES;
+    if (b_slots < 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES; }
+    if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
+    if (b_slots < 2) return cudaErrorInvalidConfiguration;
+  }
   p.a_slots = a_slots;
   p.b_slots = b_slots;
   const int smem = 1024 + a_slots * p.a_slot_bytes + b_slots * C::B_TILE_BYTES + C::STAGING_BYTES;
@@ -412,9 +470,6 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
-  p.m_tiles = ceil_div(p.g.M, BM);
-  p.n_tiles = ceil_div(p.g.N, BN);
-  p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
   const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
   conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
@@ -458,6 +513,8 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
   if (g_halo_mode < 0) {
     const char* env = getenv("EV_TC_HALO");
     g_halo_mode = env ? atoi(env) : 1;
+    const char* env2 = getenv("EV_TC_RESIDENT");
+    g_resident_mode = env2 ? atoi(env2) : 1;
   }
   TcParams p;
   p.g = g;
