@@ -146,6 +146,62 @@ extern "C" int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const
   return EV_OK;
 }
 
+namespace {
+__global__ void bf16_to_f32_kernel(const bf16* in, float* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+}  // namespace
+
+// Decoder attention alone: qkv (B, 3*H*64, T) channel-first fp32 [q | k | v sections], y_lengths (B) int64 or NULL.
+extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_lengths, int B, int T, int H, int len_shift,
+                                 int precision, float* out, void* stream) {
+  if (!ctx || !qkv || !out || B <= 0 || T <= 0 || H <= 0) return EV_ERR_INVALID;
+  cudaStream_t s = as_stream(stream);
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int inner = H * 64;
+  const size_t mark = ctx->owned.size();
+  auto release = [&]() {
+    cudaStreamSynchronize(s);
+    for (size_t i = mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+    ctx->owned.resize(mark);
+  };
+  void *xa = nullptr, *yo = nullptr, *yf = nullptr, *li = nullptr;
+  const size_t esz = precision == EV_PREC_BF16 ? 2 : 4;
+  int rc;
+  if ((rc = device_alloc(ctx, (size_t)B * T * 3 * inner * esz, &xa, false, s)) || (rc = device_alloc(ctx, (size_t)B * T * inner * esz, &yo, false, s)) ||
+      (rc = device_alloc(ctx, (size_t)B * T * inner * 4, &yf, false, s)) || (rc = device_alloc(ctx, (size_t)B * 4, &li, false, s))) { release(); return rc; }
+  int* lens = nullptr;
+  cudaError_t ce = cudaSuccess;
+  if (y_lengths) { lens = reinterpret_cast<int*>(li); ce = i64_to_i32(reinterpret_cast<const long long*>(y_lengths), lens, B, s); }
+  const RowMask none{nullptr, 0};
+  const float scale = 0.125f;
+  std::string err;
+  if (ce == cudaSuccess && precision == EV_PREC_BF16) {
+    ce = cf_to_cl<bf16>(qkv, B, 3 * inner, T, reinterpret_cast<bf16*>(xa), 3 * inner, (long long)T * 3 * inner, 1.0f, none, s);
+    AttnTcArgs at;
+    at.qkv = reinterpret_cast<bf16*>(xa); at.ld = 3 * inner; at.bs = (long long)T * 3 * inner;
+    at.B = B; at.T = T; at.H = H; at.D = 64; at.inner = inner; at.scale = scale; at.lens = lens; at.len_shift = len_shift;
+    at.out = reinterpret_cast<bf16*>(yo); at.out_ld = inner; at.out_bs = (long long)T * inner;
+    if (ce == cudaSuccess) ce = attention_tc(at, s, &err);
+    const long long n = (long long)B * T * inner;
+    if (ce == cudaSuccess) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(yo), reinterpret_cast<float*>(yf), n); ce = cudaGetLastError(); }
+  } else if (ce == cudaSuccess) {
+    ce = cf_to_cl<float>(qkv, B, 3 * inner, T, reinterpret_cast<float*>(xa), 3 * inner, (long long)T * 3 * inner, 1.0f, none, s);
+    AttnArgs at;
+    const float* q = reinterpret_cast<float*>(xa);
+    at.q = q; at.k = q + inner; at.v = q + 2 * inner; at.ld = 3 * inner; at.bs = (long long)T * 3 * inner;
+    at.B = B; at.T = T; at.H = H; at.D = 64; at.scale = scale; at.lens = lens; at.len_shift = len_shift; at.mode = 1;
+    at.out = yf; at.out_ld = inner; at.out_bs = (long long)T * inner;
+    if (ce == cudaSuccess) ce = attention_rows<float>(at, s);
+  }
+  if (ce == cudaSuccess) ce = cl_to_cf(reinterpret_cast<float*>(yf), inner, (long long)T * inner, B, inner, T, out, 1.0f, 0.0f, s);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  release();
+  if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ev_test_attention") : fail(ctx, EV_ERR_CUDA, err);
+  return EV_OK;
+}
+
 extern "C" int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream) {
   if (!ctx || !x || !out) return EV_ERR_INVALID;
   EV_CUDA(ctx, cudaSetDevice(ctx->device));

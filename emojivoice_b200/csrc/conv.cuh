@@ -12,6 +12,8 @@
 #pragma once
 #include "common.cuh"
 
+struct CUtensorMap_st;
+
 namespace ev {
 
 constexpr int kMaxTaps = 16;
@@ -90,6 +92,10 @@ cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, 
 cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, long long x_bs, int x_rows_alloc,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err);
 bool conv_tc_init(std::string* err);
+// 3-D bf16 tensor map (dims d0 fastest; strides in bytes for d1, d2; box b0 x b1 x 1; swizzle 128 or 64 bytes)
+bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
+                        uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes, std::string* err);
+int tc_sm_count();
 int conv_tc_pick_bn(int N);
 
 }  // namespace ev

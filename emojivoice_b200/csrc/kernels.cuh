@@ -55,6 +55,15 @@ struct AttnArgs {
   void* out = nullptr; long long out_ld = 0, out_bs = 0;   // (b, t, h*D + d)
 };
 template <typename ActT> cudaError_t attention_rows(const AttnArgs& a, cudaStream_t s);
+// Decoder attention (mode 1 semantics) on tcgen05 tensor cores: bf16 q|k|v packed per row, head_dim 64 (attention_tc.cu)
+struct AttnTcArgs {
+  const bf16* qkv = nullptr; long long ld = 0, bs = 0;   // (b, t, [q | k | v]), each section `inner` wide, head h at h*64
+  int B = 0, T = 0, H = 0, D = 64, inner = 0;
+  float scale = 1.0f;
+  const int* lens = nullptr; int len_shift = 0;
+  bf16* out = nullptr; long long out_ld = 0, out_bs = 0;
+};
+cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err);
 cudaError_t rope_tables(float* cos_t, float* sin_t, int T, int rope_dim, float base, cudaStream_t s);
 
 // ---- duration / alignment (integer, bit-exact) -------------------------------------------------------------------

@@ -428,15 +428,32 @@ struct Decoder {
     const TransformerW& w = m.tf[k];
     const RowMask mask{d.ylen32, shift};
     const long long bsD = (long long)Tl * D;
-    Epilogue eq; eq.out_f32 = d.qkv; eq.f32_ld = 3 * inner; eq.f32_bs = (long long)Tl * 3 * inner;
-    EV_TRY(run_conv<ActT>(ctx, w.qkv, d.n, D, bsD, B, Tl, eq, s));
-    AttnArgs at;
-    at.q = d.qkv; at.k = d.qkv + inner; at.v = d.qkv + 2 * inner; at.ld = 3 * inner; at.bs = (long long)Tl * 3 * inner;
-    at.B = B; at.T = Tl; at.H = m.cfg.dec_heads; at.D = m.cfg.dec_head_dim; at.scale = 1.0f / sqrtf((float)m.cfg.dec_head_dim);
-    at.lens = d.ylen32; at.len_shift = shift; at.mode = 1;
-    at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
-    EV_LAUNCH(ctx, s, "attention_dec", 4.0 * B * m.cfg.dec_heads * (double)Tl * Tl * m.cfg.dec_head_dim,
-              (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
+    const int Hh = m.cfg.dec_heads, hd = m.cfg.dec_head_dim;
+    const double attn_flops = 4.0 * B * Hh * (double)Tl * Tl * hd;
+    if constexpr (std::is_same<ActT, bf16>::value) {
+      // bf16 q|k|v straight from the projection epilogue -> tcgen05 attention (attention_tc.cu)
+      bf16* qkv16 = reinterpret_cast<bf16*>(d.qkv);
+      Epilogue eq; eq.out_act = qkv16; eq.act_ld = 3 * inner; eq.act_bs = (long long)Tl * 3 * inner;
+      EV_TRY(run_conv<ActT>(ctx, w.qkv, d.n, D, bsD, B, Tl, eq, s));
+      AttnTcArgs at;
+      at.qkv = qkv16; at.ld = 3 * inner; at.bs = (long long)Tl * 3 * inner;
+      at.B = B; at.T = Tl; at.H = Hh; at.D = hd; at.inner = inner; at.scale = 1.0f / sqrtf((float)hd);
+      at.lens = d.ylen32; at.len_shift = shift;
+      at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
+      std::string err;
+      cudaError_t ce;
+      { LaunchScope ls(ctx, s, "attention_tc", attn_flops, (double)B * Tl * inner * 8.0); ce = attention_tc(at, s, &err); }
+      if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "attention_tc") : fail(ctx, EV_ERR_CUDA, err);
+    } else {
+      Epilogue eq; eq.out_f32 = d.qkv; eq.f32_ld = 3 * inner; eq.f32_bs = (long long)Tl * 3 * inner;
+      EV_TRY(run_conv<ActT>(ctx, w.qkv, d.n, D, bsD, B, Tl, eq, s));
+      AttnArgs at;
+      at.q = d.qkv; at.k = d.qkv + inner; at.v = d.qkv + 2 * inner; at.ld = 3 * inner; at.bs = (long long)Tl * 3 * inner;
+      at.B = B; at.T = Tl; at.H = Hh; at.D = hd; at.scale = 1.0f / sqrtf((float)hd);
+      at.lens = d.ylen32; at.len_shift = shift; at.mode = 1;
+      at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
+      EV_LAUNCH(ctx, s, "attention_dec", attn_flops, (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
+    }
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s));
     LnArgs ln;

@@ -155,6 +155,11 @@ EV_API int ev_profile_end(ev_ctx* ctx, ev_kernel_stat* out, int max_entries, int
 EV_API int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout,
                    int K, int stride, int padding, int dilation, int transposed, int precision, float* y,
                    void* stream);
+/* Decoder self-attention alone (diffusers Attention as transformer.py:266-271 calls it: scale 1/8, float mask ADDED to the
+ * logits, all T keys in the softmax).  qkv (B, 3*H*64, T) channel-first [q | k | v]; y_lengths (B) int64 or NULL; a key
+ * t is "valid" (+1) while (t << len_shift) < y_lengths[b].  out (B, H*64, T).  precision: fp32 CUDA cores / bf16 tcgen05. */
+EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_lengths, int B, int T, int H, int len_shift,
+                      int precision, float* out, void* stream);
 /* The float32 Euler times/steps of flow_matching.py:52,68-83 as the library computes them (pure host code). */
 EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
 /* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */

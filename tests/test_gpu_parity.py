@@ -78,6 +78,28 @@ def test_conv1d_kernel_matches_torch(ctx, case, prec):
     assert rel_l2(y.cpu(), ref) < 2e-6
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", [(2, 200, 2, 0), (3, 77, 2, 1), (1, 668, 2, 0), (2, 64, 1, 0), (2, 129, 2, 1), (1, 1, 2, 0)])
+def test_decoder_attention_matches_torch_sdpa(ctx, case, prec):
+    """diffusers Attention semantics: the 0/1 mask is ADDED to the logits, padded keys stay in the softmax."""
+    B, T, H, shift = case
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = torch.randn(B, 3 * H * 64, T, generator=g) * 1.5
+    lens = torch.randint(1, (T << shift) + 1, (B,), generator=g)
+    lens[0] = T << shift
+    if prec == "bf16":
+        qkv = qkv.bfloat16().float()
+    q, k, v = (t.reshape(B, H, 64, T).transpose(2, 3).double() for t in qkv.chunk(3, dim=1))
+    mask = ((torch.arange(T)[None, :] << shift) < lens[:, None]).double()             # (B, T) 0/1, decoder.py:396-407
+    ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :])     # float mask: additive
+    ref = ref.transpose(2, 3).reshape(B, H * 64, T)
+    out = torch.empty(B, H * 64, T, device="cuda")
+    qd, ld = qkv.cuda(), lens.cuda()
+    ctx.check(_lib.lib().ev_test_attention(ctx.handle, _lib.ptr(qd), _lib.ptr(ld), B, T, H, shift, _lib.PREC[prec],
+                                           _lib.ptr(out), _lib.stream_ptr()), "ev_test_attention")
+    assert rel_l2(out.cpu(), ref) < (2e-6 if prec == "fp32" else 6e-3)    # bf16: P and the output are rounded to bf16
+
+
 def test_length_sum_follows_aten_cpu_order(ctx):
     rng = np.random.default_rng(0)
     for n in (1, 3, 7, 8, 9, 17, 151, 333, 513, 1100, 2100):
