@@ -130,9 +130,9 @@ class Context:
 
     def profile_end(self):
         """-> list of dicts {name, launches, total_ms, flops, bytes}, one per kernel class launched since begin."""
-        arr = (EvKernelStat * 64)()
+        arr = (EvKernelStat * 256)()
         n = C.c_int(0)
-        self.check(lib().ev_profile_end(self.handle, arr, 64, C.byref(n)), "ev_profile_end")
+        self.check(lib().ev_profile_end(self.handle, arr, 256, C.byref(n)), "ev_profile_end")
         return [dict(name=arr[i].name.decode(), launches=int(arr[i].launches), total_ms=float(arr[i].total_ms),
                      flops=float(arr[i].flops), bytes=float(arr[i].bytes)) for i in range(n.value)]
 

@@ -1,4 +1,5 @@
 // Context lifetime, bookkeeping and the single-kernel unit-test hooks of the C ABI (include/emojivoice_b200.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -64,6 +65,7 @@ extern "C" int ev_profile_begin(ev_ctx* ctx) {
   for (auto& r : ctx->prof) { ctx->event_pool.push_back(r.e0); ctx->event_pool.push_back(r.e1); }
   ctx->prof.clear();
   ctx->profiling = true;
+  { const char* d = getenv("EV_PROF_DETAIL"); ctx->prof_detail = d && atoi(d) != 0; }
   return EV_OK;
 }
 

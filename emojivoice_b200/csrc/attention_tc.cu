@@ -83,42 +83,44 @@ __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_consta
     }
     __syncwarp();
   } else if (warp == 5) {
-    if (lane == 0) {
-      // ---------------- MMA issuer
-      constexpr uint32_t idesc_s = make_idesc(BQ, BKV, 0, 0);   // S = Q K^T : both operands K-major
-      constexpr uint32_t idesc_o = make_idesc(BQ, HD, 0, 1);    // O += P V  : V is MN-major (rows = keys)
-      auto issue_pv = [&](int it) {
-        const int j = it - n_kb, pb = j & 1, st = it % STAGES;
-        mbar_wait(&p_full[pb], (uint32_t)(j >> 1) & 1u);
-        tcgen05_fence_after();
-        const uint32_t p_t = p_s + (uint32_t)(pb * P_BYTES), v_t = kv_s + (uint32_t)(st * 2 * KV_BYTES + KV_BYTES);
+    // ---------------- MMA issuer: warp-uniform control flow, one elected lane issues (descriptors stay in uniform registers)
+    constexpr uint32_t idesc_s = make_idesc(BQ, BKV, 0, 0);   // S = Q K^T : both operands K-major
+    constexpr uint32_t idesc_o = make_idesc(BQ, HD, 0, 1);    // O += P V  : V is MN-major (rows = keys)
+    auto issue_pv = [&](int it) {
+      const int j = it - n_kb, pb = j & 1, st = it % STAGES;
+      mbar_wait(&p_full[pb], (uint32_t)(j >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t p_t = p_s + (uint32_t)(pb * P_BYTES), v_t = kv_s + (uint32_t)(st * 2 * KV_BYTES + KV_BYTES);
+      const uint64_t da = make_smem_desc(p_t), db = make_smem_desc_ex(v_t, 1024, 8192, 2);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t da = make_smem_desc(p_t) + (uint64_t)(2 * k);                       // +32 B along K (keys)
-          const uint64_t db = make_smem_desc_ex(v_t + (uint32_t)(k * 16 * 128), 1024, 8192, 2);  // +16 key rows
-          umma_bf16(tmem_base + 128, da, db, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < BKV / 16; ++k)   // A: +32 B along K (keys); B: +16 key rows of 128 B
+          umma_bf16(tmem_base + 128, da + (uint64_t)(2 * k), db + (uint64_t)(k * 128), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(&p_empty[pb]);
-      };
-      mbar_wait(&q_full, 0);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % STAGES, sb = it & 1;
-        mbar_wait(&kv_full[st], (uint32_t)(it / STAGES) & 1u);
-        mbar_wait(&s_empty[sb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t k_t = kv_s + (uint32_t)(st * 2 * KV_BYTES);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&q_full, 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it % STAGES, sb = it & 1;
+      mbar_wait(&kv_full[st], (uint32_t)(it / STAGES) & 1u);
+      mbar_wait(&s_empty[sb], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t k_t = kv_s + (uint32_t)(st * 2 * KV_BYTES);
+      const uint64_t dq = make_smem_desc(q_s), dk = make_smem_desc(k_t);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + (uint32_t)(sb * BKV), make_smem_desc(q_s) + (uint64_t)(2 * k), make_smem_desc(k_t) + (uint64_t)(2 * k),
-                    idesc_s, k > 0 ? 1u : 0u);
+          umma_bf16(tmem_base + (uint32_t)(sb * BKV), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[sb]);
         if (it < n_kb) umma_commit(&kv_empty[st]);
-        if (it > n_kb) issue_pv(it - 1);
       }
-      issue_pv(n_it - 1);
-      umma_commit(&o_full);
+      __syncwarp();
+      if (it > n_kb) issue_pv(it - 1);
     }
+    issue_pv(n_it - 1);
+    if (elect_one()) umma_commit(&o_full);
     __syncwarp();
   } else {
     // ---------------- softmax warps: thread = query row

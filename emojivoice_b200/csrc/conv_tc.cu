@@ -1,21 +1,24 @@
 // bf16 implicit-GEMM conv1d on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM), operands
-// staged by TMA (cp.async.bulk.tensor, 128B swizzle) through an mbarrier ring.  sm_100a only.
+// staged by TMA (cp.async.bulk.tensor, hardware swizzle) through mbarrier rings.  sm_100a only.
 //
-// Tile: 128 output time steps (UMMA M = 128 = TMEM lanes) x BN output channels (UMMA N = BN TMEM columns),
-// reduced over ceil(C_in/64) K-chunks x taps (4 x UMMA K=16 per weight tile).
-//   A (activations) : 3-D tensor map (channel, time, batch) over the channel-last bf16 tensor.  ONE haloed box
-//                     [64 ch x (128 + (taps-1)*dilation) rows] is fetched per K-chunk at row m0 - pad; every tap's MMA
-//                     reads the same smem tile through a descriptor whose start address is advanced by
-//                     tap*dilation rows (the 128B swizzle is a function of absolute smem address bits, so no
-//                     base-offset is needed -- verified on hardware).  Rows outside [0,T) are zero-filled by TMA,
+// Tile: MB x 128 output time steps (UMMA M = 128 = TMEM lanes, MB in {1,2} accumulators) x BN output channels
+// (UMMA N = BN TMEM columns), reduced over K-chunks of BK channels x taps.
+//   A (activations) : 3-D tensor map (channel, time, batch) over the channel-last bf16 tensor.  ONE haloed tile
+//                     [BK ch x (MB*128 + (taps-1)*dilation) rows] is fetched per K-chunk at row m0 - pad (one or two TMA
+//                     boxes); every tap's / m-block's MMA reads the same smem tile through a descriptor whose start
+//                     address is advanced by whole rows (the swizzle is a function of absolute smem address bits, so
+//                     no base-offset is needed -- verified on hardware).  Rows outside [0,T) are zero-filled by TMA,
 //                     which IS the convolution's zero padding (no im2col, no halo copies in HBM).
 //                     The stride-2 conv reads a (T/2, 2*ld) view of the same memory (tap_col selects even/odd rows).
-//   B (weights)     : 3-D tensor map (c_in, n, tap) over [taps][N_pad][K_pad] bf16, box [64 x BN].
-// PERSISTENT CTAs (one per SM) walk the tile list; TMEM holds two accumulators so the epilogue of tile i overlaps
-// the TMA/MMA main loop of tile i+1.
+//   B (weights)     : 3-D tensor map (c_in, n, tap) over [taps][N_pad][K_pad] bf16, box [BK x BN].  A weight tile is
+//                     fetched ONCE per (K-chunk, tap) and used by all MB m-blocks (halves the L2->SM weight stream,
+//                     which -- not the tensor pipe -- bounds 128x128 tiles); narrow layers keep all taps resident.
+//   BK = 64 (128-byte swizzle) or, for layers with C_in <= 32, BK = 32 (64-byte swizzle: no zero-padded K).
+// PERSISTENT CTAs walk the tile list; TMEM holds two accumulator sets so the epilogue of tile i overlaps the TMA/MMA
+// main loop of tile i+1.  Narrow configurations run two CTAs per SM.
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..9 = epilogue: tcgen05.ld -> fp32 staging tile in smem -> row-wise coalesced pass with the fused
-// bias / mask / Euler-or-residual / MRF-mean / activation and vectorised fp32 + bf16 stores.
+// warps 2..9 = epilogue, per 64-column chunk: residual loads issued -> tcgen05.ld -> fp32 staging tile in smem ->
+// row-wise coalesced pass with the fused bias / mask / Euler-or-residual / MRF-mean / activation, fp32 + bf16 stores.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -30,43 +33,82 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;
-constexpr int EPI_THREADS = 256;
 constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 8;
+constexpr int MB_MAX = 2;
 constexpr int kMaxGroups = kMaxTaps;
+constexpr int SMEM_LIMIT = 224 * 1024;     // dynamic shared memory one CTA may ask for
 
 struct TcParams {
   ConvGeom g;
   Epilogue e;
   // taps are processed in groups that share one activation tile: with halo reuse all taps form one group whose
-  // tile covers rows [m0 + grp_row0, m0 + grp_row0 + a_rows); otherwise every tap is its own 128-row group.
+  // tile covers rows [m0 + grp_row0, m0 + grp_row0 + a_rows); otherwise every tap is its own group.
   int n_groups;
   int grp_row0[kMaxGroups], grp_col0[kMaxGroups], grp_first[kMaxGroups], grp_count[kMaxGroups];
-  int tap_byte_off[kMaxTaps];   // byte offset of tap j's first row inside its group's tile (rows are 128 B)
-  int a_rows;                   // TMA box rows of the activation tile (128 + halo, multiple of 8)
-  int a_slot_bytes;             // a_rows*128 rounded up to 1024
+  int tap_byte_off[kMaxTaps];   // byte offset of tap j's first row inside its group's tile
+  int a_boxes, a_box_rows;      // the activation tile is a_boxes TMA boxes of a_box_rows rows each
+  int a_slot_bytes;             // tile bytes rounded up to 1024
   int a_slots, b_slots;
   int kchunks;
   int vec_ok;
   int m_tiles, n_tiles, total_tiles;
   int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
+  int mb;                       // m-blocks (128 rows) per tile
+  int bk, row_bytes, ksteps;    // K-chunk channels, bytes per smem row (= swizzle width), UMMA K-steps per chunk
+  int b_tile_bytes;
+  uint32_t desc_sbo, desc_layout;
+  uint32_t tmem_cols;
+  int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
+  uint32_t tap_first16;         // (byte offset of tap 0's first row inside a haloed tile) >> 4
+  uint32_t tap_step16;          // (bytes from one tap's first row to the next one's) >> 4, two's complement when negative
 };
 
-template <int BN>
-struct Cfg {
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_LD = BN + 4;                         // floats per staged accumulator row
-  static constexpr int STAGING_BYTES = BM * STAGE_LD * 4;
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulators
-};
+// Upper / lower words of a shared-memory matrix descriptor (tc_ptx.cuh make_smem_desc_ex): the MMA warp advances the
+// low word by plain adds instead of rebuilding descriptors.
+__device__ __forceinline__ uint32_t desc_hi_word(uint32_t sbo, uint32_t layout) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ uint32_t desc_lo_word(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// All MMAs of one (K-chunk, tap): VMB m-blocks x KS K-steps, issued by the elected lane.
+template <int KS, int BN>
+__device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo, uint32_t mb_step16, int vmb,
+                                          uint32_t idesc, uint32_t acc) {
+#pragma unroll
+  for (int k = 0; k < KS; ++k) umma_bf16(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+  if (vmb > 1) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      umma_bf16(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+  }
+}
+
+constexpr int STAGE_LD = 36;                                   // floats per staged row (32 + 4: conflict-free float4 access)
+constexpr int STAGING_BYTES = 8 * 32 * STAGE_LD * 4;           // one private 32 x 32 transpose buffer per epilogue warp
+
+// generic scalar epilogue of one staged 32 x 32 block (unaligned strides / channel counts that are not multiples of 4);
+// kept out of line so the hot vector path stays compact in the instruction cache
+__device__ __noinline__ void scalar_block(const TcParams& p, const float* wstage, int b, int r0, int c0, int lane) {
+  const Epilogue& e = p.e;
+  bf16* out_act = reinterpret_cast<bf16*>(e.out_act);
+  for (int idx = lane; idx < 32 * 32; idx += 32) {
+    const int rl = idx >> 5, nl = idx & 31;
+    const int r = r0 + rl, nn = c0 + nl;
+    if (r >= p.g.M || nn >= p.g.N) continue;
+    int t, cc;
+    if (!ep_coord(e, r, nn, t, cc)) continue;
+    const float mv = e.mask.at(b, t);
+    const float v = ep_value(e, b, t, cc, wstage[rl * STAGE_LD + nl], mv);
+    if (e.out_f32) e.out_f32[b * e.f32_bs + (long long)t * e.f32_ld + cc] = v;
+    if (out_act) out_act[b * e.act_bs + (long long)t * e.act_ld + cc] = __float2bfloat16_rn(ep_act(e, cc, v, mv));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using C = Cfg<BN>;
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS], b_full[MAX_B_SLOTS], b_empty[MAX_B_SLOTS];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
@@ -74,20 +116,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = tiles0, b_base = tiles0 + (uint32_t)(p.a_slots * p.a_slot_bytes);
-  float* stage = reinterpret_cast<float*>(smem_raw + (tiles0 - smem_u32(smem_raw)) + p.a_slots * p.a_slot_bytes + p.b_slots * C::B_TILE_BYTES);
+  float* stage = reinterpret_cast<float*>(smem_raw + (tiles0 - smem_u32(smem_raw)) + p.a_slots * p.a_slot_bytes + p.b_slots * p.b_tile_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A_SLOTS = p.a_slots, B_SLOTS = p.b_slots;
+  const int tile_rows = p.mb * BM;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < MAX_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }   // every epilogue warp releases
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -99,29 +142,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ---------------- TMA producer: per tile, per K-chunk, per tap group: one (haloed) activation tile, then one
       // weight tile per tap.  Ring positions run on across tiles, so the next tile's loads start while this one computes.
-      int ai = 0, bi = 0;
-      if (p.resident) {   // narrow layers: every (K-chunk, tap) weight tile is fetched once and kept
-        const int n_w = p.kchunks * p.g.taps;
-        mbar_expect_tx(&b_full[0], (uint32_t)(n_w * C::B_TILE_BYTES));
-        for (int kc = 0; kc < p.kchunks; ++kc)
+      int sa = 0, sb = 0;
+      uint32_t pa = 1, pb = 1;      // parity to wait for on the "empty" barriers (fresh barriers pass parity 1)
+      const uint32_t a_bytes = (uint32_t)(p.a_boxes * p.a_box_rows * p.row_bytes), box_bytes = (uint32_t)(p.a_box_rows * p.row_bytes);
+      const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
+      const bool resident = p.resident != 0;
+      if (resident) {   // narrow layers: every (K-chunk, tap) weight tile is fetched once and kept
+        const int n_w = kchunks * p.g.taps;
+        mbar_expect_tx(&b_full[0], (uint32_t)(n_w * p.b_tile_bytes));
+        for (int kc = 0; kc < kchunks; ++kc)
           for (int j = 0; j < p.g.taps; ++j)
-            tma_load_3d(b_base + (uint32_t)((kc * p.g.taps + j) * C::B_TILE_BYTES), &tmB, &b_full[0], kc * BK, 0, j);
+            tma_load_3d(b_base + (uint32_t)((kc * p.g.taps + j) * p.b_tile_bytes), &tmB, &b_full[0], kc * p.bk, 0, j);
       }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
-        const int m0 = mt * BM, n0 = nt * BN;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int g = 0; g < p.n_groups; ++g, ++ai) {
-            const int sa = ai % A_SLOTS;
-            mbar_wait(&a_empty[sa], ((uint32_t)(ai / A_SLOTS) & 1u) ^ 1u);
-            mbar_expect_tx(&a_full[sa], (uint32_t)(p.a_rows * BK * 2));
-            tma_load_3d(a_base + (uint32_t)(sa * p.a_slot_bytes), &tmA, &a_full[sa], p.grp_col0[g] + kc * BK, m0 + p.grp_row0[g], b);
-            if (p.resident) continue;
-            for (int j = 0; j < p.grp_count[g]; ++j, ++bi) {
-              const int sb = bi % B_SLOTS;
-              mbar_wait(&b_empty[sb], ((uint32_t)(bi / B_SLOTS) & 1u) ^ 1u);
-              mbar_expect_tx(&b_full[sb], (uint32_t)C::B_TILE_BYTES);
-              tma_load_3d(b_base + (uint32_t)(sb * C::B_TILE_BYTES), &tmB, &b_full[sb], kc * BK, n0, p.grp_first[g] + j);
+        const int nt = tile % n_tiles, rest = tile / n_tiles, mt = rest % m_tiles, b = rest / m_tiles;
+        const int m0 = mt * tile_rows, n0 = nt * BN;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          for (int g = 0; g < n_groups; ++g) {
+            mbar_wait(&a_empty[sa], pa);
+            mbar_expect_tx(&a_full[sa], a_bytes);
+            const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
+            const int col = p.grp_col0[g] + kc * p.bk, row = m0 + p.grp_row0[g];
+            tma_load_3d(dst, &tmA, &a_full[sa], col, row, b);
+            if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, &tmA, &a_full[sa], col, row + p.a_box_rows, b);
+            if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+            if (resident) continue;
+            const int tap0 = g * grp_taps;
+            for (int j = 0; j < grp_taps; ++j) {
+              mbar_wait(&b_empty[sb], pb);
+              mbar_expect_tx(&b_full[sb], (uint32_t)p.b_tile_bytes);
+              tma_load_3d(b_base + (uint32_t)(sb * p.b_tile_bytes), &tmB, &b_full[sb], kc * p.bk, n0, tap0 + j);
+              if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
             }
           }
         }
@@ -129,204 +180,193 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer (single thread): every tap re-reads the same smem tile at a row offset
-      constexpr uint32_t idesc = make_idesc(BM, BN);
-      int ai = 0, bi = 0, ti = 0;
-      if (p.resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-        const int buf = ti & 1;
-        mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-        uint32_t first = 1;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          for (int g = 0; g < p.n_groups; ++g, ++ai) {
-            const int sa = ai % A_SLOTS;
-            mbar_wait(&a_full[sa], (uint32_t)(ai / A_SLOTS) & 1u);
-            tcgen05_fence_after();
-            const uint32_t a_tile = a_base + (uint32_t)(sa * p.a_slot_bytes);
-            for (int j = 0; j < p.grp_count[g]; ++j) {
-              const int tap = p.grp_first[g] + j;
-              uint32_t b_tile;
-              int sb = 0;
-              if (p.resident) {
-                b_tile = b_base + (uint32_t)((kc * p.g.taps + tap) * C::B_TILE_BYTES);
-              } else {
-                sb = bi % B_SLOTS;
-                mbar_wait(&b_full[sb], (uint32_t)(bi / B_SLOTS) & 1u);
-                tcgen05_fence_after();
-                b_tile = b_base + (uint32_t)(sb * C::B_TILE_BYTES);
-                ++bi;
-              }
-              const uint64_t da = make_smem_desc(a_tile + (uint32_t)p.tap_byte_off[tap]);
-              const uint64_t db = make_smem_desc(b_tile);
-#pragma unroll
-              for (int k = 0; k < BK / UMMA_K; ++k) {  // +32 B along K inside the swizzle atom = +2 in the (addr>>4) field
-                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                first = 0;
-              }
-              if (!p.resident) umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
+    // ---------------- MMA issuer: the whole warp walks the (warp-uniform) loops and waits; one elected lane issues.
+    // Every tap and m-block re-reads the same smem tile at a row offset.  The loop body is kept to a few dozen
+    // instructions per weight tile: ring slots / phases advance incrementally and descriptors by adds (a single
+    // warp issues ~1 dependent instruction per 5-8 clk, so 200 instructions per tap would cap the tensor pipe).
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    const uint32_t hi = desc_hi_word(p.desc_sbo, p.desc_layout);
+    const uint32_t mb_step16 = (uint32_t)(BM * p.row_bytes) >> 4, tap_step16 = p.tap_step16;
+    const uint32_t b_step16 = (uint32_t)p.b_tile_bytes >> 4, a_step16 = (uint32_t)p.a_slot_bytes >> 4;
+    const uint32_t a_lo0 = desc_lo_word(a_base), b_lo0 = desc_lo_word(b_base);
+    const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
+    const bool resident = p.resident != 0, ks4 = p.ksteps == 4;
+    const uint32_t acc_stride = (uint32_t)(p.mb * BN);
+    int sa = 0, sb = 0, ti = 0;
+    uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
+    if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+      const int mt = (tile / n_tiles) % m_tiles;
+      const int vmb = min(p.mb, (p.g.M - mt * tile_rows + BM - 1) / BM);     // m-blocks that hold valid rows
+      const int buf = ti & 1;
+      mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator set
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_stride;
+      uint32_t acc = 0;
+      uint32_t b_res_lo = b_lo0;    // resident weights: tiles are laid out in (K-chunk, tap) order
+      for (int kc = 0; kc < kchunks; ++kc) {
+        for (int g = 0; g < n_groups; ++g) {
+          mbar_wait(&a_full[sa], pa);
+          tcgen05_fence_after();
+          uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step16 + p.tap_first16;
+          for (int j = 0; j < grp_taps; ++j) {
+            uint32_t b_lo;
+            if (resident) {
+              b_lo = b_res_lo;
+              b_res_lo += b_step16;
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tcgen05_fence_after();
+              b_lo = b_lo0 + (uint32_t)sb * b_step16;
             }
-            umma_commit(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
+            if (elect_one()) {
+              if (ks4) issue_tap<4, BN>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
+              else issue_tap<2, BN>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
+              if (!resident) umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
+            }
+            __syncwarp();
+            acc = 1;
+            a_lo += tap_step16;
+            if (!resident) { if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; } }
           }
+          if (elect_one()) umma_commit(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
+          __syncwarp();
+          if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
-        umma_commit(&acc_full[buf]);       // accumulator complete -> epilogue
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);       // accumulators complete -> epilogue
+      __syncwarp();
     }
-    __syncwarp();
   } else {
-    // ---------------- epilogue (warps 2..9): (q, half) = TMEM lane quarter, column half
-    // phase 1: TMEM -> registers -> fp32 staging tile in smem (thread = accumulator row), then the accumulator is
-    //          handed back to the MMA warp;  phase 2: warps walk the staged tile row-wise: coalesced residual loads
-    //          issued ahead of the stores, fused epilogue arithmetic, coalesced fp32 + bf16 stores.
+    // ---------------- epilogue (warps 2..9).  Warp (q, half) owns TMEM lanes [32q, 32q+32) and every second 32-column
+    // block of them; the eight warps run free of each other (no CTA barrier):
+    //   residual loads issued -> tcgen05.ld (thread = accumulator row) -> private 32 x 32 fp32 transpose buffer ->
+    //   row-wise pass: 8 lanes x float4 per row, fused epilogue arithmetic, coalesced fp32 + bf16 stores.
     const int ew = warp - 2;
     const int q = warp & 3, half = ew >> 2;
-    const int et = threadIdx.x - 64;
     const Epilogue& e = p.e;
     bf16* out_act = reinterpret_cast<bf16*>(e.out_act);
     const bool has_res = e.res != nullptr, has_res2 = e.res2 != nullptr, has_f32 = e.out_f32 != nullptr, has_act = e.out_act != nullptr;
-    const bool use_div = e.div != 1.0f, snake = e.act == ACT_SNAKE;
+    const bool use_div = e.div != 1.0f, snake = e.act == ACT_SNAKE, use_alpha = e.alpha != 1.0f;
+    const bool mask_pre = e.mask_pre != 0, mask_act = e.mask_act != 0, polyphase = e.phase_cout != p.g.N;
+    const float inv_div = 1.0f / e.div;   // bf16-operand path: x * (1/3) instead of the reference's x / 3 (1 ulp, far inside tolerance)
     const float slope = e.act == ACT_LRELU ? e.slope : (e.act == ACT_RELU ? 0.0f : 1.0f);
     const float alpha = e.alpha;
-    constexpr int G = (BN / 4) < 32 ? (BN / 4) : 32;   // lanes per staged row
-    constexpr int RPI = 32 / G;                        // rows per warp iteration
-    constexpr int ITERS = 16 / RPI;                    // iterations per warp (16 rows each)
-    constexpr int U = ITERS < 8 ? ITERS : 8;           // iterations per batch: loads of a batch are issued together
-    constexpr int NB = ITERS / U;                      // batches per tile (1 or 2)
-    const int sub = lane / G, cl = (lane % G) * 4;
-    const float* srow0 = stage + (ew * 16 + sub) * C::STAGE_LD + cl;
+    constexpr int NBLK = BN / 32;                      // 32-column blocks per accumulator
+    constexpr int U = 8;                               // row-pass iterations: 4 rows x (8 lanes x float4) each
+    const int sub = lane >> 3, cl = (lane & 7) * 4;
+    float* wstage = stage + ew * (32 * STAGE_LD);
+    float* srow_w = wstage + lane * STAGE_LD;
+    const float* srow_r = wstage + sub * STAGE_LD + cl;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, M = p.g.M, N = p.g.N, T_out = e.T_out;
+    const int up_s = e.up_s, up_p = e.up_p;
 
-    // residual loads of one batch of one tile (issued long before they are consumed; tt[u] < 0 marks an invalid row)
-    auto issue = [&](int tile, int it0, float4 (&rr)[U], float4 (&rr2)[U], int (&tt)[U]) {
-      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
-      const int n = nt * BN + cl;
-      const bool n_ok = n < p.g.N;
-      int co = 0, phase = 0;
-      if (n_ok) { phase = n / e.phase_cout; co = n - phase * e.phase_cout; }
-      const int r_base = mt * BM + ew * 16 + sub;
-      const float* res_p = has_res ? e.res + b * e.res_bs + co : nullptr;
-      const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = r_base + (it0 + u) * RPI;
-        int t = e.up_s * r + phase - e.up_p;
-        if (!n_ok || r >= p.g.M || t >= e.T_out) t = -1;
-        tt[u] = t;
-        if (has_res) rr[u] = t >= 0 ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_res2) rr2[u] = t >= 0 ? *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    // fused epilogue arithmetic + coalesced stores of one batch
-    auto finish = [&](int tile, int it0, const float4 (&rr)[U], const float4 (&rr2)[U], const int (&tt)[U]) {
-      const int nt = tile % p.n_tiles, b = tile / (p.n_tiles * p.m_tiles);
-      const int n = nt * BN + cl;
-      const bool n_ok = n < p.g.N;
-      int co = 0;
-      if (n_ok) co = n - (n / e.phase_cout) * e.phase_cout;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
-      if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
-      if (n_ok && snake) {
-        sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
-        sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
-      }
-      const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
-      float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
-      bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int t = tt[u];
-        if (t < 0) continue;
-        const float4 a4 = *reinterpret_cast<const float4*>(srow0 + (it0 + u) * RPI * C::STAGE_LD);
-        float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
-        const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
-        if (e.mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
-        v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha;
-        if (has_res) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
-        if (has_res2) { v0 += rr2[u].x; v1 += rr2[u].y; v2 += rr2[u].z; v3 += rr2[u].w; }
-        if (use_div) { v0 = v0 / e.div; v1 = v1 / e.div; v2 = v2 / e.div; v3 = v3 / e.div; }
-        if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
-        if (has_act) {
-          float a0, a1, a2, a3;
-          if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
-            const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
-            a0 = fmaf(sb4.x, s0 * s0, v0); a1 = fmaf(sb4.y, s1 * s1, v1); a2 = fmaf(sb4.z, s2 * s2, v2); a3 = fmaf(sb4.w, s3 * s3, v3);
-          } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
-            a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
-          }
-          if (e.mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
-          __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
-        }
-      }
-    };
-
-    float4 P[U], P2[U];
-    int Pt[U];
-    if (p.vec_ok && (int)blockIdx.x < p.total_tiles) issue((int)blockIdx.x, 0, P, P2, Pt);   // first tile's residuals
     int ti = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
-      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) % p.m_tiles, b = tile / (p.n_tiles * p.m_tiles);
-      const int m0 = mt * BM, n0 = nt * BN;
+      const int nt = tile % n_tiles, rest = tile / n_tiles, mt = rest % m_tiles, b = rest / m_tiles;
+      const int m0 = mt * tile_rows, n0 = nt * BN;
+      const int vmb = min(p.mb, (M - m0 + BM - 1) / BM);
       const int buf = ti & 1;
-      mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
-      tcgen05_fence_after();
-      {
-        float* srow = stage + (q * 32 + lane) * C::STAGE_LD;
-        constexpr int CHUNKS = BN / 32;                      // 32-column chunks of the tile
-        constexpr int PER = CHUNKS >= 2 ? CHUNKS / 2 : 1;    // chunks per warp (BN=32: only half 0 works)
-        if (CHUNKS >= 2 || half == 0) {
+      const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
+      const int n_blk = vmb * NBLK;                    // this quadrant's blocks; the warp takes half, half+2, ...
+      bool waited = false;
 #pragma unroll 1
-          for (int ci = 0; ci < PER; ++ci) {
-            const int c = (CHUNKS >= 2 ? half * PER : 0) + ci;
-            uint32_t raw[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c * 32), raw);
+      for (int blk = half; blk < n_blk; blk += 2) {
+        const int mb = blk / NBLK, cb = blk - mb * NBLK;
+        const int n = n0 + cb * 32 + cl;
+        const bool n_ok = n < N;
+        int co = n, phase = 0;
+        if (polyphase && n_ok) { phase = n / e.phase_cout; co = n - phase * e.phase_cout; }
+        const int r0 = m0 + mb * BM + q * 32 + sub;
+        const int t0 = up_s * r0 + phase - up_p, dt = up_s * 4;
+        float4 rr[U];
+        if (p.vec_ok && has_res) {   // residual loads fly while the accumulator is fetched and staged
+          const float* res_p = e.res + b * e.res_bs + co;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<uint4*>(srow + c * 32 + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * dt;
+            const bool ok = n_ok && (r0 + 4 * u) < M && (unsigned)t < (unsigned)T_out;
+            rr[u] = ok ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-      }
-      tcgen05_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging complete, TMEM reads retired
-      if (et == 0) mbar_arrive(&acc_empty[buf]);
-      if (p.vec_ok) {
-        const int next = tile + (int)gridDim.x;
-        if (NB == 2) {
-          float4 Q[U], Q2[U];
-          int Qt[U];
-          issue(tile, U, Q, Q2, Qt);         // second half's residuals fly while the first half is finished
-          finish(tile, 0, P, P2, Pt);
-          if (next < p.total_tiles) issue(next, 0, P, P2, Pt);
-          finish(tile, U, Q, Q2, Qt);
+        if (!waited) {
+          mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+          tcgen05_fence_after();
+          waited = true;
+        }
+        {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + (uint32_t)(buf * p.mb * BN + mb * BN + cb * 32), raw);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(srow_w + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+        }
+        if (blk + 2 >= n_blk) {      // last TMEM read of this warp for the tile: hand the accumulators back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        __syncwarp();
+        if (p.vec_ok) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
+          if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
+          if (n_ok && snake) {
+            sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
+            sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
+          }
+          const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
+          float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
+          bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int t = t0 + u * dt;
+            const bool ok = n_ok && (r0 + 4 * u) < M && (unsigned)t < (unsigned)T_out;
+            if (!ok) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(srow_r + u * 4 * STAGE_LD);
+            float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
+            const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
+            if (mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
+            if (use_alpha) { v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha; }
+            if (has_res) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
+            if (has_res2) {
+              const float4 r2 = *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld);
+              v0 += r2.x; v1 += r2.y; v2 += r2.z; v3 += r2.w;
+            }
+            if (use_div) { v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div; }
+            if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
+            if (has_act) {
+              float a0, a1, a2, a3;
+              if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
+                const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
+                a0 = fmaf(sb4.x, s0 * s0, v0); a1 = fmaf(sb4.y, s1 * s1, v1); a2 = fmaf(sb4.z, s2 * s2, v2); a3 = fmaf(sb4.w, s3 * s3, v3);
+              } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
+                a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
+              }
+              if (mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
+              __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+            }
+          }
         } else {
-          finish(tile, 0, P, P2, Pt);
-          if (next < p.total_tiles) issue(next, 0, P, P2, Pt);   // next tile's residuals fly during its main loop
+          scalar_block(p, wstage, b, m0 + mb * BM + q * 32, n0 + cb * 32, lane);
         }
-      } else {
-        // generic scalar path (unaligned strides / channel counts that are not multiples of 4)
-        for (int idx = et; idx < BM * BN; idx += EPI_THREADS) {
-          const int rl = idx / BN, nl = idx - rl * BN;
-          const int r = m0 + rl, n = n0 + nl;
-          if (r >= p.g.M || n >= p.g.N) continue;
-          int t, co;
-          if (!ep_coord(e, r, n, t, co)) continue;
-          const float mv = e.mask.at(b, t);
-          const float v = ep_value(e, b, t, co, stage[rl * C::STAGE_LD + nl], mv);
-          if (e.out_f32) e.out_f32[b * e.f32_bs + (long long)t * e.f32_ld + co] = v;
-          if (out_act) out_act[b * e.act_bs + (long long)t * e.act_ld + co] = __float2bfloat16_rn(ep_act(e, co, v, mv));
-        }
+        __syncwarp();                // the transpose buffer may be overwritten by the next block
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");           // staging may be overwritten by the next tile
+      if (half >= n_blk) {           // a warp without a block in this tile still keeps step with the accumulator hand-over
+        mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        __syncwarp();
+      }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -359,40 +399,59 @@ bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, ui
 
 int g_sm_count = 0;
 int g_resident_mode = 1;   // EV_TC_RESIDENT=0 disables the weights-resident variant (debugging)
+int g_mb_mode = 0;         // EV_TC_MB=1|2 forces the m-blocks per tile (0 = heuristic)
+int g_bk32_mode = 1;       // EV_TC_BK32=0 disables the 64-byte-swizzle path for C_in <= 32
+int g_cta2_mode = 1;       // EV_TC_CTA2=0 keeps one CTA per SM
+
+// Shared-memory plan of one launch for `k` CTAs per SM; returns false when the rings do not fit.
+template <int BN>
+bool plan_smem(TcParams& p, int k, int* smem_out) {
+  const int per_cta = std::min(SMEM_LIMIT, (228 * 1024) / k - 2048);   // 1 KiB driver reserve + static barriers per CTA
+  const int budget = per_cta - 1024 - STAGING_BYTES;
+  const int w_tiles = p.kchunks * p.g.taps;
+  int a_slots, b_slots;
+  p.resident = (g_resident_mode != 0) && p.n_tiles == 1 && p.total_tiles >= 2 * k * g_sm_count &&
+               (w_tiles * p.b_tile_bytes + 2 * p.a_slot_bytes <= budget);
+  if (p.resident) {
+    b_slots = w_tiles;
+    a_slots = std::min(MAX_A_SLOTS, (budget - w_tiles * p.b_tile_bytes) / p.a_slot_bytes);
+  } else {
+    a_slots = p.a_slot_bytes <= 24 * 1024 ? 3 : 2;
+    b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes;
+    if (b_slots < 4 && a_slots == 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes; }
+    if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
+    if (b_slots < (k > 1 ? 4 : 2)) return false;
+  }
+  if (a_slots < 2) return false;
+  p.a_slots = a_slots;
+  p.b_slots = b_slots;
+  *smem_out = 1024 + a_slots * p.a_slot_bytes + b_slots * p.b_tile_bytes + STAGING_BYTES;
+  return true;
+}
 
 template <int BN>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t stream) {
-  using C = Cfg<BN>;
-  // smem: 1 KiB alignment slack + activation ring + weight ring (or all weights) + fp32 staging tile
-  const int budget = 200 * 1024 - 1024 - C::STAGING_BYTES;
-  p.m_tiles = ceil_div(p.g.M, BM);
+  p.m_tiles = ceil_div(p.g.M, BM * p.mb);
   p.n_tiles = ceil_div(p.g.N, BN);
   p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
-  const int w_tiles = p.kchunks * p.g.taps;
-  int a_slots, b_slots;
-  p.resident = (g_resident_mode != 0) && p.n_tiles == 1 && p.total_tiles >= 2 * g_sm_count &&
-               (w_tiles * C::B_TILE_BYTES + 2 * p.a_slot_bytes <= budget);
-  if (p.resident) {
-    b_slots = w_tiles;
-    a_slots = (budget - w_tiles * C::B_TILE_BYTES) / p.a_slot_bytes;
-    if (a_slots > MAX_A_SLOTS) a_slots = MAX_A_SLOTS;
-  } else {
-    a_slots = 3;
-    b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES;
-    if (b_slots < 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / C::B_TILE_BYTES; }
-    if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
-    if (b_slots < 2) return cudaErrorInvalidConfiguration;
-  }
-  p.a_slots = a_slots;
-  p.b_slots = b_slots;
-  const int smem = 1024 + a_slots * p.a_slot_bytes + b_slots * C::B_TILE_BYTES + C::STAGING_BYTES;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * p.mb * BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  const int k_tmem = 512 / (int)cols;
+  int k = std::min(g_cta2_mode ? 2 : 1, k_tmem), smem = 0;
+  if (p.total_tiles <= g_sm_count) k = 1;
+  while (k > 1 && !plan_smem<BN>(p, k, &smem)) --k;
+  if (k == 1 && !plan_smem<BN>(p, 1, &smem)) return cudaErrorInvalidConfiguration;
+  // never let more CTAs become co-resident than TMEM can serve (tcgen05.alloc would spin forever)
+  const int min_smem = (228 * 1024) / (k_tmem + 1) + 1;
+  if (smem < min_smem && k_tmem < 8) smem = std::min(min_smem, SMEM_LIMIT);
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
-  const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
+  const int grid = std::min(p.total_tiles, k * g_sm_count);
   conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
@@ -407,7 +466,6 @@ bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, ui
 int tc_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
 int conv_tc_pick_bn(int N) {
-  // two CTAs stay resident per SM at BN = 128 (one drains its accumulator while the other feeds the tensor core)
   if (N % 128 == 0) return 128;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
@@ -440,15 +498,26 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
     return cudaErrorInvalidValue;
   }
   if (g_halo_mode < 0) {
-    const char* env = getenv("EV_TC_HALO");
-    g_halo_mode = env ? atoi(env) : 1;
-    const char* env2 = getenv("EV_TC_RESIDENT");
-    g_resident_mode = env2 ? atoi(env2) : 1;
+    auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+    g_resident_mode = env_int("EV_TC_RESIDENT", 1);
+    g_mb_mode = env_int("EV_TC_MB", 0);
+    g_bk32_mode = env_int("EV_TC_BK32", 1);
+    g_cta2_mode = env_int("EV_TC_CTA2", 1);
+    g_halo_mode = env_int("EV_TC_HALO", 1);
   }
+  (void)x_rows;
+  const int BN = conv_tc_pick_bn(g.N);
   TcParams p;
   p.g = g;
   p.e = e;
-  p.kchunks = ceil_div(g.C_in, BK);
+  // K-chunk width: 64 channels under the 128-byte swizzle, or 32 under the 64-byte swizzle when that avoids padded K
+  p.bk = (g_bk32_mode && g.C_in <= 32) ? 32 : 64;
+  p.row_bytes = p.bk * 2;
+  p.ksteps = p.bk / UMMA_K;
+  p.desc_sbo = 8u * (uint32_t)p.row_bytes;
+  p.desc_layout = p.bk == 64 ? 2u : 4u;
+  p.b_tile_bytes = BN * p.row_bytes;
+  p.kchunks = ceil_div(g.C_in, p.bk);
   int tap_row[kMaxTaps], tap_col[kMaxTaps];
   CUtensorMap tmA, tmB;
   uint64_t d0, d1, s1;
@@ -469,34 +538,54 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
     if (err) *err = "conv_tc: unsupported stride";
     return cudaErrorInvalidValue;
   }
-  // halo reuse: all taps read one tile when they share the column origin and the row span fits a TMA box
+  // m-blocks per tile: two accumulators share every weight tile unless that costs a whole extra round of tiles
+  {
+    auto cost = [&](int mb) {
+      const long long tiles = (long long)ceil_div(g.M, BM * mb) * ceil_div(g.N, BN) * g.B;
+      const long long rounds = (tiles + g_sm_count - 1) / g_sm_count;
+      return (double)rounds * (mb + 0.3);
+    };
+    p.mb = (g.M > BM && cost(2) <= cost(1)) ? 2 : 1;
+    if (g_mb_mode == 1 || g_mb_mode == 2) p.mb = g_mb_mode;
+    if (p.mb > MB_MAX) p.mb = MB_MAX;
+  }
+  // halo reuse: all taps read one tile when they share the column origin and the row span fits two TMA boxes
   int lo = tap_row[0], hi = tap_row[0];
   bool same_col = true;
   for (int j = 1; j < g.taps; ++j) { lo = std::min(lo, tap_row[j]); hi = std::max(hi, tap_row[j]); same_col &= tap_col[j] == tap_col[0]; }
-  const bool halo = g_halo_mode != 0 && g.taps > 1 && same_col && (BM + hi - lo) <= 256;
+  const bool halo = g_halo_mode != 0 && g.taps > 1 && same_col && (hi - lo) <= 128;
+  int a_rows;
   if (halo) {
     p.n_groups = 1;
     p.grp_row0[0] = lo; p.grp_col0[0] = tap_col[0]; p.grp_first[0] = 0; p.grp_count[0] = g.taps;
-    for (int j = 0; j < g.taps; ++j) p.tap_byte_off[j] = (tap_row[j] - lo) * BK * 2;
-    p.a_rows = (int)align_up(BM + hi - lo, 8);
+    for (int j = 0; j < g.taps; ++j) p.tap_byte_off[j] = (tap_row[j] - lo) * p.row_bytes;
+    a_rows = p.mb * BM + hi - lo;
+    p.grp_taps = g.taps;
+    p.tap_first16 = (uint32_t)p.tap_byte_off[0] >> 4;
+    p.tap_step16 = (uint32_t)(((tap_row[1] - tap_row[0]) * p.row_bytes) / 16);
+    for (int j = 1; j < g.taps; ++j)
+      if (tap_row[j] - tap_row[j - 1] != tap_row[1] - tap_row[0]) { if (err) *err = "conv_tc: taps must be equally spaced"; return cudaErrorInvalidValue; }
   } else {
     p.n_groups = g.taps;
     for (int j = 0; j < g.taps; ++j) {
       p.grp_row0[j] = tap_row[j]; p.grp_col0[j] = tap_col[j]; p.grp_first[j] = j; p.grp_count[j] = 1; p.tap_byte_off[j] = 0;
     }
-    p.a_rows = BM;
+    a_rows = p.mb * BM;
+    p.grp_taps = 1;
+    p.tap_first16 = 0;
+    p.tap_step16 = 0;
   }
-  p.a_slot_bytes = (int)align_up((size_t)p.a_rows * BK * 2, 1024);
-  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * 2, BK, (uint32_t)p.a_rows, err);
+  p.a_boxes = a_rows > 256 ? 2 : 1;
+  p.a_box_rows = (int)align_up((size_t)ceil_div(a_rows, p.a_boxes), 8);
+  p.a_slot_bytes = (int)align_up((size_t)p.a_boxes * p.a_box_rows * p.row_bytes, 1024);
+  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * 2, (uint32_t)p.bk, (uint32_t)p.a_box_rows, err, p.row_bytes);
   if (!ok) return cudaErrorInvalidValue;
-  (void)x_rows;
-  const int BN = conv_tc_pick_bn(g.N);
-  if (w.N_pad_tc % BN != 0 || w.K_pad % BK != 0 || w.K_pad < p.kchunks * BK) {
+  if (w.N_pad_tc % BN != 0 || w.K_pad % 64 != 0 || w.K_pad < p.kchunks * p.bk) {
     if (err) *err = "conv_tc: packed weight padding does not match the tile shape";
     return cudaErrorInvalidValue;
   }
   ok = encode_map(&tmB, w.w_bf16, (uint64_t)w.K_pad, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, (uint64_t)w.K_pad * 2,
-                  (uint64_t)w.K_pad * w.N_pad_tc * 2, BK, (uint32_t)BN, err);
+                  (uint64_t)w.K_pad * w.N_pad_tc * 2, (uint32_t)p.bk, (uint32_t)BN, err, p.row_bytes);
   if (!ok) return cudaErrorInvalidValue;
   if (e.act != ACT_NONE && e.act != ACT_RELU && e.act != ACT_LRELU && e.act != ACT_SNAKE) {
     if (err) *err = "conv_tc: the tensor-core epilogue implements identity / (leaky) ReLU / SnakeBeta only";

@@ -81,6 +81,7 @@ struct ev_ctx {
   ev::HifiganW hifigan;
   // optional per-launch CUDA-event timing (ev_profile_begin/end); off in normal operation
   bool profiling = false;
+  bool prof_detail = false;    // EV_PROF_DETAIL=1: conv kernel classes carry the layer shape
   const char* prof_tag = "";   // appended to conv kernel names while profiling (enc / dec / voc)
   std::vector<ev::ProfRecord> prof;
   std::vector<std::string> kernel_names;

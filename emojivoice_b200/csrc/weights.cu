@@ -207,7 +207,12 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
     std::string msg;
     static const char* names[4] = {"conv_tc_bn32", "conv_tc_bn64", "conv_tc_bn128", "conv_tc_bn256"};
     const int bn = conv_tc_pick_bn(w.N);
-    const std::string nm = std::string(names[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3]) + ctx->prof_tag;
+    std::string nm = std::string(names[bn == 32 ? 0 : bn == 64 ? 1 : bn == 128 ? 2 : 3]) + ctx->prof_tag;
+    if (ctx->profiling && ctx->prof_detail) {   // EV_PROF_DETAIL=1: one class per layer shape
+      char buf[64];
+      snprintf(buf, sizeof buf, " c%d n%d k%d d%d m%d", w.C_in, w.N, w.taps, w.dilation, g.M);
+      nm += buf;
+    }
     { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg); }
     if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   }

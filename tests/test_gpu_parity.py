@@ -53,6 +53,9 @@ CONV_CASES = [
     (2, 256, 128, 256, 3, 2, 1, 1, False), (2, 256, 64, 256, 4, 2, 1, 1, True), (2, 512, 50, 256, 16, 8, 4, 1, True),
     (1, 64, 300, 32, 4, 2, 1, 1, True), (2, 256, 100, 80, 1, 1, 0, 1, False), (1, 1024, 200, 256, 1, 1, 0, 1, False),
     (2, 256, 140, 384, 1, 1, 0, 1, False), (1, 256, 1, 256, 3, 1, 1, 1, False), (3, 64, 129, 64, 3, 1, 1, 1, False),
+    # two m-blocks per tile + two TMA boxes per haloed tile (BN = 128 / 64 / 32), 64-byte swizzle (C_in <= 32), ragged tails
+    (2, 128, 700, 128, 11, 1, 25, 5, False), (1, 64, 900, 64, 7, 1, 9, 3, False), (2, 32, 1500, 32, 3, 1, 1, 1, False),
+    (1, 16, 300, 32, 5, 1, 2, 1, False), (1, 32, 257, 64, 11, 1, 5, 1, False), (4, 256, 334, 256, 3, 1, 1, 1, False),
 ]
 
 
