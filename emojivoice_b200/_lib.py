@@ -47,7 +47,8 @@ SIGNATURES = {
     "ev_load_hifigan": (_I, [_P, C.POINTER(EvTensor), _I, C.POINTER(EvHifiganCfg), _P]),
     "ev_encode_workspace_bytes": (_SZ, [_P, _I, _I]),
     "ev_encode": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "ev_align": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "ev_align_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
+    "ev_align": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "ev_decode_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "ev_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _SZ, _P]),
     "ev_vocode_workspace_bytes": (_SZ, [_P, _I, _I]),
@@ -146,6 +147,53 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+class GraphCache:
+    """CUDA graphs of one library call per shape key (the decoder's n-step loop is ~2500 launches, the vocoder ~80:
+    replaying them as a graph takes the host out of the critical path).  A key is captured the second time it is seen
+    (a one-off shape is not worth a capture); entries own their static I/O buffers and workspace; least recently used
+    entries are dropped beyond `capacity`."""
+
+    def __init__(self, capacity=4):
+        self.capacity, self.entries, self.seen = capacity, {}, {}
+
+    def get(self, key):
+        e = self.entries.get(key)
+        if e is not None:
+            self.entries[key] = self.entries.pop(key)            # move to the back (most recent)
+        return e
+
+    def should_capture(self, key):
+        self.seen[key] = self.seen.get(key, 0) + 1
+        if len(self.seen) > 4096:
+            self.seen.clear()
+        return self.seen[key] >= 2
+
+    def put(self, key, entry):
+        self.entries[key] = entry
+        while len(self.entries) > self.capacity:
+            self.entries.pop(next(iter(self.entries)))
+
+    def clear(self):
+        self.entries.clear()
+
+
+def capture(ctx, fn):
+    """Run fn() once eagerly on a side stream (one-time kernel attribute setup must not happen inside a capture) and
+    count the kernels it launches, then capture it into a torch.cuda.CUDAGraph.  -> (graph, kernels per replay)"""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    before = ctx.launch_count()
+    with torch.cuda.stream(side):
+        fn()
+    launches = ctx.launch_count() - before
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g, launches
 
 
 def tensor_list(sd: dict, device):

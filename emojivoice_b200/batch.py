@@ -1,0 +1,52 @@
+"""Batched corpus synthesis: the caller side of the hot path as `matcha/cli.py:264-317` (batched_synthesis) does it --
+collate (pad) -> MatchaTTS.synthesise -> to_waveform -> per-utterance crop `[: length * 256]` -- over the micro-batch
+plan of `sharding.py`, so the same call runs one GPU's shard or the whole list."""
+from __future__ import annotations
+
+import torch
+
+from . import sharding
+
+
+def collate(utterances, items):
+    """cli.py:109-120 batched_collate_fn: right-pad the id sequences with 0.  utterances[i] = (ids, speaker_id)."""
+    seqs = [torch.as_tensor(utterances[i][0], dtype=torch.long).reshape(-1) for i in items]
+    x = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)
+    x_lengths = torch.tensor([s.numel() for s in seqs], dtype=torch.long)
+    spks = torch.tensor([int(utterances[i][1]) for i in items], dtype=torch.long)
+    return x, x_lengths, spks
+
+
+@torch.inference_mode()
+def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10, temperature=0.667, length_scale=1.0,
+                      rank=0, world_size=1, denoiser=None, denoiser_strength=0.00025, sort=True, keep_mel=False, z_fn=None):
+    """Synthesise this rank's share of `utterances` (list of (phoneme ids, speaker id)).
+
+    -> (results, stats): results maps utterance index -> dict(waveform (L,) cpu float32, mel_length, [mel]), stats is a
+    sharding.ShardStats with this rank's device time.  `z_fn(mb, shape)` may supply the prior noise per micro-batch
+    (parity runs share it with the oracle)."""
+    lens = [len(u[0]) for u in utterances]
+    plan = sharding.shard(lens, batch_size, rank, world_size, n_timesteps=n_timesteps, sort=sort)
+    results, stats = {}, sharding.ShardStats()
+    for mb in plan:
+        x, xl, spks = collate(utterances, mb.items)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        kw = {}
+        if z_fn is not None:
+            kw["z"] = z_fn(mb, model, x, xl, spks)
+        out = model.synthesise(x, xl, n_timesteps, temperature, spks if model.n_spks > 1 else None, length_scale, **kw)
+        wav = vocoder(out["mel"]).clamp(-1, 1)                       # to_waveform, cli.py:121-126
+        if denoiser is not None:
+            wav = denoiser(wav.squeeze(1), strength=denoiser_strength).unsqueeze(1)
+        e1.record()
+        wav_cpu, mel_len = wav.cpu(), out["mel_lengths"].cpu()
+        e1.synchronize()
+        stats.add(mel_len.tolist(), xl.tolist(), n_timesteps, e0.elapsed_time(e1) / 1e3)
+        for j, i in enumerate(mb.items):
+            n = int(mel_len[j])
+            rec = {"waveform": wav_cpu[j, 0, : n * 256].clone(), "mel_length": n}     # cli.py:308-309 crop
+            if keep_mel:
+                rec["mel"] = out["mel"][j, :, :n].cpu()
+            results[i] = rec
+    return results, stats

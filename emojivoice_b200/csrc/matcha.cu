@@ -308,25 +308,29 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
 }
 
 // ================================================================================================ alignment
+extern "C" size_t ev_align_workspace_bytes(const ev_ctx* ctx, int B, int Tx, int T_pad) {
+  if (!ctx || B <= 0 || Tx <= 0 || T_pad <= 0) return 0;
+  return align_up(((size_t)2 * B + (size_t)B * T_pad) * sizeof(int), 256) + 256;   // lengths as int32 + frame->token map
+}
+
 extern "C" int ev_align(ev_ctx* ctx, const float* w_ceil, const int64_t* x_lengths, const int64_t* y_lengths,
-                        const float* mu_x, int B, int Tx, int T_pad, float* attn, float* mu_y, float* y_mask, void* stream) {
+                        const float* mu_x, int B, int Tx, int T_pad, float* attn, float* mu_y, float* y_mask,
+                        void* workspace, size_t workspace_bytes, void* stream) {
   if (!ctx) return EV_ERR_INVALID;
   if (!ctx->matcha.loaded) return fail(ctx, EV_ERR_STATE, "ev_align: matcha weights not loaded");
   if (!w_ceil || !x_lengths || !y_lengths || !mu_x || !attn || !mu_y || !y_mask || B <= 0 || Tx <= 0 || T_pad <= 0)
     return fail(ctx, EV_ERR_INVALID, "ev_align: null argument or empty shape");
+  if (!workspace || workspace_bytes < ev_align_workspace_bytes(ctx, B, Tx, T_pad) - 256)
+    return fail(ctx, EV_ERR_STATE, "ev_align: workspace too small");
   cudaStream_t s = as_stream(stream);
   EV_CUDA(ctx, cudaSetDevice(ctx->device));
-  // scratch: lengths as int32 + frame->token map; small enough to come from the stream-ordered allocator
-  int* scratch = nullptr;
-  const size_t n = (size_t)2 * B + (size_t)B * T_pad;
-  EV_CUDA(ctx, cudaMallocAsync(reinterpret_cast<void**>(&scratch), n * sizeof(int), s));
+  int* scratch = reinterpret_cast<int*>(workspace);
   int* xl = scratch; int* yl = scratch + B; int* tok = scratch + 2 * B;
   const int Fm = ctx->matcha.cfg.n_feats;
   EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), xl, B, s));
   EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), yl, B, s));
   EV_LAUNCH(ctx, s, "generate_path", 0, 4.0 * B * (double)Tx * T_pad, generate_path(w_ceil, xl, yl, B, Tx, T_pad, attn, tok, s));
   EV_LAUNCH(ctx, s, "gather_mu", 0, 8.0 * B * (double)Fm * T_pad, gather_mu(mu_x, tok, yl, B, Fm, Tx, T_pad, mu_y, y_mask, s));
-  EV_CUDA(ctx, cudaFreeAsync(scratch, s));
   return 0;
 }
 

@@ -11,7 +11,7 @@ from .config import HIFIGAN_V1
 
 
 class Generator:
-    def __init__(self, h=None, device=None, precision="bf16"):
+    def __init__(self, h=None, device=None, precision="bf16", cuda_graphs=True):
         self.h = dict(h) if h is not None else dict(HIFIGAN_V1)
         if str(self.h.get("resblock", "1")) != "1":
             raise ValueError("only ResBlock1 (config v1) is implemented")
@@ -21,6 +21,9 @@ class Generator:
         self._device = torch.device(device) if device is not None else None
         self._sd = None
         self._ctx = None
+        self.cuda_graphs = cuda_graphs            # replay the generator as a CUDA graph once a (B, T) shape repeats
+        self._graphs = _lib.GraphCache()
+        self._replayed_launches = 0
         self.hop = 1
         for u in self.h["upsample_rates"]:
             self.hop *= int(u)
@@ -86,17 +89,38 @@ class Generator:
         with torch.cuda.device(dev):
             mel = mel.to(device=dev, dtype=torch.float32).contiguous()
             B, _, T = mel.shape
-            wav = torch.empty(B, 1, T * self.hop, device=dev)
-            ws = ctx.workspace(L.ev_vocode_workspace_bytes(ctx.handle, B, T))
             prec = _lib.PREC[dtype if dtype is not None else self.precision]
-            ctx.check(L.ev_vocode(ctx.handle, _lib.ptr(mel), B, T, prec, _lib.ptr(wav), _lib.ptr(ws), ws.numel(),
-                                  _lib.stream_ptr()), "ev_vocode")
+            nb = L.ev_vocode_workspace_bytes(ctx.handle, B, T)
+
+            def call(mel_, wav_, ws_):
+                ctx.check(L.ev_vocode(ctx.handle, _lib.ptr(mel_), B, T, prec, _lib.ptr(wav_), _lib.ptr(ws_), ws_.numel(),
+                                      _lib.stream_ptr()), "ev_vocode")
+
+            key = (B, T, prec)
+            ent = self._graphs.get(key) if self.cuda_graphs else None
+            if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
+                ent = dict(mel=mel.clone(), wav=torch.empty(B, 1, T * self.hop, device=dev),
+                           ws=torch.empty(nb + 4096, dtype=torch.uint8, device=dev))
+                ent["graph"], ent["launches"] = _lib.capture(ctx, lambda: call(ent["mel"], ent["wav"], ent["ws"]))
+                self._graphs.put(key, ent)
+            if ent is None:
+                wav = torch.empty(B, 1, T * self.hop, device=dev)
+                call(mel, wav, ctx.workspace(nb))
+            else:
+                ent["mel"].copy_(mel)
+                ent["graph"].replay()
+                self._replayed_launches += ent["launches"]
+                wav = ent["wav"].clone()
         return wav
 
     forward = __call__
 
     def launch_count(self, reset=False):
-        return self._ctx.launch_count(reset)
+        """Kernels launched by this generator's context, graph replays included."""
+        n = self._ctx.launch_count(reset) + self._replayed_launches
+        if reset:
+            self._replayed_launches = 0
+        return n
 
 
 class Denoiser:

@@ -18,7 +18,7 @@ from .config import MatchaConfig
 class MatchaTTS:
     def __init__(self, n_vocab, n_spks, spk_emb_dim, n_feats, encoder, decoder, cfm, data_statistics, out_size=None,
                  optimizer=None, scheduler=None, prior_loss=True, use_precomputed_durations=False, device=None,
-                 precision="bf16"):
+                 precision="bf16", cuda_graphs=True):
         self.cfg = MatchaConfig.from_constructor_kwargs(n_vocab, n_spks, spk_emb_dim, n_feats, encoder, decoder, cfm,
                                                         data_statistics)
         self.n_vocab, self.n_spks, self.spk_emb_dim, self.n_feats = n_vocab, n_spks, spk_emb_dim, n_feats
@@ -31,6 +31,8 @@ class MatchaTTS:
         self._device = torch.device(device) if device is not None else None
         self._ctx = None
         self._loaded = False
+        self.cuda_graphs = cuda_graphs            # replay the decoder as a CUDA graph once a (B, T_pad, n, ...) key repeats
+        self._graphs = _lib.GraphCache()
 
     # -- nn.Module-ish surface the callers touch (feel_me.py:156-159, cli.py:110-118)
     def eval(self):
@@ -127,21 +129,16 @@ class MatchaTTS:
             attn = torch.empty(B, Tx, T_pad, device=dev)
             mu_y = torch.empty(B, F, T_pad, device=dev)
             y_mask = torch.empty(B, 1, T_pad, device=dev)
+            ws = ctx.workspace(L.ev_align_workspace_bytes(ctx.handle, B, Tx, T_pad))
             ctx.check(L.ev_align(ctx.handle, _lib.ptr(w_ceil), _lib.ptr(x_lengths), _lib.ptr(y_lengths), _lib.ptr(mu_x), B, Tx,
-                                 T_pad, _lib.ptr(attn), _lib.ptr(mu_y), _lib.ptr(y_mask), st), "ev_align")
+                                 T_pad, _lib.ptr(attn), _lib.ptr(mu_y), _lib.ptr(y_mask), _lib.ptr(ws), ws.numel(), st), "ev_align")
             if z is None:
                 z = torch.randn_like(mu_y)                               # flow_matching.py:51
             else:
                 z = z.to(device=dev, dtype=torch.float32).contiguous()
                 if tuple(z.shape) != (B, F, T_pad):
                     raise ValueError(f"z must have shape {(B, F, T_pad)}, got {tuple(z.shape)}")
-            dec = torch.empty(B, F, T_pad, device=dev)
-            mel = torch.empty(B, F, T_pad, device=dev)
-            nb = L.ev_decode_workspace_bytes(ctx.handle, B, T_pad, int(n_timesteps))
-            ws = ctx.workspace(nb)
-            ctx.check(L.ev_decode(ctx.handle, _lib.ptr(mu_y), _lib.ptr(y_lengths), _lib.ptr(z), _lib.ptr(spk_emb), B, T_pad,
-                                  int(n_timesteps), float(temperature), prec, _lib.ptr(dec), _lib.ptr(mel), _lib.ptr(ws),
-                                  ws.numel(), st), "ev_decode")
+            dec, mel = self._decode(mu_y, y_lengths, z, spk_emb, B, T_pad, int(n_timesteps), float(temperature), prec)
         t = (dt.datetime.now() - t0).total_seconds()
         rtf = t * 22050 / (max(y_max_length, 1) * 256)                    # matcha_tts.py:142-143 (host clock, no sync)
         return {
@@ -158,5 +155,47 @@ class MatchaTTS:
             "decoder_outputs_full": dec, "mel_full": mel,
         }
 
+    def _decode(self, mu_y, y_lengths, z, spk_emb, B, T_pad, n_timesteps, temperature, prec):
+        """ev_decode, eagerly or -- once the same shape key has been seen before -- as a CUDA-graph replay over static
+        buffers (inputs are copied in, outputs copied out, so callers still own fresh tensors as with the reference)."""
+        ctx, L, dev, F = self._ctx, _lib.lib(), self._ctx.device, self.n_feats
+
+        def call(mu_y, y_lengths, z, spk_emb, dec, mel, ws):
+            ctx.check(L.ev_decode(ctx.handle, _lib.ptr(mu_y), _lib.ptr(y_lengths), _lib.ptr(z), _lib.ptr(spk_emb), B, T_pad,
+                                  n_timesteps, temperature, prec, _lib.ptr(dec), _lib.ptr(mel), _lib.ptr(ws), ws.numel(),
+                                  _lib.stream_ptr()), "ev_decode")
+
+        nb = L.ev_decode_workspace_bytes(ctx.handle, B, T_pad, n_timesteps)
+        key = (B, T_pad, n_timesteps, temperature, prec)
+        ent = self._graphs.get(key) if self.cuda_graphs else None
+        if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
+            st = dict(mu_y=torch.empty_like(mu_y), y_lengths=torch.empty_like(y_lengths), z=torch.empty_like(z),
+                      spk_emb=None if spk_emb is None else torch.empty_like(spk_emb), dec=torch.empty(B, F, T_pad, device=dev),
+                      mel=torch.empty(B, F, T_pad, device=dev), ws=torch.empty(nb + 4096, dtype=torch.uint8, device=dev))
+            st["mu_y"].copy_(mu_y); st["y_lengths"].copy_(y_lengths); st["z"].copy_(z)
+            if spk_emb is not None:
+                st["spk_emb"].copy_(spk_emb)
+            st["graph"], st["launches"] = _lib.capture(
+                ctx, lambda: call(st["mu_y"], st["y_lengths"], st["z"], st["spk_emb"], st["dec"], st["mel"], st["ws"]))
+            self._graphs.put(key, st)
+            ent = st
+        if ent is None:
+            dec = torch.empty(B, F, T_pad, device=dev)
+            mel = torch.empty(B, F, T_pad, device=dev)
+            call(mu_y, y_lengths, z, spk_emb, dec, mel, ctx.workspace(nb))
+            return dec, mel
+        ent["mu_y"].copy_(mu_y); ent["y_lengths"].copy_(y_lengths); ent["z"].copy_(z)
+        if spk_emb is not None:
+            ent["spk_emb"].copy_(spk_emb)
+        ent["graph"].replay()
+        self._replayed_launches += ent["launches"]
+        return ent["dec"].clone(), ent["mel"].clone()
+
+    _replayed_launches = 0
+
     def launch_count(self, reset=False):
-        return self._ctx.launch_count(reset)
+        """Kernels launched by this model's context, graph replays included (a replay launches every captured kernel)."""
+        n = self._ctx.launch_count(reset) + self._replayed_launches
+        if reset:
+            self._replayed_launches = 0
+        return n

@@ -103,8 +103,10 @@ EV_API int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths, co
  * mu_y = attn^T mu_x (a gather).  T_pad = fix_len_compatibility(max y_lengths) is computed by the caller
  * (it fixes the output shapes; utils/model.py:14-20).
  *   out: attn (B,Tx,T_pad) 0/1 fp32, mu_y (B,n_feats,T_pad), y_mask (B,1,T_pad) */
+EV_API size_t ev_align_workspace_bytes(const ev_ctx* ctx, int B, int Tx, int T_pad);
 EV_API int ev_align(ev_ctx* ctx, const float* w_ceil, const int64_t* x_lengths, const int64_t* y_lengths,
-             const float* mu_x, int B, int Tx, int T_pad, float* attn, float* mu_y, float* y_mask, void* stream);
+             const float* mu_x, int B, int Tx, int T_pad, float* attn, float* mu_y, float* y_mask, void* workspace,
+             size_t workspace_bytes, void* stream);
 
 /* ---- flow-matching decoder -----------------------------------------------------------------------------
  * Replaces CFM.forward + solve_euler + Decoder.forward + denormalize (flow_matching.py:32-85,

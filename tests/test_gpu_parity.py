@@ -258,3 +258,42 @@ def test_end_to_end_emoji_text_to_waveform(matcha, matcha_sd, vocoders):
             gen.precision = "bf16"
         assert wav.shape == ref_wav.shape
         assert rel_l2(wav, ref_wav) < 2 * TOL[prec]
+
+
+def test_corpus_driver_matches_oracle_on_identical_microbatches(matcha_sd, vocoders):
+    """the micro-batch list is part of the input -- the oracle is run on the same micro-batches, with the
+    same prior noise; every utterance's cropped waveform (cli.py:308-309) must match.  Two "ranks" cover the list."""
+    gen, hsd = vocoders["hifigan_gain1"]
+    model = ev.MatchaTTS(**VCTK.constructor_kwargs(), precision="fp32")
+    model.load_state_dict(matcha_sd)
+    g = torch.Generator().manual_seed(77)
+    utts = []
+    for i, p in enumerate((9, 4, 14, 6, 11)):
+        ids = ev.intersperse(torch.randint(1, 178, (p,), generator=g).tolist())
+        utts.append((ids, list(ev.EMOJI_MAPPING_FEMALE.values())[i]))
+    ref_wavs, noise = {}, {}
+
+    def z_fn(mb, model_, x, xl, spks):
+        probe = mo.synthesise(matcha_sd, VCTK, x, xl, 1, 0.667, spks, 0.8)
+        noise[mb.index] = synthetic.prior_noise(x.shape[0], 80, probe["t_pad"], seed=100 + mb.index)
+        ref = mo.synthesise(matcha_sd, VCTK, x, xl, 2, 0.667, spks, 0.8, z=noise[mb.index])
+        wav = ho.generator(hsd, HIFIGAN_V1, ref["mel"]).clamp(-1, 1)
+        for j, i in enumerate(mb.items):
+            ref_wavs[i] = wav[j, 0, : int(ref["mel_lengths"][j]) * 256]
+        return noise[mb.index]
+
+    gen.precision = "fp32"
+    try:
+        got = {}
+        for rank in range(2):
+            res, stats = ev.synthesise_corpus(model, gen, utts, batch_size=2, n_timesteps=2, temperature=0.667, length_scale=0.8,
+                                              rank=rank, world_size=2, z_fn=z_fn)
+            assert stats.utterances == len(res) and stats.seconds > 0
+            assert not set(res) & set(got)
+            got.update(res)
+    finally:
+        gen.precision = "bf16"
+    assert sorted(got) == list(range(5))
+    for i in range(5):
+        assert got[i]["waveform"].shape == ref_wavs[i].shape == (got[i]["mel_length"] * 256,)
+        assert rel_l2(got[i]["waveform"], ref_wavs[i]) < 2e-4
