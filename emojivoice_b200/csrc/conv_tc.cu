@@ -34,7 +34,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;
+constexpr int NUM_THREADS = 320;              // 2 role warps + 8 epilogue warps (two CTAs per SM)
+constexpr int NUM_THREADS_WIDE = 576;         // 2 role warps + 16 epilogue warps (one CTA per SM)
 constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 8;
 constexpr int MB_MAX = 2;
 constexpr int kMaxGroups = kMaxTaps;
@@ -60,6 +61,7 @@ struct TcParams {
   int b_tile_bytes;
   uint32_t desc_sbo, desc_layout;
   uint32_t tmem_cols;
+  int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
   int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
   uint32_t tap_first16;         // (byte offset of tap 0's first row inside a haloed tile) >> 4
   uint32_t tap_step16;          // (bytes from one tap's first row to the next one's) >> 4, two's complement when negative
@@ -85,7 +87,8 @@ __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t hi, uint32_t
 }
 
 constexpr int STAGE_LD = 36;                                   // floats per staged row (32 + 4: conflict-free float4 access)
-constexpr int STAGING_BYTES = 8 * 32 * STAGE_LD * 4;           // one private 32 x 32 transpose buffer per epilogue warp
+constexpr int STAGING_WARP_BYTES = 32 * STAGE_LD * 4;          // one private 32 x 32 transpose buffer per epilogue warp
+constexpr int ACT_PITCH = 80;                                  // bytes per staged bf16 row (64 + 16: conflict-free 16-byte access)
 
 // generic scalar epilogue of one staged 32 x 32 block (unaligned strides / channel counts that are not multiples of 4);
 // kept out of line so the hot vector path stays compact in the instruction cache
@@ -107,7 +110,7 @@ __device__ __noinline__ void scalar_block(const TcParams& p, const float* wstage
 
 // ------------------------------------------------------------------------------------------------ the kernel
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS_WIDE, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[MAX_A_SLOTS], a_empty[MAX_A_SLOTS], b_full[MAX_B_SLOTS], b_empty[MAX_B_SLOTS];
@@ -126,7 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < MAX_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }   // every epilogue warp releases
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (blockDim.x >> 5) - 2); }   // every epilogue warp releases
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -243,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //   residual loads issued -> tcgen05.ld (thread = accumulator row) -> private 32 x 32 fp32 transpose buffer ->
     //   row-wise pass: 8 lanes x float4 per row, fused epilogue arithmetic, coalesced fp32 + bf16 stores.
     const int ew = warp - 2;
-    const int q = warp & 3, half = ew >> 2;
+    const int q = warp & 3, slot = ew >> 2, n_slots = ((int)(blockDim.x >> 5) - 2) >> 2;   // 2 or 4 warps per lane quadrant
     const Epilogue& e = p.e;
     bf16* out_act = reinterpret_cast<bf16*>(e.out_act);
     const bool has_res = e.res != nullptr, has_res2 = e.res2 != nullptr, has_f32 = e.out_f32 != nullptr, has_act = e.out_act != nullptr;
@@ -256,6 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int U = 8;                               // row-pass iterations: 4 rows x (8 lanes x float4) each
     const int sub = lane >> 3, cl = (lane & 7) * 4;
     float* wstage = stage + ew * (32 * STAGE_LD);
+    const bool act_only = p.act_only != 0;
     float* srow_w = wstage + lane * STAGE_LD;
     const float* srow_r = wstage + sub * STAGE_LD + cl;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -269,11 +273,70 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int vmb = min(p.mb, (M - m0 + BM - 1) / BM);
       const int buf = ti & 1;
       const int len_b = e.mask.lens ? __ldg(e.mask.lens + b) : 0x7fffffff;
-      const int n_blk = vmb * NBLK;                    // this quadrant's blocks; the warp takes half, half+2, ...
+      const int n_blk = vmb * NBLK;                    // this quadrant's blocks; the warp takes slot, slot+n_slots, ...
       bool waited = false;
 #pragma unroll 1
-      for (int blk = half; blk < n_blk; blk += 2) {
+      for (int blk = slot; blk < n_blk; blk += n_slots) {
         const int mb = blk / NBLK, cb = blk - mb * NBLK;
+        if (act_only) {
+          // ---- lean path: bias + activation + bf16 pack in the accumulator layout (thread = row), bf16 staging
+          if (!waited) {
+            mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+            tcgen05_fence_after();
+            waited = true;
+          }
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + (uint32_t)(buf * p.mb * BN + mb * BN + cb * 32), raw);
+          if (blk + n_slots >= n_blk) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          const int nb = n0 + cb * 32;                 // first output channel of the block (N % 32 == 0 on this path)
+          const int row = m0 + mb * BM + q * 32 + lane;
+          const float mv = (mask_act && !((row << e.mask.shift) < len_b)) ? 0.0f : 1.0f;
+          uint8_t* brow = reinterpret_cast<uint8_t*>(wstage) + lane * ACT_PITCH;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+            const float4 b0 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nb + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + nb + j + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[0] = __uint_as_float(raw[j]) + b0.x; v[1] = __uint_as_float(raw[j + 1]) + b0.y;
+            v[2] = __uint_as_float(raw[j + 2]) + b0.z; v[3] = __uint_as_float(raw[j + 3]) + b0.w;
+            v[4] = __uint_as_float(raw[j + 4]) + b1.x; v[5] = __uint_as_float(raw[j + 5]) + b1.y;
+            v[6] = __uint_as_float(raw[j + 6]) + b1.z; v[7] = __uint_as_float(raw[j + 7]) + b1.w;
+            if (snake) {
+              const float4 sa0 = __ldg(reinterpret_cast<const float4*>(e.snake_a + nb + j)), sa1 = __ldg(reinterpret_cast<const float4*>(e.snake_a + nb + j + 4));
+              const float4 sb0 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + nb + j)), sb1 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + nb + j + 4));
+              const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
+              const float sb[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { const float sn = __sinf(v[i] * sa[i]); v[i] = fmaf(sb[i], sn * sn, v[i]) * mv; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope) * mv;
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h2); }
+            *reinterpret_cast<uint4*>(brow + j * 2) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          __syncwarp();
+          {   // row-wise: 4 lanes x 16 B per row, 8 rows per warp instruction
+            const int rsub = lane >> 2, ch = lane & 3;
+            bf16* dst = out_act + b * e.act_bs + nb + ch * 8;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(wstage) + ch * 16;
+            const int rb = m0 + mb * BM + q * 32 + rsub;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = rb + it * 8;
+              if (r < M && r < T_out)
+                *reinterpret_cast<uint4*>(dst + (long long)r * e.act_ld) = *reinterpret_cast<const uint4*>(src + (rsub + it * 8) * ACT_PITCH);
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         const int n = n0 + cb * 32 + cl;
         const bool n_ok = n < N;
         int co = n, phase = 0;
@@ -302,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<uint4*>(srow_w + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
         }
-        if (blk + 2 >= n_blk) {      // last TMEM read of this warp for the tile: hand the accumulators back
+        if (blk + n_slots >= n_blk) {      // last TMEM read of this warp for the tile: hand the accumulators back
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -356,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();                // the transpose buffer may be overwritten by the next block
       }
-      if (half >= n_blk) {           // a warp without a block in this tile still keeps step with the accumulator hand-over
+      if (slot >= n_blk) {           // a warp without a block in this tile still keeps step with the accumulator hand-over
         mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         __syncwarp();
@@ -402,12 +465,15 @@ int g_resident_mode = 1;   // EV_TC_RESIDENT=0 disables the weights-resident var
 int g_mb_mode = 0;         // EV_TC_MB=1|2 forces the m-blocks per tile (0 = heuristic)
 int g_bk32_mode = 1;       // EV_TC_BK32=0 disables the 64-byte-swizzle path for C_in <= 32
 int g_cta2_mode = 1;       // EV_TC_CTA2=0 keeps one CTA per SM
+int g_wide_mode = 1;       // EV_TC_WIDE=0 keeps 8 epilogue warps
+int g_lean_mode = 1;       // EV_TC_LEAN=0 disables the activation-only epilogue path
 
-// Shared-memory plan of one launch for `k` CTAs per SM; returns false when the rings do not fit.
+// Shared-memory plan of one launch for `k` CTAs per SM with `epi_warps` epilogue warps; false when the rings do not fit.
 template <int BN>
-bool plan_smem(TcParams& p, int k, int* smem_out) {
+bool plan_smem(TcParams& p, int k, int epi_warps, int* smem_out) {
+  const int staging = epi_warps * STAGING_WARP_BYTES;
   const int per_cta = std::min(SMEM_LIMIT, (228 * 1024) / k - 2048);   // 1 KiB driver reserve + static barriers per CTA
-  const int budget = per_cta - 1024 - STAGING_BYTES;
+  const int budget = per_cta - 1024 - staging;
   const int w_tiles = p.kchunks * p.g.taps;
   int a_slots, b_slots;
   p.resident = (g_resident_mode != 0) && p.n_tiles == 1 && p.total_tiles >= 2 * k * g_sm_count &&
@@ -420,12 +486,12 @@ bool plan_smem(TcParams& p, int k, int* smem_out) {
     b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes;
     if (b_slots < 4 && a_slots == 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes; }
     if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
-    if (b_slots < (k > 1 ? 4 : 2)) return false;
+    if (b_slots < (k > 1 ? 4 : 3)) return false;
   }
   if (a_slots < 2) return false;
   p.a_slots = a_slots;
   p.b_slots = b_slots;
-  *smem_out = 1024 + a_slots * p.a_slot_bytes + b_slots * p.b_tile_bytes + STAGING_BYTES;
+  *smem_out = 1024 + a_slots * p.a_slot_bytes + b_slots * p.b_tile_bytes + staging;
   return true;
 }
 
@@ -438,10 +504,18 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   while (cols < (uint32_t)(2 * p.mb * BN)) cols <<= 1;
   p.tmem_cols = cols;
   const int k_tmem = 512 / (int)cols;
-  int k = std::min(g_cta2_mode ? 2 : 1, k_tmem), smem = 0;
-  if (p.total_tiles <= g_sm_count) k = 1;
-  while (k > 1 && !plan_smem<BN>(p, k, &smem)) --k;
-  if (k == 1 && !plan_smem<BN>(p, 1, &smem)) return cudaErrorInvalidConfiguration;
+  // two CTAs per SM (8 epilogue warps each) when shared memory and TMEM allow and a tile has few 32-column blocks;
+  // otherwise one CTA with 16 epilogue warps (the epilogue is issue-bound: more warps hide its dependent latencies)
+  int k = 1, smem = 0, threads = NUM_THREADS_WIDE;
+  bool ok = false;
+  if (g_cta2_mode && k_tmem >= 2 && p.total_tiles > g_sm_count && p.mb * (BN / 32) <= 4 && plan_smem<BN>(p, 2, 8, &smem)) {
+    k = 2; threads = NUM_THREADS; ok = true;
+  }
+  if (!ok && g_wide_mode && plan_smem<BN>(p, 1, 16, &smem)) ok = true;
+  if (!ok) {
+    threads = NUM_THREADS;
+    if (!plan_smem<BN>(p, 1, 8, &smem)) return cudaErrorInvalidConfiguration;
+  }
   // never let more CTAs become co-resident than TMEM can serve (tcgen05.alloc would spin forever)
   const int min_smem = (228 * 1024) / (k_tmem + 1) + 1;
   if (smem < min_smem && k_tmem < 8) smem = std::min(min_smem, SMEM_LIMIT);
@@ -452,7 +526,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
     configured = true;
   }
   const int grid = std::min(p.total_tiles, k * g_sm_count);
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
+  conv_tc_kernel<BN><<<grid, threads, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
 
@@ -503,6 +577,8 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
     g_mb_mode = env_int("EV_TC_MB", 0);
     g_bk32_mode = env_int("EV_TC_BK32", 1);
     g_cta2_mode = env_int("EV_TC_CTA2", 1);
+    g_wide_mode = env_int("EV_TC_WIDE", 1);
+    g_lean_mode = env_int("EV_TC_LEAN", 1);
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
   (void)x_rows;
@@ -597,6 +673,9 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
              ((reinterpret_cast<uintptr_t>(e.res) | reinterpret_cast<uintptr_t>(e.res2) |
                reinterpret_cast<uintptr_t>(e.out_f32) | reinterpret_cast<uintptr_t>(e.bias)) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(e.out_act) & 7) == 0;
+  p.act_only = g_lean_mode && p.vec_ok && e.out_act && !e.out_f32 && !e.res && !e.res2 && e.alpha == 1.0f && e.div == 1.0f &&
+               !e.mask_pre && e.phase_cout == g.N && g.N % 32 == 0 && (e.act_ld % 8) == 0 && (e.act_bs % 8) == 0 &&
+               (reinterpret_cast<uintptr_t>(e.out_act) & 15) == 0;
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream);
     case 64: return launch_bn<64>(tmA, tmB, p, stream);

@@ -23,9 +23,9 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     a = ap.parse_args()
-    model = ev.MatchaTTS(**VCTK.constructor_kwargs(), precision="bf16")
+    model = ev.MatchaTTS(**VCTK.constructor_kwargs(), precision="bf16", cuda_graphs=False)
     model.load_state_dict(synthetic.matcha_state_dict(VCTK, seed=1234))
-    voc = ev.Generator(HIFIGAN_V1, precision="bf16")
+    voc = ev.Generator(HIFIGAN_V1, precision="bf16", cuda_graphs=False)
     voc.load_state_dict(synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321))
     voc.remove_weight_norm()
     x, xl, spk = synthetic.phoneme_batch(a.batch, 60, 90, seed=2000)
