@@ -196,9 +196,31 @@ __global__ void gn_stats_kernel(const float* __restrict__ x, int T, int C, int c
   }
 }
 
-template <typename ActT, int VPL>
+// Mish for the bf16-operand path: x*tanh(softplus(x)) = x*w/(w+2) with w = e^x (e^x + 2); one ex2 + one fast divide
+// (relative error ~1e-6, far inside the bf16 tolerance).  The fp32 parity path keeps the exact formulation.
+template <typename ActT> __device__ __forceinline__ float mish_sel(float x) { return mish_f(x); }
+template <> __device__ __forceinline__ float mish_sel<bf16>(float x) {
+  const float n = __expf(fminf(x, 20.0f));
+  const float w = n * (n + 2.0f);
+  return x > 20.0f ? x : x * __fdividef(w, w + 2.0f);
+}
+
+template <typename ActT> __device__ __forceinline__ void store_act4(ActT* p, float4 v);
+template <> __device__ __forceinline__ void store_act4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store_act4<bf16>(bf16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+constexpr int GN_APPLY_ROWS = 4;   // rows per warp
+
+template <typename ActT, int V4>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
-  // warp per (b,t) row; lane owns channels lane + 32*i, which belong to group (lane + 32 i) / cpg
+  // warp per (b,t) row, GN_APPLY_ROWS rows per warp; lane owns the float4 channel groups 4*(lane + 32*i), each inside
+  // one GroupNorm group (channels-per-group is a multiple of 4)
   extern __shared__ float stat[];  // [G][2] mean, rstd for this block's batch item
   const int b = blockIdx.y;
   const int G = a.groups, cpg = a.C / G;
@@ -218,43 +240,84 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (t >= a.T) return;
-  const long long row = (long long)b * a.T + t;
-  const float* x = a.x + row * a.C;
-  const float m = a.mask.at(b, t);
-  float y[VPL];
-  float sum = 0.0f;
+  // per-lane constants of its channel groups: scale = rstd*gamma, shift = beta - mean*rstd*gamma
+  float4 sc[V4], sh[V4], te[V4], lg[V4], lb[V4];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int c = lane + 32 * i;
-    float v = 0.0f;
+  for (int i = 0; i < V4; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    sc[i] = sh[i] = te[i] = lg[i] = lb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < a.C) {
       const int g = c / cpg;
-      v = (x[c] - stat[2 * g]) * stat[2 * g + 1] * a.gamma[c] + a.beta[c];
-      v = mish_f(v) * m;                                   // Block1D: Mish then *mask (decoder.py:41-43)
-      if (a.temb) v = (v + a.temb[c]) * m;                 // h += mlp(t); next Block1D multiplies by mask again
-      if (a.res) v += a.res[row * a.res_ld + c];
-      if (a.out_f32) a.out_f32[row * a.f32_ld + c] = v;
-      if (a.out_act) reinterpret_cast<ActT*>(a.out_act)[row * a.act_ld + c] = from_float<ActT>(v);
+      const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+      const float4 ga = *reinterpret_cast<const float4*>(a.gamma + c), be = *reinterpret_cast<const float4*>(a.beta + c);
+      sc[i] = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
+      sh[i] = make_float4(be.x - mean * sc[i].x, be.y - mean * sc[i].y, be.z - mean * sc[i].z, be.w - mean * sc[i].w);
+      if (a.temb) te[i] = *reinterpret_cast<const float4*>(a.temb + c);
+      if (a.out_ln) { lg[i] = *reinterpret_cast<const float4*>(a.ln_gamma + c); lb[i] = *reinterpret_cast<const float4*>(a.ln_beta + c); }
     }
-    y[i] = v;
-    sum += v;
   }
-  if (a.out_ln) {  // fused pre-LN of the transformer block that follows (transformer.py:262), eps 1e-5
-    const float mean = warp_sum(sum) / (float)a.C;
-    float sq = 0.0f;
+  const int t_base = (blockIdx.x * (blockDim.x >> 5) + warp) * GN_APPLY_ROWS;
+#pragma unroll 1
+  for (int rr = 0; rr < GN_APPLY_ROWS; ++rr) {
+    const int t = t_base + rr;
+    if (t >= a.T) return;
+    const long long row = (long long)b * a.T + t;
+    const float* x = a.x + row * a.C;
+    const float m = a.mask.at(b, t);
+    float4 y[V4];
+    float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float d = (lane + 32 * i < a.C) ? y[i] - mean : 0.0f;
-      sq += d * d;
+    for (int i = 0; i < V4; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < a.C) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + c);
+        // same operation order as the reference: ((x - mean) * rstd) * gamma + beta is refactored only in bf16 mode
+        if (sizeof(ActT) == 4) {
+          const int g = c / cpg;
+          const float mean = stat[2 * g], rstd = stat[2 * g + 1];
+          const float4 ga = *reinterpret_cast<const float4*>(a.gamma + c), be = *reinterpret_cast<const float4*>(a.beta + c);
+          v.x = (xv.x - mean) * rstd * ga.x + be.x; v.y = (xv.y - mean) * rstd * ga.y + be.y;
+          v.z = (xv.z - mean) * rstd * ga.z + be.z; v.w = (xv.w - mean) * rstd * ga.w + be.w;
+        } else {
+          v.x = fmaf(xv.x, sc[i].x, sh[i].x); v.y = fmaf(xv.y, sc[i].y, sh[i].y);
+          v.z = fmaf(xv.z, sc[i].z, sh[i].z); v.w = fmaf(xv.w, sc[i].w, sh[i].w);
+        }
+        v.x = mish_sel<ActT>(v.x) * m; v.y = mish_sel<ActT>(v.y) * m;      // Block1D: Mish then *mask (decoder.py:41-43)
+        v.z = mish_sel<ActT>(v.z) * m; v.w = mish_sel<ActT>(v.w) * m;
+        if (a.temb) {                                                       // h += mlp(t); next Block1D multiplies by mask again
+          v.x = (v.x + te[i].x) * m; v.y = (v.y + te[i].y) * m; v.z = (v.z + te[i].z) * m; v.w = (v.w + te[i].w) * m;
+        }
+        if (a.res) {
+          const float4 r = *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + row * a.f32_ld + c) = v;
+        if (a.out_act) store_act4<ActT>(reinterpret_cast<ActT*>(a.out_act) + row * a.act_ld + c, v);
+      }
+      y[i] = v;
+      sum += (v.x + v.y) + (v.z + v.w);
     }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)a.C + 1e-5f);
+    if (a.out_ln) {  // fused pre-LN of the transformer block that follows (transformer.py:262), eps 1e-5
+      const float mean = warp_sum(sum) / (float)a.C;
+      float sq = 0.0f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int c = lane + 32 * i;
-      if (c < a.C)
-        reinterpret_cast<ActT*>(a.out_ln)[row * a.ln_ld + c] = from_float<ActT>((y[i] - mean) * rstd * a.ln_gamma[c] + a.ln_beta[c]);
+      for (int i = 0; i < V4; ++i) {
+        if (4 * (lane + 32 * i) < a.C) {
+          const float d0 = y[i].x - mean, d1 = y[i].y - mean, d2 = y[i].z - mean, d3 = y[i].w - mean;
+          sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        }
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)a.C + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < V4; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < a.C) {
+          const float4 o = make_float4((y[i].x - mean) * rstd * lg[i].x + lb[i].x, (y[i].y - mean) * rstd * lg[i].y + lb[i].y,
+                                       (y[i].z - mean) * rstd * lg[i].z + lb[i].z, (y[i].w - mean) * rstd * lg[i].w + lb[i].w);
+          store_act4<ActT>(reinterpret_cast<ActT*>(a.out_ln) + row * a.ln_ld + c, o);
+        }
+      }
     }
   }
 }
@@ -381,11 +444,13 @@ cudaError_t group_norm_stats(const float* x, int B, int T, int C, int groups, do
 
 template <typename ActT>
 cudaError_t group_norm_apply(const GnApplyArgs& a, cudaStream_t s) {
-  const int vpl = ceil_div(a.C, 32);
-  dim3 grid(ceil_div(a.T, 8), a.B);
+  const int cpg = a.C / a.groups;
+  if ((a.C & 3) || (cpg & 3) || (a.res_ld & 3) || (a.f32_ld & 3) || (a.act_ld & 3) || (a.ln_ld & 3)) return cudaErrorInvalidValue;
+  const int v4 = ceil_div(a.C, 128);
+  dim3 grid(ceil_div(a.T, 8 * GN_APPLY_ROWS), a.B);
   const size_t sh = (size_t)a.groups * 2 * sizeof(float);
-  if (vpl <= 8) gn_apply_kernel<ActT, 8><<<grid, 256, sh, s>>>(a);
-  else if (vpl <= 32) gn_apply_kernel<ActT, 32><<<grid, 256, sh, s>>>(a);
+  if (v4 <= 2) gn_apply_kernel<ActT, 2><<<grid, 256, sh, s>>>(a);
+  else if (v4 <= 8) gn_apply_kernel<ActT, 8><<<grid, 256, sh, s>>>(a);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
