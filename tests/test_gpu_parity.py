@@ -214,6 +214,36 @@ def test_vocoder_matches_oracle_and_reference_fixture(vocoders, name, prec):
     assert float(wav.abs().max()) <= 1.0
 
 
+@pytest.mark.parametrize("name", list(golden_io.HIFIGAN))
+def test_denoiser_matches_oracle_and_reference_fixture(vocoders, name):
+    """hifigan/denoiser.py: bias spectrum of vocoder(zeros) and the STFT -> subtract -> ISTFT path, against the oracle
+    and against what the reference itself produced (tests/golden)."""
+    gen, sd = vocoders[name]
+    g = golden_io.load(name)
+    b, frames, seed = (int(v) for v in g["meta"])
+    gen.precision = "fp32"                              # the bias spectrum is computed with the generator's own precision
+    try:
+        den = ev.Denoiser(gen, mode="zeros")
+        wav = gen(synthetic.synthetic_mel(b, frames, seed=seed)).clamp(-1, 1)
+    finally:
+        gen.precision = "bf16"
+    bias_ref = ho.denoiser_bias(sd, HIFIGAN_V1)
+    assert den.bias_spec.shape == bias_ref.shape == (1, 513, 1)
+    assert rel_l2(den.bias_spec.cpu(), bias_ref) < 1e-4
+    assert rel_l2(den.bias_spec.cpu(), torch.from_numpy(g["bias_spec"])) < 1e-4
+    for strength in (0.00025, 0.0005, 0.1):            # app default (feel_me.py:185), class default, a strong setting
+        out = den(wav.squeeze(1), strength=strength)
+        ref = ho.denoise(wav.cpu().squeeze(1), bias_ref, strength)
+        assert out.shape == ref.shape
+        assert rel_l2(out.cpu(), ref) < 1e-4
+    out = den(wav.squeeze(1), strength=0.00025)
+    assert rel_l2(out.cpu(), torch.from_numpy(g["denoised"])) < 2e-4
+    one = den(wav[0, 0], strength=0.00025)             # 1-D input, as to_waveform passes it after squeeze()
+    assert one.dim() == 1 and torch.equal(one, out[0])
+    with pytest.raises(Exception):
+        ev.Denoiser(gen, mode="normal")
+
+
 def test_vocoder_accepts_weight_norm_checkpoint_form():
     wn = synthetic.hifigan_state_dict(HIFIGAN_V1, seed=7, gain=0.5, weight_norm=True)
     gen = ev.Generator(HIFIGAN_V1)
