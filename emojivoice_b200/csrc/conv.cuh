@@ -47,6 +47,10 @@ struct Epilogue {
   int phase_cout = 0;  // C_out per phase (== N for ordinary convs)
   int up_s = 1, up_p = 0;
   int T_out = 0;       // valid output rows per batch item
+  // optional fused GroupNorm statistics of the fp32 output (tensor-core path, 32 channels per group): per (b, group)
+  // sum and sum of squares over ALL rows are accumulated into gn_sum[(b*G + g)*2 + {0,1}] (zeroed by the caller)
+  double* gn_sum = nullptr;
+  int gn_groups = 0;
 };
 
 // (GEMM row r, GEMM column n) -> (output time t, output channel co); returns false when the slot is outside the output.

@@ -381,6 +381,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
           float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
           bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
+          float gs = 0.0f, gq = 0.0f;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int t = t0 + u * dt;
@@ -398,6 +399,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (use_div) { v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div; }
             if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
+            if (e.gn_sum) { gs += (v0 + v1) + (v2 + v3); gq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3); }
             if (has_act) {
               float a0, a1, a2, a3;
               if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
@@ -412,6 +414,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               pk.x = *reinterpret_cast<uint32_t*>(&lo);
               pk.y = *reinterpret_cast<uint32_t*>(&hi);
               *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+            }
+          }
+          if (e.gn_sum) {   // the block's 32 columns are one GroupNorm group: one fp64 atomic pair per warp and block
+            gs = warp_sum(gs); gq = warp_sum(gq);
+            if (lane == 0) {
+              double* dst = e.gn_sum + ((long long)b * e.gn_groups + ((n0 + cb * 32) >> 5)) * 2;
+              atomicAdd(dst, (double)gs);
+              atomicAdd(dst + 1, (double)gq);
             }
           }
         } else {
@@ -676,6 +686,10 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
   p.act_only = g_lean_mode && p.vec_ok && e.out_act && !e.out_f32 && !e.res && !e.res2 && e.alpha == 1.0f && e.div == 1.0f &&
                !e.mask_pre && e.phase_cout == g.N && g.N % 32 == 0 && (e.act_ld % 8) == 0 && (e.act_bs % 8) == 0 &&
                (reinterpret_cast<uintptr_t>(e.out_act) & 15) == 0;
+  if (e.gn_sum && (!p.vec_ok || !e.out_f32 || e.phase_cout != g.N || g.N % 32 != 0 || g.N / 32 != e.gn_groups)) {
+    if (err) *err = "conv_tc: fused GroupNorm statistics need 32 channels per group on the vector path";
+    return cudaErrorInvalidValue;
+  }
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream);
     case 64: return launch_bn<64>(tmA, tmB, p, stream);

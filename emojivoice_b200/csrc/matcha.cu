@@ -342,6 +342,7 @@ struct DecBuffers {
   int* ylen32; float* t_steps; float* sinus; float* th1; float* th2; float* tproj;
   float* xstate; ActT* xin; ActT* cat0; ActT* cat1; ActT* din;
   float* h; float* r; float* xr; ActT* a; ActT* n; float* qkv; ActT* att; ActT* ff; double* gn_partial;
+  double* gn_fused; size_t gn_fused_count;   // [n_steps][13][B][8][2] sums written by the conv epilogues (bf16 path)
 };
 
 template <typename ActT>
@@ -369,6 +370,8 @@ void plan_decode(const ev_matcha_cfg& c, int B, int T, int n_steps, Workspace& w
   d->att = w.take<ActT>(R * inner);
   d->ff = w.take<ActT>(R * 4 * D);
   d->gn_partial = w.take<double>((size_t)B * ceil_div(T, 32) * 8 * 2);
+  d->gn_fused_count = (size_t)n_steps * 13 * B * 8 * 2;
+  d->gn_fused = w.take<double>(d->gn_fused_count);
 }
 
 // Fixed-step Euler times exactly as flow_matching.py:52,68-83 computes them in float32 (t_span = linspace(0,1,n+1),
@@ -400,6 +403,11 @@ void euler_schedule(int n, std::vector<float>* t_of_step, std::vector<float>* dt
 template <typename ActT>
 struct Decoder {
   ev_ctx* ctx; const MatchaW& m; DecBuffers<ActT>& d; int B, T; cudaStream_t s; int D, inner;
+  int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
+  // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
+  // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
+  bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
+  double* next_gn_slot() { double* p = d.gn_fused + (size_t)(gn_slot++) * B * 8 * 2; return p; }
 
   // ResnetBlock1D (decoder.py:46-61) followed by the pre-LN of the transformer block; in: masked operand tensor
   int resnet(int k, const ActT* in, long long in_ld, int Tl, int shift, const float* temb) {
@@ -407,20 +415,23 @@ struct Decoder {
     const RowMask mask{d.ylen32, shift};
     const long long bsD = (long long)Tl * D, in_bs = (long long)Tl * in_ld;
     Epilogue e1; e1.out_f32 = d.h; e1.f32_ld = D; e1.f32_bs = bsD;
+    const double* part = d.gn_partial;
+    if (fuse_gn()) { e1.gn_sum = next_gn_slot(); e1.gn_groups = 8; part = e1.gn_sum; }
     EV_TRY(run_conv<ActT>(ctx, w.conv1, in, in_ld, in_bs, B, Tl, e1, s));
-    int chunks = 0;
+    int chunks = 1;
     const double RD = (double)B * Tl * D;
-    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
+    if (!fuse_gn()) EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g1;
-    g1.x = d.h; g1.partial = d.gn_partial; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
+    g1.x = d.h; g1.partial = part; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
     g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.out_act = d.a; g1.act_ld = D;
     EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
+    if (fuse_gn()) { e1.gn_sum = next_gn_slot(); part = e1.gn_sum; }
     EV_TRY(run_conv<ActT>(ctx, w.conv2, d.a, D, bsD, B, Tl, e1, s));
     Epilogue er; er.out_f32 = d.r; er.f32_ld = D; er.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.res, in, in_ld, in_bs, B, Tl, er, s));
-    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
+    if (!fuse_gn()) EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g2;
-    g2.x = d.h; g2.partial = d.gn_partial; g2.n_chunks = chunks; g2.gamma = w.gn2_g; g2.beta = w.gn2_b;
+    g2.x = d.h; g2.partial = part; g2.n_chunks = chunks; g2.gamma = w.gn2_g; g2.beta = w.gn2_b;
     g2.B = B; g2.T = Tl; g2.C = D; g2.mask = mask; g2.res = d.r; g2.res_ld = D; g2.out_f32 = d.xr; g2.f32_ld = D;
     g2.ln_gamma = m.tf[k].ln1_g; g2.ln_beta = m.tf[k].ln1_b; g2.out_ln = d.n; g2.ln_ld = D;
     EV_LAUNCH(ctx, s, "gn_apply_ln", 0, RD * (12.0 + sizeof(ActT)), group_norm_apply<ActT>(g2, s));
@@ -504,13 +515,15 @@ struct Decoder {
     { Epilogue e; e.out_act = d.n; e.act_ld = D; e.act_bs = (long long)T * D; e.mask = mask0; e.mask_act = 1;
       EV_TRY(run_conv<ActT>(ctx, m.up1_conv, d.a, D, (long long)T * D, B, T, e, s)); }
     // final_block (conv3 -> GN -> Mish -> *mask), final_proj fused with the Euler update x += dt * (proj*mask)
+    const double* part = d.gn_partial;
     { Epilogue e; e.out_f32 = d.h; e.f32_ld = D; e.f32_bs = (long long)T * D;
+      if (fuse_gn()) { e.gn_sum = next_gn_slot(); e.gn_groups = 8; part = e.gn_sum; }
       EV_TRY(run_conv<ActT>(ctx, m.final_conv, d.n, D, (long long)T * D, B, T, e, s)); }
-    int chunks = 0;
+    int chunks = 1;
     const double RD = (double)B * T * D;
-    EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, T, D, 8, d.gn_partial, &chunks, s));
+    if (!fuse_gn()) EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, T, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g;
-    g.x = d.h; g.partial = d.gn_partial; g.n_chunks = chunks; g.gamma = m.final_g; g.beta = m.final_b;
+    g.x = d.h; g.partial = part; g.n_chunks = chunks; g.gamma = m.final_g; g.beta = m.final_b;
     g.B = B; g.T = T; g.C = D; g.mask = mask0; g.out_act = d.a; g.act_ld = D;
     EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g, s));
     const int F = m.cfg.n_feats;
@@ -553,6 +566,7 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
   EV_LAUNCH(ctx, s, "decoder_pack_input", 0, (double)B * T * (12.0 * F + sizeof(ActT) * dec_in),
             (decoder_pack_input<ActT>(z, mu_y, spk_emb, B, F, S, T, temperature, mask0, d.xstate, d.xin, dec_in, s)));
   Decoder<ActT> dec{ctx, m, d, B, T, s, D, c.dec_heads * c.dec_head_dim};
+  if (dec.fuse_gn()) EV_CUDA(ctx, cudaMemsetAsync(d.gn_fused, 0, d.gn_fused_count * sizeof(double), s));
   for (int k = 0; k < n_steps; ++k) EV_TRY(dec.step(d.tproj + (size_t)k * 6 * D, dts[k]));
   EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, decoder_out, 1.0f, 0.0f, s));
   if (mel) EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, mel, c.mel_std, c.mel_mean, s));
