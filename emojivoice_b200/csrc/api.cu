@@ -38,6 +38,7 @@ extern "C" int ev_create(ev_ctx** out, int device) {
   ev_ctx* ctx = new ev_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  { const char* v = getenv("EV_ENC_TC"); ctx->enc_tc = v && atoi(v) != 0; }
   *out = ctx;
   return EV_OK;
 }
@@ -120,7 +121,8 @@ extern "C" int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const
   WeightStore ws(ctx, list, bias ? 2 : 1, s);
   ConvWeights cw;
   int rc = make_conv(ctx, ws, {"w"}, bias ? std::vector<std::string>{"b"} : std::vector<std::string>{}, Cout, Cin, K, stride,
-                     padding, dilation, transposed ? CONV_TRANSPOSED : CONV_NORMAL, true, &cw);
+                     padding, dilation, transposed ? CONV_TRANSPOSED : CONV_NORMAL, precision == 2 ? TC_TF32X3 : TC_BF16, &cw);
+  if (!rc && precision == 2 && !cw.w_tf32) rc = fail(ctx, EV_ERR_INVALID, "ev_test_conv1d: this shape has no 3xTF32 path");
   if (rc) { release(); return rc; }
   ConvGeom g;
   const int T_out = conv_geometry(cw, B, T, &g);
@@ -134,6 +136,14 @@ extern "C" int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const
   if (precision == EV_PREC_BF16) {
     ce = cf_to_cl<bf16>(x, B, Cin, T, reinterpret_cast<bf16*>(xa), Cin, (long long)T * Cin, 1.0f, none, s);
     if (ce == cudaSuccess) rc = run_conv<bf16>(ctx, cw, reinterpret_cast<bf16*>(xa), Cin, (long long)T * Cin, B, T, e, s);
+  } else if (precision == 2) {
+    void* sc = nullptr;
+    if ((rc = device_alloc(ctx, (size_t)B * T * Cin * 8, &sc, false, s))) { release(); return rc; }
+    ce = cf_to_cl<float>(x, B, Cin, T, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, 1.0f, none, s);
+    const bool keep = ctx->enc_tc;
+    ctx->enc_tc = true;
+    if (ce == cudaSuccess) rc = run_conv_tf32(ctx, cw, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, B, T, e, reinterpret_cast<float*>(sc), s);
+    ctx->enc_tc = keep;
   } else {
     ce = cf_to_cl<float>(x, B, Cin, T, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, 1.0f, none, s);
     if (ce == cudaSuccess) rc = run_conv<float>(ctx, cw, reinterpret_cast<float*>(xa), Cin, (long long)T * Cin, B, T, e, s);

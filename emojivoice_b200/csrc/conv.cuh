@@ -40,6 +40,7 @@ struct Epilogue {
   RowMask mask = {nullptr, 0};
   int mask_pre = 0, mask_act = 0;
   float alpha = 1.0f, div = 1.0f;
+  int f32_is_act = 0;  // tensor-core path: out_f32 receives the activated, masked value instead of the pre-activation one
   int act = ACT_NONE;
   float slope = 0.0f;
   const float* snake_a = nullptr;     // exp(alpha)            [C_out]
@@ -83,6 +84,8 @@ __device__ __forceinline__ float ep_act(const Epilogue& e, int co, float v, floa
 struct ConvWeights {
   float* w_f32 = nullptr;   // [taps][C_in][N_pad]      (N contiguous; SIMT B-operand)
   bf16* w_bf16 = nullptr;   // [taps][N_pad128][K_pad]  (C_in contiguous, K-major; TMA/UMMA B-operand)
+  float* w_tf32 = nullptr;  // [taps][N_pad128][3*K32]  split fp32 for the 3xTF32 path: [hi | lo | hi], K32 = C_in padded to 32
+  int K32 = 0;
   float* bias = nullptr;    // [C_out] or nullptr
   int taps = 0, C_in = 0, N = 0, N_pad = 0, N_pad_tc = 0, K_pad = 0;
   // geometry template
@@ -93,7 +96,8 @@ struct ConvWeights {
 cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, long long x_bs, const ConvWeights& w,
                              const Epilogue& e, cudaStream_t stream);
 // conv_tc.cu
-cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, long long x_bs, int x_rows_alloc,
+// x: bf16 activations, or (tf32x3 != 0) the split fp32 pair [hi | lo] of width 2*C_in per row (x_ld, x_bs in elements)
+cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err);
 bool conv_tc_init(std::string* err);
 // 3-D bf16 tensor map (dims d0 fastest; strides in bytes for d1, d2; box b0 x b1 x 1; swizzle 128 or 64 bytes)

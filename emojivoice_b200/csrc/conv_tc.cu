@@ -63,6 +63,10 @@ struct TcParams {
   uint32_t tmem_cols;
   int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
   int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
+  uint32_t idesc;               // instruction descriptor (kind::f16 bf16, or kind::tf32)
+  int tf32;                     // operands are 32-bit (3xTF32 split path): K-chunks walk the sections [hi | hi | lo] of A
+  int kch1;                     // K-chunks per section (== kchunks unless tf32)
+  int sec_off[3];               // column offset of each A section
   uint32_t tap_first16;         // (byte offset of tap 0's first row inside a haloed tile) >> 4
   uint32_t tap_step16;          // (bytes from one tap's first row to the next one's) >> 4, two's complement when negative
 };
@@ -74,15 +78,20 @@ __device__ __forceinline__ uint32_t desc_lo_word(uint32_t saddr) { return ((sadd
 __device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // All MMAs of one (K-chunk, tap): VMB m-blocks x KS K-steps, issued by the elected lane.
-template <int KS, int BN>
+template <int KS, int BN, bool TF32>
 __device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo, uint32_t mb_step16, int vmb,
                                           uint32_t idesc, uint32_t acc) {
 #pragma unroll
-  for (int k = 0; k < KS; ++k) umma_bf16(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+  for (int k = 0; k < KS; ++k) {
+    if (TF32) umma_tf32(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+    else umma_bf16(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+  }
   if (vmb > 1) {
 #pragma unroll
-    for (int k = 0; k < KS; ++k)
-      umma_bf16(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+    for (int k = 0; k < KS; ++k) {
+      if (TF32) umma_tf32(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+      else umma_bf16(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
+    }
   }
 }
 
@@ -103,7 +112,7 @@ __device__ __noinline__ void scalar_block(const TcParams& p, const float* wstage
     if (!ep_coord(e, r, nn, t, cc)) continue;
     const float mv = e.mask.at(b, t);
     const float v = ep_value(e, b, t, cc, wstage[rl * STAGE_LD + nl], mv);
-    if (e.out_f32) e.out_f32[b * e.f32_bs + (long long)t * e.f32_ld + cc] = v;
+    if (e.out_f32) e.out_f32[b * e.f32_bs + (long long)t * e.f32_ld + cc] = e.f32_is_act ? ep_act(e, cc, v, mv) : v;
     if (out_act) out_act[b * e.act_bs + (long long)t * e.act_ld + cc] = __float2bfloat16_rn(ep_act(e, cc, v, mv));
   }
 }
@@ -165,7 +174,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&a_empty[sa], pa);
             mbar_expect_tx(&a_full[sa], a_bytes);
             const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
-            const int col = p.grp_col0[g] + kc * p.bk, row = m0 + p.grp_row0[g];
+            const int sec = kc / p.kch1;   // 3xTF32: K-chunks walk the A sections [hi | hi | lo]; otherwise one section
+            const int col = p.grp_col0[g] + p.sec_off[sec] + (kc - sec * p.kch1) * p.bk, row = m0 + p.grp_row0[g];
             tma_load_3d(dst, &tmA, &a_full[sa], col, row, b);
             if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, &tmA, &a_full[sa], col, row + p.a_box_rows, b);
             if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
@@ -187,7 +197,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Every tap and m-block re-reads the same smem tile at a row offset.  The loop body is kept to a few dozen
     // instructions per weight tile: ring slots / phases advance incrementally and descriptors by adds (a single
     // warp issues ~1 dependent instruction per 5-8 clk, so 200 instructions per tap would cap the tensor pipe).
-    constexpr uint32_t idesc = make_idesc(BM, BN);
+    const uint32_t idesc = p.idesc;
+    const bool tf32 = p.tf32 != 0;
     const uint32_t hi = desc_hi_word(p.desc_sbo, p.desc_layout);
     const uint32_t mb_step16 = (uint32_t)(BM * p.row_bytes) >> 4, tap_step16 = p.tap_step16;
     const uint32_t b_step16 = (uint32_t)p.b_tile_bytes >> 4, a_step16 = (uint32_t)p.a_slot_bytes >> 4;
@@ -223,8 +234,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               b_lo = b_lo0 + (uint32_t)sb * b_step16;
             }
             if (elect_one()) {
-              if (ks4) issue_tap<4, BN>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
-              else issue_tap<2, BN>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
+              if (tf32) issue_tap<4, BN, true>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
+              else if (ks4) issue_tap<4, BN, false>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
+              else issue_tap<2, BN, false>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
               if (!resident) umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
             }
             __syncwarp();
@@ -252,6 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool has_res = e.res != nullptr, has_res2 = e.res2 != nullptr, has_f32 = e.out_f32 != nullptr, has_act = e.out_act != nullptr;
     const bool use_div = e.div != 1.0f, snake = e.act == ACT_SNAKE, use_alpha = e.alpha != 1.0f;
     const bool mask_pre = e.mask_pre != 0, mask_act = e.mask_act != 0, polyphase = e.phase_cout != p.g.N;
+    const bool f32_act = has_f32 && e.f32_is_act != 0;
     const float inv_div = 1.0f / e.div;   // bf16-operand path: x * (1/3) instead of the reference's x / 3 (1 ulp, far inside tolerance)
     const float slope = e.act == ACT_LRELU ? e.slope : (e.act == ACT_RELU ? 0.0f : 1.0f);
     const float alpha = e.alpha;
@@ -398,9 +411,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               v0 += r2.x; v1 += r2.y; v2 += r2.z; v3 += r2.w;
             }
             if (use_div) { v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div; }
-            if (has_f32) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
+            if (has_f32 && !f32_act) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
             if (e.gn_sum) { gs += (v0 + v1) + (v2 + v3); gq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3); }
-            if (has_act) {
+            if (has_act || f32_act) {
               float a0, a1, a2, a3;
               if (snake) {   // y + sin^2(y*e^alpha) / (e^beta + 1e-9); fast sine is ample for bf16 operands
                 const float s0 = __sinf(v0 * sa4.x), s1 = __sinf(v1 * sa4.y), s2 = __sinf(v2 * sa4.z), s3 = __sinf(v3 * sa4.w);
@@ -409,11 +422,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
               }
               if (mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
-              __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
-              uint2 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&lo);
-              pk.y = *reinterpret_cast<uint32_t*>(&hi);
-              *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+              if (f32_act) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(a0, a1, a2, a3);
+              if (has_act) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(act_p + (long long)t * e.act_ld) = pk;
+              }
             }
           }
           if (e.gn_sum) {   // the block's 32 columns are one GroupNorm group: one fp64 atomic pair per warp and block
@@ -448,13 +464,13 @@ PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 int g_halo_mode = -1;   // EV_TC_HALO=0 disables halo reuse (one activation tile per tap) for debugging
 
 bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
-                uint64_t s2_bytes, uint32_t b0, uint32_t b1, std::string* err, int swizzle_bytes = 128) {
+                uint64_t s2_bytes, uint32_t b0, uint32_t b1, std::string* err, int swizzle_bytes = 128, bool f32 = false) {
   cuuint64_t dims[3] = {d0, d1, d2};
   cuuint64_t strides[2] = {s1_bytes, s2_bytes};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -574,10 +590,11 @@ bool conv_tc_init(std::string* err) {
 }
 
 // x: channel-last bf16 activations (b, t, c) at x + b*x_bs + t*x_ld + c, `x_rows` addressable rows per item.
-cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, long long x_bs, int x_rows,
+cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err) {
   if (!g_encode && !conv_tc_init(err)) return cudaErrorNotSupported;
-  if ((x_ld & 7) || (x_bs & 7) || (reinterpret_cast<uintptr_t>(x) & 15)) {
+  const int esz = tf32x3 ? 4 : 2;
+  if ((x_ld * esz & 15) || (x_bs * esz & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) {
     if (err) *err = "conv_tc: activation tensor is not 16-byte aligned / strided";
     return cudaErrorInvalidValue;
   }
@@ -591,25 +608,39 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
     g_lean_mode = env_int("EV_TC_LEAN", 1);
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
-  (void)x_rows;
   const int BN = conv_tc_pick_bn(g.N);
   TcParams p;
   p.g = g;
   p.e = e;
   // K-chunk width: 64 channels under the 128-byte swizzle, or 32 under the 64-byte swizzle when that avoids padded K
-  p.bk = (g_bk32_mode && g.C_in <= 32) ? 32 : 64;
-  p.row_bytes = p.bk * 2;
-  p.ksteps = p.bk / UMMA_K;
+  p.tf32 = tf32x3 ? 1 : 0;
+  if (tf32x3) {      // 32 fp32 channels per 128-byte row, UMMA K = 8; K-chunks walk [x_hi | x_hi | x_lo] x [w_hi | w_lo | w_hi]
+    if (g.conv_stride != 1 || !w.w_tf32) { if (err) *err = "conv_tc: the 3xTF32 path needs stride 1 and split weights"; return cudaErrorInvalidValue; }
+    p.bk = 32;
+    p.row_bytes = 128;
+    p.ksteps = 4;
+    p.kch1 = w.K32 / 32;
+    p.kchunks = 3 * p.kch1;
+    p.sec_off[0] = 0; p.sec_off[1] = 0; p.sec_off[2] = g.C_in;
+    p.idesc = make_idesc_tf32(BM, BN);
+  } else {
+    p.bk = (g_bk32_mode && g.C_in <= 32) ? 32 : 64;
+    p.row_bytes = p.bk * 2;
+    p.ksteps = p.bk / UMMA_K;
+    p.kchunks = ceil_div(g.C_in, p.bk);
+    p.kch1 = p.kchunks;
+    p.sec_off[0] = p.sec_off[1] = p.sec_off[2] = 0;
+    p.idesc = make_idesc(BM, BN);
+  }
   p.desc_sbo = 8u * (uint32_t)p.row_bytes;
-  p.desc_layout = p.bk == 64 ? 2u : 4u;
+  p.desc_layout = p.row_bytes == 128 ? 2u : 4u;
   p.b_tile_bytes = BN * p.row_bytes;
-  p.kchunks = ceil_div(g.C_in, p.bk);
   int tap_row[kMaxTaps], tap_col[kMaxTaps];
   CUtensorMap tmA, tmB;
   uint64_t d0, d1, s1;
   if (g.conv_stride == 1) {
     for (int j = 0; j < g.taps; ++j) { tap_row[j] = g.tap_off[j]; tap_col[j] = 0; }
-    d0 = (uint64_t)g.C_in; d1 = (uint64_t)g.T_in; s1 = (uint64_t)x_ld * 2;
+    d0 = (uint64_t)(tf32x3 ? 2 * g.C_in : g.C_in); d1 = (uint64_t)g.T_in; s1 = (uint64_t)x_ld * esz;
   } else if (g.conv_stride == 2) {
     // (T, ld) viewed as (T/2, 2*ld): time 2j+h is row j, columns [h*ld, h*ld + C_in)
     if (g.T_in & 1) { if (err) *err = "conv_tc: stride-2 conv needs an even input length"; return cudaErrorInvalidValue; }
@@ -664,15 +695,22 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const bf16* x, long long x_ld, lon
   p.a_boxes = a_rows > 256 ? 2 : 1;
   p.a_box_rows = (int)align_up((size_t)ceil_div(a_rows, p.a_boxes), 8);
   p.a_slot_bytes = (int)align_up((size_t)p.a_boxes * p.a_box_rows * p.row_bytes, 1024);
-  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * 2, (uint32_t)p.bk, (uint32_t)p.a_box_rows, err, p.row_bytes);
+  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * esz, (uint32_t)p.bk, (uint32_t)p.a_box_rows, err, p.row_bytes, tf32x3 != 0);
   if (!ok) return cudaErrorInvalidValue;
-  if (w.N_pad_tc % BN != 0 || w.K_pad % 64 != 0 || w.K_pad < p.kchunks * p.bk) {
-    if (err) *err = "conv_tc: packed weight padding does not match the tile shape";
-    return cudaErrorInvalidValue;
+  if (tf32x3) {
+    if (w.N_pad_tc % BN != 0 || w.K32 % 32 != 0) { if (err) *err = "conv_tc: split weight padding does not match the tile shape"; return cudaErrorInvalidValue; }
+    const uint64_t k3 = 3ull * w.K32;
+    ok = encode_map(&tmB, w.w_tf32, k3, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, k3 * 4, k3 * w.N_pad_tc * 4, 32u, (uint32_t)BN, err, 128, true);
+  } else {
+    if (w.N_pad_tc % BN != 0 || w.K_pad % 64 != 0 || w.K_pad < p.kchunks * p.bk) {
+      if (err) *err = "conv_tc: packed weight padding does not match the tile shape";
+      return cudaErrorInvalidValue;
+    }
+    ok = encode_map(&tmB, w.w_bf16, (uint64_t)w.K_pad, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, (uint64_t)w.K_pad * 2,
+                    (uint64_t)w.K_pad * w.N_pad_tc * 2, (uint32_t)p.bk, (uint32_t)BN, err, p.row_bytes);
   }
-  ok = encode_map(&tmB, w.w_bf16, (uint64_t)w.K_pad, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, (uint64_t)w.K_pad * 2,
-                  (uint64_t)w.K_pad * w.N_pad_tc * 2, (uint32_t)p.bk, (uint32_t)BN, err, p.row_bytes);
   if (!ok) return cudaErrorInvalidValue;
+  if (tf32x3 && e.out_act) { if (err) *err = "conv_tc: the 3xTF32 path writes fp32 outputs only"; return cudaErrorInvalidValue; }
   if (e.act != ACT_NONE && e.act != ACT_RELU && e.act != ACT_LRELU && e.act != ACT_SNAKE) {
     if (err) *err = "conv_tc: the tensor-core epilogue implements identity / (leaky) ReLU / SnakeBeta only";
     return cudaErrorInvalidValue;

@@ -80,6 +80,10 @@ struct ev_ctx {
   ev::MatchaW matcha;
   ev::HifiganW hifigan;
   // optional per-launch CUDA-event timing (ev_profile_begin/end); off in normal operation
+  // text encoder convs on tcgen05 via the 3xTF32 split: OPT-IN (EV_ENC_TC=1).  Measured 7.5e-6 relative error against
+  // 3.8e-7 for the fp32 CUDA-core kernel (the tensor core's fp32 accumulation truncates; K ~ 3000), which would make
+  // ceil(exp(logw)) flip ~20x more often -- durations must stay bit-exact, so the default is the CUDA-core path.
+  bool enc_tc = false;
   bool profiling = false;
   bool prof_detail = false;    // EV_PROF_DETAIL=1: conv kernel classes carry the layer shape
   const char* prof_tag = "";   // appended to conv kernel names while profiling (enc / dec / voc)
@@ -146,9 +150,10 @@ struct WeightStore {
 };
 
 enum ConvKind { CONV_NORMAL = 0, CONV_TRANSPOSED = 1 };
+enum TcMode { TC_NONE = 0, TC_BF16 = 1, TC_TF32X3 = 2 };   // which tensor-core operand layout make_conv also packs
 // Allocate + pack one conv / linear layer.  `names` may list several tensors stacked along N (fused QKV, stacked mlps).
 int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weight_names, const std::vector<std::string>& bias_names,
-              int c_out_each, int c_in, int ksize, int stride, int pad, int dilation, ConvKind kind, bool want_bf16,
+              int c_out_each, int c_in, int ksize, int stride, int pad, int dilation, ConvKind kind, int tc_mode,
               ConvWeights* out);
 int device_alloc(ev_ctx* ctx, size_t bytes, void** out, bool zero, cudaStream_t s);
 
@@ -156,6 +161,10 @@ int device_alloc(ev_ctx* ctx, size_t bytes, void** out, bool zero, cudaStream_t 
 int conv_geometry(const ConvWeights& w, int B, int T_in, ConvGeom* g);
 
 // Launch `w` on x (ActT = float -> CUDA-core fp32, bf16 -> tcgen05); e carries the fused epilogue.
+// fp32-accurate tensor-core convolution (3xTF32 split); `scratch` holds B*T_in*2*C_in floats
+int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x_ld, long long x_bs, int B, int T_in, Epilogue e,
+                  float* scratch, cudaStream_t s);
+
 template <typename ActT>
 int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, long long x_bs, int B, int T_in,
              Epilogue e, cudaStream_t s);

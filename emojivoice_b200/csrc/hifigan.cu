@@ -92,14 +92,14 @@ extern "C" int ev_load_hifigan(ev_ctx* ctx, const ev_tensor* weights, int n_weig
   }
   WeightStore ws(ctx, all.data(), (int)all.size(), s);
   const int c0 = c.upsample_initial_channel;
-  EV_TRY(make_conv(ctx, ws, {"conv_pre.weight"}, {"conv_pre.bias"}, c0, c.num_mels, 7, 1, 3, 1, CONV_NORMAL, true, &h.conv_pre));
+  EV_TRY(make_conv(ctx, ws, {"conv_pre.weight"}, {"conv_pre.bias"}, c0, c.num_mels, 7, 1, 3, 1, CONV_NORMAL, TC_BF16, &h.conv_pre));
   h.total_up = 1;
   for (int i = 0; i < c.n_ups; ++i) {
     const int cin = c0 >> i, ch = c0 >> (i + 1);
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
     h.total_up *= u;
     const std::string up = "ups." + std::to_string(i);
-    EV_TRY(make_conv(ctx, ws, {up + ".weight"}, {up + ".bias"}, ch, cin, k, u, (k - u) / 2, 1, CONV_TRANSPOSED, true, &h.ups[i]));
+    EV_TRY(make_conv(ctx, ws, {up + ".weight"}, {up + ".bias"}, ch, cin, k, u, (k - u) / 2, 1, CONV_TRANSPOSED, TC_BF16, &h.ups[i]));
     for (int j = 0; j < c.n_kernels; ++j) {
       const int rk = c.resblock_kernel_sizes[j];
       for (int l = 0; l < 3; ++l) {
@@ -107,8 +107,8 @@ extern "C" int ev_load_hifigan(ev_ctx* ctx, const ev_tensor* weights, int n_weig
         const std::string rb = "resblocks." + std::to_string(i * c.n_kernels + j);
         const std::string a = rb + ".convs1." + std::to_string(l), b = rb + ".convs2." + std::to_string(l);
         // get_padding(k, d) = (k*d - d)/2  (hifigan/xutils.py:37-38)
-        EV_TRY(make_conv(ctx, ws, {a + ".weight"}, {a + ".bias"}, ch, ch, rk, 1, (rk * dl - dl) / 2, dl, CONV_NORMAL, true, &h.c1[i][j][l]));
-        EV_TRY(make_conv(ctx, ws, {b + ".weight"}, {b + ".bias"}, ch, ch, rk, 1, (rk - 1) / 2, 1, CONV_NORMAL, true, &h.c2[i][j][l]));
+        EV_TRY(make_conv(ctx, ws, {a + ".weight"}, {a + ".bias"}, ch, ch, rk, 1, (rk * dl - dl) / 2, dl, CONV_NORMAL, TC_BF16, &h.c1[i][j][l]));
+        EV_TRY(make_conv(ctx, ws, {b + ".weight"}, {b + ".bias"}, ch, ch, rk, 1, (rk - 1) / 2, 1, CONV_NORMAL, TC_BF16, &h.c2[i][j][l]));
       }
     }
   }

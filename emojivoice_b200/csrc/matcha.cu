@@ -15,9 +15,9 @@ cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 // ------------------------------------------------------------------------------------------------ loading
 int load_resnet(ev_ctx* ctx, WeightStore& ws, const std::string& p, int c_in, int c, int td, ResnetW* r) {
   r->c_in = c_in;
-  EV_TRY(make_conv(ctx, ws, {p + ".block1.block.0.weight"}, {p + ".block1.block.0.bias"}, c, c_in, 3, 1, 1, 1, CONV_NORMAL, true, &r->conv1));
-  EV_TRY(make_conv(ctx, ws, {p + ".block2.block.0.weight"}, {p + ".block2.block.0.bias"}, c, c, 3, 1, 1, 1, CONV_NORMAL, true, &r->conv2));
-  EV_TRY(make_conv(ctx, ws, {p + ".res_conv.weight"}, {p + ".res_conv.bias"}, c, c_in, 1, 1, 0, 1, CONV_NORMAL, true, &r->res));
+  EV_TRY(make_conv(ctx, ws, {p + ".block1.block.0.weight"}, {p + ".block1.block.0.bias"}, c, c_in, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &r->conv1));
+  EV_TRY(make_conv(ctx, ws, {p + ".block2.block.0.weight"}, {p + ".block2.block.0.bias"}, c, c, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &r->conv2));
+  EV_TRY(make_conv(ctx, ws, {p + ".res_conv.weight"}, {p + ".res_conv.bias"}, c, c_in, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &r->res));
   EV_TRY(ws.copy_vec(p + ".block1.block.1.weight", c, &r->gn1_g));
   EV_TRY(ws.copy_vec(p + ".block1.block.1.bias", c, &r->gn1_b));
   EV_TRY(ws.copy_vec(p + ".block2.block.1.weight", c, &r->gn2_g));
@@ -39,10 +39,10 @@ int load_transformer(ev_ctx* ctx, WeightStore& ws, const std::string& p, int c, 
   EV_TRY(ws.copy_vec(p + ".norm1.bias", c, &t->ln1_b));
   EV_TRY(ws.copy_vec(p + ".norm3.weight", c, &t->ln3_g));
   EV_TRY(ws.copy_vec(p + ".norm3.bias", c, &t->ln3_b));
-  EV_TRY(make_conv(ctx, ws, {p + ".attn1.to_q.weight", p + ".attn1.to_k.weight", p + ".attn1.to_v.weight"}, {}, inner, c, 1, 1, 0, 1, CONV_NORMAL, true, &t->qkv));
-  EV_TRY(make_conv(ctx, ws, {p + ".attn1.to_out.0.weight"}, {p + ".attn1.to_out.0.bias"}, c, inner, 1, 1, 0, 1, CONV_NORMAL, true, &t->out));
-  EV_TRY(make_conv(ctx, ws, {p + ".ff.net.0.proj.weight"}, {p + ".ff.net.0.proj.bias"}, 4 * c, c, 1, 1, 0, 1, CONV_NORMAL, true, &t->ff1));
-  EV_TRY(make_conv(ctx, ws, {p + ".ff.net.2.weight"}, {p + ".ff.net.2.bias"}, c, 4 * c, 1, 1, 0, 1, CONV_NORMAL, true, &t->ff2));
+  EV_TRY(make_conv(ctx, ws, {p + ".attn1.to_q.weight", p + ".attn1.to_k.weight", p + ".attn1.to_v.weight"}, {}, inner, c, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &t->qkv));
+  EV_TRY(make_conv(ctx, ws, {p + ".attn1.to_out.0.weight"}, {p + ".attn1.to_out.0.bias"}, c, inner, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &t->out));
+  EV_TRY(make_conv(ctx, ws, {p + ".ff.net.0.proj.weight"}, {p + ".ff.net.0.proj.bias"}, 4 * c, c, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &t->ff1));
+  EV_TRY(make_conv(ctx, ws, {p + ".ff.net.2.weight"}, {p + ".ff.net.2.bias"}, c, 4 * c, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &t->ff2));
   const ev_tensor* al = ws.get(p + ".ff.net.0.alpha", {4LL * c});
   const ev_tensor* be = ws.get(p + ".ff.net.0.beta", {4LL * c});
   if (!al || !be) return EV_ERR_MISSING;
@@ -85,11 +85,11 @@ extern "C" int ev_load_matcha(ev_ctx* ctx, const ev_tensor* weights, int n_weigh
   if (c.enc_prenet) {
     for (int i = 0; i < 3; ++i) {
       const std::string p = "encoder.prenet.conv_layers." + std::to_string(i), n = "encoder.prenet.norm_layers." + std::to_string(i);
-      EV_TRY(make_conv(ctx, ws, {p + ".weight"}, {p + ".bias"}, C, C, 5, 1, 2, 1, CONV_NORMAL, false, &m.pre_conv[i]));
+      EV_TRY(make_conv(ctx, ws, {p + ".weight"}, {p + ".bias"}, C, C, 5, 1, 2, 1, CONV_NORMAL, TC_TF32X3, &m.pre_conv[i]));
       EV_TRY(ws.copy_vec(n + ".gamma", C, &m.pre_g[i]));
       EV_TRY(ws.copy_vec(n + ".beta", C, &m.pre_b[i]));
     }
-    EV_TRY(make_conv(ctx, ws, {"encoder.prenet.proj.weight"}, {"encoder.prenet.proj.bias"}, C, C, 1, 1, 0, 1, CONV_NORMAL, false, &m.pre_proj));
+    EV_TRY(make_conv(ctx, ws, {"encoder.prenet.proj.weight"}, {"encoder.prenet.proj.bias"}, C, C, 1, 1, 0, 1, CONV_NORMAL, TC_TF32X3, &m.pre_proj));
   }
   m.enc.resize(c.enc_layers);
   const int ek = c.enc_kernel;
@@ -97,20 +97,20 @@ extern "C" int ev_load_matcha(ev_ctx* ctx, const ev_tensor* weights, int n_weigh
     EncLayerW& L = m.enc[i];
     const std::string a = "encoder.encoder.attn_layers." + std::to_string(i), f = "encoder.encoder.ffn_layers." + std::to_string(i);
     EV_TRY(make_conv(ctx, ws, {a + ".conv_q.weight", a + ".conv_k.weight", a + ".conv_v.weight"},
-                     {a + ".conv_q.bias", a + ".conv_k.bias", a + ".conv_v.bias"}, H, H, 1, 1, 0, 1, CONV_NORMAL, false, &L.qkv));
-    EV_TRY(make_conv(ctx, ws, {a + ".conv_o.weight"}, {a + ".conv_o.bias"}, H, H, 1, 1, 0, 1, CONV_NORMAL, false, &L.o));
-    EV_TRY(make_conv(ctx, ws, {f + ".conv_1.weight"}, {f + ".conv_1.bias"}, c.enc_filter_channels, H, ek, 1, ek / 2, 1, CONV_NORMAL, false, &L.ffn1));
-    EV_TRY(make_conv(ctx, ws, {f + ".conv_2.weight"}, {f + ".conv_2.bias"}, H, c.enc_filter_channels, ek, 1, ek / 2, 1, CONV_NORMAL, false, &L.ffn2));
+                     {a + ".conv_q.bias", a + ".conv_k.bias", a + ".conv_v.bias"}, H, H, 1, 1, 0, 1, CONV_NORMAL, TC_TF32X3, &L.qkv));
+    EV_TRY(make_conv(ctx, ws, {a + ".conv_o.weight"}, {a + ".conv_o.bias"}, H, H, 1, 1, 0, 1, CONV_NORMAL, TC_TF32X3, &L.o));
+    EV_TRY(make_conv(ctx, ws, {f + ".conv_1.weight"}, {f + ".conv_1.bias"}, c.enc_filter_channels, H, ek, 1, ek / 2, 1, CONV_NORMAL, TC_TF32X3, &L.ffn1));
+    EV_TRY(make_conv(ctx, ws, {f + ".conv_2.weight"}, {f + ".conv_2.bias"}, H, c.enc_filter_channels, ek, 1, ek / 2, 1, CONV_NORMAL, TC_TF32X3, &L.ffn2));
     EV_TRY(ws.copy_vec("encoder.encoder.norm_layers_1." + std::to_string(i) + ".gamma", H, &L.ln1_g));
     EV_TRY(ws.copy_vec("encoder.encoder.norm_layers_1." + std::to_string(i) + ".beta", H, &L.ln1_b));
     EV_TRY(ws.copy_vec("encoder.encoder.norm_layers_2." + std::to_string(i) + ".gamma", H, &L.ln2_g));
     EV_TRY(ws.copy_vec("encoder.encoder.norm_layers_2." + std::to_string(i) + ".beta", H, &L.ln2_b));
   }
-  EV_TRY(make_conv(ctx, ws, {"encoder.proj_m.weight"}, {"encoder.proj_m.bias"}, c.n_feats, H, 1, 1, 0, 1, CONV_NORMAL, false, &m.proj_m));
+  EV_TRY(make_conv(ctx, ws, {"encoder.proj_m.weight"}, {"encoder.proj_m.bias"}, c.n_feats, H, 1, 1, 0, 1, CONV_NORMAL, TC_TF32X3, &m.proj_m));
   const int Fd = c.enc_filter_channels_dp;
-  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.conv_1.weight"}, {"encoder.proj_w.conv_1.bias"}, Fd, H, 3, 1, 1, 1, CONV_NORMAL, false, &m.dp_conv1));
-  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.conv_2.weight"}, {"encoder.proj_w.conv_2.bias"}, Fd, Fd, 3, 1, 1, 1, CONV_NORMAL, false, &m.dp_conv2));
-  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.proj.weight"}, {"encoder.proj_w.proj.bias"}, 1, Fd, 1, 1, 0, 1, CONV_NORMAL, false, &m.dp_proj));
+  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.conv_1.weight"}, {"encoder.proj_w.conv_1.bias"}, Fd, H, 3, 1, 1, 1, CONV_NORMAL, TC_TF32X3, &m.dp_conv1));
+  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.conv_2.weight"}, {"encoder.proj_w.conv_2.bias"}, Fd, Fd, 3, 1, 1, 1, CONV_NORMAL, TC_TF32X3, &m.dp_conv2));
+  EV_TRY(make_conv(ctx, ws, {"encoder.proj_w.proj.weight"}, {"encoder.proj_w.proj.bias"}, 1, Fd, 1, 1, 0, 1, CONV_NORMAL, TC_NONE, &m.dp_proj));
   EV_TRY(ws.copy_vec("encoder.proj_w.norm_1.gamma", Fd, &m.dp_g1));
   EV_TRY(ws.copy_vec("encoder.proj_w.norm_1.beta", Fd, &m.dp_b1));
   EV_TRY(ws.copy_vec("encoder.proj_w.norm_2.gamma", Fd, &m.dp_g2));
@@ -129,8 +129,8 @@ extern "C" int ev_load_matcha(ev_ctx* ctx, const ev_tensor* weights, int n_weigh
   // ---- estimator
   const std::string E = "decoder.estimator.";
   const int TD = 4 * D;
-  EV_TRY(make_conv(ctx, ws, {E + "time_mlp.linear_1.weight"}, {E + "time_mlp.linear_1.bias"}, TD, dec_in, 1, 1, 0, 1, CONV_NORMAL, false, &m.time1));
-  EV_TRY(make_conv(ctx, ws, {E + "time_mlp.linear_2.weight"}, {E + "time_mlp.linear_2.bias"}, TD, TD, 1, 1, 0, 1, CONV_NORMAL, false, &m.time2));
+  EV_TRY(make_conv(ctx, ws, {E + "time_mlp.linear_1.weight"}, {E + "time_mlp.linear_1.bias"}, TD, dec_in, 1, 1, 0, 1, CONV_NORMAL, TC_NONE, &m.time1));
+  EV_TRY(make_conv(ctx, ws, {E + "time_mlp.linear_2.weight"}, {E + "time_mlp.linear_2.bias"}, TD, TD, 1, 1, 0, 1, CONV_NORMAL, TC_NONE, &m.time2));
   const std::string rn_names[6] = {E + "down_blocks.0.0", E + "down_blocks.1.0", E + "mid_blocks.0.0", E + "mid_blocks.1.0",
                                    E + "up_blocks.0.0", E + "up_blocks.1.0"};
   const std::string tf_names[6] = {E + "down_blocks.0.1.0", E + "down_blocks.1.1.0", E + "mid_blocks.0.1.0",
@@ -143,15 +143,15 @@ extern "C" int ev_load_matcha(ev_ctx* ctx, const ev_tensor* weights, int n_weigh
     mlp_w.push_back(rn_names[i] + ".mlp.1.weight");
     mlp_b.push_back(rn_names[i] + ".mlp.1.bias");
   }
-  EV_TRY(make_conv(ctx, ws, mlp_w, mlp_b, D, TD, 1, 1, 0, 1, CONV_NORMAL, false, &m.temb_proj));
-  EV_TRY(make_conv(ctx, ws, {E + "down_blocks.0.2.conv.weight"}, {E + "down_blocks.0.2.conv.bias"}, D, D, 3, 2, 1, 1, CONV_NORMAL, true, &m.down0));
-  EV_TRY(make_conv(ctx, ws, {E + "down_blocks.1.2.weight"}, {E + "down_blocks.1.2.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, true, &m.down1_conv));
-  EV_TRY(make_conv(ctx, ws, {E + "up_blocks.0.2.conv.weight"}, {E + "up_blocks.0.2.conv.bias"}, D, D, 4, 2, 1, 1, CONV_TRANSPOSED, true, &m.up0));
-  EV_TRY(make_conv(ctx, ws, {E + "up_blocks.1.2.weight"}, {E + "up_blocks.1.2.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, true, &m.up1_conv));
-  EV_TRY(make_conv(ctx, ws, {E + "final_block.block.0.weight"}, {E + "final_block.block.0.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, true, &m.final_conv));
+  EV_TRY(make_conv(ctx, ws, mlp_w, mlp_b, D, TD, 1, 1, 0, 1, CONV_NORMAL, TC_NONE, &m.temb_proj));
+  EV_TRY(make_conv(ctx, ws, {E + "down_blocks.0.2.conv.weight"}, {E + "down_blocks.0.2.conv.bias"}, D, D, 3, 2, 1, 1, CONV_NORMAL, TC_BF16, &m.down0));
+  EV_TRY(make_conv(ctx, ws, {E + "down_blocks.1.2.weight"}, {E + "down_blocks.1.2.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &m.down1_conv));
+  EV_TRY(make_conv(ctx, ws, {E + "up_blocks.0.2.conv.weight"}, {E + "up_blocks.0.2.conv.bias"}, D, D, 4, 2, 1, 1, CONV_TRANSPOSED, TC_BF16, &m.up0));
+  EV_TRY(make_conv(ctx, ws, {E + "up_blocks.1.2.weight"}, {E + "up_blocks.1.2.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &m.up1_conv));
+  EV_TRY(make_conv(ctx, ws, {E + "final_block.block.0.weight"}, {E + "final_block.block.0.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &m.final_conv));
   EV_TRY(ws.copy_vec(E + "final_block.block.1.weight", D, &m.final_g));
   EV_TRY(ws.copy_vec(E + "final_block.block.1.bias", D, &m.final_b));
-  EV_TRY(make_conv(ctx, ws, {E + "final_proj.weight"}, {E + "final_proj.bias"}, c.n_feats, D, 1, 1, 0, 1, CONV_NORMAL, true, &m.final_proj));
+  EV_TRY(make_conv(ctx, ws, {E + "final_proj.weight"}, {E + "final_proj.bias"}, c.n_feats, D, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &m.final_proj));
   EV_CUDA(ctx, cudaStreamSynchronize(s));
   m.loaded = true;
   return 0;
@@ -163,6 +163,7 @@ namespace {
 struct EncBuffers {
   int* xlen32; float* h0; float* pa; float* pb; float* tmp; float* X; float* X1; float* qkv; float* att; float* F;
   float* mu_cl; float* D1; float* D2;
+  float* split;   // [rows][2 * widest C_in]: the [hi | lo] operand of the 3xTF32 tensor-core convs
 };
 
 void plan_encode(const ev_matcha_cfg& c, int B, int Tx, Workspace& w, EncBuffers* e) {
@@ -182,6 +183,7 @@ void plan_encode(const ev_matcha_cfg& c, int B, int Tx, Workspace& w, EncBuffers
   e->mu_cl = w.take<float>(R * c.n_feats);
   e->D1 = w.take<float>(R * c.enc_filter_channels_dp);
   e->D2 = w.take<float>(R * c.enc_filter_channels_dp);
+  e->split = w.take<float>(R * 2 * std::max(std::max(H, c.enc_filter_channels), c.enc_filter_channels_dp));
 }
 
 }  // namespace
@@ -229,7 +231,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     for (int i = 0; i < 3; ++i) {
       Epilogue ep;
       ep.out_f32 = e.tmp; ep.f32_ld = C; ep.f32_bs = bsC;
-      EV_TRY(run_conv<float>(ctx, m.pre_conv[i], cur, C, bsC, B, Tx, ep, s));
+      EV_TRY(run_conv_tf32(ctx, m.pre_conv[i], cur, C, bsC, B, Tx, ep, e.split, s));
       LnArgs ln;
       ln.x = e.tmp; ln.x_ld = C; ln.gamma = m.pre_g[i]; ln.beta = m.pre_b[i]; ln.eps = 1e-4f; ln.post_relu = 1; ln.mask = mask;
       ln.out_f32 = pp[i & 1]; ln.f32_ld = C; ln.B = B; ln.T = Tx; ln.C = C;
@@ -239,7 +241,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     Epilogue ep;
     ep.res = e.h0; ep.res_ld = C; ep.res_bs = bsC;
     ep.out_act = e.X; ep.act_ld = H; ep.act_bs = bsH; ep.mask = mask; ep.mask_act = 1;
-    EV_TRY(run_conv<float>(ctx, m.pre_proj, cur, C, bsC, B, Tx, ep, s));
+    EV_TRY(run_conv_tf32(ctx, m.pre_proj, cur, C, bsC, B, Tx, ep, e.split, s));
   } else {
     EV_CUDA(ctx, cudaMemcpy2DAsync(e.X, (size_t)H * 4, e.h0, (size_t)C * 4, (size_t)C * 4, (size_t)B * Tx, cudaMemcpyDeviceToDevice, s));
   }
@@ -253,7 +255,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     const EncLayerW& L = m.enc[i];
     Epilogue ep;
     ep.out_f32 = e.qkv; ep.f32_ld = 3 * H; ep.f32_bs = (long long)Tx * 3 * H;
-    EV_TRY(run_conv<float>(ctx, L.qkv, e.X, H, bsH, B, Tx, ep, s));
+    EV_TRY(run_conv_tf32(ctx, L.qkv, e.X, H, bsH, B, Tx, ep, e.split, s));
     AttnArgs at;
     at.q = e.qkv; at.k = e.qkv + H; at.v = e.qkv + 2 * H; at.ld = 3 * H; at.bs = (long long)Tx * 3 * H;
     at.B = B; at.T = Tx; at.H = c.enc_heads; at.D = hd; at.scale = 1.0f / sqrtf((float)hd);
@@ -263,7 +265,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
     Epilogue eo;  // x + y
     eo.res = e.X; eo.res_ld = H; eo.res_bs = bsH; eo.out_f32 = e.tmp; eo.f32_ld = H; eo.f32_bs = bsH;
-    EV_TRY(run_conv<float>(ctx, L.o, e.att, H, bsH, B, Tx, eo, s));
+    EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH, B, Tx, eo, e.split, s));
     LnArgs l1;
     l1.x = e.tmp; l1.x_ld = H; l1.gamma = L.ln1_g; l1.beta = L.ln1_b; l1.eps = 1e-4f; l1.mask = mask;
     l1.out_f32 = e.X1; l1.f32_ld = H; l1.B = B; l1.T = Tx; l1.C = H;
@@ -271,11 +273,11 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     Epilogue e1;  // relu(conv_1(x*mask)) * mask
     e1.act = ACT_RELU; e1.mask = mask; e1.mask_act = 1;
     e1.out_act = e.F; e1.act_ld = c.enc_filter_channels; e1.act_bs = (long long)Tx * c.enc_filter_channels;
-    EV_TRY(run_conv<float>(ctx, L.ffn1, e.X1, H, bsH, B, Tx, e1, s));
+    EV_TRY(run_conv_tf32(ctx, L.ffn1, e.X1, H, bsH, B, Tx, e1, e.split, s));
     Epilogue e2;  // x + conv_2(..)*mask
     e2.mask = mask; e2.mask_pre = 1; e2.res = e.X1; e2.res_ld = H; e2.res_bs = bsH;
     e2.out_f32 = e.tmp; e2.f32_ld = H; e2.f32_bs = bsH;
-    EV_TRY(run_conv<float>(ctx, L.ffn2, e.F, c.enc_filter_channels, (long long)Tx * c.enc_filter_channels, B, Tx, e2, s));
+    EV_TRY(run_conv_tf32(ctx, L.ffn2, e.F, c.enc_filter_channels, (long long)Tx * c.enc_filter_channels, B, Tx, e2, e.split, s));
     LnArgs l2 = l1;
     l2.gamma = L.ln2_g; l2.beta = L.ln2_b; l2.out_f32 = e.X;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * H * 8.0, layer_norm_rows<float>(l2, s));
@@ -283,7 +285,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
   {  // mu = proj_m(x) * mask  (text_encoder.py:405) -> channel-first output
     Epilogue ep;
     ep.mask = mask; ep.mask_pre = 1; ep.out_f32 = e.mu_cl; ep.f32_ld = c.n_feats; ep.f32_bs = (long long)Tx * c.n_feats;
-    EV_TRY(run_conv<float>(ctx, m.proj_m, e.X, H, bsH, B, Tx, ep, s));
+    EV_TRY(run_conv_tf32(ctx, m.proj_m, e.X, H, bsH, B, Tx, ep, e.split, s));
     EV_LAUNCH(ctx, s, "cl_to_cf", 0, R * c.n_feats * 8.0, cl_to_cf(e.mu_cl, c.n_feats, (long long)Tx * c.n_feats, B, c.n_feats, Tx, mu_x, 1.0f, 0.0f, s));
   }
   {  // DurationPredictor (text_encoder.py:84-94): conv -> relu -> LN (x2), 1x1 proj, masks in between
@@ -291,17 +293,17 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     const long long bsF = (long long)Tx * Fd;
     Epilogue ep;
     ep.out_f32 = e.tmp; ep.f32_ld = Fd; ep.f32_bs = bsF;
-    EV_TRY(run_conv<float>(ctx, m.dp_conv1, e.X, H, bsH, B, Tx, ep, s));
+    EV_TRY(run_conv_tf32(ctx, m.dp_conv1, e.X, H, bsH, B, Tx, ep, e.split, s));
     LnArgs ln;
     ln.x = e.tmp; ln.x_ld = Fd; ln.pre_relu = 1; ln.gamma = m.dp_g1; ln.beta = m.dp_b1; ln.eps = 1e-4f; ln.mask = mask;
     ln.out_f32 = e.D1; ln.f32_ld = Fd; ln.B = B; ln.T = Tx; ln.C = Fd;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
-    EV_TRY(run_conv<float>(ctx, m.dp_conv2, e.D1, Fd, bsF, B, Tx, ep, s));
+    EV_TRY(run_conv_tf32(ctx, m.dp_conv2, e.D1, Fd, bsF, B, Tx, ep, e.split, s));
     ln.gamma = m.dp_g2; ln.beta = m.dp_b2; ln.out_f32 = e.D2;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
     Epilogue el;
     el.mask = mask; el.mask_pre = 1; el.out_f32 = logw; el.f32_ld = 1; el.f32_bs = Tx;
-    EV_TRY(run_conv<float>(ctx, m.dp_proj, e.D2, Fd, bsF, B, Tx, el, s));
+    EV_TRY(run_conv_tf32(ctx, m.dp_proj, e.D2, Fd, bsF, B, Tx, el, e.split, s));
     EV_LAUNCH(ctx, s, "durations", 0, R * 8.0, durations(logw, e.xlen32, B, Tx, length_scale, w_ceil, reinterpret_cast<long long*>(y_lengths), s));
   }
   return 0;

@@ -100,6 +100,18 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn = 0, in
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32 (32-bit operands, 10-bit mantissa), both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar) { mbar_arrive(bar); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

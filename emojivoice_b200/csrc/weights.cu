@@ -92,11 +92,45 @@ __global__ void pack_conv_kernel(const float* __restrict__ src, int C_out, int C
     if (dst_bf16) dst_bf16[((long long)tap * N_pad_tc + n_off + n) * K_pad + ci] = __float2bfloat16_rn(v);
   }
 }
+// 3xTF32 split of the fp32 weights, K-major: per (tap, n): [w_hi(K32) | w_lo(K32) | w_hi(K32)] with w_hi = w truncated to
+// tf32 (10-bit mantissa, low 13 bits cleared) and w_lo = w - w_hi (exact).  Pairs with activations [x_hi | x_hi | x_lo].
+__global__ void pack_conv_tf32_kernel(const float* __restrict__ src, int C_out, int C_in, int K, int taps, int n_local, int n_off,
+                                      float* __restrict__ dst, int N_pad_tc, int K32) {
+  const long long total = (long long)taps * C_in * n_local;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % n_local);
+    const int ci = (int)((idx / n_local) % C_in);
+    const int tap = (int)(idx / ((long long)n_local * C_in));
+    const float v = src[((long long)n * C_in + ci) * K + tap];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float lo = v - hi;
+    float* row = dst + ((long long)tap * N_pad_tc + n_off + n) * (3LL * K32);
+    row[ci] = hi;
+    row[K32 + ci] = lo;
+    row[2 * K32 + ci] = hi;
+  }
+}
+
+// x (rows x C fp32, row stride ld) -> [x_hi | x_lo] (rows x 2C): the A operand of the 3xTF32 path
+__global__ void split_tf32_kernel(const float* __restrict__ x, long long ld, int C, long long rows, float* __restrict__ out) {
+  const long long n4 = rows * (C >> 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C >> 2);
+    const int c = (int)(i - r * (C >> 2)) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    float4 h;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    *reinterpret_cast<float4*>(out + r * 2 * C + c) = h;
+    *reinterpret_cast<float4*>(out + r * 2 * C + C + c) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
 }  // namespace
 
 int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weight_names,
               const std::vector<std::string>& bias_names, int c_out_each, int c_in, int ksize, int stride, int pad,
-              int dilation, ConvKind kind, bool want_bf16, ConvWeights* out) {
+              int dilation, ConvKind kind, int tc_mode, ConvWeights* out) {
+  const bool want_bf16 = tc_mode == TC_BF16, want_tf32 = tc_mode == TC_TF32X3 && kind == CONV_NORMAL && stride == 1 && c_in % 32 == 0;
   ConvWeights w;
   const int parts = (int)weight_names.size();
   w.transposed = kind == CONV_TRANSPOSED;
@@ -132,6 +166,11 @@ int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weig
     EV_TRY(device_alloc(ctx, (size_t)w.taps * w.N_pad_tc * w.K_pad * sizeof(bf16), &p, true, ws.stream));
     w.w_bf16 = reinterpret_cast<bf16*>(p);
   }
+  if (want_tf32) {
+    w.K32 = (int)align_up(c_in, 32);
+    EV_TRY(device_alloc(ctx, (size_t)w.taps * w.N_pad_tc * 3 * w.K32 * sizeof(float), &p, true, ws.stream));
+    w.w_tf32 = reinterpret_cast<float*>(p);
+  }
   for (int i = 0; i < parts; ++i) {
     const ev_tensor* t = ws.get(weight_names[i], {(long long)c_out_each, (long long)c_in, (long long)ksize});
     if (!t) return ctx->err.rfind("missing", 0) == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
@@ -140,6 +179,11 @@ int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weig
     pack_conv_kernel<<<blocks, 256, 0, ws.stream>>>(t->data, c_out_each, c_in, ksize, w.transposed, stride, w.taps,
                                                     n_local, i * n_local, w.w_f32, w.N_pad, w.w_bf16, w.N_pad_tc, w.K_pad);
     EV_CUDA(ctx, cudaGetLastError());
+    if (w.w_tf32) {
+      pack_conv_tf32_kernel<<<blocks, 256, 0, ws.stream>>>(t->data, c_out_each, c_in, ksize, w.taps, n_local, i * n_local, w.w_tf32,
+                                                           w.N_pad_tc, w.K32);
+      EV_CUDA(ctx, cudaGetLastError());
+    }
   }
   if (!bias_names.empty()) {
     if ((int)bias_names.size() != parts) return fail(ctx, EV_ERR_INVALID, "bias list does not match weight list");
@@ -213,11 +257,48 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
       snprintf(buf, sizeof buf, " c%d n%d k%d d%d m%d", w.C_in, w.N, w.taps, w.dilation, g.M);
       nm += buf;
     }
-    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, T_in, w, e, s, &msg); }
+    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, 0, w, e, s, &msg); }
     if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   }
   return 0;
 }
+// fp32-accurate convolution on the tensor cores (3xTF32): x is split into [hi | lo] in `scratch` (B*T_in*2*C_in floats),
+// then one tcgen05 GEMM over the concatenated K does x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with fp32 accumulation.
+// Falls back to the CUDA-core kernel when the layer has no split weights or the tile path cannot serve the epilogue.
+int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x_ld, long long x_bs, int B, int T_in, Epilogue e,
+                  float* scratch, cudaStream_t s) {
+  const bool aligned = (e.f32_ld % 4 == 0) && (e.f32_bs % 4 == 0) && (e.act_ld % 4 == 0) && (e.res_ld % 4 == 0) && w.N % 4 == 0;
+  const bool act_ok = e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LRELU;
+  if (!w.w_tf32 || !scratch || x_bs != (long long)T_in * x_ld || !aligned || !act_ok || (e.out_act && e.out_f32) || !ctx->enc_tc)
+    return run_conv<float>(ctx, w, x, x_ld, x_bs, B, T_in, e, s);
+  ConvGeom g;
+  const int T_out = conv_geometry(w, B, T_in, &g);
+  e.bias = w.bias;
+  e.T_out = T_out;
+  e.phase_cout = w.N;
+  e.up_s = 1;
+  e.up_p = 0;
+  if (e.out_act) {   // the fp32 graph's "activated" output becomes the fp32 output of the tensor-core epilogue
+    e.out_f32 = reinterpret_cast<float*>(e.out_act); e.f32_ld = e.act_ld; e.f32_bs = e.act_bs; e.f32_is_act = 1;
+    e.out_act = nullptr;
+  }
+  const long long rows = (long long)B * T_in;
+  const double flops = 2.0 * B * (double)T_out * w.C_out * w.taps * w.C_in;
+  const double bytes = 4.0 * (rows * w.C_in + (double)w.taps * w.N * w.C_in + (double)B * T_out * w.C_out * (e.res ? 2 : 1));
+  {
+    const int blocks = (int)std::min<long long>(2048, ceil_div_ll(rows * (w.C_in / 4), 256));
+    cudaError_t ce;
+    { LaunchScope ls(ctx, s, "split_tf32", 0, 12.0 * rows * w.C_in); split_tf32_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w.C_in, rows, scratch); ce = cudaGetLastError(); }
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "split_tf32");
+  }
+  std::string msg;
+  cudaError_t ce;
+  const std::string nm = std::string("conv_tc_tf32x3") + ctx->prof_tag;
+  { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, scratch, 2LL * w.C_in, (long long)T_in * 2 * w.C_in, 1, w, e, s, &msg); }
+  if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch(tf32x3): " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
+  return 0;
+}
+
 template int run_conv<float>(ev_ctx*, const ConvWeights&, const float*, long long, long long, int, int, Epilogue, cudaStream_t);
 template int run_conv<bf16>(ev_ctx*, const ConvWeights&, const bf16*, long long, long long, int, int, Epilogue, cudaStream_t);
 

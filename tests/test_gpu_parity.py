@@ -81,6 +81,34 @@ def test_conv1d_kernel_matches_torch(ctx, case, prec):
     assert rel_l2(y.cpu(), ref) < 2e-6
 
 
+TF32_CASES = [  # B, Cin, T, Cout, K, pad, dil -- the text encoder's layer shapes (text_encoder.py) and ragged variants
+    (2, 192, 181, 192, 5, 2, 1), (2, 256, 181, 768, 1, 0, 1), (3, 256, 77, 768, 3, 1, 1), (2, 768, 181, 256, 3, 1, 1),
+    (1, 256, 300, 80, 1, 0, 1), (2, 256, 130, 256, 3, 1, 1), (1, 64, 9, 32, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", TF32_CASES)
+def test_conv1d_3xtf32_tensor_core_path_is_fp32_accurate(ctx, case):
+    """Opt-in tensor-core path for the text encoder (EV_ENC_TC=1): x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with tf32 operands.
+    It is ~1e-5 accurate (the tensor core's fp32 accumulation truncates), an order of magnitude looser than the fp32
+    CUDA-core kernel -- which is why the CUDA-core kernel stays the default wherever ceil(exp(logw)) is downstream."""
+    B, Cin, T, Cout, K, pad, dil = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv1d(x.double(), w.double(), b.double(), padding=pad, dilation=dil)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    err = {}
+    for prec in ("tf32x3", "fp32"):
+        y = torch.empty(ref.shape, device="cuda")
+        ctx.check(_lib.lib().ev_test_conv1d(ctx.handle, _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), B, Cin, T, Cout, K, 1, pad, dil, 0,
+                                            _lib.PREC[prec], _lib.ptr(y), _lib.stream_ptr()), "ev_test_conv1d")
+        err[prec] = rel_l2(y.cpu(), ref)
+    assert err["fp32"] < 1e-6
+    assert err["tf32x3"] < 2e-5, err
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", [(2, 200, 2, 0), (3, 77, 2, 1), (1, 668, 2, 0), (2, 64, 1, 0), (2, 129, 2, 1), (1, 1, 2, 0)])
 def test_decoder_attention_matches_torch_sdpa(ctx, case, prec):
