@@ -104,6 +104,12 @@ bool conv_tc_init(std::string* err);
 bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                         uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes, std::string* err);
 int tc_sm_count();
+
+// resblock_tc.cu: one fused HiFi-GAN ResBlock1 (six convs, residual stream resident in TMEM)
+bool resblock_tc_supported(int C, int k, const int* dil);
+cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
+                               const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
+                               int write_f32, cudaStream_t s, std::string* err);
 int conv_tc_pick_bn(int N);
 
 }  // namespace ev

@@ -58,6 +58,8 @@ struct HifiganW {
   ConvWeights conv_pre;
   ConvWeights ups[8];
   ConvWeights c1[8][4][3], c2[8][4][3];
+  float* bacc[8][4][3] = {};  // cumulative conv2 biases of each ResBlock (fused kernel: residual stream kept bias-free in TMEM)
+  bool fuse_resblocks = true; // EV_RB_FUSE=0: layer-by-layer convs everywhere
   float* post_w = nullptr;   // [7][C_last]
   float* post_b = nullptr;
   int c_last = 0, total_up = 1;

@@ -1,6 +1,8 @@
 // HiFi-GAN v1 generator on the GPU (hifigan/models.py:148-206): conv_pre, 4 x [LeakyReLU, polyphase transposed
 // conv, mean of three dilated ResBlock1 branches], LeakyReLU(0.01), conv_post, tanh, clamp.  Every conv is the
 // shared implicit GEMM; activations/residual adds/MRF mean are fused into its epilogue.
+#include <cstdlib>
+
 #include "ctx.cuh"
 
 using namespace ev;
@@ -28,6 +30,11 @@ __global__ void fold_weight_norm_kernel(const float* __restrict__ g, const float
   __syncthreads();
   const float scale = g[r] / sqrtf(red[0]);
   for (int i = threadIdx.x; i < cols; i += blockDim.x) w[(long long)r * cols + i] = vr[i] * scale;
+}
+
+__global__ void bias_cumsum_kernel(const float* b0, const float* b1, const float* b2, int C, float* o0, float* o1, float* o2) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { const float s0 = b0[c], s1 = s0 + b1[c]; o0[c] = s0; o1[c] = s1; o2[c] = s1 + b2[c]; }
 }
 
 __global__ void pack_post_kernel(const float* src, int C, int K, float* dst) {  // (1,C,K) -> [K][C]
@@ -110,6 +117,16 @@ extern "C" int ev_load_hifigan(ev_ctx* ctx, const ev_tensor* weights, int n_weig
         EV_TRY(make_conv(ctx, ws, {a + ".weight"}, {a + ".bias"}, ch, ch, rk, 1, (rk * dl - dl) / 2, dl, CONV_NORMAL, TC_BF16, &h.c1[i][j][l]));
         EV_TRY(make_conv(ctx, ws, {b + ".weight"}, {b + ".bias"}, ch, ch, rk, 1, (rk - 1) / 2, 1, CONV_NORMAL, TC_BF16, &h.c2[i][j][l]));
       }
+      for (int l = 0; l < 3; ++l) {
+        void* q;
+        EV_TRY(device_alloc(ctx, (size_t)align_up(ch, 4) * sizeof(float), &q, true, s));
+        h.bacc[i][j][l] = reinterpret_cast<float*>(q);
+      }
+      if (h.c2[i][j][0].bias && h.c2[i][j][1].bias && h.c2[i][j][2].bias) {
+        bias_cumsum_kernel<<<ceil_div(ch, 128), 128, 0, s>>>(h.c2[i][j][0].bias, h.c2[i][j][1].bias, h.c2[i][j][2].bias, ch,
+                                                             h.bacc[i][j][0], h.bacc[i][j][1], h.bacc[i][j][2]);
+        EV_CUDA(ctx, cudaGetLastError());
+      }
     }
   }
   h.c_last = c0 >> c.n_ups;
@@ -186,6 +203,31 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
     }
     const bool last_stage = (i == c.n_ups - 1);
     for (int j = 0; j < c.n_kernels; ++j) {
+      if constexpr (std::is_same<ActT, bf16>::value) {
+        // fused ResBlock: six convs in one kernel, residual stream resident in TMEM (resblock_tc.cu)
+        if (h.fuse_resblocks && c.n_kernels >= 2 && L >= 1024 &&
+            resblock_tc_supported(C, c.resblock_kernel_sizes[j], c.resblock_dilation_sizes[j])) {
+          const ConvWeights* c1p[3] = {&h.c1[i][j][0], &h.c1[i][j][1], &h.c1[i][j][2]};
+          const ConvWeights* c2p[3] = {&h.c2[i][j][0], &h.c2[i][j][1], &h.c2[i][j][2]};
+          const float* bp[3] = {h.bacc[i][j][0], h.bacc[i][j][1], h.bacc[i][j][2]};
+          const bool last_branch = j == c.n_kernels - 1;
+          const int mode = last_branch ? 2 : (j == 0 ? 0 : 1);
+          const int rk = c.resblock_kernel_sizes[j];
+          double fl = 0.0;
+          for (int l = 0; l < 3; ++l) fl += 2.0 * 2.0 * B * (double)L * C * (double)C * rk;
+          std::string msg;
+          cudaError_t ce;
+          {
+            char nm[48];
+            snprintf(nm, sizeof nm, "resblock_tc/voc c%d k%d", C, rk);
+            LaunchScope ls(ctx, s, ctx->prof_detail ? nm : "resblock_tc/voc", fl, (double)B * L * C * (4.0 + (mode ? 8.0 : 4.0)));
+            ce = resblock_tc_launch(C, rk, c1p, c2p, bp, v.x0, v.sum, (last_branch && !last_stage) ? v.stage_in : nullptr, B, (int)L, mode,
+                                    1.0f / (float)c.n_kernels, kSlope, last_stage ? 1 : 0, s, &msg);
+          }
+          if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "resblock_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
+          continue;
+        }
+      }
       const float* in_f32 = v.x0;
       const ActT* in_act = v.x0a;
       for (int l = 0; l < 3; ++l) {  // ResBlock1.forward (hifigan/models.py:90-97)

@@ -1,0 +1,448 @@
+// Fused HiFi-GAN ResBlock1 (hifigan/models.py:59-97) on tcgen05: all six convolutions of one block
+//     for l in 0..2:  x = x + conv2_l( lrelu( conv1_l( lrelu(x) ; dilation d_l ) ) )
+// run inside one kernel per time tile.  Only x (fp32, once) is read from and y (once) written to HBM -- the
+// layer-by-layer path moves 16 B per element per conv pair, i.e. ~6x more, and is HBM-bound for C <= 128.
+//
+// Per CTA (persistent, one per SM) and per window of W = MB*128 time steps (halo H = 6(k-1) recomputed per tile):
+//   * the fp32 RESIDUAL STREAM lives in TMEM (acc_x, MB x C columns) for the whole block: it is loaded once with
+//     tcgen05.st and every conv2 simply accumulates onto it (accumulate = 1), so the residual add costs nothing;
+//     conv2 biases are tracked as a per-channel offset that is added whenever acc_x is read.
+//   * conv1 accumulates into a second TMEM region (acc_mid).
+//   * ONE shared-memory operand buffer (bf16, K-major, hardware swizzle layout written by hand) holds lrelu(x) for
+//     conv1, is overwritten by lrelu(conv1 + b) for conv2, then by lrelu(x_new) for the next pair.  Taps are row
+//     offsets into it; zero margins / rows outside [0, L) implement each conv's own zero padding.
+//   * weight tiles [C x C] per (conv, tap, K-chunk) stream from L2 through a TMA ring.
+// Warps: 0 = TMA producer (weights), 1 = TMEM allocator + MMA issuer, 2..17 = 16 "epilogue" warps that load x, convert
+// accumulators into the next operand, and write y.  Phases alternate strictly MMA -> epilogue (two mbarriers); the
+// epilogue phases are short next to the MMA phases (<= 30 % even at k = 3).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "conv.cuh"
+#include "tc_ptx.cuh"
+
+namespace ev {
+using namespace tc;
+namespace {
+
+constexpr int RB_MAX_EPI_WARPS = 16;          // 16 epilogue warps (576 threads), or 8 when shared memory is needed for resident weights
+constexpr int RB_MARG = 32;            // zero rows on both sides of the operand buffer (>= largest tap reach, 25)
+constexpr int RB_STAGE_LD = 36;
+constexpr int RB_MAX_SLOTS = 8;
+
+struct RbMaps { CUtensorMap m[6]; };   // weights of conv1_0, conv2_0, conv1_1, conv2_1, conv1_2, conv2_2
+
+struct RbParams {
+  const float* x; long long x_bs;      // (b, t, c) fp32, dense rows of C
+  float* sum; long long sum_bs;        // fp32 (b, t, c): MRF accumulator / output
+  bf16* act_out; long long act_bs;     // optional bf16 (b, t, c): lrelu of the MRF mean (next stage's operand)
+  const float* bias1[3];               // conv1_l bias [C]
+  const float* bacc[3];                // sum_{i<=l} conv2_i bias [C]
+  int L, k, dil[3];
+  int mode;                            // 0: sum = y   1: sum += y   2: v = (sum + y) * inv_n -> sum (if write_f32) / act_out
+  float inv_n, slope_out;
+  int write_f32;
+  int tiles_per_item, total_tiles, Wv, H;
+  int w_slots;
+  int resident;                        // all 6*k weight tiles stay in shared memory (C = 32): no per-tap barrier traffic
+};
+
+template <int C> struct RbCfg {
+  static constexpr int MB = C == 128 ? 2 : 4;
+  static constexpr int W = MB * 128;
+  static constexpr int KC = C == 128 ? 2 : 1;            // K-chunks = planes of the operand buffer
+  static constexpr int RB = C == 32 ? 64 : 128;          // bytes per operand row per plane (= swizzle width)
+  static constexpr int KS = RB / 32;                     // UMMA K-steps (16 bf16) per chunk
+  static constexpr int A_ROWS = W + 2 * RB_MARG;
+  static constexpr int A_PLANE = A_ROWS * RB;
+  static constexpr int W_TILE = C * RB;                  // one weight tile: C output rows x RB bytes
+  static constexpr int NCB = C / 32;                     // 32-column blocks per accumulator
+  static constexpr uint32_t TMEM_COLS = 2 * MB * C <= 256 ? 256 : 512;
+  static constexpr uint32_t LAYOUT = RB == 128 ? 2u : 4u;
+  static constexpr int STAGE_WARP = 32 * RB_STAGE_LD * 4;
+};
+
+template <int C>
+__global__ void __launch_bounds__(64 + 32 * RB_MAX_EPI_WARPS, 1)
+resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ RbParams p) {
+  using G = RbCfg<C>;
+  constexpr int MB = G::MB, W = G::W, KC = G::KC, RB = G::RB, KS = G::KS, NCB = G::NCB;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t w_full[RB_MAX_SLOTS], w_empty[RB_MAX_SLOTS], mma_done, epi_done;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_s = base, w_s = base + KC * G::A_PLANE;
+  uint8_t* a_gen = base_gen;
+  const int n_epi = (int)(blockDim.x >> 5) - 2, n_slots = n_epi >> 2;   // epilogue warps; warps per TMEM lane quadrant
+  const int w_tiles = p.resident ? 6 * p.k : p.w_slots;
+  float* stage = reinterpret_cast<float*>(base_gen + KC * G::A_PLANE + w_tiles * G::W_TILE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
+    for (int s = 0; s < RB_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(&mma_done, 1);
+    mbar_init(&epi_done, (blockDim.x >> 5) - 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(G::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the operand buffer once: its margins are never written again
+  for (int i = threadIdx.x; i < KC * G::A_PLANE / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_gen)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t acc_x = tmem_base, acc_mid = tmem_base + (uint32_t)(MB * C);
+  const int k = p.k, half_k = (p.k - 1) / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: weight tiles in the exact order the MMA warp consumes them
+      int sl = 0;
+      uint32_t ph = 1;
+      if (p.resident) {     // every (conv, tap) tile once, kept for the CTA's lifetime
+        mbar_expect_tx(&w_full[0], (uint32_t)(6 * k * G::W_TILE));
+        for (int ci = 0; ci < 6; ++ci)
+          for (int j = 0; j < k; ++j)
+            tma_load_3d(w_s + (uint32_t)((ci * k + j) * G::W_TILE), &maps.m[ci], &w_full[0], 0, 0, j);
+      }
+      for (int tile = blockIdx.x; tile < p.total_tiles && !p.resident; tile += gridDim.x) {
+        for (int ci = 0; ci < 6; ++ci)
+          for (int kc = 0; kc < KC; ++kc)
+            for (int j = 0; j < k; ++j) {
+              mbar_wait(&w_empty[sl], ph);
+              mbar_expect_tx(&w_full[sl], (uint32_t)G::W_TILE);
+              tma_load_3d(w_s + (uint32_t)(sl * G::W_TILE), &maps.m[ci], &w_full[sl], kc * (RB / 2), 0, j);
+              if (++sl == p.w_slots) { sl = 0; ph ^= 1u; }
+            }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues)
+    constexpr uint32_t idesc = make_idesc(128, C);
+    const uint32_t hi = ((uint32_t)(8 * RB) >> 4) | (1u << 14) | (G::LAYOUT << 29);
+    const uint32_t a_lo0 = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), w_lo0 = ((w_s & 0x3FFFFu) >> 4) | (1u << 16);
+    int sl = 0;
+    uint32_t wph = 0, eph = 0;
+    const bool resident = p.resident != 0;
+    if (resident) { mbar_wait(&w_full[0], 0); tcgen05_fence_after(); }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int ci = 0; ci < 6; ++ci) {
+        const int l = ci >> 1, second = ci & 1;
+        const int d = second ? 1 : p.dil[l];
+        const uint32_t d_tmem = second ? acc_x : acc_mid;
+        mbar_wait(&epi_done, eph);          // the operand buffer holds this conv's input
+        eph ^= 1u;
+        tcgen05_fence_after();
+        uint32_t fresh = second ? 0u : 1u;  // conv2 accumulates onto the residual stream from its first MMA on
+        if (resident) {                     // KC == 1: one straight run of MMAs per conv, no barrier traffic
+          if (elect_one()) {
+            uint32_t b_lo = w_lo0 + (uint32_t)((ci * k * G::W_TILE) >> 4);
+            uint32_t a_lo = a_lo0 + (uint32_t)(((RB_MARG - half_k * d) * RB) >> 4);
+            const uint32_t a_step = (uint32_t)((d * RB) >> 4), b_step = (uint32_t)(G::W_TILE >> 4);
+            for (int j = 0; j < k; ++j) {
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                  const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((mb * 128 * RB) >> 4) + 2u * ks);
+                  const uint64_t db = ((uint64_t)hi << 32) | (b_lo + 2u * ks);
+                  umma_bf16(d_tmem + (uint32_t)(mb * C), da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
+                }
+              }
+              fresh = 0;
+              a_lo += a_step;
+              b_lo += b_step;
+            }
+            umma_commit(&mma_done);
+          }
+          __syncwarp();
+          continue;
+        }
+        for (int kc = 0; kc < KC; ++kc) {
+          for (int j = 0; j < k; ++j) {
+            mbar_wait(&w_full[sl], wph);
+            tcgen05_fence_after();
+            const uint32_t b_lo = w_lo0 + (uint32_t)((sl * G::W_TILE) >> 4);
+            const uint32_t a_lo = a_lo0 + (uint32_t)((kc * G::A_PLANE + (RB_MARG + (j - half_k) * d) * RB) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                  const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((mb * 128 * RB) >> 4) + 2u * ks);
+                  const uint64_t db = ((uint64_t)hi << 32) | (b_lo + 2u * ks);
+                  umma_bf16(d_tmem + (uint32_t)(mb * C), da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
+                }
+              }
+              umma_commit(&w_empty[sl]);
+            }
+            __syncwarp();
+            fresh = 0;
+            if (++sl == p.w_slots) { sl = 0; wph ^= 1u; }
+          }
+        }
+        if (elect_one()) umma_commit(&mma_done);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------- 16 epilogue warps.  Warp (q, slot): TMEM lanes [32q, 32q+32), blocks slot, slot+4, ... of the
+    // MB*NCB (m-block, 32-column block) pairs of that lane quadrant.
+    const int ew = warp - 2, q = warp & 3, slot = ew >> 2;   // n_slots warps share a lane quadrant
+    const int sub = lane >> 3, cl = (lane & 7) * 4;
+    float* wstage = stage + ew * (32 * RB_STAGE_LD);
+    const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+    const int L = p.L, H = p.H;
+    uint32_t mph = 0;
+
+    // write 32 activated channels of one row into the operand buffer (bf16, swizzled K-major layout)
+    auto put_operand = [&](int wr, int cb, const float (&v)[32]) {
+      const int row = RB_MARG + wr;
+      const int plane = (cb * 32) / (RB / 2), c16 = ((cb * 32) % (RB / 2)) / 8;     // 16-byte chunk index inside the row
+      uint8_t* rp = a_gen + plane * G::A_PLANE + row * RB;
+      const int sw = RB == 128 ? (row & 7) : ((row >> 1) & 3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * e], v[8 * i + 2 * e + 1]);
+          w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(rp + (((c16 + i) ^ sw) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    };
+    auto phase_done = [&]() {
+      tcgen05_fence_before();
+      fence_proxy_async();               // operand buffer writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&epi_done);
+    };
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_item, ti = tile - b * p.tiles_per_item;
+      const int w0 = ti * p.Wv - H;
+      const float* xb = p.x + b * p.x_bs;
+      // ---- phase 0: x -> acc_x (fp32, TMEM) and lrelu(x) -> operand buffer
+#pragma unroll 1
+      for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+        const int mb = blk / NCB, cb = blk - mb * NCB;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {          // coalesced: 8 lanes x float4 per row, 4 rows per instruction
+          const int wr = mb * 128 + q * 32 + u * 4 + sub, t = w0 + wr;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t >= 0 && t < L) v = *reinterpret_cast<const float4*>(xb + (long long)t * C + cb * 32 + cl);
+          *reinterpret_cast<float4*>(wstage + (u * 4 + sub) * RB_STAGE_LD + cl) = v;
+        }
+        __syncwarp();
+        uint32_t raw[32];
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(wstage + lane * RB_STAGE_LD + j);
+          raw[j] = __float_as_uint(v.x); raw[j + 1] = __float_as_uint(v.y); raw[j + 2] = __float_as_uint(v.z); raw[j + 3] = __float_as_uint(v.w);
+          a[j] = fmaxf(v.x, 0.1f * v.x); a[j + 1] = fmaxf(v.y, 0.1f * v.y); a[j + 2] = fmaxf(v.z, 0.1f * v.z); a[j + 3] = fmaxf(v.w, 0.1f * v.w);
+        }
+        tmem_st32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
+        put_operand(mb * 128 + q * 32 + lane, cb, a);
+        __syncwarp();
+      }
+      tmem_st_wait();
+      phase_done();
+
+#pragma unroll 1
+      for (int l = 0; l < 3; ++l) {
+        // ---- after conv1_l: operand <- lrelu(acc_mid + b1), zero outside the sequence (conv2's zero padding)
+        mbar_wait(&mma_done, mph);
+        mph ^= 1u;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+          const int mb = blk / NCB, cb = blk - mb * NCB;
+          const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
+          const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
+          uint32_t raw[32];
+          tmem_ld32(acc_mid + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1[l] + cb * 32 + j));
+            const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
+            const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
+            a[j] = fmaxf(v0, 0.1f * v0) * keep; a[j + 1] = fmaxf(v1, 0.1f * v1) * keep;
+            a[j + 2] = fmaxf(v2, 0.1f * v2) * keep; a[j + 3] = fmaxf(v3, 0.1f * v3) * keep;
+          }
+          put_operand(wr, cb, a);
+        }
+        phase_done();
+        // ---- after conv2_l: acc_x now holds x_new - (accumulated conv2 biases)
+        mbar_wait(&mma_done, mph);
+        mph ^= 1u;
+        tcgen05_fence_after();
+#pragma unroll 1
+        for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+          const int mb = blk / NCB, cb = blk - mb * NCB;
+          const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
+          uint32_t raw[32];
+          tmem_ld32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
+          float a[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bacc[l] + cb * 32 + j));
+            a[j] = __uint_as_float(raw[j]) + bv.x; a[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+            a[j + 2] = __uint_as_float(raw[j + 2]) + bv.z; a[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+          }
+          if (l < 2) {
+            const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.1f * a[j]) * keep;
+            put_operand(wr, cb, a);
+          } else {
+            // ---- block output: transpose through the private buffer, then coalesced rows
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(wstage + lane * RB_STAGE_LD + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int wr2 = mb * 128 + q * 32 + u * 4 + sub, t2 = w0 + wr2;
+              if (wr2 < H || wr2 >= W - H || t2 < 0 || t2 >= L) continue;
+              float4 v = *reinterpret_cast<const float4*>(wstage + (u * 4 + sub) * RB_STAGE_LD + cl);
+              const long long off = (long long)t2 * C + cb * 32 + cl;
+              float* sp = p.sum + b * p.sum_bs + off;
+              if (p.mode >= 1) {
+                const float4 s4 = *reinterpret_cast<const float4*>(sp);
+                v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+              }
+              if (p.mode == 2) { v.x *= p.inv_n; v.y *= p.inv_n; v.z *= p.inv_n; v.w *= p.inv_n; }
+              if (p.mode < 2 || p.write_f32) *reinterpret_cast<float4*>(sp) = v;
+              if (p.mode == 2 && p.act_out) {
+                const float s = p.slope_out;
+                __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v.x, s * v.x), fmaxf(v.y, s * v.y));
+                __nv_bfloat162 hi2 = __floats2bfloat162_rn(fmaxf(v.z, s * v.z), fmaxf(v.w, s * v.w));
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+                *reinterpret_cast<uint2*>(p.act_out + b * p.act_bs + off) = pk;
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (l < 2) phase_done();
+      }
+      tcgen05_fence_before();   // acc_x is rewritten by the next tile's phase 0
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
+  }
+}
+
+int g_rb_resident = 1;   // EV_RB_RESIDENT=0: stream weights through the ring even when they would fit
+
+template <int C>
+cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
+  using G = RbCfg<C>;
+  p.H = 6 * (p.k - 1);                    // sum over the three pairs of (k-1)/2 * (d_l + 1), d = 1, 3, 5
+  p.Wv = G::W - 2 * p.H;
+  p.tiles_per_item = ceil_div(p.L, p.Wv);
+  p.total_tiles = p.tiles_per_item * B;
+  const int limit = 224 * 1024;
+  const int fixed16 = 1024 + G::KC * G::A_PLANE + 16 * G::STAGE_WARP, fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP;
+  const int res_bytes = 6 * p.k * G::W_TILE;
+  int n_epi = 16, smem;
+  p.resident = 0;
+  if (G::KC == 1 && g_rb_resident && fixed16 + res_bytes <= limit) { p.resident = 1; smem = fixed16 + res_bytes; }
+  else if (G::KC == 1 && g_rb_resident && fixed8 + res_bytes <= limit) { p.resident = 1; n_epi = 8; smem = fixed8 + res_bytes; }
+  else {
+    int slots = std::min((limit - fixed16) / G::W_TILE, RB_MAX_SLOTS);
+    if (slots < 3) return cudaErrorInvalidConfiguration;
+    p.w_slots = slots;
+    smem = fixed16 + slots * G::W_TILE;
+  }
+  if (p.resident) p.w_slots = 1;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (ce != cudaSuccess) return ce;
+    configured = true;
+  }
+  const int grid = std::min(p.total_tiles, tc_sm_count());
+  // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
+  resblock_tc_kernel<C><<<grid, 64 + 32 * n_epi, std::max(smem, 120 * 1024), s>>>(maps, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int g_rb_policy = -1;    // EV_RB_FUSE: 0 = never, 1 = where measured faster (default), 2 = wherever the kernel can run
+
+bool resblock_tc_supported(int C, int k, const int* dil) {
+  if (g_rb_policy < 0) { const char* v = getenv("EV_RB_FUSE"); g_rb_policy = v ? atoi(v) : 1; }
+  if (g_rb_policy == 0) return false;
+  if (C != 32 && C != 64 && C != 128) return false;
+  if (k != 3 && k != 7 && k != 11) return false;
+  if (dil[0] != 1 || dil[1] != 3 || dil[2] != 5) return false;
+  if (g_rb_policy >= 2) return true;
+  // Measured on B200 (profiles/r01_layers_v11.txt vs v9, us per ResBlock at B=32 x 668 frames, fused / layer-by-layer):
+  //   C=128: k3 1258/1686  k7 2804/2319  k11 -/3036     C=64: k3 1084/1764  k7 1999/2145  k11 2864/2793
+  //   C=32 : k3  919/1644  k7 1760/1953  k11 2784/2238
+  // The fused kernel wins where the layer-by-layer path is HBM/epilogue-bound (k = 3, and k = 7 at C <= 64); at larger k
+  // the layer-by-layer convs are already MMA-bound and the halo recompute (H = 6(k-1) rows per window side) costs more.
+  if (k == 3) return true;
+  if (k == 7) return C <= 64;
+  return false;
+}
+
+// One fused ResBlock1.  c1[l] / c2[l]: packed conv weights (bf16 K-major, as conv_tc uses); bacc[l] = cumulative conv2
+// biases (device, [C]).  x, sum: fp32 (B, L, C); act_out: bf16 (B, L, C) or nullptr.
+cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
+                               const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
+                               int write_f32, cudaStream_t s, std::string* err) {
+  { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0); once = true; } }
+  RbMaps maps;
+  RbParams p{};
+  const int rb = C == 32 ? 64 : 128;
+  for (int l = 0; l < 3; ++l) {
+    const ConvWeights* cw[2] = {c1[l], c2[l]};
+    for (int h = 0; h < 2; ++h) {
+      const ConvWeights& w = *cw[h];
+      if (!w.w_bf16 || w.C_in != C || w.N != C || w.taps != k || w.N_pad_tc != C || !w.bias) {
+        if (err) *err = "resblock_tc: unexpected weight packing";
+        return cudaErrorInvalidValue;
+      }
+      if (!tc_encode_bf16_map(&maps.m[2 * l + h], w.w_bf16, (uint64_t)w.K_pad, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, (uint64_t)w.K_pad * 2,
+                              (uint64_t)w.K_pad * w.N_pad_tc * 2, (uint32_t)(rb / 2), (uint32_t)C, rb, err))
+        return cudaErrorInvalidValue;
+    }
+    p.bias1[l] = c1[l]->bias;
+    p.bacc[l] = bacc[l];
+    p.dil[l] = c1[l]->dilation;
+  }
+  p.x = x; p.x_bs = (long long)L * C;
+  p.sum = sum; p.sum_bs = (long long)L * C;
+  p.act_out = act_out; p.act_bs = (long long)L * C;
+  p.L = L; p.k = k; p.mode = mode; p.inv_n = inv_n; p.slope_out = slope_out; p.write_f32 = write_f32;
+  switch (C) {
+    case 32: return launch_rb<32>(maps, p, B, s);
+    case 64: return launch_rb<64>(maps, p, B, s);
+    default: return launch_rb<128>(maps, p, B, s);
+  }
+}
+
+}  // namespace ev
