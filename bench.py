@@ -160,6 +160,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true",
+                    help="after warm-up, bracket ONE step with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,6 +243,15 @@ def main():
     t_pad = int(out["t_pad"])
     ws_bytes = (_lib_mod.lib().ev_vocode_workspace_bytes(voc._ctx.handle, BATCH, int(out["mel"].shape[2])) +
                 _lib_mod.lib().ev_decode_workspace_bytes(model._ctx.handle, BATCH, t_pad, N_TIMESTEPS))
+
+    if args.profile_one_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_step": True, "t_pad": t_pad, "frames": frames}))
+        return
 
     # ---------------- timed region: K steps, inputs resident in HBM
     sampler = ClockSampler(local_rank)
