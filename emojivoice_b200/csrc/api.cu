@@ -38,7 +38,7 @@ extern "C" int ev_create(ev_ctx** out, int device) {
   ev_ctx* ctx = new ev_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  { const char* v = getenv("EV_ENC_TC"); ctx->enc_tc = v && atoi(v) != 0; }
+  { const char* v = getenv("EV_ENC_TC"); ctx->enc_tc = !(v && atoi(v) == 0); }
   *out = ctx;
   return EV_OK;
 }

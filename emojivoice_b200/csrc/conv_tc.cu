@@ -66,6 +66,8 @@ struct TcParams {
   uint32_t idesc;               // instruction descriptor (kind::f16 bf16, or kind::tf32)
   int tf32;                     // operands are 32-bit (3xTF32 split path): K-chunks walk the sections [hi | hi | lo] of A
   int kch1;                     // K-chunks per section (== kchunks unless tf32)
+  int flush_kc;                 // K-chunks per accumulation group: the TMEM partial sum is flushed into an fp32 master
+                                // accumulator (rounded adds) after every group; == kchunks means one group per tile
   int sec_off[3];               // column offset of each A section
   uint32_t tap_first16;         // (byte offset of tap 0's first row inside a haloed tile) >> 4
   uint32_t tap_step16;          // (bytes from one tap's first row to the next one's) >> 4, two's complement when negative
@@ -206,19 +208,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
     const bool resident = p.resident != 0, ks4 = p.ksteps == 4;
     const uint32_t acc_stride = (uint32_t)(p.mb * BN);
-    int sa = 0, sb = 0, ti = 0;
+    int sa = 0, sb = 0, vt = 0;     // vt counts accumulator-set uses: one per tile, or one per flush group (3xTF32)
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
+    const int flush_kc = p.flush_kc;
     if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int mt = (tile / n_tiles) % m_tiles;
       const int vmb = min(p.mb, (p.g.M - mt * tile_rows + BM - 1) / BM);     // m-blocks that hold valid rows
-      const int buf = ti & 1;
-      mbar_wait(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator set
-      tcgen05_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)buf * acc_stride;
+      int buf = 0, in_group = 0;
+      uint32_t d_tmem = 0;
       uint32_t acc = 0;
       uint32_t b_res_lo = b_lo0;    // resident weights: tiles are laid out in (K-chunk, tap) order
       for (int kc = 0; kc < kchunks; ++kc) {
+        if (in_group == 0) {        // open an accumulation group on the next accumulator set
+          buf = vt & 1;
+          mbar_wait(&acc_empty[buf], ((uint32_t)(vt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator set
+          tcgen05_fence_after();
+          d_tmem = tmem_base + (uint32_t)buf * acc_stride;
+          acc = 0;
+        }
         for (int g = 0; g < n_groups; ++g) {
           mbar_wait(&a_full[sa], pa);
           tcgen05_fence_after();
@@ -248,9 +256,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
+        if (++in_group == flush_kc || kc == kchunks - 1) {   // group complete -> epilogue (output pass or partial-sum flush)
+          if (elect_one()) umma_commit(&acc_full[buf]);
+          __syncwarp();
+          in_group = 0;
+          ++vt;
+        }
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);       // accumulators complete -> epilogue
-      __syncwarp();
     }
   } else {
     // ---------------- epilogue (warps 2..9).  Warp (q, half) owns TMEM lanes [32q, 32q+32) and every second 32-column
@@ -279,8 +291,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, M = p.g.M, N = p.g.N, T_out = e.T_out;
     const int up_s = e.up_s, up_p = e.up_p;
 
-    int ti = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++ti) {
+    int ti = 0;                      // accumulator-set use counter (see the MMA warp's vt)
+    const int n_grp = (p.kchunks + p.flush_kc - 1) / p.flush_kc;   // accumulation groups per tile (1 unless 3xTF32)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti += n_grp) {
       const int nt = tile % n_tiles, rest = tile / n_tiles, mt = rest % m_tiles, b = rest / m_tiles;
       const int m0 = mt * tile_rows, n0 = nt * BN;
       const int vmb = min(p.mb, (M - m0 + BM - 1) / BM);
@@ -366,24 +379,48 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             rr[u] = ok ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        if (!waited) {
-          mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
-          tcgen05_fence_after();
-          waited = true;
-        }
-        {
-          uint32_t raw[32];
-          tmem_ld32(lane_addr + (uint32_t)(buf * p.mb * BN + mb * BN + cb * 32), raw);
+        if (n_grp > 1) {
+          // two-level accumulation (3xTF32): this warp owns exactly one block; every group's TMEM partial sum is added
+          // with rounded fp32 adds into the master accumulator kept in the warp's transpose buffer
+#pragma unroll 1
+          for (int grp = 0; grp < n_grp; ++grp) {
+            const int v = ti + grp, vb = v & 1;
+            mbar_wait(&acc_full[vb], (uint32_t)(v >> 1) & 1u);
+            tcgen05_fence_after();
+            uint32_t raw[32];
+            tmem_ld32(lane_addr + (uint32_t)(vb * p.mb * BN + mb * BN + cb * 32), raw);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[vb]);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<uint4*>(srow_w + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
-        }
-        if (blk + n_slots >= n_blk) {      // last TMEM read of this warp for the tile: hand the accumulators back
-          tcgen05_fence_before();
+            for (int j = 0; j < 32; j += 4) {
+              float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (grp > 0) m4 = *reinterpret_cast<const float4*>(srow_w + j);
+              m4.x += __uint_as_float(raw[j]); m4.y += __uint_as_float(raw[j + 1]); m4.z += __uint_as_float(raw[j + 2]); m4.w += __uint_as_float(raw[j + 3]);
+              *reinterpret_cast<float4*>(srow_w + j) = m4;
+            }
+          }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        } else {
+          if (!waited) {
+            mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+            tcgen05_fence_after();
+            waited = true;
+          }
+          {
+            uint32_t raw[32];
+            tmem_ld32(lane_addr + (uint32_t)(buf * p.mb * BN + mb * BN + cb * 32), raw);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<uint4*>(srow_w + j) = make_uint4(raw[j], raw[j + 1], raw[j + 2], raw[j + 3]);
+          }
+          if (blk + n_slots >= n_blk) {      // last TMEM read of this warp for the tile: hand the accumulators back
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (p.vec_ok) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sb4 = bias4;
           if (n_ok && e.bias) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + co));
@@ -446,9 +483,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();                // the transpose buffer may be overwritten by the next block
       }
       if (slot >= n_blk) {           // a warp without a block in this tile still keeps step with the accumulator hand-over
-        mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
-        if (lane == 0) mbar_arrive(&acc_empty[buf]);
-        __syncwarp();
+        for (int grp = 0; grp < n_grp; ++grp) {
+          const int v = ti + grp;
+          mbar_wait(&acc_full[v & 1], (uint32_t)(v >> 1) & 1u);
+          if (lane == 0) mbar_arrive(&acc_empty[v & 1]);
+          __syncwarp();
+        }
       }
     }
   }
@@ -493,6 +533,7 @@ int g_bk32_mode = 1;       // EV_TC_BK32=0 disables the 64-byte-swizzle path for
 int g_cta2_mode = 1;       // EV_TC_CTA2=0 keeps one CTA per SM
 int g_wide_mode = 1;       // EV_TC_WIDE=0 keeps 8 epilogue warps
 int g_lean_mode = 1;       // EV_TC_LEAN=0 disables the activation-only epilogue path
+int g_tf32_flush = 1;      // EV_TF32_FLUSH=0: 3xTF32 without two-level accumulation (shows the tensor core's truncation error)
 
 // Shared-memory plan of one launch for `k` CTAs per SM with `epi_warps` epilogue warps; false when the rings do not fit.
 template <int BN>
@@ -534,10 +575,13 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   // otherwise one CTA with 16 epilogue warps (the epilogue is issue-bound: more warps hide its dependent latencies)
   int k = 1, smem = 0, threads = NUM_THREADS_WIDE;
   bool ok = false;
-  if (g_cta2_mode && k_tmem >= 2 && p.total_tiles > g_sm_count && p.mb * (BN / 32) <= 4 && plan_smem<BN>(p, 2, 8, &smem)) {
+  const bool flush = p.flush_kc < p.kchunks;
+  if (flush && (BN != 128 || p.mb != 1)) return cudaErrorInvalidConfiguration;   // one block per epilogue warp
+  if (!flush && g_cta2_mode && k_tmem >= 2 && p.total_tiles > g_sm_count && p.mb * (BN / 32) <= 4 && plan_smem<BN>(p, 2, 8, &smem)) {
     k = 2; threads = NUM_THREADS; ok = true;
   }
-  if (!ok && g_wide_mode && plan_smem<BN>(p, 1, 16, &smem)) ok = true;
+  if (!ok && (g_wide_mode || flush) && plan_smem<BN>(p, 1, 16, &smem)) ok = true;
+  if (!ok && flush) return cudaErrorInvalidConfiguration;
   if (!ok) {
     threads = NUM_THREADS;
     if (!plan_smem<BN>(p, 1, 8, &smem)) return cudaErrorInvalidConfiguration;
@@ -606,6 +650,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     g_cta2_mode = env_int("EV_TC_CTA2", 1);
     g_wide_mode = env_int("EV_TC_WIDE", 1);
     g_lean_mode = env_int("EV_TC_LEAN", 1);
+    g_tf32_flush = env_int("EV_TF32_FLUSH", 1);
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
   const int BN = conv_tc_pick_bn(g.N);
@@ -623,6 +668,8 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     p.kchunks = 3 * p.kch1;
     p.sec_off[0] = 0; p.sec_off[1] = 0; p.sec_off[2] = g.C_in;
     p.idesc = make_idesc_tf32(BM, BN);
+    p.flush_kc = std::max(1, 16 / (g.taps * p.ksteps));    // <= 16 truncating tensor-core accumulations per partial sum
+    if (g_tf32_flush == 0) p.flush_kc = p.kchunks;
   } else {
     p.bk = (g_bk32_mode && g.C_in <= 32) ? 32 : 64;
     p.row_bytes = p.bk * 2;
@@ -631,6 +678,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     p.kch1 = p.kchunks;
     p.sec_off[0] = p.sec_off[1] = p.sec_off[2] = 0;
     p.idesc = make_idesc(BM, BN);
+    p.flush_kc = p.kchunks;
   }
   p.desc_sbo = 8u * (uint32_t)p.row_bytes;
   p.desc_layout = p.row_bytes == 128 ? 2u : 4u;
@@ -664,6 +712,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     };
     p.mb = (g.M > BM && cost(2) <= cost(1)) ? 2 : 1;
     if (g_mb_mode == 1 || g_mb_mode == 2) p.mb = g_mb_mode;
+    if (tf32x3) p.mb = 1;            // two-level accumulation: one 32 x 32 block per epilogue warp (16 warps, 128 x 128 tile)
     if (p.mb > MB_MAX) p.mb = MB_MAX;
   }
   // halo reuse: all taps read one tile when they share the column origin and the row span fits two TMA boxes

@@ -82,10 +82,11 @@ struct ev_ctx {
   ev::MatchaW matcha;
   ev::HifiganW hifigan;
   // optional per-launch CUDA-event timing (ev_profile_begin/end); off in normal operation
-  // text encoder convs on tcgen05 via the 3xTF32 split: OPT-IN (EV_ENC_TC=1).  Measured 7.5e-6 relative error against
-  // 3.8e-7 for the fp32 CUDA-core kernel (the tensor core's fp32 accumulation truncates; K ~ 3000), which would make
-  // ceil(exp(logw)) flip ~20x more often -- durations must stay bit-exact, so the default is the CUDA-core path.
-  bool enc_tc = false;
+  // text encoder convs on tcgen05 via the 3xTF32 split with TWO-LEVEL ACCUMULATION (EV_ENC_TC=0: fp32 CUDA cores).
+  // The tensor core's fp32 accumulation truncates: over K ~ 3000 a single TMEM accumulator measures 2e-6..2e-5 relative
+  // error; flushing the partial sum into an fp32 master accumulator (rounded adds) every <= 16 MMAs brings it to
+  // 4.0-4.9e-7, the same as the fp32 CUDA-core kernel (2e-7..6e-7) -- accurate enough for ceil(exp(logw)).
+  bool enc_tc = true;
   bool profiling = false;
   bool prof_detail = false;    // EV_PROF_DETAIL=1: conv kernel classes carry the layer shape
   const char* prof_tag = "";   // appended to conv kernel names while profiling (enc / dec / voc)

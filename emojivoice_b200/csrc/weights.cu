@@ -269,7 +269,8 @@ int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x
                   float* scratch, cudaStream_t s) {
   const bool aligned = (e.f32_ld % 4 == 0) && (e.f32_bs % 4 == 0) && (e.act_ld % 4 == 0) && (e.res_ld % 4 == 0) && w.N % 4 == 0;
   const bool act_ok = e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LRELU;
-  if (!w.w_tf32 || !scratch || x_bs != (long long)T_in * x_ld || !aligned || !act_ok || (e.out_act && e.out_f32) || !ctx->enc_tc)
+  if (!w.w_tf32 || !scratch || x_bs != (long long)T_in * x_ld || !aligned || !act_ok || (e.out_act && e.out_f32) || !ctx->enc_tc ||
+      conv_tc_pick_bn(w.N) != 128)   // two-level accumulation is built for 128-wide tiles (one 32 x 32 block per epilogue warp)
     return run_conv<float>(ctx, w, x, x_ld, x_bs, B, T_in, e, s);
   ConvGeom g;
   const int T_out = conv_geometry(w, B, T_in, &g);

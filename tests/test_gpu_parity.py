@@ -83,15 +83,15 @@ def test_conv1d_kernel_matches_torch(ctx, case, prec):
 
 TF32_CASES = [  # B, Cin, T, Cout, K, pad, dil -- the text encoder's layer shapes (text_encoder.py) and ragged variants
     (2, 192, 181, 192, 5, 2, 1), (2, 256, 181, 768, 1, 0, 1), (3, 256, 77, 768, 3, 1, 1), (2, 768, 181, 256, 3, 1, 1),
-    (1, 256, 300, 80, 1, 0, 1), (2, 256, 130, 256, 3, 1, 1), (1, 64, 9, 32, 3, 1, 1),
+    (1, 256, 300, 80, 1, 0, 1), (2, 256, 130, 256, 3, 1, 1), (1, 64, 9, 160, 3, 1, 1),
 ]
 
 
 @pytest.mark.parametrize("case", TF32_CASES)
 def test_conv1d_3xtf32_tensor_core_path_is_fp32_accurate(ctx, case):
-    """Opt-in tensor-core path for the text encoder (EV_ENC_TC=1): x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with tf32 operands.
-    It is ~1e-5 accurate (the tensor core's fp32 accumulation truncates), an order of magnitude looser than the fp32
-    CUDA-core kernel -- which is why the CUDA-core kernel stays the default wherever ceil(exp(logw)) is downstream."""
+    """The text encoder's convs run on tcgen05 as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi (tf32 operands) with two-level
+    accumulation: the tensor core's truncating fp32 accumulator is flushed into a rounded fp32 master sum every <= 16
+    MMAs.  The result must be as close to the exact product as the fp32 CUDA-core kernel's (durations feed a ceil())."""
     B, Cin, T, Cout, K, pad, dil = case
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(B, Cin, T, generator=g)
@@ -106,7 +106,7 @@ def test_conv1d_3xtf32_tensor_core_path_is_fp32_accurate(ctx, case):
                                             _lib.PREC[prec], _lib.ptr(y), _lib.stream_ptr()), "ev_test_conv1d")
         err[prec] = rel_l2(y.cpu(), ref)
     assert err["fp32"] < 1e-6
-    assert err["tf32x3"] < 2e-5, err
+    assert err["tf32x3"] < 1e-6, err
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
