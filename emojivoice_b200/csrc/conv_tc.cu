@@ -16,9 +16,13 @@
 //   BK = 64 (128-byte swizzle) or, for layers with C_in <= 32, BK = 32 (64-byte swizzle: no zero-padded K).
 // PERSISTENT CTAs walk the tile list; TMEM holds two accumulator sets so the epilogue of tile i overlaps the TMA/MMA
 // main loop of tile i+1.  Narrow configurations run two CTAs per SM.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..9 = epilogue, per 64-column chunk: residual loads issued -> tcgen05.ld -> fp32 staging tile in smem ->
-// row-wise coalesced pass with the fused bias / mask / Euler-or-residual / MRF-mean / activation, fp32 + bf16 stores.
+// Warp roles: warp 0 = TMA producer; warps 1-2 = MMA issuers, one per m-block (warp 1 also owns the TMEM allocation):
+// the tensor core's instruction queue is shallow, so a single issuer's barrier waits and bookkeeping (~450 clk per
+// weight tile) left the pipe idle about half of the time -- with all loads and stores disabled the MMA-bound layers
+// ran no faster; two issuers on independent accumulators overlap one's bookkeeping with the other's MMAs;
+// warps 3.. = 8 or 16 epilogue warps, per 32 x 32 block: residual loads issued -> tcgen05.ld -> private fp32 transpose
+// buffer -> row-wise coalesced pass with the fused bias / mask / Euler-or-residual / MRF-mean / activation and stores
+// (or the lean activation-only path, or the two-level-accumulation flush of the 3xTF32 mode).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -34,8 +38,8 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;              // 2 role warps + 8 epilogue warps (two CTAs per SM)
-constexpr int NUM_THREADS_WIDE = 576;         // 2 role warps + 16 epilogue warps (one CTA per SM)
+constexpr int NUM_THREADS = 32 * (2 + 8);         // producer + 1 MMA issuer + 8 epilogue warps (two CTAs per SM: 96 regs x 640 threads)
+constexpr int NUM_THREADS_WIDE = 32 * (3 + 16);   // producer + 2 MMA issuers (one per m-block) + 16 epilogue warps (one CTA per SM)
 constexpr int MAX_A_SLOTS = 4, MAX_B_SLOTS = 8;
 constexpr int MB_MAX = 2;
 constexpr int kMaxGroups = kMaxTaps;
@@ -61,6 +65,8 @@ struct TcParams {
   int b_tile_bytes;
   uint32_t desc_sbo, desc_layout;
   uint32_t tmem_cols;
+  int debug_nob;                // EV_TC_DEBUG_NOB=1: skip weight loads (upper bound on what removing weight traffic buys)
+  int n_issuers;                // MMA issuer warps: 2 (one per m-block) in the wide configuration, else 1
   int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
   int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
   uint32_t idesc;               // instruction descriptor (kind::f16 bf16, or kind::tf32)
@@ -80,20 +86,12 @@ __device__ __forceinline__ uint32_t desc_lo_word(uint32_t saddr) { return ((sadd
 __device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // All MMAs of one (K-chunk, tap): VMB m-blocks x KS K-steps, issued by the elected lane.
-template <int KS, int BN, bool TF32>
-__device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo, uint32_t mb_step16, int vmb,
-                                          uint32_t idesc, uint32_t acc) {
+template <int KS, bool TF32>
+__device__ __forceinline__ void issue_tap(uint32_t d_tmem, uint32_t hi, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
     if (TF32) umma_tf32(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
     else umma_bf16(d_tmem, desc_join(hi, a_lo + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
-  }
-  if (vmb > 1) {
-#pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      if (TF32) umma_tf32(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
-      else umma_bf16(d_tmem + (uint32_t)BN, desc_join(hi, a_lo + mb_step16 + 2u * k), desc_join(hi, b_lo + 2u * k), idesc, (acc | (uint32_t)k) ? 1u : 0u);
-    }
   }
 }
 
@@ -134,13 +132,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int A_SLOTS = p.a_slots, B_SLOTS = p.b_slots;
   const int tile_rows = p.mb * BM;
+  const int ROLE_WARPS = 1 + p.n_issuers;   // producer + issuers; the epilogue warps follow
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < MAX_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], (blockDim.x >> 5) - 2); }   // every epilogue warp releases
+    // two MMA-issuer warps: each one commits on the slot / accumulator barriers
+    for (int s = 0; s < MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], p.n_issuers); }
+    for (int s = 0; s < MAX_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], p.n_issuers); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], p.n_issuers); mbar_init(&acc_empty[s], (blockDim.x >> 5) - ROLE_WARPS); }   // every epilogue warp releases
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -174,19 +174,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int g = 0; g < n_groups; ++g) {
             mbar_wait(&a_empty[sa], pa);
+            if (p.debug_nob & 2) { mbar_arrive(&a_full[sa]); if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; } if (resident) continue; goto b_loads; }
             mbar_expect_tx(&a_full[sa], a_bytes);
+            {
             const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
             const int sec = kc / p.kch1;   // 3xTF32: K-chunks walk the A sections [hi | hi | lo]; otherwise one section
             const int col = p.grp_col0[g] + p.sec_off[sec] + (kc - sec * p.kch1) * p.bk, row = m0 + p.grp_row0[g];
             tma_load_3d(dst, &tmA, &a_full[sa], col, row, b);
             if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, &tmA, &a_full[sa], col, row + p.a_box_rows, b);
+            }
             if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
             if (resident) continue;
+          b_loads:
             const int tap0 = g * grp_taps;
             for (int j = 0; j < grp_taps; ++j) {
               mbar_wait(&b_empty[sb], pb);
+              if (p.debug_nob & 1) { mbar_arrive(&b_full[sb]); }   // timing experiment only: no weight traffic (results are wrong)
+              else {
               mbar_expect_tx(&b_full[sb], (uint32_t)p.b_tile_bytes);
               tma_load_3d(b_base + (uint32_t)(sb * p.b_tile_bytes), &tmB, &b_full[sb], kc * p.bk, n0, tap0 + j);
+              }
               if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
             }
           }
@@ -194,8 +201,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------- MMA issuer: the whole warp walks the (warp-uniform) loops and waits; one elected lane issues.
+  } else if (warp < ROLE_WARPS) {
+    // ---------------- two MMA issuer warps: warp 1 owns m-block 0, warp 2 owns m-block 1 of every tile (independent
+    // accumulators), so one warp's barrier / bookkeeping work overlaps the other's MMAs -- the tensor core's instruction
+    // queue is shallow and a single issuer left the pipe idle ~half of the time.  Each warp walks the (warp-uniform) loops and waits the (warp-uniform) loops and waits; one elected lane issues.
     // Every tap and m-block re-reads the same smem tile at a row offset.  The loop body is kept to a few dozen
     // instructions per weight tile: ring slots / phases advance incrementally and descriptors by adds (a single
     // warp issues ~1 dependent instruction per 5-8 clk, so 200 instructions per tap would cap the tensor pipe).
@@ -208,6 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
     const bool resident = p.resident != 0, ks4 = p.ksteps == 4;
     const uint32_t acc_stride = (uint32_t)(p.mb * BN);
+    const int my_mb = warp - 1, mb_stride = p.n_issuers;   // this issuer owns m-blocks my_mb, my_mb + mb_stride, ...
     int sa = 0, sb = 0, vt = 0;     // vt counts accumulator-set uses: one per tile, or one per flush group (3xTF32)
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
     const int flush_kc = p.flush_kc;
@@ -242,10 +252,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               b_lo = b_lo0 + (uint32_t)sb * b_step16;
             }
             if (elect_one()) {
-              if (tf32) issue_tap<4, BN, true>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
-              else if (ks4) issue_tap<4, BN, false>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
-              else issue_tap<2, BN, false>(d_tmem, hi, a_lo, b_lo, mb_step16, vmb, idesc, acc);
-              if (!resident) umma_commit(&b_empty[sb]);   // weight slot is free once these MMAs have read it
+              // straight-line issue (MB_MAX = 2): this issuer's own m-block, plus m-block 1 when it is the only issuer;
+              // an issuer without a valid m-block only keeps the barrier protocol going
+              const bool second = mb_stride == 1 && vmb > 1;
+              const uint32_t dm = d_tmem + (uint32_t)(my_mb * BN), am = a_lo + (uint32_t)my_mb * mb_step16;
+              if (tf32) {
+                if (my_mb < vmb) issue_tap<4, true>(dm, hi, am, b_lo, idesc, acc);
+                if (second) issue_tap<4, true>(dm + (uint32_t)BN, hi, am + mb_step16, b_lo, idesc, acc);
+              } else if (ks4) {
+                if (my_mb < vmb) issue_tap<4, false>(dm, hi, am, b_lo, idesc, acc);
+                if (second) issue_tap<4, false>(dm + (uint32_t)BN, hi, am + mb_step16, b_lo, idesc, acc);
+              } else {
+                if (my_mb < vmb) issue_tap<2, false>(dm, hi, am, b_lo, idesc, acc);
+                if (second) issue_tap<2, false>(dm + (uint32_t)BN, hi, am + mb_step16, b_lo, idesc, acc);
+              }
+              if (!resident) umma_commit(&b_empty[sb]);   // weight slot is free once both issuers' MMAs have read it
             }
             __syncwarp();
             acc = 1;
@@ -269,8 +290,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // block of them; the eight warps run free of each other (no CTA barrier):
     //   residual loads issued -> tcgen05.ld (thread = accumulator row) -> private 32 x 32 fp32 transpose buffer ->
     //   row-wise pass: 8 lanes x float4 per row, fused epilogue arithmetic, coalesced fp32 + bf16 stores.
-    const int ew = warp - 2;
-    const int q = warp & 3, slot = ew >> 2, n_slots = ((int)(blockDim.x >> 5) - 2) >> 2;   // 2 or 4 warps per lane quadrant
+    const int ew = warp - ROLE_WARPS;
+    const int q = warp & 3, slot = ew >> 2, n_slots = ((int)(blockDim.x >> 5) - ROLE_WARPS) >> 2;   // 2 or 4 warps per lane quadrant
     const Epilogue& e = p.e;
     bf16* out_act = reinterpret_cast<bf16*>(e.out_act);
     const bool has_res = e.res != nullptr, has_res2 = e.res2 != nullptr, has_f32 = e.out_f32 != nullptr, has_act = e.out_act != nullptr;
@@ -356,7 +377,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
               const int r = rb + it * 8;
-              if (r < M && r < T_out)
+              if (r < M && r < T_out && !(p.debug_nob & 4))
                 *reinterpret_cast<uint4*>(dst + (long long)r * e.act_ld) = *reinterpret_cast<const uint4*>(src + (rsub + it * 8) * ACT_PITCH);
             }
           }
@@ -595,6 +616,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
+  p.n_issuers = threads == NUM_THREADS_WIDE ? 2 : 1;
   const int grid = std::min(p.total_tiles, k * g_sm_count);
   conv_tc_kernel<BN><<<grid, threads, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
@@ -777,6 +799,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     if (err) *err = "conv_tc: fused GroupNorm statistics need 32 channels per group on the vector path";
     return cudaErrorInvalidValue;
   }
+  { static const int nob = []() { const char* v = getenv("EV_TC_DEBUG_NOB"); return v ? atoi(v) : 0; }(); p.debug_nob = nob; }
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream);
     case 64: return launch_bn<64>(tmA, tmB, p, stream);
