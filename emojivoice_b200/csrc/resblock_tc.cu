@@ -12,7 +12,8 @@
 //     conv1, is overwritten by lrelu(conv1 + b) for conv2, then by lrelu(x_new) for the next pair.  Taps are row
 //     offsets into it; zero margins / rows outside [0, L) implement each conv's own zero padding.
 //   * weight tiles [C x C] per (conv, tap, K-chunk) stream from L2 through a TMA ring.
-// Warps: 0 = TMA producer (weights), 1 = TMEM allocator + MMA issuer, 2..17 = 16 "epilogue" warps that load x, convert
+// Warps: 0 = TMA producer (weights), 1-2 = MMA issuers (half of the m-blocks each; warp 1 owns the TMEM allocation),
+// 3.. = 16 (or 8) "epilogue" warps that load x, convert
 // accumulators into the next operand, and write y.  Phases alternate strictly MMA -> epilogue (two mbarriers); the
 // epilogue phases are short next to the MMA phases (<= 30 % even at k = 3).
 #include <cuda.h>
@@ -66,7 +67,7 @@ template <int C> struct RbCfg {
 };
 
 template <int C>
-__global__ void __launch_bounds__(64 + 32 * RB_MAX_EPI_WARPS, 1)
+__global__ void __launch_bounds__(96 + 32 * RB_MAX_EPI_WARPS, 1)
 resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ RbParams p) {
   using G = RbCfg<C>;
   constexpr int MB = G::MB, W = G::W, KC = G::KC, RB = G::RB, KS = G::KS, NCB = G::NCB;
@@ -78,16 +79,17 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t a_s = base, w_s = base + KC * G::A_PLANE;
   uint8_t* a_gen = base_gen;
-  const int n_epi = (int)(blockDim.x >> 5) - 2, n_slots = n_epi >> 2;   // epilogue warps; warps per TMEM lane quadrant
+  const int n_epi = (int)(blockDim.x >> 5) - 3, n_slots = n_epi >> 2;   // epilogue warps; warps per TMEM lane quadrant
   const int w_tiles = p.resident ? 6 * p.k : p.w_slots;
   float* stage = reinterpret_cast<float*>(base_gen + KC * G::A_PLANE + w_tiles * G::W_TILE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 6; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
-    for (int s = 0; s < RB_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(&mma_done, 1);
-    mbar_init(&epi_done, (blockDim.x >> 5) - 2);
+    // two MMA issuer warps (m-blocks split between them): both commit on the weight-slot and phase barriers
+    for (int s = 0; s < RB_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+    mbar_init(&mma_done, 2);
+    mbar_init(&epi_done, (blockDim.x >> 5) - 3);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -127,8 +129,11 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ---------------- MMA issuer (warp-uniform control flow, one elected lane issues)
+  } else if (warp < 3) {
+    // ---------------- two MMA issuers (warp-uniform control flow, one elected lane each): warp 1 issues the first
+    // half of the m-blocks, warp 2 the second half, so one warp's barrier / bookkeeping work overlaps the other's MMAs
+    constexpr int MBH = MB / 2;
+    const int mb0 = (warp - 1) * MBH;
     constexpr uint32_t idesc = make_idesc(128, C);
     const uint32_t hi = ((uint32_t)(8 * RB) >> 4) | (1u << 14) | (G::LAYOUT << 29);
     const uint32_t a_lo0 = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), w_lo0 = ((w_s & 0x3FFFFu) >> 4) | (1u << 16);
@@ -152,7 +157,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             const uint32_t a_step = (uint32_t)((d * RB) >> 4), b_step = (uint32_t)(G::W_TILE >> 4);
             for (int j = 0; j < k; ++j) {
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb) {
+              for (int m = 0; m < MBH; ++m) {
+                const int mb = mb0 + m;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                   const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((mb * 128 * RB) >> 4) + 2u * ks);
@@ -177,7 +183,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             const uint32_t a_lo = a_lo0 + (uint32_t)((kc * G::A_PLANE + (RB_MARG + (j - half_k) * d) * RB) >> 4);
             if (elect_one()) {
 #pragma unroll
-              for (int mb = 0; mb < MB; ++mb) {
+              for (int m = 0; m < MBH; ++m) {
+                const int mb = mb0 + m;
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks) {
                   const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((mb * 128 * RB) >> 4) + 2u * ks);
@@ -199,7 +206,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   } else {
     // ---------------- 16 epilogue warps.  Warp (q, slot): TMEM lanes [32q, 32q+32), blocks slot, slot+4, ... of the
     // MB*NCB (m-block, 32-column block) pairs of that lane quadrant.
-    const int ew = warp - 2, q = warp & 3, slot = ew >> 2;   // n_slots warps share a lane quadrant
+    const int ew = warp - 3, q = warp & 3, slot = ew >> 2;   // n_slots warps share a lane quadrant
     const int sub = lane >> 3, cl = (lane & 7) * 4;
     float* wstage = stage + ew * (32 * RB_STAGE_LD);
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
@@ -384,7 +391,7 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
   }
   const int grid = std::min(p.total_tiles, tc_sm_count());
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
-  resblock_tc_kernel<C><<<grid, 64 + 32 * n_epi, std::max(smem, 120 * 1024), s>>>(maps, p);
+  resblock_tc_kernel<C><<<grid, 96 + 32 * n_epi, std::max(smem, 120 * 1024), s>>>(maps, p);
   return cudaGetLastError();
 }
 
@@ -399,13 +406,16 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
   if (k != 3 && k != 7 && k != 11) return false;
   if (dil[0] != 1 || dil[1] != 3 || dil[2] != 5) return false;
   if (g_rb_policy >= 2) return true;
-  // Measured on B200 (profiles/r01_layers_v11.txt vs v9, us per ResBlock at B=32 x 668 frames, fused / layer-by-layer):
-  //   C=128: k3 1258/1686  k7 2804/2319  k11 -/3036     C=64: k3 1084/1764  k7 1999/2145  k11 2864/2793
-  //   C=32 : k3  919/1644  k7 1760/1953  k11 2784/2238
-  // The fused kernel wins where the layer-by-layer path is HBM/epilogue-bound (k = 3, and k = 7 at C <= 64); at larger k
-  // the layer-by-layer convs are already MMA-bound and the halo recompute (H = 6(k-1) rows per window side) costs more.
+  // Measured on B200 (profiles/r01_layers_v16_fused_all.txt vs r01_layers_v15_two_issuers.txt, us per ResBlock at B=32 x 668
+  // frames, fused / layer-by-layer):
+  //   C=128: k3 1152/1686  k7 2424/2265  k11 4075/2844     C=64: k3 1044/1764  k7 1833/2145  k11 2534/2682
+  //   C=32 : k3  930/1644  k7 1780/1953  k11 2815/2649
+  // The fused kernel wins where the layer-by-layer path is HBM/epilogue-bound (k = 3; k = 7 at C <= 64; k = 11 at C = 64); at
+  // C = 128 the separate convs are already MMA-bound (1.1-1.2 PFLOP/s) and the halo recompute (H = 6(k-1) rows per window
+  // side, 256-row windows) costs more than the saved traffic; at C = 32 a 128x32x16 MMA costs ~87 clk whatever feeds it.
   if (k == 3) return true;
   if (k == 7) return C <= 64;
+  if (k == 11) return C == 64;
   return false;
 }
 
