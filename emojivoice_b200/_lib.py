@@ -113,15 +113,19 @@ class Context:
             raise RuntimeError(f"ev_create failed ({rc}): {lib().ev_last_error(None).decode()}")
         self.handle = h
         self._ws = None
+        self.ws_version = 0          # bumped whenever the workspace is reallocated (captured graphs hold its address)
 
     def check(self, rc, what):
         if rc != 0:
             raise RuntimeError(f"{what} failed ({rc}): {lib().ev_last_error(self.handle).decode()}")
 
     def workspace(self, nbytes: int) -> torch.Tensor:
+        """The context's one scratch buffer (calls run one after another on the stream, so eager calls and every captured
+        graph share it).  Growing it invalidates the graphs captured so far: `ws_version` tells the caches."""
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = None
-            self._ws = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+            self.ws_version += 1
         return self._ws
 
     def launch_count(self, reset=False) -> int:
@@ -151,16 +155,20 @@ class Context:
 
 
 class GraphCache:
-    """CUDA graphs of one library call per shape key (the decoder's n-step loop is ~2500 launches, the vocoder ~80:
+    """CUDA graphs of one library call per shape key (the decoder's n-step loop is ~750 launches, the vocoder ~50:
     replaying them as a graph takes the host out of the critical path).  A key is captured the second time it is seen
-    (a one-off shape is not worth a capture); entries own their static I/O buffers and workspace; least recently used
-    entries are dropped beyond `capacity`."""
+    (a one-off shape is not worth a capture); entries own their small static I/O buffers and share the context's
+    workspace (so a corpus of many micro-batch shapes stays cheap); least recently used entries are dropped beyond
+    `capacity`, and every entry is dropped when the workspace has been reallocated since its capture."""
 
-    def __init__(self, capacity=4):
+    def __init__(self, capacity=64):
         self.capacity, self.entries, self.seen = capacity, {}, {}
 
-    def get(self, key):
+    def get(self, key, ws_version=None):
         e = self.entries.get(key)
+        if e is not None and ws_version is not None and e.get("ws_version") != ws_version:
+            self.entries.pop(key)                                # captured against a workspace that no longer exists
+            return None
         if e is not None:
             self.entries[key] = self.entries.pop(key)            # move to the back (most recent)
         return e

@@ -97,15 +97,15 @@ class Generator:
                                       _lib.stream_ptr()), "ev_vocode")
 
             key = (B, T, prec)
-            ent = self._graphs.get(key) if self.cuda_graphs else None
+            ws_shared = ctx.workspace(nb)                   # (may grow the workspace: do it before looking graphs up)
+            ent = self._graphs.get(key, ctx.ws_version) if self.cuda_graphs else None
             if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
-                ent = dict(mel=mel.clone(), wav=torch.empty(B, 1, T * self.hop, device=dev),
-                           ws=torch.empty(nb + 4096, dtype=torch.uint8, device=dev))
+                ent = dict(mel=mel.clone(), wav=torch.empty(B, 1, T * self.hop, device=dev), ws=ws_shared, ws_version=ctx.ws_version)
                 ent["graph"], ent["launches"] = _lib.capture(ctx, lambda: call(ent["mel"], ent["wav"], ent["ws"]))
                 self._graphs.put(key, ent)
             if ent is None:
                 wav = torch.empty(B, 1, T * self.hop, device=dev)
-                call(mel, wav, ctx.workspace(nb))
+                call(mel, wav, ws_shared)
             else:
                 ent["mel"].copy_(mel)
                 ent["graph"].replay()

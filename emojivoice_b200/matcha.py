@@ -167,11 +167,12 @@ class MatchaTTS:
 
         nb = L.ev_decode_workspace_bytes(ctx.handle, B, T_pad, n_timesteps)
         key = (B, T_pad, n_timesteps, temperature, prec)
-        ent = self._graphs.get(key) if self.cuda_graphs else None
+        ws_shared = ctx.workspace(nb)                       # (may grow the workspace: do it before looking graphs up)
+        ent = self._graphs.get(key, ctx.ws_version) if self.cuda_graphs else None
         if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
             st = dict(mu_y=torch.empty_like(mu_y), y_lengths=torch.empty_like(y_lengths), z=torch.empty_like(z),
                       spk_emb=None if spk_emb is None else torch.empty_like(spk_emb), dec=torch.empty(B, F, T_pad, device=dev),
-                      mel=torch.empty(B, F, T_pad, device=dev), ws=torch.empty(nb + 4096, dtype=torch.uint8, device=dev))
+                      mel=torch.empty(B, F, T_pad, device=dev), ws=ws_shared, ws_version=ctx.ws_version)
             st["mu_y"].copy_(mu_y); st["y_lengths"].copy_(y_lengths); st["z"].copy_(z)
             if spk_emb is not None:
                 st["spk_emb"].copy_(spk_emb)
@@ -182,7 +183,7 @@ class MatchaTTS:
         if ent is None:
             dec = torch.empty(B, F, T_pad, device=dev)
             mel = torch.empty(B, F, T_pad, device=dev)
-            call(mu_y, y_lengths, z, spk_emb, dec, mel, ctx.workspace(nb))
+            call(mu_y, y_lengths, z, spk_emb, dec, mel, ws_shared)
             return dec, mel
         ent["mu_y"].copy_(mu_y); ent["y_lengths"].copy_(y_lengths); ent["z"].copy_(z)
         if spk_emb is not None:
