@@ -65,7 +65,8 @@ struct TcParams {
   int b_tile_bytes;
   uint32_t desc_sbo, desc_layout;
   uint32_t tmem_cols;
-  int debug_nob;                // EV_TC_DEBUG_NOB=1: skip weight loads (upper bound on what removing weight traffic buys)
+  int debug_nob;                // EV_TC_DEBUG_NOB bit 0 / 1 / 2: skip weight loads / activation loads / lean-path stores.  Timing
+                                // experiments only (results are wrong): they showed the MMA-bound layers are issue-bound, not memory-bound
   int n_issuers;                // MMA issuer warps: 2 (one per m-block) in the wide configuration, else 1
   int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
   int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
@@ -554,6 +555,7 @@ int g_bk32_mode = 1;       // EV_TC_BK32=0 disables the 64-byte-swizzle path for
 int g_cta2_mode = 1;       // EV_TC_CTA2=0 keeps one CTA per SM
 int g_wide_mode = 1;       // EV_TC_WIDE=0 keeps 8 epilogue warps
 int g_lean_mode = 1;       // EV_TC_LEAN=0 disables the activation-only epilogue path
+int g_min_b2 = 4;          // EV_TC_MINB2: fewest weight-ring slots accepted for the two-CTAs-per-SM configuration
 int g_tf32_flush = 1;      // EV_TF32_FLUSH=0: 3xTF32 without two-level accumulation (shows the tensor core's truncation error)
 
 // Shared-memory plan of one launch for `k` CTAs per SM with `epi_warps` epilogue warps; false when the rings do not fit.
@@ -574,7 +576,7 @@ bool plan_smem(TcParams& p, int k, int epi_warps, int* smem_out) {
     b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes;
     if (b_slots < 4 && a_slots == 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes; }
     if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
-    if (b_slots < (k > 1 ? 4 : 3)) return false;
+    if (b_slots < (k > 1 ? g_min_b2 : 3)) return false;
   }
   if (a_slots < 2) return false;
   p.a_slots = a_slots;
@@ -673,6 +675,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     g_wide_mode = env_int("EV_TC_WIDE", 1);
     g_lean_mode = env_int("EV_TC_LEAN", 1);
     g_tf32_flush = env_int("EV_TF32_FLUSH", 1);
+    g_min_b2 = env_int("EV_TC_MINB2", 4);
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
   const int BN = conv_tc_pick_bn(g.N);
