@@ -6,6 +6,13 @@
 
 using namespace ev;
 
+namespace ev {
+bool pdl_enabled() {
+  static const bool on = []() { const char* v = getenv("EV_PDL"); return !(v && atoi(v) == 0); }();
+  return on;
+}
+}  // namespace ev
+
 namespace {
 thread_local std::string g_create_error;
 cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

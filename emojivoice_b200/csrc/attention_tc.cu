@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_consta
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -237,8 +239,7 @@ cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err) 
   p.lens = a.lens; p.len_shift = a.len_shift;
   p.out = a.out; p.out_ld = a.out_ld; p.out_bs = a.out_bs;
   dim3 grid(ceil_div(a.T, BQ), a.H, a.B);
-  attn_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(tm, p);
-  return cudaGetLastError();
+  return launch_pdl(attn_tc_kernel, grid, dim3(THREADS), (size_t)SMEM_BYTES, s, tm, p);
 }
 
 }  // namespace ev

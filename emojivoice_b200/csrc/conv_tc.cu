@@ -152,6 +152,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_trigger();     // the next kernel may start its prologue
+  pdl_wait();        // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -620,8 +622,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   }
   p.n_issuers = threads == NUM_THREADS_WIDE ? 2 : 1;
   const int grid = std::min(p.total_tiles, k * g_sm_count);
-  conv_tc_kernel<BN><<<grid, threads, smem, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<BN>, dim3(grid), dim3(threads), (size_t)smem, stream, tmA, tmB, p);
 }
 
 }  // namespace

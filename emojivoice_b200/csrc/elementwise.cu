@@ -75,6 +75,8 @@ __global__ void fill_speaker_kernel(const float* spk, int T, int dim, RowMask ma
 // ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
 template <typename ActT, int VPL>  // VPL = ceil(C/32) values per lane
 __global__ void __launch_bounds__(256) layer_norm_kernel(LnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int rows = a.B * a.T;
   if (warp >= rows) return;
@@ -219,6 +221,8 @@ constexpr int GN_APPLY_ROWS = 4;   // rows per warp
 
 template <typename ActT, int V4>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
+  pdl_trigger();
+  pdl_wait();
   // warp per (b,t) row, GN_APPLY_ROWS rows per warp; lane owns the float4 channel groups 4*(lane + 32*i), each inside
   // one GroupNorm group (channels-per-group is a multiple of 4)
   extern __shared__ float stat[];  // [G][2] mean, rstd for this block's batch item
@@ -407,11 +411,10 @@ cudaError_t layer_norm_rows(const LnArgs& a, cudaStream_t s) {
   const int rows = a.B * a.T;
   const int blocks = ceil_div(rows, 8);
   const int vpl = ceil_div(a.C, 32);
-  if (vpl <= 6) layer_norm_kernel<ActT, 6><<<blocks, 256, 0, s>>>(a);
-  else if (vpl <= 8) layer_norm_kernel<ActT, 8><<<blocks, 256, 0, s>>>(a);
-  else if (vpl <= 32) layer_norm_kernel<ActT, 32><<<blocks, 256, 0, s>>>(a);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (vpl <= 6) return launch_pdl(layer_norm_kernel<ActT, 6>, dim3(blocks), dim3(256), 0, s, a);
+  if (vpl <= 8) return launch_pdl(layer_norm_kernel<ActT, 8>, dim3(blocks), dim3(256), 0, s, a);
+  if (vpl <= 32) return launch_pdl(layer_norm_kernel<ActT, 32>, dim3(blocks), dim3(256), 0, s, a);
+  return cudaErrorInvalidValue;
 }
 template cudaError_t layer_norm_rows<float>(const LnArgs&, cudaStream_t);
 template cudaError_t layer_norm_rows<bf16>(const LnArgs&, cudaStream_t);
@@ -449,10 +452,9 @@ cudaError_t group_norm_apply(const GnApplyArgs& a, cudaStream_t s) {
   const int v4 = ceil_div(a.C, 128);
   dim3 grid(ceil_div(a.T, 8 * GN_APPLY_ROWS), a.B);
   const size_t sh = (size_t)a.groups * 2 * sizeof(float);
-  if (v4 <= 2) gn_apply_kernel<ActT, 2><<<grid, 256, sh, s>>>(a);
-  else if (v4 <= 8) gn_apply_kernel<ActT, 8><<<grid, 256, sh, s>>>(a);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (v4 <= 2) return launch_pdl(gn_apply_kernel<ActT, 2>, grid, dim3(256), sh, s, a);
+  if (v4 <= 8) return launch_pdl(gn_apply_kernel<ActT, 8>, grid, dim3(256), sh, s, a);
+  return cudaErrorInvalidValue;
 }
 template cudaError_t group_norm_apply<float>(const GnApplyArgs&, cudaStream_t);
 template cudaError_t group_norm_apply<bf16>(const GnApplyArgs&, cudaStream_t);

@@ -103,6 +103,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_trigger();
+  pdl_wait();        // prologue (barriers, TMEM, zeroed operand buffer) overlapped the previous kernel's tail
   const uint32_t acc_x = tmem_base, acc_mid = tmem_base + (uint32_t)(MB * C);
   const int k = p.k, half_k = (p.k - 1) / 2;
 
@@ -391,8 +393,7 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
   }
   const int grid = std::min(p.total_tiles, tc_sm_count());
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
-  resblock_tc_kernel<C><<<grid, 96 + 32 * n_epi, std::max(smem, 120 * 1024), s>>>(maps, p);
-  return cudaGetLastError();
+  return launch_pdl(resblock_tc_kernel<C>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
 }
 
 }  // namespace
