@@ -1,4 +1,5 @@
 // Context lifetime, bookkeeping and the single-kernel unit-test hooks of the C ABI (include/emojivoice_b200.h).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -46,6 +47,14 @@ extern "C" int ev_create(ev_ctx** out, int device) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   { const char* v = getenv("EV_ENC_TC"); ctx->enc_tc = !(v && atoi(v) == 0); }
+  { const char* v = getenv("EV_DEC_LANES"); if (v) ctx->dec_lanes = std::min(std::max(atoi(v), 1), (int)ev_ctx::kMaxLanes); }
+  // lane streams / events are created here: stream creation is not allowed while a caller captures a CUDA graph
+  ce = cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming);
+  for (int i = 0; i < ev_ctx::kMaxLanes - 1 && ce == cudaSuccess; ++i) {
+    ce = cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming);
+  }
+  if (ce != cudaSuccess) { g_create_error = std::string("lane streams: ") + cudaGetErrorString(ce); delete ctx; return EV_ERR_CUDA; }
   *out = ctx;
   return EV_OK;
 }
@@ -55,6 +64,11 @@ extern "C" int ev_destroy(ev_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (void* p : ctx->owned) cudaFree(p);
+  for (int i = 0; i < ev_ctx::kMaxLanes - 1; ++i) {
+    if (ctx->lane_stream[i]) cudaStreamDestroy(ctx->lane_stream[i]);
+    if (ctx->lane_join[i]) cudaEventDestroy(ctx->lane_join[i]);
+  }
+  if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
   delete ctx;
   return EV_OK;
 }

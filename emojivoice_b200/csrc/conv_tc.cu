@@ -602,7 +602,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   bool ok = false;
   const bool flush = p.flush_kc < p.kchunks;
   if (flush && (BN != 128 || p.mb != 1)) return cudaErrorInvalidConfiguration;   // one block per epilogue warp
-  if (!flush && g_cta2_mode && k_tmem >= 2 && p.total_tiles > g_sm_count && p.mb * (BN / 32) <= 4 && plan_smem<BN>(p, 2, 8, &smem)) {
+  if (!flush && g_cta2_mode && k_tmem >= 2 && (p.total_tiles > g_sm_count || g_cta2_mode == 2) && p.mb * (BN / 32) <= 4 && plan_smem<BN>(p, 2, 8, &smem)) {
     k = 2; threads = NUM_THREADS; ok = true;
   }
   if (!ok && (g_wide_mode || flush) && plan_smem<BN>(p, 1, 16, &smem)) ok = true;

@@ -93,6 +93,13 @@ struct ev_ctx {
   std::vector<ev::ProfRecord> prof;
   std::vector<std::string> kernel_names;
   std::vector<cudaEvent_t> event_pool;
+  // decoder lanes: the batch is cut into up to EV_MAX_LANES independent slices whose kernels run on separate streams
+  // (forked from / joined into the caller's stream, so a CUDA-graph capture sees parallel branches).  The decoder's
+  // kernels at B = 32 are launch/prologue-latency bound (3 us of MMA in a 13 us kernel); concurrent lanes overlap them.
+  static constexpr int kMaxLanes = 4;
+  int dec_lanes = 2;            // EV_DEC_LANES
+  cudaStream_t lane_stream[kMaxLanes - 1] = {};
+  cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes - 1] = {};
 };
 
 namespace ev {

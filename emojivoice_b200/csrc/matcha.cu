@@ -2,6 +2,7 @@
 // flow-matching U-Net decoder integrated with Euler steps.  Layer order follows the reference exactly
 // (text_encoder.py:378-410, matcha_tts.py:116-143, flow_matching.py:55-85, decoder.py:363-443); see DESIGN.md for
 // the buffer plan.  All intermediate tensors are channel-last and live in the caller's workspace.
+#include <algorithm>
 #include <cmath>
 
 #include "ctx.cuh"
@@ -538,6 +539,13 @@ struct Decoder {
   }
 };
 
+// Batch slices ("lanes") the decoder runs concurrently: every per-item quantity of the estimator (GroupNorm statistics,
+// attention, masks) is independent of the other items of the batch, so slices of the batch are exact.
+int decode_lane_count(const ev_ctx* ctx, int B) {
+  if (ctx->profiling) return 1;            // per-launch event timing wants one serial stream
+  return std::max(1, std::min(ctx->dec_lanes, B / 4));
+}
+
 template <typename ActT>
 int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const float* z, const float* spk_emb, int B,
                 int T, int n_steps, float temperature, float* decoder_out, float* mel, void* workspace, size_t ws_bytes,
@@ -545,13 +553,19 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
   const MatchaW& m = ctx->matcha;
   const ev_matcha_cfg& c = m.cfg;
   Workspace w(workspace, ws_bytes);
-  DecBuffers<ActT> d;
-  plan_decode<ActT>(c, B, T, n_steps, w, &d);
+  const int n_lanes = decode_lane_count(ctx, B);
+  int lane_b0[ev_ctx::kMaxLanes], lane_nb[ev_ctx::kMaxLanes];
+  DecBuffers<ActT> dl[ev_ctx::kMaxLanes];
+  for (int l = 0, b0 = 0; l < n_lanes; ++l) {
+    lane_b0[l] = b0;
+    lane_nb[l] = B / n_lanes + (l < B % n_lanes ? 1 : 0);
+    b0 += lane_nb[l];
+    plan_decode<ActT>(c, lane_nb[l], T, n_steps, w, &dl[l]);
+  }
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_decode: workspace too small");
   ctx->prof_tag = "/dec";
   const int D = c.dec_channels, F = c.n_feats, S = c.n_spks > 1 ? c.spk_emb_dim : 0, dec_in = 2 * F + S;
-  EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(y_lengths), d.ylen32, B, s));
-  const RowMask mask0{d.ylen32, 0};
+  DecBuffers<ActT>& d = dl[0];
   // time embeddings of all steps at once (they do not depend on the batch): sinusoid -> Linear -> SiLU -> Linear,
   // then Mish -> the six resnet mlp Linears stacked along N (decoder.py:381-382, :49,58)
   std::vector<float> ts, dts;
@@ -565,13 +579,41 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
     EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_steps, e, s)); }
   { Epilogue e; e.out_f32 = d.tproj; e.f32_ld = 6 * D; e.f32_bs = 0;
     EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_steps, e, s)); }
-  EV_LAUNCH(ctx, s, "decoder_pack_input", 0, (double)B * T * (12.0 * F + sizeof(ActT) * dec_in),
-            (decoder_pack_input<ActT>(z, mu_y, spk_emb, B, F, S, T, temperature, mask0, d.xstate, d.xin, dec_in, s)));
-  Decoder<ActT> dec{ctx, m, d, B, T, s, D, c.dec_heads * c.dec_head_dim};
-  if (dec.fuse_gn()) EV_CUDA(ctx, cudaMemsetAsync(d.gn_fused, 0, d.gn_fused_count * sizeof(double), s));
-  for (int k = 0; k < n_steps; ++k) EV_TRY(dec.step(d.tproj + (size_t)k * 6 * D, dts[k]));
-  EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, decoder_out, 1.0f, 0.0f, s));
-  if (mel) EV_LAUNCH(ctx, s, "cl_to_cf", 0, 8.0 * B * T * F, cl_to_cf(d.xstate, F, (long long)T * F, B, F, T, mel, c.mel_std, c.mel_mean, s));
+  // fork: lane 0 stays on the caller's stream, the others wait for the time embeddings on their own streams
+  cudaStream_t ls[ev_ctx::kMaxLanes];
+  ls[0] = s;
+  if (n_lanes > 1) EV_CUDA(ctx, cudaEventRecord(ctx->lane_fork, s));
+  for (int l = 1; l < n_lanes; ++l) {
+    ls[l] = ctx->lane_stream[l - 1];
+    EV_CUDA(ctx, cudaStreamWaitEvent(ls[l], ctx->lane_fork, 0));
+  }
+  std::vector<Decoder<ActT>> dec;
+  dec.reserve(n_lanes);
+  const long long item = (long long)F * T;
+  for (int l = 0; l < n_lanes; ++l) {
+    const int b0 = lane_b0[l], nb = lane_nb[l];
+    DecBuffers<ActT>& q = dl[l];
+    EV_LAUNCH(ctx, ls[l], "i64_to_i32", 0, 12.0 * nb, i64_to_i32(reinterpret_cast<const long long*>(y_lengths) + b0, q.ylen32, nb, ls[l]));
+    const RowMask mask0{q.ylen32, 0};
+    EV_LAUNCH(ctx, ls[l], "decoder_pack_input", 0, (double)nb * T * (12.0 * F + sizeof(ActT) * dec_in),
+              (decoder_pack_input<ActT>(z + b0 * item, mu_y + b0 * item, spk_emb ? spk_emb + (long long)b0 * S : nullptr, nb, F, S, T,
+                                        temperature, mask0, q.xstate, q.xin, dec_in, ls[l])));
+    dec.push_back(Decoder<ActT>{ctx, m, q, nb, T, ls[l], D, c.dec_heads * c.dec_head_dim});
+    if (dec.back().fuse_gn()) EV_CUDA(ctx, cudaMemsetAsync(q.gn_fused, 0, q.gn_fused_count * sizeof(double), ls[l]));
+  }
+  // launches interleave across lanes step by step so that eager (un-captured) calls overlap as well
+  for (int k = 0; k < n_steps; ++k)
+    for (int l = 0; l < n_lanes; ++l) EV_TRY(dec[l].step(d.tproj + (size_t)k * 6 * D, dts[k]));
+  for (int l = 0; l < n_lanes; ++l) {
+    const int b0 = lane_b0[l], nb = lane_nb[l];
+    DecBuffers<ActT>& q = dl[l];
+    EV_LAUNCH(ctx, ls[l], "cl_to_cf", 0, 8.0 * nb * T * F, cl_to_cf(q.xstate, F, (long long)T * F, nb, F, T, decoder_out + b0 * item, 1.0f, 0.0f, ls[l]));
+    if (mel) EV_LAUNCH(ctx, ls[l], "cl_to_cf", 0, 8.0 * nb * T * F, cl_to_cf(q.xstate, F, (long long)T * F, nb, F, T, mel + b0 * item, c.mel_std, c.mel_mean, ls[l]));
+    if (l > 0) {
+      EV_CUDA(ctx, cudaEventRecord(ctx->lane_join[l - 1], ls[l]));
+      EV_CUDA(ctx, cudaStreamWaitEvent(s, ctx->lane_join[l - 1], 0));
+    }
+  }
   return 0;
 }
 
@@ -581,8 +623,12 @@ extern "C" size_t ev_decode_workspace_bytes(const ev_ctx* ctx, int B, int T_pad,
   if (!ctx || !ctx->matcha.loaded || B <= 0 || T_pad <= 0 || n_timesteps <= 0) return 0;
   Workspace w(nullptr, 0);
   DecBuffers<float> d;  // fp32 operands are the larger plan; it also covers bf16
-  plan_decode<float>(ctx->matcha.cfg, B, T_pad, n_timesteps, w, &d);
-  return w.off + 256;
+  const int n_lanes = std::min(std::max(ctx->dec_lanes, 1), std::max(1, B / 4));   // upper bound of decode_lane_count
+  for (int l = 0; l < n_lanes; ++l) plan_decode<float>(ctx->matcha.cfg, B / n_lanes + (l < B % n_lanes ? 1 : 0), T_pad, n_timesteps, w, &d);
+  size_t lanes_bytes = w.off;
+  Workspace w1(nullptr, 0);                // the single-lane plan (profiling mode) must fit too
+  plan_decode<float>(ctx->matcha.cfg, B, T_pad, n_timesteps, w1, &d);
+  return std::max(lanes_bytes, w1.off) + 256;
 }
 
 extern "C" int ev_decode(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const float* z, const float* spk_emb,

@@ -32,7 +32,7 @@ namespace {
 constexpr int RB_MAX_EPI_WARPS = 16;          // 16 epilogue warps (576 threads), or 8 when shared memory is needed for resident weights
 constexpr int RB_MARG = 32;            // zero rows on both sides of the operand buffer (>= largest tap reach, 25)
 constexpr int RB_STAGE_LD = 36;
-constexpr int RB_MAX_SLOTS = 8;
+constexpr int RB_MAX_SLOTS = 16;
 
 struct RbMaps { CUtensorMap m[6]; };   // weights of conv1_0, conv2_0, conv1_1, conv2_1, conv1_2, conv2_2
 
@@ -42,6 +42,7 @@ struct RbParams {
   bf16* act_out; long long act_bs;     // optional bf16 (b, t, c): lrelu of the MRF mean (next stage's operand)
   const float* bias1[3];               // conv1_l bias [C]
   const float* bacc[3];                // sum_{i<=l} conv2_i bias [C]
+  const float* bias2[3];               // conv2_l bias [C] (bias-by-MMA path)
   int L, k, dil[3];
   int mode;                            // 0: sum = y   1: sum += y   2: v = (sum + y) * inv_n -> sum (if write_f32) / act_out
   float inv_n, slope_out;
@@ -64,10 +65,24 @@ template <int C> struct RbCfg {
   static constexpr uint32_t TMEM_COLS = 2 * MB * C <= 256 ? 256 : 512;
   static constexpr uint32_t LAYOUT = RB == 128 ? 2u : 4u;
   static constexpr int STAGE_WARP = 32 * RB_STAGE_LD * 4;
+  // Biases by MMA (C <= 64, where the kernel is bound by the epilogue warps' instruction issue): every conv gets one
+  // extra K = 16 MMA per m-block, A = a constant tile whose rows are [1, 1, 0, ...], B = [bias_hi, bias_lo, 0, ...] per
+  // output channel (bf16 hi + lo split: the bias stays accurate to 2^-17), both in the un-swizzled K-major core-matrix
+  // layout (8 rows x 16 B core matrices, LBO = 128 B between the two K halves, SBO = 256 B between 8-row groups).  That
+  // removes 32 FADDs and 8 bias loads per thread and block from every epilogue phase and keeps the residual stream in
+  // TMEM bias-complete.
+  static constexpr bool BIAS_MMA = C <= 64;
+  static constexpr int ONES_BYTES = BIAS_MMA ? 128 * 32 : 0;
+  static constexpr int BIAS_TILE = BIAS_MMA ? C * 32 : 0;
+  static constexpr int EXTRA = ONES_BYTES + 6 * BIAS_TILE;
 };
 
-template <int C>
-__global__ void __launch_bounds__(96 + 32 * RB_MAX_EPI_WARPS, 1)
+// OCC = CTAs per SM: 2 (C = 32 only: 8 epilogue warps, 256 TMEM columns and <= 112 KB of shared memory per CTA) lets one
+// CTA's epilogue phases run under the other's MMA phases -- the phases of one window are short (k*8 MMAs of 40 clk
+// against ~1.5k clk of accumulator -> operand conversion) and strictly alternate, so a lone CTA leaves the tensor pipe
+// idle more than half of the time.
+template <int C, int OCC>
+__global__ void __launch_bounds__(OCC == 2 ? 96 + 32 * 8 : 96 + 32 * RB_MAX_EPI_WARPS, OCC)
 resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ RbParams p) {
   using G = RbCfg<C>;
   constexpr int MB = G::MB, W = G::W, KC = G::KC, RB = G::RB, KS = G::KS, NCB = G::NCB;
@@ -83,6 +98,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   const int w_tiles = p.resident ? 6 * p.k : p.w_slots;
   float* stage = reinterpret_cast<float*>(base_gen + KC * G::A_PLANE + w_tiles * G::W_TILE);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t extra_off = (uint32_t)(KC * G::A_PLANE + w_tiles * G::W_TILE + n_epi * G::STAGE_WARP);
+  const uint32_t ones_s = base + extra_off, bias_s = ones_s + (uint32_t)G::ONES_BYTES;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 6; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
@@ -98,6 +115,21 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   }
   // zero the operand buffer once: its margins are never written again
   for (int i = threadIdx.x; i < KC * G::A_PLANE / 16; i += blockDim.x) reinterpret_cast<uint4*>(a_gen)[i] = make_uint4(0, 0, 0, 0);
+  if constexpr (G::BIAS_MMA) {
+    uint8_t* ex = base_gen + extra_off;
+    for (int i = threadIdx.x; i < G::EXTRA / 16; i += blockDim.x) reinterpret_cast<uint4*>(ex)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (int r = threadIdx.x; r < 128; r += blockDim.x)       // A: every row [1, 1, 0, ...]
+      *reinterpret_cast<uint32_t*>(ex + (r >> 3) * 256 + (r & 7) * 16) = 0x3F803F80u;
+    for (int i = threadIdx.x; i < 6 * C; i += blockDim.x) {    // B: row n of conv ci = [bias_hi, bias_lo, 0, ...] (weights: safe before pdl_wait)
+      const int ci = i / C, n = i - ci * C;
+      const float bv = __ldg(((ci & 1) ? p.bias2[ci >> 1] : p.bias1[ci >> 1]) + n);
+      const __nv_bfloat16 bh = __float2bfloat16_rn(bv);
+      const __nv_bfloat16 bl = __float2bfloat16_rn(bv - __bfloat162float(bh));
+      const uint32_t pk = (uint32_t)__bfloat16_as_ushort(bh) | ((uint32_t)__bfloat16_as_ushort(bl) << 16);
+      *reinterpret_cast<uint32_t*>(ex + G::ONES_BYTES + ci * G::BIAS_TILE + (n >> 3) * 256 + (n & 7) * 16) = pk;
+    }
+  }
   fence_proxy_async();
   tcgen05_fence_before();
   __syncthreads();
@@ -142,6 +174,10 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     int sl = 0;
     uint32_t wph = 0, eph = 0;
     const bool resident = p.resident != 0;
+    // un-swizzled K-major descriptors of the constant-ones tile and the bias tiles (SBO = 256 B, LBO = 128 B)
+    const uint32_t hi_ns = (256u >> 4) | (1u << 14);
+    const uint64_t d_ones = ((uint64_t)hi_ns << 32) | (((ones_s & 0x3FFFFu) >> 4) | (8u << 16));
+    const uint32_t bias_lo0 = ((bias_s & 0x3FFFFu) >> 4) | (8u << 16);
     if (resident) { mbar_wait(&w_full[0], 0); tcgen05_fence_after(); }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int ci = 0; ci < 6; ++ci) {
@@ -154,6 +190,12 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         uint32_t fresh = second ? 0u : 1u;  // conv2 accumulates onto the residual stream from its first MMA on
         if (resident) {                     // KC == 1: one straight run of MMAs per conv, no barrier traffic
           if (elect_one()) {
+            if constexpr (G::BIAS_MMA) {
+              const uint64_t d_bias = ((uint64_t)hi_ns << 32) | (bias_lo0 + (uint32_t)((ci * G::BIAS_TILE) >> 4));
+#pragma unroll
+              for (int m = 0; m < MBH; ++m) umma_bf16(d_tmem + (uint32_t)((mb0 + m) * C), d_ones, d_bias, idesc, fresh ? 0u : 1u);
+              fresh = 0;
+            }
             uint32_t b_lo = w_lo0 + (uint32_t)((ci * k * G::W_TILE) >> 4);
             uint32_t a_lo = a_lo0 + (uint32_t)(((RB_MARG - half_k * d) * RB) >> 4);
             const uint32_t a_step = (uint32_t)((d * RB) >> 4), b_step = (uint32_t)(G::W_TILE >> 4);
@@ -176,6 +218,15 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           }
           __syncwarp();
           continue;
+        }
+        if constexpr (G::BIAS_MMA) {
+          if (elect_one()) {
+            const uint64_t d_bias = ((uint64_t)hi_ns << 32) | (bias_lo0 + (uint32_t)((ci * G::BIAS_TILE) >> 4));
+#pragma unroll
+            for (int m = 0; m < MBH; ++m) umma_bf16(d_tmem + (uint32_t)((mb0 + m) * C), d_ones, d_bias, idesc, fresh ? 0u : 1u);
+          }
+          __syncwarp();
+          fresh = 0;
         }
         for (int kc = 0; kc < KC; ++kc) {
           for (int j = 0; j < k; ++j) {
@@ -242,6 +293,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_item, ti = tile - b * p.tiles_per_item;
       const int w0 = ti * p.Wv - H;
+      const bool interior = w0 >= 0 && w0 + W <= L;    // no row of this window lies outside the sequence: no zero-padding fix-ups
       const float* xb = p.x + b * p.x_bs;
       // ---- phase 0: x -> acc_x (fp32, TMEM) and lrelu(x) -> operand buffer
 #pragma unroll 1
@@ -284,13 +336,22 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           uint32_t raw[32];
           tmem_ld32(acc_mid + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
           float a[32];
+          if constexpr (G::BIAS_MMA) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1[l] + cb * 32 + j));
-            const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
-            const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
-            a[j] = fmaxf(v0, 0.1f * v0) * keep; a[j + 1] = fmaxf(v1, 0.1f * v1) * keep;
-            a[j + 2] = fmaxf(v2, 0.1f * v2) * keep; a[j + 3] = fmaxf(v3, 0.1f * v3) * keep;
+            for (int j = 0; j < 32; ++j) { const float v = __uint_as_float(raw[j]); a[j] = fmaxf(v, 0.1f * v); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1[l] + cb * 32 + j));
+              const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
+              const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
+              a[j] = fmaxf(v0, 0.1f * v0); a[j + 1] = fmaxf(v1, 0.1f * v1);
+              a[j + 2] = fmaxf(v2, 0.1f * v2); a[j + 3] = fmaxf(v3, 0.1f * v3);
+            }
+          }
+          if (!interior) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] *= keep;
           }
           put_operand(wr, cb, a);
         }
@@ -306,16 +367,25 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           uint32_t raw[32];
           tmem_ld32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
           float a[32];
+          if constexpr (G::BIAS_MMA) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bacc[l] + cb * 32 + j));
-            a[j] = __uint_as_float(raw[j]) + bv.x; a[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
-            a[j + 2] = __uint_as_float(raw[j + 2]) + bv.z; a[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+            for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(raw[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bacc[l] + cb * 32 + j));
+              a[j] = __uint_as_float(raw[j]) + bv.x; a[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+              a[j + 2] = __uint_as_float(raw[j + 2]) + bv.z; a[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+            }
           }
           if (l < 2) {
-            const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.1f * a[j]) * keep;
+            for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.1f * a[j]);
+            if (!interior) {
+              const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] *= keep;
+            }
             put_operand(wr, cb, a);
           } else {
             // ---- block output: transpose through the private buffer, then coalesced rows
@@ -364,15 +434,46 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
 
 int g_rb_resident = 1;   // EV_RB_RESIDENT=0: stream weights through the ring even when they would fit
 
+int g_rb_occ2 = 1;       // EV_RB_OCC2=0: one CTA per SM also at C = 32
+
 template <int C>
 cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
   using G = RbCfg<C>;
+  if constexpr (C == 32) {
+    if (g_rb_occ2) {
+      p.H = 6 * (p.k - 1);
+      p.Wv = G::W - 2 * p.H;
+      p.tiles_per_item = ceil_div(p.L, p.Wv);
+      p.total_tiles = p.tiles_per_item * B;
+      const int per_cta = (228 * 1024) / 2 - 2048;
+      const int fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP + G::EXTRA;
+      const int res_bytes = 6 * p.k * G::W_TILE;
+      int smem;
+      if (g_rb_resident && fixed8 + res_bytes <= per_cta) { p.resident = 1; p.w_slots = 1; smem = fixed8 + res_bytes; }
+      else {
+        p.resident = 0;
+        p.w_slots = std::min((per_cta - fixed8) / G::W_TILE, RB_MAX_SLOTS);
+        smem = fixed8 + p.w_slots * G::W_TILE;
+      }
+      if (p.w_slots >= 1 && (p.resident || p.w_slots >= 4)) {
+        static bool configured2 = false;
+        if (!configured2) {
+          cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          if (ce != cudaSuccess) return ce;
+          configured2 = true;
+        }
+        const int grid = std::min(p.total_tiles, 2 * tc_sm_count());
+        // at least a third of the SM's shared memory: a third CTA would not find TMEM columns (2 x 256 are taken)
+        return launch_pdl(resblock_tc_kernel<C, 2>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
+      }
+    }
+  }
   p.H = 6 * (p.k - 1);                    // sum over the three pairs of (k-1)/2 * (d_l + 1), d = 1, 3, 5
   p.Wv = G::W - 2 * p.H;
   p.tiles_per_item = ceil_div(p.L, p.Wv);
   p.total_tiles = p.tiles_per_item * B;
   const int limit = 224 * 1024;
-  const int fixed16 = 1024 + G::KC * G::A_PLANE + 16 * G::STAGE_WARP, fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP;
+  const int fixed16 = 1024 + G::KC * G::A_PLANE + 16 * G::STAGE_WARP + G::EXTRA, fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP + G::EXTRA;
   const int res_bytes = 6 * p.k * G::W_TILE;
   int n_epi = 16, smem;
   p.resident = 0;
@@ -387,13 +488,13 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
   if (p.resident) p.w_slots = 1;
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
   const int grid = std::min(p.total_tiles, tc_sm_count());
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
-  return launch_pdl(resblock_tc_kernel<C>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
+  return launch_pdl(resblock_tc_kernel<C, 1>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
 }
 
 }  // namespace
@@ -425,7 +526,8 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
 cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
                                const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
                                int write_f32, cudaStream_t s, std::string* err) {
-  { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0); once = true; } }
+  { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0);
+                                           v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0); once = true; } }
   RbMaps maps;
   RbParams p{};
   const int rb = C == 32 ? 64 : 128;
@@ -442,6 +544,7 @@ cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], con
         return cudaErrorInvalidValue;
     }
     p.bias1[l] = c1[l]->bias;
+    p.bias2[l] = c2[l]->bias;
     p.bacc[l] = bacc[l];
     p.dil[l] = c1[l]->dilation;
   }

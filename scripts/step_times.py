@@ -18,7 +18,7 @@ model.load_state_dict(synthetic.matcha_state_dict(VCTK, seed=1234))
 voc = ev.Generator(HIFIGAN_V1, precision="bf16")
 voc.load_state_dict(synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321))
 voc.remove_weight_norm()
-x, xl, spk = synthetic.phoneme_batch(32, 60, 90, seed=2000)
+x, xl, spk = synthetic.phoneme_batch(int(os.environ.get("EV_BATCH", "32")), 60, 90, seed=2000)
 x, xl, spk = x.cuda(), xl.cuda(), spk.cuda()
 host = None
 for mode in ("async", "sync+d2h"):
