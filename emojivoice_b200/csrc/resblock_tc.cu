@@ -508,16 +508,15 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
   if (k != 3 && k != 7 && k != 11) return false;
   if (dil[0] != 1 || dil[1] != 3 || dil[2] != 5) return false;
   if (g_rb_policy >= 2) return true;
-  // Measured on B200 (profiles/r01_layers_v16_fused_all.txt vs r01_layers_v15_two_issuers.txt, us per ResBlock at B=32 x 668
+  // Measured on B200 (profiles/r01_resblocks_v17_biasmma_occ2.txt vs r01_layers_v15_two_issuers.txt, us per ResBlock at B=32 x 668
   // frames, fused / layer-by-layer):
-  //   C=128: k3 1152/1686  k7 2424/2265  k11 4075/2844     C=64: k3 1044/1764  k7 1833/2145  k11 2534/2682
-  //   C=32 : k3  930/1644  k7 1780/1953  k11 2815/2649
-  // The fused kernel wins where the layer-by-layer path is HBM/epilogue-bound (k = 3; k = 7 at C <= 64; k = 11 at C = 64); at
-  // C = 128 the separate convs are already MMA-bound (1.1-1.2 PFLOP/s) and the halo recompute (H = 6(k-1) rows per window
-  // side, 256-row windows) costs more than the saved traffic; at C = 32 a 128x32x16 MMA costs ~87 clk whatever feeds it.
+  //   C=128: k3 1145/1686  k7 2408/2265  k11 4128/2844     C=64: k3  888/1764  k7 1668/2145  k11 2341/2682
+  //   C=32 : k3  662/1644  k7 1356/1953  k11 1915/2649
+  // The fused kernel wins wherever the layer-by-layer path is HBM/epilogue-bound (everything at C <= 64, k = 3 at C = 128); at
+  // C = 128 with k >= 7 the separate convs are already MMA-bound (1.1-1.2 PFLOP/s) and the halo recompute (H = 6(k-1) rows
+  // per window side, 256-row windows) costs more than the saved traffic.
+  if (C <= 64) return true;
   if (k == 3) return true;
-  if (k == 7) return C <= 64;
-  if (k == 11) return C == 64;
   return false;
 }
 
