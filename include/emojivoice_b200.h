@@ -135,6 +135,16 @@ EV_API int ev_denoiser_init(ev_ctx* ctx, float* bias_spec_out, void* workspace, 
 EV_API int ev_denoise(ev_ctx* ctx, const float* audio, int B, int L, float strength, float* out, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* ---- monotonic alignment search (training-side, the reference's only native component) ------------
+ * replaces  maximum_path_c(paths, values, t_xs, t_ys, max_neg_val)   Matcha-TTS/matcha/utils/monotonic_align/core.pyx:42-47
+ * (called through monotonic_align.maximum_path, __init__.py:7-22, from MatchaTTS.forward, models/matcha_tts.py:198).
+ *   value (B,Tx,Ty) fp32 log-likelihoods (already multiplied by the mask, as __init__.py:13 does), t_xs / t_ys (B) int32
+ *   valid extents -> path (B,Tx,Ty) int32 0/1, bit-identical to the Cython code.  `value` is NOT modified (the
+ *   reference accumulates in a private copy).  As in the reference, t_ys[b] >= t_xs[b] is required. */
+EV_API size_t ev_maximum_path_workspace_bytes(const ev_ctx* ctx, int B, int Tx, int Ty);
+EV_API int ev_maximum_path(ev_ctx* ctx, const float* value, const int32_t* t_xs, const int32_t* t_ys, int B, int Tx, int Ty,
+                    float max_neg_val, int32_t* path, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- bookkeeping the bench reads: kernels launched by this context since the last reset ------------------- */
 EV_API int64_t ev_launch_count(const ev_ctx* ctx, int reset);
 
