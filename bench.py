@@ -33,7 +33,7 @@ if ROOT not in sys.path:
 SR, HOP = 22050, 256
 N_TIMESTEPS, TEMPERATURE, LENGTH_SCALE = 10, 0.667, 0.8      # feel_me.py:71-77 (the operating point of every app)
 BATCH, P_LO, P_HI = 32, 60, 90                                # Tx = 2P+1 in [121, 181]
-CPU_SAMPLE = 2                                                # utterances of the batch the CPU baseline synthesises
+CPU_SAMPLE = 8                                                # utterances of the batch the CPU baseline synthesises (~3 s of CPU work per pass)
 
 
 def load_peaks():
@@ -88,6 +88,27 @@ class ClockSampler:
         reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "reasons": reasons,
                 "samples": len(self.sm)}
+
+
+def measured_traffic(kernel_class: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this same command
+    (profiles/r01_launch_summary.json, written by scripts/ncu_launch_summary.py); None when no capture is committed."""
+    import re
+
+    path = os.path.join(ROOT, "profiles", "r01_launch_summary.json")
+    if not os.path.exists(path):
+        return None, None
+    k = json.load(open(path))["kernels"]
+    m = re.match(r"conv_tc_(bn|tf32x)(\d+)", kernel_class)
+    fn = "conv_tc_kernel<%s>" % (m.group(2) if m.group(1) == "bn" else "128") if m else None
+    if kernel_class.startswith("resblock_tc"):
+        hits = [v for n, v in k.items() if n.startswith("resblock_tc_kernel")]
+        if hits:
+            n = sum(h["launches"] for h in hits)
+            return sum(h["dram_bytes_per_launch"] * h["launches"] for h in hits) / n, "resblock_tc_kernel<*>"
+    if fn in k:
+        return k[fn]["dram_bytes_per_launch"], fn
+    return None, None
 
 
 def audio_seconds(mel_lengths) -> float:
@@ -336,10 +357,17 @@ def main():
         ach, peak, unit, bound = top["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
     roofline = {"kernel": top["name"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
                 "frac": round(ach / peak, 4), "traffic": None, "launches": top["launches"],
+                "algorithmic_bytes_per_launch": round(top["bytes"] / max(top["launches"], 1)),
+                "algorithmic_flops_per_launch": round(top["flops"] / max(top["launches"], 1)),
                 "avg_launch_us": round(top["total_ms"] * 1e3 / max(top["launches"], 1), 2),
                 "share_of_step": round(top["total_ms"] / ksum, 4), "arith_intensity": round(ai, 1),
                 "peak_source": peaks["source"], "how": "CUDA events around every launch on the launching stream, one "
                 "instrumented step right after the timed region; algorithmic FLOPs/bytes (valid un-padded work)"}
+    tr, tr_fn = measured_traffic(top["name"])
+    if tr is not None:
+        roofline["traffic"] = round(tr)
+        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of %s, averaged over the launches of one "
+                                      "bench step (profiles/r01_launch_summary.json, ncu --clock-control none)" % tr_fn)
     # whole-path algorithmic FLOPs as a fraction of the tensor roofline
     tx = xl.double()
     flops_step = float((tx * (19309056 + 6144 * tx)).sum()) + 0.0
@@ -369,12 +397,12 @@ def main():
         once, n = cpu_oracle_rate(x, xl, spks, CPU_SAMPLE)
         once()
         best = None
-        for _ in range(2):
+        for _ in range(3):
             a, dt, _ = once()
             best = (a, dt) if best is None or dt < best[1] else best
         result["cpu_baseline"] = {"value": round(best[0] / best[1], 3), "unit": "audio-s/s", "cores": torch.get_num_threads(),
                                   "kind": "port", "sample": f"first {n} utterances of the batch ({best[0]:.1f} audio-s), fp32 "
-                                  f"torch CPU oracle, warm-up 1, best of 2, {os.cpu_count()} host cpus"}
+                                  f"torch CPU oracle, warm-up 1, best of 3, {os.cpu_count()} host cpus"}
     elif rank == 0:
         result["cpu_baseline"] = None
     if rank == 0:

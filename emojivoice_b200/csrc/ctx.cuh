@@ -97,7 +97,8 @@ struct ev_ctx {
   // (forked from / joined into the caller's stream, so a CUDA-graph capture sees parallel branches).  The decoder's
   // kernels at B = 32 are launch/prologue-latency bound (3 us of MMA in a 13 us kernel); concurrent lanes overlap them.
   static constexpr int kMaxLanes = 4;
-  int dec_lanes = 2;            // EV_DEC_LANES
+  int dec_lanes = 1;            // EV_DEC_LANES (default 1: measured 16.86 ms -> 16.5 ms with 2 lanes, 17.5 ms with 4 -- the decoder's
+                                // kernels already cover most SMs, so concurrent lanes mostly queue behind each other)
   cudaStream_t lane_stream[kMaxLanes - 1] = {};
   cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes - 1] = {};
 };
