@@ -235,6 +235,15 @@ extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y
   return EV_OK;
 }
 
+// diagnostic (EV_TC_TRACE=1): per-CTA clock stamps [n_cta][16] of the most recent conv_tc launch, host buffer
+extern "C" int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
+  if (!ctx || !out_host || n <= 0) return EV_ERR_INVALID;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, cudaDeviceSynchronize());
+  EV_CUDA(ctx, conv_tc_read_trace(reinterpret_cast<unsigned long long*>(out_host), n));
+  return EV_OK;
+}
+
 extern "C" int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream) {
   if (!ctx || !x || !out) return EV_ERR_INVALID;
   EV_CUDA(ctx, cudaSetDevice(ctx->device));

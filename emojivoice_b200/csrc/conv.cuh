@@ -104,6 +104,7 @@ bool conv_tc_init(std::string* err);
 bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
                         uint64_t s2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes, std::string* err);
 int tc_sm_count();
+cudaError_t conv_tc_read_trace(unsigned long long* host, int n);   // diagnostic: clock stamps of the last traced launch
 
 // resblock_tc.cu: one fused HiFi-GAN ResBlock1 (six convs, residual stream resident in TMEM)
 bool resblock_tc_supported(int C, int k, const int* dil);

@@ -46,39 +46,56 @@ constexpr int kMaxGroups = kMaxTaps;
 constexpr int SMEM_LIMIT = 224 * 1024;     // dynamic shared memory one CTA may ask for
 
 struct TcParams {
-  ConvGeom g;
-  Epilogue e;
-  // taps are processed in groups that share one activation tile: with halo reuse all taps form one group whose
-  // tile covers rows [m0 + grp_row0, m0 + grp_row0 + a_rows); otherwise every tap is its own group.
-  int n_groups;
-  int grp_row0[kMaxGroups], grp_col0[kMaxGroups], grp_first[kMaxGroups], grp_count[kMaxGroups];
-  int tap_byte_off[kMaxTaps];   // byte offset of tap j's first row inside its group's tile
+  // ---- scalars first: everything the TMA producer / MMA issuers read before their first instruction of real work sits
+  // in the first two constant-cache lines of the parameter block (a traced launch showed the lone producer thread
+  // spending ~2400 clk between griddepcontrol.wait and its first TMA, mostly on cold constant loads and two IDIVs)
+  int m_tiles, n_tiles, total_tiles;
+  int mb;                       // m-blocks (128 rows) per tile
+  int kchunks;
+  int n_groups;                 // taps are processed in groups that share one activation tile (see grp_* below)
+  int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
   int a_boxes, a_box_rows;      // the activation tile is a_boxes TMA boxes of a_box_rows rows each
   int a_slot_bytes;             // tile bytes rounded up to 1024
   int a_slots, b_slots;
-  int kchunks;
-  int vec_ok;
-  int m_tiles, n_tiles, total_tiles;
-  int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
-  int mb;                       // m-blocks (128 rows) per tile
   int bk, row_bytes, ksteps;    // K-chunk channels, bytes per smem row (= swizzle width), UMMA K-steps per chunk
   int b_tile_bytes;
-  uint32_t desc_sbo, desc_layout;
-  uint32_t tmem_cols;
-  int debug_nob;                // EV_TC_DEBUG_NOB bit 0 / 1 / 2: skip weight loads / activation loads / lean-path stores.  Timing
-                                // experiments only (results are wrong): they showed the MMA-bound layers are issue-bound, not memory-bound
-  int n_issuers;                // MMA issuer warps: 2 (one per m-block) in the wide configuration, else 1
-  int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
-  int grp_taps;                 // taps per group (all groups alike: `taps` with halo reuse, else 1)
-  uint32_t idesc;               // instruction descriptor (kind::f16 bf16, or kind::tf32)
+  int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
   int tf32;                     // operands are 32-bit (3xTF32 split path): K-chunks walk the sections [hi | hi | lo] of A
   int kch1;                     // K-chunks per section (== kchunks unless tf32)
+  int sec_off[3];               // column offset of each A section
+  int debug_nob;                // EV_TC_DEBUG_NOB bit 0 / 1 / 2: skip weight loads / activation loads / lean-path stores.  Timing
+                                // experiments only (results are wrong): they showed the MMA-bound layers are issue-bound, not memory-bound
+  int trace;                    // EV_TC_TRACE=1: per-CTA clock64 stamps of the pipeline's milestones (scripts/conv_trace.py)
+  unsigned long long div_n, div_m;   // ceil(2^44 / n_tiles), ceil(2^44 / m_tiles): tile -> (b, m-tile, n-tile) without IDIV
   int flush_kc;                 // K-chunks per accumulation group: the TMEM partial sum is flushed into an fp32 master
                                 // accumulator (rounded adds) after every group; == kchunks means one group per tile
-  int sec_off[3];               // column offset of each A section
+  int n_issuers;                // MMA issuer warps: 2 (one per m-block) in the wide configuration, else 1
+  int act_only;                 // epilogue writes only the bf16 operand tensor (no residual / fp32 output): lean path
+  int vec_ok;
+  uint32_t desc_sbo, desc_layout;
+  uint32_t tmem_cols;
+  uint32_t idesc;               // instruction descriptor (kind::f16 bf16, or kind::tf32)
   uint32_t tap_first16;         // (byte offset of tap 0's first row inside a haloed tile) >> 4
   uint32_t tap_step16;          // (bytes from one tap's first row to the next one's) >> 4, two's complement when negative
+  // with halo reuse all taps form one group whose tile covers rows [m0 + grp_row0, m0 + grp_row0 + a_rows); otherwise
+  // every tap is its own group
+  int grp_row0[kMaxGroups], grp_col0[kMaxGroups], grp_first[kMaxGroups], grp_count[kMaxGroups];
+  int tap_byte_off[kMaxTaps];   // byte offset of tap j's first row inside its group's tile
+  ConvGeom g;
+  Epilogue e;
 };
+
+// tile index -> (batch item, m-tile, n-tile) with two multiplies (exact for tile < 2^22 and divisors < 2^20)
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& b, int& mt, int& nt) {
+  const uint32_t rest = (uint32_t)(((unsigned long long)(uint32_t)tile * p.div_n) >> 44);
+  nt = tile - (int)rest * p.n_tiles;
+  b = (int)(((unsigned long long)rest * p.div_m) >> 44);
+  mt = (int)rest - b * p.m_tiles;
+}
+
+// [CTA][16] clock stamps of the most recent traced launch (diagnostic; read back by ev_test_conv_trace)
+__device__ unsigned long long g_trace[512 * 16];
+#define EV_TR(i) do { if (p.trace && lane == 0 && blockIdx.x < 512) g_trace[blockIdx.x * 16 + (i)] = (unsigned long long)clock64(); } while (0)
 
 // Upper / lower words of a shared-memory matrix descriptor (tc_ptx.cuh make_smem_desc_ex): the MMA warp advances the
 // low word by plain adds instead of rebuilding descriptors.
@@ -131,6 +148,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_base = tiles0, b_base = tiles0 + (uint32_t)(p.a_slots * p.a_slot_bytes);
   float* stage = reinterpret_cast<float*>(smem_raw + (tiles0 - smem_u32(smem_raw)) + p.a_slots * p.a_slot_bytes + p.b_slots * p.b_tile_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    EV_TR(0);
+    if (p.trace && lane == 0 && blockIdx.x < 512) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_trace[blockIdx.x * 16 + 11] = gt; }
+  }
   const int A_SLOTS = p.a_slots, B_SLOTS = p.b_slots;
   const int tile_rows = p.mb * BM;
   const int ROLE_WARPS = 1 + p.n_issuers;   // producer + issuers; the epilogue warps follow
@@ -148,12 +169,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // every role decodes its first tile (and pulls the parameter block through the constant cache) BEFORE the barrier and
+  // the programmatic-dependency wait: this part overlaps the TMEM allocation and, under PDL, the previous kernel's tail
+  int first_b, first_mt, first_nt;
+  decode_tile(p, (int)blockIdx.x, first_b, first_mt, first_nt);
+  asm volatile("" ::"r"(first_b), "r"(first_mt), "r"(first_nt));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (warp == 0) EV_TR(1);
   pdl_trigger();     // the next kernel may start its prologue
   pdl_wait();        // everything above overlapped the previous kernel's tail; its results are visible from here on
+  if (warp == 0) EV_TR(2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -162,7 +190,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, sb = 0;
       uint32_t pa = 1, pb = 1;      // parity to wait for on the "empty" barriers (fresh barriers pass parity 1)
       const uint32_t a_bytes = (uint32_t)(p.a_boxes * p.a_box_rows * p.row_bytes), box_bytes = (uint32_t)(p.a_box_rows * p.row_bytes);
-      const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
+      const int kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
       const bool resident = p.resident != 0;
       if (resident) {   // narrow layers: every (K-chunk, tap) weight tile is fetched once and kept
         const int n_w = kchunks * p.g.taps;
@@ -171,22 +199,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < p.g.taps; ++j)
             tma_load_3d(b_base + (uint32_t)((kc * p.g.taps + j) * p.b_tile_bytes), &tmB, &b_full[0], kc * p.bk, 0, j);
       }
+      EV_TR(12);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles, rest = tile / n_tiles, mt = rest % m_tiles, b = rest / m_tiles;
+        int nt = first_nt, mt = first_mt, b = first_b;
+        if (tile != (int)blockIdx.x) decode_tile(p, tile, b, mt, nt);
         const int m0 = mt * tile_rows, n0 = nt * BN;
+        if (tile == (int)blockIdx.x) EV_TR(13);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int g = 0; g < n_groups; ++g) {
             mbar_wait(&a_empty[sa], pa);
+            if (tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(14);
             if (p.debug_nob & 2) { mbar_arrive(&a_full[sa]); if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; } if (resident) continue; goto b_loads; }
             mbar_expect_tx(&a_full[sa], a_bytes);
             {
             const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
-            const int sec = kc / p.kch1;   // 3xTF32: K-chunks walk the A sections [hi | hi | lo]; otherwise one section
+            const int sec = (kc >= p.kch1) + (kc >= 2 * p.kch1);   // 3xTF32: K-chunks walk the A sections [hi | hi | lo]; otherwise one section
             const int col = p.grp_col0[g] + p.sec_off[sec] + (kc - sec * p.kch1) * p.bk, row = m0 + p.grp_row0[g];
             tma_load_3d(dst, &tmA, &a_full[sa], col, row, b);
             if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, &tmA, &a_full[sa], col, row + p.a_box_rows, b);
             }
             if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+            if (tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(3);
             if (resident) continue;
           b_loads:
             const int tap0 = g * grp_taps;
@@ -217,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t mb_step16 = (uint32_t)(BM * p.row_bytes) >> 4, tap_step16 = p.tap_step16;
     const uint32_t b_step16 = (uint32_t)p.b_tile_bytes >> 4, a_step16 = (uint32_t)p.a_slot_bytes >> 4;
     const uint32_t a_lo0 = desc_lo_word(a_base), b_lo0 = desc_lo_word(b_base);
-    const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
+    const int kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
     const bool resident = p.resident != 0, ks4 = p.ksteps == 4;
     const uint32_t acc_stride = (uint32_t)(p.mb * BN);
     const int my_mb = warp - 1, mb_stride = p.n_issuers;   // this issuer owns m-blocks my_mb, my_mb + mb_stride, ...
@@ -226,7 +259,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int flush_kc = p.flush_kc;
     if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int mt = (tile / n_tiles) % m_tiles;
+      int mt = first_mt;
+      if (tile != (int)blockIdx.x) { int b_, nt_; decode_tile(p, tile, b_, mt, nt_); }
       const int vmb = min(p.mb, (p.g.M - mt * tile_rows + BM - 1) / BM);     // m-blocks that hold valid rows
       int buf = 0, in_group = 0;
       uint32_t d_tmem = 0;
@@ -243,6 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int g = 0; g < n_groups; ++g) {
           mbar_wait(&a_full[sa], pa);
           tcgen05_fence_after();
+          if (warp == 1 && tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(4);
           uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step16 + p.tap_first16;
           for (int j = 0; j < grp_taps; ++j) {
             uint32_t b_lo;
@@ -283,6 +318,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++in_group == flush_kc || kc == kchunks - 1) {   // group complete -> epilogue (output pass or partial-sum flush)
           if (elect_one()) umma_commit(&acc_full[buf]);
           __syncwarp();
+          if (warp == 1) { if (tile == (int)blockIdx.x) EV_TR(5); EV_TR(6); }
           in_group = 0;
           ++vt;
         }
@@ -312,13 +348,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* srow_w = wstage + lane * STAGE_LD;
     const float* srow_r = wstage + sub * STAGE_LD + cl;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_tiles = p.n_tiles, m_tiles = p.m_tiles, M = p.g.M, N = p.g.N, T_out = e.T_out;
+    const int M = p.g.M, N = p.g.N, T_out = e.T_out;
     const int up_s = e.up_s, up_p = e.up_p;
 
     int ti = 0;                      // accumulator-set use counter (see the MMA warp's vt)
     const int n_grp = (p.kchunks + p.flush_kc - 1) / p.flush_kc;   // accumulation groups per tile (1 unless 3xTF32)
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti += n_grp) {
-      const int nt = tile % n_tiles, rest = tile / n_tiles, mt = rest % m_tiles, b = rest / m_tiles;
+      int nt = first_nt, mt = first_mt, b = first_b;
+      if (tile != (int)blockIdx.x) decode_tile(p, tile, b, mt, nt);
       const int m0 = mt * tile_rows, n0 = nt * BN;
       const int vmb = min(p.mb, (M - m0 + BM - 1) / BM);
       const int buf = ti & 1;
@@ -430,6 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
             tcgen05_fence_after();
             waited = true;
+            if (ew == 0 && tile == (int)blockIdx.x) EV_TR(7);
           }
           {
             uint32_t raw[32];
@@ -505,7 +543,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           scalar_block(p, wstage, b, m0 + mb * BM + q * 32, n0 + cb * 32, lane);
         }
         __syncwarp();                // the transpose buffer may be overwritten by the next block
+        if (ew == 0 && tile == (int)blockIdx.x && blk == slot) EV_TR(15);
       }
+      if (ew == 0) { if (tile == (int)blockIdx.x) EV_TR(8); EV_TR(9); }
       if (slot >= n_blk) {           // a warp without a block in this tile still keeps step with the accumulator hand-over
         for (int grp = 0; grp < n_grp; ++grp) {
           const int v = ti + grp;
@@ -520,6 +560,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    EV_TR(10);
   }
 }
 
@@ -592,6 +633,9 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   p.m_tiles = ceil_div(p.g.M, BM * p.mb);
   p.n_tiles = ceil_div(p.g.N, BN);
   p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
+  p.div_n = ((1ull << 44) + (unsigned long long)p.n_tiles - 1) / (unsigned long long)p.n_tiles;
+  p.div_m = ((1ull << 44) + (unsigned long long)p.m_tiles - 1) / (unsigned long long)p.m_tiles;
+  if (p.total_tiles >= (1 << 22)) return cudaErrorInvalidConfiguration;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * p.mb * BN)) cols <<= 1;
   p.tmem_cols = cols;
@@ -633,6 +677,9 @@ bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, ui
   return encode_map(map, base, d0, d1, d2, s1_bytes, s2_bytes, b0, b1, err, swizzle_bytes);
 }
 int tc_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+cudaError_t conv_tc_read_trace(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * std::min(n, 512 * 16));
+}
 
 int conv_tc_pick_bn(int N) {
   if (N % 128 == 0) return 128;
@@ -804,6 +851,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     return cudaErrorInvalidValue;
   }
   { static const int nob = []() { const char* v = getenv("EV_TC_DEBUG_NOB"); return v ? atoi(v) : 0; }(); p.debug_nob = nob; }
+  { static const int tr = []() { const char* v = getenv("EV_TC_TRACE"); return v ? atoi(v) : 0; }(); p.trace = tr; }
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream);
     case 64: return launch_bn<64>(tmA, tmB, p, stream);

@@ -261,27 +261,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
     }
   }
   const int t_base = (blockIdx.x * (blockDim.x >> 5) + warp) * GN_APPLY_ROWS;
-  // all rows' loads are issued before the first row is processed: the kernel is latency-bound (its input was just
-  // written by the producing conv and sits in L2), so four serialized round trips per warp were most of its run time
-  constexpr bool PREFETCH = V4 <= 2;
-  float4 xr[PREFETCH ? GN_APPLY_ROWS : 1][V4], rr4[PREFETCH ? GN_APPLY_ROWS : 1][V4];
-  if (PREFETCH) {
-#pragma unroll
-    for (int rr = 0; rr < GN_APPLY_ROWS; ++rr) {
-      const int t = min(t_base + rr, a.T - 1);
-      const long long row = (long long)b * a.T + t;
-#pragma unroll
-      for (int i = 0; i < V4; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        xr[rr][i] = rr4[rr][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < a.C) {
-          xr[rr][i] = *reinterpret_cast<const float4*>(a.x + row * a.C + c);
-          if (a.res) rr4[rr][i] = *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c);
-        }
-      }
-    }
-  }
-#pragma unroll
+#pragma unroll 1
   for (int rr = 0; rr < GN_APPLY_ROWS; ++rr) {
     const int t = t_base + rr;
     if (t >= a.T) return;
@@ -295,7 +275,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
       const int c = 4 * (lane + 32 * i);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < a.C) {
-        const float4 xv = PREFETCH ? xr[rr][i] : *reinterpret_cast<const float4*>(x + c);
+        const float4 xv = *reinterpret_cast<const float4*>(x + c);
         // same operation order as the reference: ((x - mean) * rstd) * gamma + beta is refactored only in bf16 mode
         if (sizeof(ActT) == 4) {
           const int g = c / cpg;
@@ -313,7 +293,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
           v.x = (v.x + te[i].x) * m; v.y = (v.y + te[i].y) * m; v.z = (v.z + te[i].z) * m; v.w = (v.w + te[i].w) * m;
         }
         if (a.res) {
-          const float4 r = PREFETCH ? rr4[rr][i] : *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c);
+          const float4 r = *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c);
           v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + row * a.f32_ld + c) = v;

@@ -176,6 +176,11 @@ EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_len
 EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
 /* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */
 EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream);
+/* Diagnostic (EV_TC_TRACE=1): clock64 stamps [CTA][16] of the most recent tensor-core conv launch's pipeline milestones
+ * (0 entry, 1 prologue done, 2 after griddepcontrol.wait, 3 first TMA issued, 4 first operands landed, 5 first tile's MMAs
+ * committed, 6 last commit, 7 first accumulator seen by the epilogue, 8 first tile stored, 9 last tile stored, 10 exit,
+ * 11 %globaltimer at entry); synchronises the device.  scripts/conv_trace.py prints the medians. */
+EV_API int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n);
 
 #ifdef __cplusplus
 }
