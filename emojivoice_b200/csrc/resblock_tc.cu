@@ -81,13 +81,20 @@ template <int C> struct RbCfg {
 // CTA's epilogue phases run under the other's MMA phases -- the phases of one window are short (k*8 MMAs of 40 clk
 // against ~1.5k clk of accumulator -> operand conversion) and strictly alternate, so a lone CTA leaves the tensor pipe
 // idle more than half of the time.
-template <int C, int OCC>
+//
+// WAVE = m-block wavefront (resident weights only): instead of "all MMAs of a conv, then all of its epilogue", the issuer
+// walks the m-blocks of the window one after the other and commits each on its own mbarrier; the epilogue warps of m-block
+// j convert its accumulator as soon as the MMAs of m-block j+1 have completed (they still read j's last rows through
+// their taps), and the next conv's MMAs on m-block j start once the operand rows of j-1, j, j+1 are in place.  The
+// tensor pipe then only idles when one m-block's epilogue (~400 clk) outlasts the next m-block's MMAs (k*KS*40-48 clk).
+template <int C, int OCC, bool WAVE>
 __global__ void __launch_bounds__(OCC == 2 ? 96 + 32 * 8 : 96 + 32 * RB_MAX_EPI_WARPS, OCC)
 resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ RbParams p) {
   using G = RbCfg<C>;
   constexpr int MB = G::MB, W = G::W, KC = G::KC, RB = G::RB, KS = G::KS, NCB = G::NCB;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full[RB_MAX_SLOTS], w_empty[RB_MAX_SLOTS], mma_done, epi_done;
+  __shared__ __align__(8) uint64_t mma_done_mb[4], epi_done_mb[4];   // WAVE: one pair per m-block
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -107,6 +114,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     for (int s = 0; s < RB_MAX_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
     mbar_init(&mma_done, 2);
     mbar_init(&epi_done, (blockDim.x >> 5) - 3);
+    for (int m = 0; m < 4; ++m) { mbar_init(&mma_done_mb[m], 1); mbar_init(&epi_done_mb[m], 4 * NCB); }   // one arrival per (lane quadrant, 32-column block)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -163,6 +171,53 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (WAVE && warp < 3) {
+    // ---------------- wavefront issuer: warp 1 alone (one thread with straight-line code saturates the pipe at N <= 64)
+    if (warp == 1) {
+      constexpr uint32_t idesc = make_idesc(128, C);
+      const uint32_t hi = ((uint32_t)(8 * RB) >> 4) | (1u << 14) | (G::LAYOUT << 29);
+      const uint32_t a_lo0 = ((a_s & 0x3FFFFu) >> 4) | (1u << 16), w_lo0 = ((w_s & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t hi_ns = (256u >> 4) | (1u << 14);
+      const uint64_t d_ones = ((uint64_t)hi_ns << 32) | (((ones_s & 0x3FFFFu) >> 4) | (8u << 16));
+      const uint32_t bias_lo0 = ((bias_s & 0x3FFFFu) >> 4) | (8u << 16);
+      mbar_wait(&w_full[0], 0);
+      tcgen05_fence_after();
+      uint32_t cn = 0;                      // convs issued so far: epi_done_mb[*] completion number to wait for
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int ci = 0; ci < 6; ++ci, ++cn) {
+          const int l = ci >> 1, second = ci & 1;
+          const int d = second ? 1 : p.dil[l];
+          const uint32_t d_base = second ? acc_x : acc_mid;
+          const uint32_t par = cn & 1u;
+          const uint64_t d_bias = ((uint64_t)hi_ns << 32) | (bias_lo0 + (uint32_t)((ci * G::BIAS_TILE) >> 4));
+          const uint32_t a_step = (uint32_t)((d * RB) >> 4), b_step = (uint32_t)(G::W_TILE >> 4);
+          const uint32_t b_first = w_lo0 + (uint32_t)((ci * k * G::W_TILE) >> 4);
+          const uint32_t a_first = a_lo0 + (uint32_t)(((RB_MARG - half_k * d) * RB) >> 4);
+#pragma unroll 1
+          for (int mb = 0; mb < MB; ++mb) {
+            // operand rows of m-blocks mb-1, mb, mb+1 must hold this conv's input
+            if (mb == 0) { mbar_wait(&epi_done_mb[0], par); if (MB > 1) mbar_wait(&epi_done_mb[1], par); }
+            else if (mb + 1 < MB) mbar_wait(&epi_done_mb[mb + 1], par);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t dt = d_base + (uint32_t)(mb * C);
+              umma_bf16(dt, d_ones, d_bias, idesc, second ? 1u : 0u);      // bias row: initialises conv1's accumulator
+              uint32_t a_lo = a_first + (uint32_t)((mb * 128 * RB) >> 4), b_lo = b_first;
+              for (int j = 0; j < k; ++j) {
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                  umma_bf16(dt, ((uint64_t)hi << 32) | (a_lo + 2u * ks), ((uint64_t)hi << 32) | (b_lo + 2u * ks), idesc, 1u);
+                a_lo += a_step;
+                b_lo += b_step;
+              }
+              umma_commit(&mma_done_mb[mb]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
   } else if (warp < 3) {
     // ---------------- two MMA issuers (warp-uniform control flow, one elected lane each): warp 1 issues the first
     // half of the m-blocks, warp 2 the second half, so one warp's barrier / bookkeeping work overlaps the other's MMAs
@@ -284,10 +339,26 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     };
     auto phase_done = [&]() {
+      if constexpr (WAVE) return;        // wavefront mode hands over block by block (block_done)
       tcgen05_fence_before();
       fence_proxy_async();               // operand buffer writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&epi_done);
+    };
+    uint32_t cn = 0;                     // WAVE: convs consumed so far = mma_done_mb[*] completion number to wait for
+    auto wave_wait = [&](int mb) {       // m-block mb may be converted once mb+1's MMAs (which read mb's last rows) are done
+      if constexpr (WAVE) {
+        mbar_wait(&mma_done_mb[mb + 1 < MB ? mb + 1 : MB - 1], cn & 1u);
+        tcgen05_fence_after();
+      }
+    };
+    auto block_done = [&](int mb) {
+      if constexpr (WAVE) {
+        tcgen05_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&epi_done_mb[mb]);
+      }
     };
 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -318,6 +389,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         tmem_st32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
         put_operand(mb * 128 + q * 32 + lane, cb, a);
         __syncwarp();
+        if constexpr (WAVE) { tmem_st_wait(); block_done(mb); }
       }
       tmem_st_wait();
       phase_done();
@@ -325,14 +397,17 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
         // ---- after conv1_l: operand <- lrelu(acc_mid + b1), zero outside the sequence (conv2's zero padding)
-        mbar_wait(&mma_done, mph);
-        mph ^= 1u;
-        tcgen05_fence_after();
+        if constexpr (!WAVE) {
+          mbar_wait(&mma_done, mph);
+          mph ^= 1u;
+          tcgen05_fence_after();
+        }
 #pragma unroll 1
         for (int blk = slot; blk < MB * NCB; blk += n_slots) {
           const int mb = blk / NCB, cb = blk - mb * NCB;
           const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
           const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
+          wave_wait(mb);
           uint32_t raw[32];
           tmem_ld32(acc_mid + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
           float a[32];
@@ -354,16 +429,21 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) a[j] *= keep;
           }
           put_operand(wr, cb, a);
+          block_done(mb);
         }
+        ++cn;
         phase_done();
         // ---- after conv2_l: acc_x now holds x_new - (accumulated conv2 biases)
-        mbar_wait(&mma_done, mph);
-        mph ^= 1u;
-        tcgen05_fence_after();
+        if constexpr (!WAVE) {
+          mbar_wait(&mma_done, mph);
+          mph ^= 1u;
+          tcgen05_fence_after();
+        }
 #pragma unroll 1
         for (int blk = slot; blk < MB * NCB; blk += n_slots) {
           const int mb = blk / NCB, cb = blk - mb * NCB;
           const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
+          wave_wait(mb);
           uint32_t raw[32];
           tmem_ld32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
           float a[32];
@@ -387,6 +467,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) a[j] *= keep;
             }
             put_operand(wr, cb, a);
+            block_done(mb);
           } else {
             // ---- block output: transpose through the private buffer, then coalesced rows
 #pragma unroll
@@ -419,6 +500,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             __syncwarp();
           }
         }
+        ++cn;
         if (l < 2) phase_done();
       }
       tcgen05_fence_before();   // acc_x is rewritten by the next tile's phase 0
@@ -435,6 +517,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
 int g_rb_resident = 1;   // EV_RB_RESIDENT=0: stream weights through the ring even when they would fit
 
 int g_rb_occ2 = 1;       // EV_RB_OCC2=0: one CTA per SM also at C = 32
+int g_rb_wave = 0;       // EV_RB_WAVE=1: m-block wavefront schedule instead of phase alternation (measured equal: the kernel is
+                         // bound by shared-memory bandwidth -- MMA operand fetch alone takes 32 + N/4 of every 40-48 clk)
 
 template <int C>
 cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
@@ -458,13 +542,15 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
       if (p.w_slots >= 1 && (p.resident || p.w_slots >= 4)) {
         static bool configured2 = false;
         if (!configured2) {
-          cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
           if (ce != cudaSuccess) return ce;
           configured2 = true;
         }
         const int grid = std::min(p.total_tiles, 2 * tc_sm_count());
         // at least a third of the SM's shared memory: a third CTA would not find TMEM columns (2 x 256 are taken)
-        return launch_pdl(resblock_tc_kernel<C, 2>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
+        if (p.resident && g_rb_wave) return launch_pdl(resblock_tc_kernel<C, 2, true>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
+        return launch_pdl(resblock_tc_kernel<C, 2, false>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
       }
     }
   }
@@ -488,13 +574,16 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
   if (p.resident) p.w_slots = 1;
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (ce == cudaSuccess && G::BIAS_MMA && G::KC == 1) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
   const int grid = std::min(p.total_tiles, tc_sm_count());
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
-  return launch_pdl(resblock_tc_kernel<C, 1>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
+  if (G::BIAS_MMA && G::KC == 1 && p.resident && g_rb_wave)
+    return launch_pdl(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
+  return launch_pdl(resblock_tc_kernel<C, 1, false>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
 }
 
 }  // namespace
@@ -526,7 +615,8 @@ cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], con
                                const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
                                int write_f32, cudaStream_t s, std::string* err) {
   { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0);
-                                           v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0); once = true; } }
+                                           v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0);
+                                           v = getenv("EV_RB_WAVE"); g_rb_wave = v && atoi(v) != 0; once = true; } }
   RbMaps maps;
   RbParams p{};
   const int rb = C == 32 ? 64 : 128;

@@ -355,3 +355,55 @@ def test_corpus_driver_matches_oracle_on_identical_microbatches(matcha_sd, vocod
     for i in range(5):
         assert got[i]["waveform"].shape == ref_wavs[i].shape == (got[i]["mel_length"] * 256,)
         assert rel_l2(got[i]["waveform"], ref_wavs[i]) < 2e-4
+
+
+# ------------------------------------------------------------------------------------------------ full size (config 2)
+def test_full_size_batch_properties_and_anchor_items(matcha, matcha_sd, vocoders):
+    """BASELINE configs[1] at its full size (32 utterances of ~5 s, n_timesteps = 10), through size-independent properties:
+      * the two items the oracle can afford -- the longest utterance (it fixes T_pad, so the oracle's own 2-item batch pads
+        exactly like the 32-item one; SURVEY H1: items only interact through the padded extent) and one more -- match the
+        oracle within the fp32 tolerance; their durations / alignment are bit-exact;
+      * every alignment is a monotonic 0/1 path with one token per valid frame; padded frames carry z * temperature;
+      * bf16 (tensor-core) and fp32 (CUDA-core) modes agree within the bf16 tolerance on the whole batch, mel and waveform;
+      * the CUDA-graph replay (third call with the same shape) is bit-identical to the eager call."""
+    gen, hsd = vocoders["hifigan_gain1"]
+    x, xl, spk = synthetic.phoneme_batch(32, 60, 90, seed=2000)
+    probe = matcha.synthesise(x, xl, 1, 0.667, spk, 0.8, dtype="fp32")
+    t_pad, lens = probe["t_pad"], probe["mel_lengths"].cpu()
+    z = synthetic.prior_noise(32, 80, t_pad, seed=7)
+    out32 = matcha.synthesise(x, xl, 10, 0.667, spk, 0.8, z=z, dtype="fp32")
+    assert torch.equal(out32["mel_lengths"].cpu(), lens)
+    # anchors: longest item + item 0 (or 1) in one oracle batch -> same T_pad
+    i_long = int(lens.argmax())
+    i_other = 0 if i_long != 0 else 1
+    sel = torch.tensor([i_long, i_other])
+    tx = int(xl[sel].max())
+    ref = mo.synthesise(matcha_sd, VCTK, x[sel, :tx], xl[sel], 10, 0.667, spk[sel], 0.8, z=z[sel])
+    assert ref["t_pad"] == t_pad
+    assert ref["mel_lengths"].tolist() == lens[sel].tolist()
+    attn = out32["attn"][:, 0].cpu()
+    assert torch.equal(attn[sel][:, :tx], ref["attn"][:, 0])
+    assert rel_l2(out32["mel"].cpu()[sel], ref["mel"]) < 1e-4
+    # alignment properties on all 32 items
+    assert bool(((attn == 0) | (attn == 1)).all())
+    frames = torch.arange(t_pad)[None, :] < lens[:, None]
+    assert torch.equal(attn.sum(1), frames.float())
+    tok = attn.argmax(1)
+    for b in range(32):
+        tb = tok[b, : int(lens[b])]
+        # non-decreasing token index per frame (with length_scale < 1 a token may receive no frame at all, so steps can exceed 1)
+        assert int(tb[0]) == 0 and int(tb[-1]) <= int(xl[b]) - 1 and bool((tb[1:] - tb[:-1] >= 0).all())
+    full = out32["decoder_outputs_full"].cpu()
+    for b in (0, 7, 31):
+        assert torch.equal(full[b, :, int(lens[b]):], (z * 0.667)[b, :, int(lens[b]):])
+    # bf16 vs fp32 on the whole batch; graph replay == eager
+    runs = [matcha.synthesise(x, xl, 10, 0.667, spk, 0.8, z=z, dtype="bf16") for _ in range(3)]
+    assert torch.equal(runs[0]["mel"], runs[2]["mel"])
+    assert rel_l2(runs[2]["mel"].cpu(), out32["mel"].cpu()) < TOL["bf16"]
+    wav32 = gen(out32["mel"], dtype="fp32")
+    wavs = [gen(out32["mel"], dtype="bf16") for _ in range(3)]
+    assert torch.equal(wavs[0], wavs[2])
+    assert wav32.shape == (32, 1, 256 * out32["mel"].shape[2])
+    assert rel_l2(wavs[2].cpu(), wav32.cpu()) < 2 * TOL["bf16"]
+    ref_wav = ho.generator(hsd, HIFIGAN_V1, out32["mel"].cpu()[sel[:1]])
+    assert rel_l2(wav32.cpu()[sel[:1]], ref_wav) < 1e-4
