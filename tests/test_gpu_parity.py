@@ -407,3 +407,26 @@ def test_full_size_batch_properties_and_anchor_items(matcha, matcha_sd, vocoders
     assert rel_l2(wavs[2].cpu(), wav32.cpu()) < 2 * TOL["bf16"]
     ref_wav = ho.generator(hsd, HIFIGAN_V1, out32["mel"].cpu()[sel[:1]])
     assert rel_l2(wav32.cpu()[sel[:1]], ref_wav) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ scheduling knobs
+def test_scheduling_knobs_do_not_change_results():
+    """Decoder batch lanes on forked streams, the ResBlock wavefront schedule, one vs two CTAs per SM and programmatic
+    dependent launch only reorder work: mel and waveform must be bit-identical to the default schedule."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(**env):
+        e = dict(os.environ, **{k: str(v) for k, v in env.items()})
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "knob_check.py")], capture_output=True, text=True, env=e, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
+
+    base = run()
+    assert run(EV_DEC_LANES=2) == base
+    assert run(EV_RB_WAVE=1) == base
+    assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
+    assert run(EV_PDL=0) == base
