@@ -94,8 +94,12 @@ __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& b,
 }
 
 // [CTA][16] clock stamps of the most recent traced launch (diagnostic; read back by ev_test_conv_trace)
-__device__ unsigned long long g_trace[512 * 16];
-#define EV_TR(i) do { if (p.trace && lane == 0 && blockIdx.x < 512) g_trace[blockIdx.x * 16 + (i)] = (unsigned long long)clock64(); } while (0)
+__device__ unsigned long long g_trace[512 * 24];
+#define EV_TR(i) do { if (p.trace && lane == 0 && blockIdx.x < 512) g_trace[blockIdx.x * 24 + (i)] = (unsigned long long)clock64(); } while (0)
+// accumulated clocks a role spent inside mbarrier waits (slots 16..19), written once at the end of the role's loop
+#define EV_TW_BEGIN() long long _tw0 = p.trace ? clock64() : 0
+#define EV_TW_END(acc) do { if (p.trace) (acc) += clock64() - _tw0; } while (0)
+#define EV_TW_STORE(i, acc) do { if (p.trace && lane == 0 && blockIdx.x < 512) g_trace[blockIdx.x * 24 + (i)] = (unsigned long long)(acc); } while (0)
 
 // Upper / lower words of a shared-memory matrix descriptor (tc_ptx.cuh make_smem_desc_ex): the MMA warp advances the
 // low word by plain adds instead of rebuilding descriptors.
@@ -150,7 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
     EV_TR(0);
-    if (p.trace && lane == 0 && blockIdx.x < 512) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_trace[blockIdx.x * 16 + 11] = gt; }
+    if (p.trace && lane == 0 && blockIdx.x < 512) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); g_trace[blockIdx.x * 24 + 11] = gt; }
   }
   const int A_SLOTS = p.a_slots, B_SLOTS = p.b_slots;
   const int tile_rows = p.mb * BM;
@@ -188,6 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ---------------- TMA producer: per tile, per K-chunk, per tap group: one (haloed) activation tile, then one
       // weight tile per tap.  Ring positions run on across tiles, so the next tile's loads start while this one computes.
       int sa = 0, sb = 0;
+      long long tw_a = 0, tw_b = 0;
       uint32_t pa = 1, pb = 1;      // parity to wait for on the "empty" barriers (fresh barriers pass parity 1)
       const uint32_t a_bytes = (uint32_t)(p.a_boxes * p.a_box_rows * p.row_bytes), box_bytes = (uint32_t)(p.a_box_rows * p.row_bytes);
       const int kchunks = p.kchunks, n_groups = p.n_groups, grp_taps = p.grp_taps;
@@ -207,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (tile == (int)blockIdx.x) EV_TR(13);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int g = 0; g < n_groups; ++g) {
-            mbar_wait(&a_empty[sa], pa);
+            { EV_TW_BEGIN(); mbar_wait(&a_empty[sa], pa); EV_TW_END(tw_a); }
             if (tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(14);
             if (p.debug_nob & 2) { mbar_arrive(&a_full[sa]); if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; } if (resident) continue; goto b_loads; }
             mbar_expect_tx(&a_full[sa], a_bytes);
@@ -224,7 +229,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           b_loads:
             const int tap0 = g * grp_taps;
             for (int j = 0; j < grp_taps; ++j) {
-              mbar_wait(&b_empty[sb], pb);
+              { EV_TW_BEGIN(); mbar_wait(&b_empty[sb], pb); EV_TW_END(tw_b); }
               if (p.debug_nob & 1) { mbar_arrive(&b_full[sb]); }   // timing experiment only: no weight traffic (results are wrong)
               else {
               mbar_expect_tx(&b_full[sb], (uint32_t)p.b_tile_bytes);
@@ -235,6 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      EV_TW_STORE(18, tw_b); EV_TW_STORE(19, tw_a);
     }
     __syncwarp();
   } else if (warp < ROLE_WARPS) {
@@ -255,6 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_stride = (uint32_t)(p.mb * BN);
     const int my_mb = warp - 1, mb_stride = p.n_issuers;   // this issuer owns m-blocks my_mb, my_mb + mb_stride, ...
     int sa = 0, sb = 0, vt = 0;     // vt counts accumulator-set uses: one per tile, or one per flush group (3xTF32)
+    long long tw_a = 0, tw_b = 0;
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
     const int flush_kc = p.flush_kc;
     if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
@@ -275,7 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           acc = 0;
         }
         for (int g = 0; g < n_groups; ++g) {
-          mbar_wait(&a_full[sa], pa);
+          { EV_TW_BEGIN(); mbar_wait(&a_full[sa], pa); EV_TW_END(tw_a); }
           tcgen05_fence_after();
           if (warp == 1 && tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(4);
           uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step16 + p.tap_first16;
@@ -285,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               b_lo = b_res_lo;
               b_res_lo += b_step16;
             } else {
-              mbar_wait(&b_full[sb], pb);
+              { EV_TW_BEGIN(); mbar_wait(&b_full[sb], pb); EV_TW_END(tw_b); }
               tcgen05_fence_after();
               b_lo = b_lo0 + (uint32_t)sb * b_step16;
             }
@@ -324,6 +331,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (warp == 1) { EV_TW_STORE(16, tw_b); EV_TW_STORE(17, tw_a); }
   } else {
     // ---------------- epilogue (warps 2..9).  Warp (q, half) owns TMEM lanes [32q, 32q+32) and every second 32-column
     // block of them; the eight warps run free of each other (no CTA barrier):
@@ -678,7 +686,7 @@ bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, ui
 }
 int tc_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 cudaError_t conv_tc_read_trace(unsigned long long* host, int n) {
-  return cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * std::min(n, 512 * 16));
+  return cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * std::min(n, 512 * 24));
 }
 
 int conv_tc_pick_bn(int N) {

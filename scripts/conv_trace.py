@@ -18,7 +18,9 @@ from emojivoice_b200 import _lib  # noqa: E402
 
 NAMES = ["entry", "prologue done", "after pdl wait", "first TMA issued", "first operands landed", "first tile MMAs committed",
          "last commit", "first accumulator seen (epilogue)", "first tile stored", "last tile stored", "exit", "(globaltimer)",
-         "producer: tile loop entered", "producer: first tile decoded", "producer: first slot free", "epilogue warp 0: first block done"]
+         "producer: tile loop entered", "producer: first tile decoded", "producer: first slot free", "epilogue warp 0: first block done",
+         "MMA warp: clk waiting for weight tiles", "MMA warp: clk waiting for activation tiles", "producer: clk waiting for a free weight slot",
+         "producer: clk waiting for a free activation slot"]
 
 
 def main():
@@ -33,17 +35,18 @@ def main():
     for rep in range(3):
         ctx.check(L.ev_test_conv1d(ctx.handle, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), B, Cin, T, Cout, K, 1, K // 2, 1, 0, 1,
                                    _lib.ptr(y), _lib.stream_ptr()), "ev_test_conv1d")
-    buf = np.zeros(512 * 16, dtype=np.uint64)
+    buf = np.zeros(512 * 24, dtype=np.uint64)
     ctx.check(L.ev_test_conv_trace(ctx.handle, buf.ctypes.data_as(C.c_void_p), buf.size), "ev_test_conv_trace")
-    t = buf.reshape(512, 16).astype(np.int64)
+    t = buf.reshape(512, 24).astype(np.int64)
     live = t[:, 0] != 0
     t = t[live]
     print(f"conv B={B} Cin={Cin} T={T} Cout={Cout} K={K}: {t.shape[0]} CTAs traced")
-    rel = t[:, :16] - t[:, :1]
+    rel = t[:, :20] - t[:, :1]
+    rel[:, 16:20] = t[:, 16:20]          # accumulated waits, not time stamps
     for i, n in enumerate(NAMES):
         if i == 11:
             continue
-        col = rel[:, i][t[:, i] != 0]
+        col = rel[:, i][t[:, i] != 0] if i < 16 else rel[:, i]
         if col.size:
             print(f"  {i:2d} {n:<36} median {int(np.median(col)):>7} clk   min {int(col.min()):>7}   max {int(col.max()):>7}")
     gt = t[:, 11]
