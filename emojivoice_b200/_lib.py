@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libemojivoice_b200.so")
+LIB_PATH = os.environ.get("EV_LIB_PATH") or os.path.join(_HERE, "lib", "libemojivoice_b200.so")   # EV_LIB_PATH: A/B-test another build
 
 PREC = {"fp32": 0, "float32": 0, torch.float32: 0, "bf16": 1, "bfloat16": 1, torch.bfloat16: 1,
         "tf32x3": 2}    # unit-test hook only: fp32-accurate tensor-core path (3xTF32 split) the text encoder uses

@@ -110,35 +110,48 @@ class MatchaTTS:
                 spks = spks.to(device=dev).long().contiguous()          # matcha_tts.py:118 spks.long()
                 if spks.numel() != B:
                     raise ValueError("spks must hold one id per utterance")
-                spk_emb = torch.empty(B, self.spk_emb_dim, device=dev)
             else:
-                spk_emb = None
+                spks = None
             F = self.n_feats
-            mu_x = torch.empty(B, F, Tx, device=dev)
-            logw = torch.empty(B, 1, Tx, device=dev)
-            w_ceil = torch.empty(B, 1, Tx, device=dev)
-            y_lengths = torch.empty(B, dtype=torch.int64, device=dev)
-            st = _lib.stream_ptr()
-            nb = L.ev_encode_workspace_bytes(ctx.handle, B, Tx)
-            ws = ctx.workspace(nb)
-            ctx.check(L.ev_encode(ctx.handle, _lib.ptr(x), _lib.ptr(x_lengths), _lib.ptr(spks), B, Tx, float(length_scale),
-                                  _lib.ptr(spk_emb), _lib.ptr(mu_x), _lib.ptr(logw), _lib.ptr(w_ceil), _lib.ptr(y_lengths),
-                                  _lib.ptr(ws), ws.numel(), st), "ev_encode")
+            S = self.spk_emb_dim if self.n_spks > 1 else 0
+
+            def encode(i, o, ws):
+                ctx.check(L.ev_encode(ctx.handle, _lib.ptr(i["x"]), _lib.ptr(i["x_lengths"]), _lib.ptr(i["spks"]), B, Tx,
+                                      float(length_scale), _lib.ptr(o.get("spk_emb")), _lib.ptr(o["mu_x"]), _lib.ptr(o["logw"]),
+                                      _lib.ptr(o["w_ceil"]), _lib.ptr(o["y_lengths"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                          "ev_encode")
+
+            f32, i64 = torch.float32, torch.int64
+            enc_out = {"mu_x": ((B, F, Tx), f32), "logw": ((B, 1, Tx), f32), "w_ceil": ((B, 1, Tx), f32), "y_lengths": ((B,), i64)}
+            if S:
+                enc_out["spk_emb"] = ((B, S), f32)
+            e = self._run("encode", (B, Tx, float(length_scale)), L.ev_encode_workspace_bytes(ctx.handle, B, Tx),
+                          {"x": x, "x_lengths": x_lengths, "spks": spks}, enc_out, encode)
+            mu_x, logw, w_ceil, y_lengths, spk_emb = e["mu_x"], e["logw"], e["w_ceil"], e["y_lengths"], e.get("spk_emb")
             y_max_length = int(y_lengths.max().item())                    # the reference's one host sync (utils/model.py:18)
             T_pad = self.fix_len_compatibility(y_max_length)
-            attn = torch.empty(B, Tx, T_pad, device=dev)
-            mu_y = torch.empty(B, F, T_pad, device=dev)
-            y_mask = torch.empty(B, 1, T_pad, device=dev)
-            ws = ctx.workspace(L.ev_align_workspace_bytes(ctx.handle, B, Tx, T_pad))
-            ctx.check(L.ev_align(ctx.handle, _lib.ptr(w_ceil), _lib.ptr(x_lengths), _lib.ptr(y_lengths), _lib.ptr(mu_x), B, Tx,
-                                 T_pad, _lib.ptr(attn), _lib.ptr(mu_y), _lib.ptr(y_mask), _lib.ptr(ws), ws.numel(), st), "ev_align")
             if z is None:
-                z = torch.randn_like(mu_y)                               # flow_matching.py:51
+                z = torch.randn(B, F, T_pad, device=dev)                 # flow_matching.py:51
             else:
                 z = z.to(device=dev, dtype=torch.float32).contiguous()
                 if tuple(z.shape) != (B, F, T_pad):
                     raise ValueError(f"z must have shape {(B, F, T_pad)}, got {tuple(z.shape)}")
-            dec, mel = self._decode(mu_y, y_lengths, z, spk_emb, B, T_pad, int(n_timesteps), float(temperature), prec)
+            n_steps, temp = int(n_timesteps), float(temperature)
+
+            def align_decode(i, o, ws):
+                ctx.check(L.ev_align(ctx.handle, _lib.ptr(i["w_ceil"]), _lib.ptr(i["x_lengths"]), _lib.ptr(i["y_lengths"]),
+                                     _lib.ptr(i["mu_x"]), B, Tx, T_pad, _lib.ptr(o["attn"]), _lib.ptr(o["mu_y"]), _lib.ptr(o["y_mask"]),
+                                     _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ev_align")
+                ctx.check(L.ev_decode(ctx.handle, _lib.ptr(o["mu_y"]), _lib.ptr(i["y_lengths"]), _lib.ptr(i["z"]), _lib.ptr(i["spk_emb"]),
+                                      B, T_pad, n_steps, temp, prec, _lib.ptr(o["dec"]), _lib.ptr(o["mel"]), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()), "ev_decode")
+
+            nb = max(L.ev_align_workspace_bytes(ctx.handle, B, Tx, T_pad), L.ev_decode_workspace_bytes(ctx.handle, B, T_pad, n_steps))
+            d = self._run("decode", (B, Tx, T_pad, n_steps, temp, prec), nb,
+                          {"w_ceil": w_ceil, "x_lengths": x_lengths, "y_lengths": y_lengths, "mu_x": mu_x, "z": z, "spk_emb": spk_emb},
+                          {"attn": ((B, Tx, T_pad), f32), "mu_y": ((B, F, T_pad), f32), "y_mask": ((B, 1, T_pad), f32),
+                           "dec": ((B, F, T_pad), f32), "mel": ((B, F, T_pad), f32)}, align_decode)
+            attn, mu_y, y_mask, dec, mel = d["attn"], d["mu_y"], d["y_mask"], d["dec"], d["mel"]
         t = (dt.datetime.now() - t0).total_seconds()
         rtf = t * 22050 / (max(y_max_length, 1) * 256)                    # matcha_tts.py:142-143 (host clock, no sync)
         return {
@@ -155,42 +168,34 @@ class MatchaTTS:
             "decoder_outputs_full": dec, "mel_full": mel,
         }
 
-    def _decode(self, mu_y, y_lengths, z, spk_emb, B, T_pad, n_timesteps, temperature, prec):
-        """ev_decode, eagerly or -- once the same shape key has been seen before -- as a CUDA-graph replay over static
-        buffers (inputs are copied in, outputs copied out, so callers still own fresh tensors as with the reference)."""
-        ctx, L, dev, F = self._ctx, _lib.lib(), self._ctx.device, self.n_feats
-
-        def call(mu_y, y_lengths, z, spk_emb, dec, mel, ws):
-            ctx.check(L.ev_decode(ctx.handle, _lib.ptr(mu_y), _lib.ptr(y_lengths), _lib.ptr(z), _lib.ptr(spk_emb), B, T_pad,
-                                  n_timesteps, temperature, prec, _lib.ptr(dec), _lib.ptr(mel), _lib.ptr(ws), ws.numel(),
-                                  _lib.stream_ptr()), "ev_decode")
-
-        nb = L.ev_decode_workspace_bytes(ctx.handle, B, T_pad, n_timesteps)
-        key = (B, T_pad, n_timesteps, temperature, prec)
-        ws_shared = ctx.workspace(nb)                       # (may grow the workspace: do it before looking graphs up)
-        ent = self._graphs.get(key, ctx.ws_version) if self.cuda_graphs else None
-        if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
-            st = dict(mu_y=torch.empty_like(mu_y), y_lengths=torch.empty_like(y_lengths), z=torch.empty_like(z),
-                      spk_emb=None if spk_emb is None else torch.empty_like(spk_emb), dec=torch.empty(B, F, T_pad, device=dev),
-                      mel=torch.empty(B, F, T_pad, device=dev), ws=ws_shared, ws_version=ctx.ws_version)
-            st["mu_y"].copy_(mu_y); st["y_lengths"].copy_(y_lengths); st["z"].copy_(z)
-            if spk_emb is not None:
-                st["spk_emb"].copy_(spk_emb)
-            st["graph"], st["launches"] = _lib.capture(
-                ctx, lambda: call(st["mu_y"], st["y_lengths"], st["z"], st["spk_emb"], st["dec"], st["mel"], st["ws"]))
-            self._graphs.put(key, st)
-            ent = st
+    def _run(self, name, key, nbytes, inputs, out_specs, call):
+        """One stage (`call(inputs, outputs, workspace)` enqueues library calls only), eagerly or -- once the same shape key has
+        been seen before -- as a CUDA-graph replay over static buffers: inputs are copied in, outputs cloned out, so callers
+        own fresh tensors as with the reference.  The text encoder (~230 launches), alignment + the decoder's n-step loop (~750)
+        and the vocoder (~50) are replayed this way, which takes the host out of the critical path."""
+        ctx, dev = self._ctx, self._ctx.device
+        ws = ctx.workspace(nbytes)                              # (may grow the workspace: do it before looking graphs up)
+        gkey = (name,) + tuple(key)
+        ent = self._graphs.get(gkey, ctx.ws_version) if self.cuda_graphs else None
+        if ent is None and self.cuda_graphs and self._graphs.should_capture(gkey):
+            st_in = {k: (None if v is None else torch.empty_like(v)) for k, v in inputs.items()}
+            for k, v in inputs.items():
+                if v is not None:
+                    st_in[k].copy_(v)
+            st_out = {k: torch.empty(shape, dtype=dtp, device=dev) for k, (shape, dtp) in out_specs.items()}
+            graph, launches = _lib.capture(ctx, lambda: call(st_in, st_out, ws))
+            ent = dict(inp=st_in, out=st_out, graph=graph, launches=launches, ws_version=ctx.ws_version)
+            self._graphs.put(gkey, ent)
         if ent is None:
-            dec = torch.empty(B, F, T_pad, device=dev)
-            mel = torch.empty(B, F, T_pad, device=dev)
-            call(mu_y, y_lengths, z, spk_emb, dec, mel, ws_shared)
-            return dec, mel
-        ent["mu_y"].copy_(mu_y); ent["y_lengths"].copy_(y_lengths); ent["z"].copy_(z)
-        if spk_emb is not None:
-            ent["spk_emb"].copy_(spk_emb)
+            out = {k: torch.empty(shape, dtype=dtp, device=dev) for k, (shape, dtp) in out_specs.items()}
+            call(inputs, out, ws)
+            return out
+        for k, v in inputs.items():
+            if v is not None:
+                ent["inp"][k].copy_(v)
         ent["graph"].replay()
         self._replayed_launches += ent["launches"]
-        return ent["dec"].clone(), ent["mel"].clone()
+        return {k: v.clone() for k, v in ent["out"].items()}
 
     _replayed_launches = 0
 
