@@ -430,3 +430,28 @@ def test_scheduling_knobs_do_not_change_results():
     assert run(EV_RB_WAVE=1) == base
     assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
     assert run(EV_PDL=0) == base
+
+
+def test_long_utterance_matches_oracle(matcha, matcha_sd, vocoders):
+    """One ~20 s utterance (Tx = 601 tokens, ~1.8 k mel frames): many key blocks in the tensor-core attention, dozens of
+    tiles per conv, RoPE far into its table; plus a 2-frame neighbour so that almost the whole batch is padding (H1)."""
+    gen, hsd = vocoders["hifigan_gain1"]
+    g = torch.Generator().manual_seed(91)
+    ids = torch.zeros(2, 601, dtype=torch.long)
+    ids[0, 1::2] = torch.randint(1, 178, (300,), generator=g)
+    ids[1, :3] = torch.tensor([0, 17, 0])
+    xl = torch.tensor([601, 3])
+    spk = torch.tensor([18, 54])
+    probe = mo.synthesise(matcha_sd, VCTK, ids, xl, 1, 0.667, spk, 1.0)
+    z = synthetic.prior_noise(2, 80, probe["t_pad"], seed=92)
+    ref = mo.synthesise(matcha_sd, VCTK, ids, xl, 2, 0.667, spk, 1.0, z=z)
+    assert ref["t_pad"] > 1500
+    for prec in ("fp32", "bf16"):
+        out = matcha.synthesise(ids, xl, 2, 0.667, spk, 1.0, z=z, dtype=prec)
+        assert out["mel_lengths"].cpu().tolist() == ref["mel_lengths"].tolist()
+        assert torch.equal(out["attn"].cpu(), ref["attn"])
+        assert rel_l2(out["mel"].cpu(), ref["mel"]) < TOL[prec]
+        assert rel_l2(out["decoder_outputs_full"].cpu(), ref["decoder_outputs_full"]) < TOL[prec]
+    wav = gen(out["mel"], dtype="fp32")
+    ref_wav = ho.generator(hsd, HIFIGAN_V1, out["mel"].cpu())
+    assert rel_l2(wav.cpu(), ref_wav) < 1e-4
