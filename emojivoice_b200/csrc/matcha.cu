@@ -4,6 +4,7 @@
 // the buffer plan.  All intermediate tensors are channel-last and live in the caller's workspace.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "ctx.cuh"
 
@@ -427,7 +428,8 @@ struct Decoder {
     GnApplyArgs g1;
     g1.x = d.h; g1.partial = part; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
     g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.out_act = d.a; g1.act_ld = D;
-    EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
+    static const int dbg_skip = []() { const char* v = getenv("EV_DEC_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
+    if (!(dbg_skip & 8)) EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); part = e1.gn_sum; }
     EV_TRY(run_conv<ActT>(ctx, w.conv2, d.a, D, bsD, B, Tl, e1, s));
     Epilogue er; er.out_f32 = d.r; er.f32_ld = D; er.f32_bs = bsD;
@@ -444,6 +446,7 @@ struct Decoder {
   // BasicTransformerBlock (transformer.py:243-316); expects d.xr (stream) and d.n = LN1(xr); writes x*mask to `out`
   int transformer(int k, int Tl, int shift, ActT* out, long long out_ld) {
     const TransformerW& w = m.tf[k];
+    static const int dbg_skip = []() { const char* v = getenv("EV_DEC_DEBUG_SKIP"); return v ? atoi(v) : 0; }();   // timing experiments only (wrong results)
     const RowMask mask{d.ylen32, shift};
     const long long bsD = (long long)Tl * D;
     const int Hh = m.cfg.dec_heads, hd = m.cfg.dec_head_dim;
@@ -460,6 +463,7 @@ struct Decoder {
       at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
       std::string err;
       cudaError_t ce;
+      if (dbg_skip & 4) ce = cudaSuccess; else
       { LaunchScope ls(ctx, s, "attention_tc", attn_flops, (double)B * Tl * inner * 8.0); ce = attention_tc(at, s, &err); }
       if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "attention_tc") : fail(ctx, EV_ERR_CUDA, err);
     } else {
@@ -480,10 +484,10 @@ struct Decoder {
     EV_LAUNCH(ctx, s, "layer_norm", 0, (double)B * Tl * D * (4.0 + sizeof(ActT)), layer_norm_rows<ActT>(ln, s));
     Epilogue e1; e1.act = ACT_SNAKE; e1.snake_a = w.snake_a; e1.snake_invb = w.snake_invb;
     e1.out_act = d.ff; e1.act_ld = 4 * D; e1.act_bs = (long long)Tl * 4 * D;
-    EV_TRY(run_conv<ActT>(ctx, w.ff1, d.n, D, bsD, B, Tl, e1, s));
+    if (!(dbg_skip & 1)) EV_TRY(run_conv<ActT>(ctx, w.ff1, d.n, D, bsD, B, Tl, e1, s));
     Epilogue e2; e2.res = d.xr; e2.res_ld = D; e2.res_bs = bsD;
     e2.out_act = out; e2.act_ld = out_ld; e2.act_bs = (long long)Tl * out_ld; e2.mask = mask; e2.mask_act = 1;
-    EV_TRY(run_conv<ActT>(ctx, w.ff2, d.ff, 4 * D, (long long)Tl * 4 * D, B, Tl, e2, s));
+    if (!(dbg_skip & 2)) EV_TRY(run_conv<ActT>(ctx, w.ff2, d.ff, 4 * D, (long long)Tl * 4 * D, B, Tl, e2, s));
     return 0;
   }
 
