@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-vocoder", action="store_true",
+                    help="vocode the padded frames of every utterance too (the default skips the time tiles past each utterance's "
+                         "own length: identical waveform on [: length*256], zero beyond -- what cli.py:307-311 crops away)")
     ap.add_argument("--profile-one-step", action="store_true",
                     help="after warm-up, bracket ONE step with cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -224,10 +227,15 @@ def main():
     x_pin, xl_pin, spk_pin = x.pin_memory(), xl.pin_memory(), spks.pin_memory()
     x_dev, xl_dev, spk_dev = x.to(dev), xl.to(dev), spks.to(dev)
 
+    ragged = [not args.dense_vocoder]
+
+    def vocode(out):
+        # to_waveform (feel_me.py:183).  Ragged: item b is vocoded up to mel_lengths[b] (+ receptive field) only
+        return voc(out["mel"], lengths=out["mel_lengths"] if ragged[0] else None).clamp(-1, 1)
+
     def step_resident():
         out = model.synthesise(x_dev, xl_dev, N_TIMESTEPS, TEMPERATURE, spk_dev, LENGTH_SCALE)
-        wav = voc(out["mel"]).clamp(-1, 1)                      # to_waveform, feel_me.py:183
-        return out, wav
+        return out, vocode(out)
 
     wav_host = [None]
     len_host = torch.empty(BATCH, dtype=torch.int64).pin_memory()
@@ -237,7 +245,7 @@ def main():
         ld = xl_pin.to(dev, non_blocking=True)
         sd_ = spk_pin.to(dev, non_blocking=True)
         out = model.synthesise(xd, ld, N_TIMESTEPS, TEMPERATURE, sd_, LENGTH_SCALE)
-        wav = voc(out["mel"]).clamp(-1, 1)
+        wav = vocode(out)
         if wav_host[0] is None or wav_host[0].shape != wav.shape:
             wav_host[0] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
         wav_host[0].copy_(wav, non_blocking=True)               # .cpu() of to_waveform (feel_me.py:187)
@@ -289,6 +297,22 @@ def main():
     launches = model.launch_count() + voc.launch_count()
     clocks = sampler.stop()
 
+    # ---------------- the same K steps with the padded frames vocoded too (reference-identical waveform everywhere)
+    ms_dense = None
+    if ragged[0]:
+        ragged[0] = False
+        for _ in range(3):
+            step_resident()
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record()
+        for _ in range(args.steps):
+            step_resident()
+        d1.record()
+        barrier()
+        ms_dense = d0.elapsed_time(d1)
+        ragged[0] = True
+
     # ---------------- e2e: same steps through the public API with pinned host inputs and the waveform read back
     recent = []
     while True:                                                  # settle like the warm-up above
@@ -307,7 +331,7 @@ def main():
     barrier()
     ms_e2e = f0.elapsed_time(f1)
 
-    tt = torch.tensor([ms, ms_e2e, -secs_per_step], dtype=torch.float64, device=dev)
+    tt = torch.tensor([ms, ms_e2e, -secs_per_step, ms_dense or 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)                # slowest rank bounds the job
         tot = torch.tensor([secs_per_step, float(launches)], dtype=torch.float64, device=dev)
@@ -316,6 +340,7 @@ def main():
     else:
         total_secs = secs_per_step
     ms, ms_e2e = float(tt[0]), float(tt[1])
+    ms_dense = float(tt[3]) if ms_dense is not None else None
     value = total_secs * args.steps / (ms / 1e3)
     value_e2e = total_secs * args.steps / (ms_e2e / 1e3)
     h2d = x.numel() * 8 + xl.numel() * 8 + spks.numel() * 8
@@ -383,12 +408,18 @@ def main():
         "config": dict(workload_config(), audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames,
                        t_pad=t_pad, l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
                        "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
-                       launch="decoder and vocoder replayed as CUDA graphs (captured during warm-up); encoder + alignment eager"),
+                       launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up)",
+                       vocoder=("ragged: time tiles past each utterance's own length (+ the generator's 14-frame receptive field) are "
+                                "not computed; waveform bit-identical to the dense generator on [: mel_length*256] and zero beyond "
+                                "-- the part the reference's batched caller crops away (cli.py:307-311); `padded_vocoder` is the "
+                                "same run with the padded frames vocoded too") if not args.dense_vocoder else "dense (padded frames vocoded too)"),
         "rtf": round(1.0 / value, 8), "x_realtime": round(value, 1),
         "clocks": clocks,
         "e2e": {"value": round(value_e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
+        "padded_vocoder": ({"value": round(total_secs * args.steps / (ms_dense / 1e3), 2), "unit": "audio-s/s",
+                            "ms_per_step": round(ms_dense / args.steps, 3)} if ms_dense else None),
         "roofline": roofline,
         "path_tflops": round(path_tflops, 2), "path_frac_of_tensor_peak": round(path_tflops / (peaks["tflops"] * world), 4),
         "kernels": table,

@@ -54,6 +54,7 @@ SIGNATURES = {
     "ev_decode": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P, _P, _P, _SZ, _P]),
     "ev_vocode_workspace_bytes": (_SZ, [_P, _I, _I]),
     "ev_vocode": (_I, [_P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "ev_vocode_ragged": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
     "ev_denoise_workspace_bytes": (_SZ, [_P, _I, _I]),
     "ev_denoiser_init": (_I, [_P, _P, _P, _SZ, _P]),
     "ev_denoise": (_I, [_P, _P, _I, _I, _F, _P, _P, _SZ, _P]),

@@ -19,12 +19,15 @@ def collate(utterances, items):
 
 @torch.inference_mode()
 def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10, temperature=0.667, length_scale=1.0,
-                      rank=0, world_size=1, denoiser=None, denoiser_strength=0.00025, sort=True, keep_mel=False, z_fn=None):
+                      rank=0, world_size=1, denoiser=None, denoiser_strength=0.00025, sort=True, keep_mel=False, z_fn=None,
+                      ragged=True):
     """Synthesise this rank's share of `utterances` (list of (phoneme ids, speaker id)).
 
     -> (results, stats): results maps utterance index -> dict(waveform (L,) cpu float32, mel_length, [mel]), stats is a
     sharding.ShardStats with this rank's device time.  `z_fn(mb, shape)` may supply the prior noise per micro-batch
-    (parity runs share it with the oracle)."""
+    (parity runs share it with the oracle).  ragged: the vocoder skips the time tiles past each utterance's own length
+    (identical cropped waveforms, see Generator.__call__); ignored with a denoiser, whose STFT windows at an utterance's
+    end reach into the padded region."""
     lens = [len(u[0]) for u in utterances]
     plan = sharding.shard(lens, batch_size, rank, world_size, n_timesteps=n_timesteps, sort=sort)
     results, stats = {}, sharding.ShardStats()
@@ -36,7 +39,8 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
         if z_fn is not None:
             kw["z"] = z_fn(mb, model, x, xl, spks)
         out = model.synthesise(x, xl, n_timesteps, temperature, spks if model.n_spks > 1 else None, length_scale, **kw)
-        wav = vocoder(out["mel"]).clamp(-1, 1)                       # to_waveform, cli.py:121-126
+        use_ragged = ragged and denoiser is None
+        wav = vocoder(out["mel"], lengths=out["mel_lengths"] if use_ragged else None).clamp(-1, 1)   # to_waveform, cli.py:121-126
         if denoiser is not None:
             wav = denoiser(wav.squeeze(1), strength=denoiser_strength).unsqueeze(1)
         e1.record()

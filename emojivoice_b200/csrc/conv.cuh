@@ -92,13 +92,36 @@ struct ConvWeights {
   int conv_stride = 1, dilation = 1, pad = 0, transposed = 0, up_s = 1, up_p = 0, C_out = 0, ksize = 1;
 };
 
+// ---- ragged batches (ragged.cu) ---------------------------------------------------------------------------------
+// The vocoder is purely convolutional, so the samples of utterance b up to len_b*hop depend only on mel frames up to
+// len_b + (receptive field); tiles that start beyond (len_b + margin) * rows_per_frame are never computed.  The tile
+// kernels walk a COMPACT list of (item, m-tile) pairs instead of the dense B x m_tiles grid:
+//     table[0] = number of pairs,  table[1 + i] = (b << 16) | m_tile      (built on the device from the lengths, so a
+// captured CUDA graph follows the lengths of each replay).  Tables are cached per (rows_per_frame, tile_rows, M).
+struct RaggedPlanner {
+  const int* lens = nullptr;      // device [B], valid frames per item; nullptr = dense batch
+  int B = 0, margin = 0;          // margin in frames (>= the generator's receptive field, see hifigan.cu)
+  int rows_per_frame = 1;         // GEMM rows per frame of the launches that follow (set by the caller per stage)
+  int* arena = nullptr;           // table storage (caller's workspace)
+  size_t arena_ints = 0, arena_off = 0;
+  struct Entry { int rpf, tile_rows, M; const int* table; };
+  Entry cache[32];
+  int n_cache = 0;
+  long long* launch_counter = nullptr;   // bumped once per table kernel (the context's launch statistics)
+  bool active() const { return lens != nullptr; }
+  // compact tile list for tiles of `tile_rows` GEMM rows over M rows per item; nullptr -> run dense (always correct)
+  const int* table(int tile_rows, int M, cudaStream_t s);
+};
+constexpr int kRaggedMaxB = 2048;
+
 // conv_simt.cu
 cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, long long x_bs, const ConvWeights& w,
                              const Epilogue& e, cudaStream_t stream);
 // conv_tc.cu
 // x: bf16 activations, or (tf32x3 != 0) the split fp32 pair [hi | lo] of width 2*C_in per row (x_ld, x_bs in elements)
 cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
-                           const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err);
+                           const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err,
+                           RaggedPlanner* ragged = nullptr);
 bool conv_tc_init(std::string* err);
 // 3-D bf16 tensor map (dims d0 fastest; strides in bytes for d1, d2; box b0 x b1 x 1; swizzle 128 or 64 bytes)
 bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1_bytes,
@@ -110,7 +133,7 @@ cudaError_t conv_tc_read_trace(unsigned long long* host, int n);   // diagnostic
 bool resblock_tc_supported(int C, int k, const int* dil);
 cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
                                const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
-                               int write_f32, cudaStream_t s, std::string* err);
+                               int write_f32, cudaStream_t s, std::string* err, RaggedPlanner* ragged = nullptr);
 int conv_tc_pick_bn(int N);
 
 }  // namespace ev

@@ -50,6 +50,7 @@ struct TcParams {
   // in the first two constant-cache lines of the parameter block (a traced launch showed the lone producer thread
   // spending ~2400 clk between griddepcontrol.wait and its first TMA, mostly on cold constant loads and two IDIVs)
   int m_tiles, n_tiles, total_tiles;
+  const int* rag;               // ragged batch: compact (item, m-tile) list (RaggedPlanner, conv.cuh) or nullptr = dense grid
   int mb;                       // m-blocks (128 rows) per tile
   int kchunks;
   int n_groups;                 // taps are processed in groups that share one activation tile (see grp_* below)
@@ -89,6 +90,12 @@ struct TcParams {
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& b, int& mt, int& nt) {
   const uint32_t rest = (uint32_t)(((unsigned long long)(uint32_t)tile * p.div_n) >> 44);
   nt = tile - (int)rest * p.n_tiles;
+  if (p.rag) {      // ragged batch: the (item, m-tile) pairs that hold needed rows are listed explicitly
+    const int pair = __ldg(p.rag + 1 + rest);
+    b = pair >> 16;
+    mt = pair & 0xffff;
+    return;
+  }
   b = (int)(((unsigned long long)rest * p.div_m) >> 44);
   mt = (int)rest - b * p.m_tiles;
 }
@@ -175,8 +182,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   // every role decodes its first tile (and pulls the parameter block through the constant cache) BEFORE the barrier and
   // the programmatic-dependency wait: this part overlaps the TMEM allocation and, under PDL, the previous kernel's tail
-  int first_b, first_mt, first_nt;
-  decode_tile(p, (int)blockIdx.x, first_b, first_mt, first_nt);
+  int first_b = 0, first_mt = 0, first_nt = 0;
+  if (!p.rag) decode_tile(p, (int)blockIdx.x, first_b, first_mt, first_nt);
   asm volatile("" ::"r"(first_b), "r"(first_mt), "r"(first_nt));
   tcgen05_fence_before();
   __syncthreads();
@@ -186,6 +193,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_trigger();     // the next kernel may start its prologue
   pdl_wait();        // everything above overlapped the previous kernel's tail; its results are visible from here on
   if (warp == 0) EV_TR(2);
+  // ragged batch: the tile count and the tile list live in device memory (written by an earlier kernel of the stream)
+  const int total_tiles = p.rag ? __ldg(p.rag) * p.n_tiles : p.total_tiles;
+  if (p.rag && (int)blockIdx.x < total_tiles) decode_tile(p, (int)blockIdx.x, first_b, first_mt, first_nt);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -205,7 +215,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_3d(b_base + (uint32_t)((kc * p.g.taps + j) * p.b_tile_bytes), &tmB, &b_full[0], kc * p.bk, 0, j);
       }
       EV_TR(12);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int nt = first_nt, mt = first_mt, b = first_b;
         if (tile != (int)blockIdx.x) decode_tile(p, tile, b, mt, nt);
         const int m0 = mt * tile_rows, n0 = nt * BN;
@@ -265,7 +275,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
     const int flush_kc = p.flush_kc;
     if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int mt = first_mt;
       if (tile != (int)blockIdx.x) { int b_, nt_; decode_tile(p, tile, b_, mt, nt_); }
       const int vmb = min(p.mb, (p.g.M - mt * tile_rows + BM - 1) / BM);     // m-blocks that hold valid rows
@@ -361,7 +371,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     int ti = 0;                      // accumulator-set use counter (see the MMA warp's vt)
     const int n_grp = (p.kchunks + p.flush_kc - 1) / p.flush_kc;   // accumulation groups per tile (1 unless 3xTF32)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ti += n_grp) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ti += n_grp) {
       int nt = first_nt, mt = first_mt, b = first_b;
       if (tile != (int)blockIdx.x) decode_tile(p, tile, b, mt, nt);
       const int m0 = mt * tile_rows, n0 = nt * BN;
@@ -637,8 +647,9 @@ bool plan_smem(TcParams& p, int k, int epi_warps, int* smem_out) {
 }
 
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t stream) {
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t stream, RaggedPlanner* ragged) {
   p.m_tiles = ceil_div(p.g.M, BM * p.mb);
+  p.rag = (ragged && !p.tf32) ? ragged->table(BM * p.mb, p.g.M, stream) : nullptr;
   p.n_tiles = ceil_div(p.g.N, BN);
   p.total_tiles = p.m_tiles * p.n_tiles * p.g.B;
   p.div_n = ((1ull << 44) + (unsigned long long)p.n_tiles - 1) / (unsigned long long)p.n_tiles;
@@ -715,7 +726,7 @@ bool conv_tc_init(std::string* err) {
 
 // x: channel-last bf16 activations (b, t, c) at x + b*x_bs + t*x_ld + c, `x_rows` addressable rows per item.
 cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
-                           const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err) {
+                           const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err, RaggedPlanner* ragged) {
   if (!g_encode && !conv_tc_init(err)) return cudaErrorNotSupported;
   const int esz = tf32x3 ? 4 : 2;
   if ((x_ld * esz & 15) || (x_bs * esz & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) {
@@ -861,9 +872,9 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
   { static const int nob = []() { const char* v = getenv("EV_TC_DEBUG_NOB"); return v ? atoi(v) : 0; }(); p.debug_nob = nob; }
   { static const int tr = []() { const char* v = getenv("EV_TC_TRACE"); return v ? atoi(v) : 0; }(); p.trace = tr; }
   switch (BN) {
-    case 32: return launch_bn<32>(tmA, tmB, p, stream);
-    case 64: return launch_bn<64>(tmA, tmB, p, stream);
-    default: return launch_bn<128>(tmA, tmB, p, stream);
+    case 32: return launch_bn<32>(tmA, tmB, p, stream, ragged);
+    case 64: return launch_bn<64>(tmA, tmB, p, stream, ragged);
+    default: return launch_bn<128>(tmA, tmB, p, stream, ragged);
   }
 }
 

@@ -99,6 +99,9 @@ struct ev_ctx {
   static constexpr int kMaxLanes = 4;
   int dec_lanes = 1;            // EV_DEC_LANES (default 1: measured 16.86 ms -> 16.5 ms with 2 lanes, 17.5 ms with 4 -- the decoder's
                                 // kernels already cover most SMs, so concurrent lanes mostly queue behind each other)
+  // ragged vocoding (ev_vocode_ragged): active only while that call issues its launches
+  ev::RaggedPlanner rag;
+  double prof_scale = 1.0;      // profiling: algorithmic FLOPs/bytes of the launches are scaled by the valid-row fraction
   cudaStream_t lane_stream[kMaxLanes - 1] = {};
   cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes - 1] = {};
 };

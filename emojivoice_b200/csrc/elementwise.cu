@@ -329,11 +329,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
 // ---------------------------------------------------------------------------------------------- vocoder tail
 template <int C>
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, int L, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, float* __restrict__ wav) {
+                                                        const float* __restrict__ bias, float* __restrict__ wav,
+                                                        const int* __restrict__ lens, int hop) {
   // 256 output samples per block; the (256+6) x C input window is staged in shared memory with LeakyReLU(0.01) applied
   __shared__ float xs[(256 + 6) * (C + 1)];
   __shared__ float ws[7 * C];
   const int b = blockIdx.y, t0 = blockIdx.x * 256;
+  // ragged batch: samples beyond the utterance's own length were never computed upstream -> the waveform is zero there
+  const long long valid = lens ? min((long long)L, (long long)max(lens[b], 0) * hop) : (long long)L;
+  if (t0 >= valid) {
+    if (t0 + (int)threadIdx.x < L) wav[(long long)b * L + t0 + threadIdx.x] = 0.0f;
+    return;
+  }
   for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
   const float* xb = x + (long long)b * L * C;
   for (int i = threadIdx.x; i < (256 + 6) * C; i += 256) {
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
   }
   float y = tanhf(acc);
   y = fminf(fmaxf(y, -1.0f), 1.0f);
-  wav[(long long)b * L + t] = y;
+  wav[(long long)b * L + t] = t < valid ? y : 0.0f;
 }
 
 }  // namespace
@@ -459,10 +466,11 @@ cudaError_t group_norm_apply(const GnApplyArgs& a, cudaStream_t s) {
 template cudaError_t group_norm_apply<float>(const GnApplyArgs&, cudaStream_t);
 template cudaError_t group_norm_apply<bf16>(const GnApplyArgs&, cudaStream_t);
 
-cudaError_t conv_post_tanh(const float* x, int B, int L, int C, const float* w, const float* bias, float* wav, cudaStream_t s) {
+cudaError_t conv_post_tanh(const float* x, int B, int L, int C, const float* w, const float* bias, float* wav, const int* lens,
+                           int hop, cudaStream_t s) {
   dim3 grid(ceil_div(L, 256), B);
-  if (C == 32) conv_post_kernel<32><<<grid, 256, 0, s>>>(x, L, w, bias, wav);
-  else if (C == 16) conv_post_kernel<16><<<grid, 256, 0, s>>>(x, L, w, bias, wav);
+  if (C == 32) conv_post_kernel<32><<<grid, 256, 0, s>>>(x, L, w, bias, wav, lens, hop);
+  else if (C == 16) conv_post_kernel<16><<<grid, 256, 0, s>>>(x, L, w, bias, wav, lens, hop);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

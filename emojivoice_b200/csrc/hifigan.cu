@@ -151,7 +151,28 @@ namespace {
 template <typename ActT>
 struct VocBuffers {
   ActT* mel; ActT* stage_in; float* x0; ActT* x0a; float* xb; ActT* xba; ActT* mid; float* sum;
+  int* lens32; int* rag_arena; size_t rag_ints;
 };
+
+// Receptive field of the generator behind the first upsampler, in mel frames: how many frames past an utterance's end
+// its last valid sample can still see.  Walks the stages backwards in samples of each stage's rate: conv_post (k = 7),
+// the widest ResBlock1 of the stage (sum over l of (k-1)/2 * (d_l + 1)), then the transposed conv (output t reads
+// inputs floor((t + p) / s) and the (k/s - 1) before it).
+int vocoder_margin_frames(const ev_hifigan_cfg& c) {
+  long long h = 3;
+  for (int i = c.n_ups - 1; i >= 0; --i) {
+    long long rb = 0;
+    for (int j = 0; j < c.n_kernels; ++j) {
+      long long r = 0;
+      for (int l = 0; l < 3; ++l) r += (long long)(c.resblock_kernel_sizes[j] - 1) / 2 * (c.resblock_dilation_sizes[j][l] + 1);
+      rb = std::max(rb, r);
+    }
+    h += rb;
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    h = (h + u - 1) / u + (k + u - 1) / u;
+  }
+  return (int)h + 2;
+}
 
 template <typename ActT>
 void plan_vocode(const HifiganW& h, int B, int T, Workspace& w, VocBuffers<ActT>* v) {
@@ -170,10 +191,15 @@ void plan_vocode(const HifiganW& h, int B, int T, Workspace& w, VocBuffers<ActT>
   v->xba = w.take<ActT>(big);
   v->mid = w.take<ActT>(big);
   v->sum = w.take<float>(big);
+  // ragged batches: int32 lengths + the compact tile lists (at most 32 geometries of <= B * ceil(L/128) + 64 entries)
+  v->lens32 = w.take<int>((size_t)B);
+  v->rag_ints = std::min<size_t>((size_t)32 * ((size_t)B * ((L + 127) / 128) + 64), (size_t)16 << 20);
+  v->rag_arena = w.take<int>(v->rag_ints);
 }
 
 template <typename ActT>
-int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* workspace, size_t ws_bytes, cudaStream_t s) {
+int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int B, int T, float* wav, void* workspace,
+                size_t ws_bytes, cudaStream_t s) {
   const HifiganW& h = ctx->hifigan;
   const ev_hifigan_cfg& c = h.cfg;
   Workspace w(workspace, ws_bytes);
@@ -182,6 +208,30 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_vocode: workspace too small");
   ctx->prof_tag = "/voc";
   const RowMask none{nullptr, 0};
+  // Ragged batch: tiles that start past (len_b + margin) frames are skipped by the tensor-core kernels; the waveform of
+  // item b is bit-identical to the dense computation on [0, len_b * hop) and zero beyond.
+  struct RagGuard {
+    ev_ctx* c;
+    ~RagGuard() { c->rag = RaggedPlanner(); c->prof_scale = 1.0; }
+  } guard{ctx};
+  const int* lens32 = nullptr;
+  if (mel_lengths) {
+    EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(mel_lengths, v.lens32, B, s));
+    lens32 = v.lens32;
+    RaggedPlanner& r = ctx->rag;
+    r = RaggedPlanner();
+    r.lens = lens32; r.B = B; r.margin = vocoder_margin_frames(c);
+    r.arena = v.rag_arena; r.arena_ints = v.rag_ints;
+    r.launch_counter = &ctx->launches;
+    if (ctx->profiling) {   // algorithmic work = the valid frames only (instrumented eager step: a host copy is fine here)
+      std::vector<long long> hl(B);
+      EV_CUDA(ctx, cudaMemcpyAsync(hl.data(), mel_lengths, sizeof(long long) * B, cudaMemcpyDeviceToHost, s));
+      EV_CUDA(ctx, cudaStreamSynchronize(s));
+      double valid = 0.0;
+      for (int b = 0; b < B; ++b) valid += (double)std::min<long long>(std::max<long long>(hl[b], 0), T);
+      ctx->prof_scale = valid / ((double)B * T);
+    }
+  }
   EV_LAUNCH(ctx, s, "cf_to_cl", 0, (double)B * T * c.num_mels * (4.0 + sizeof(ActT)),
             (cf_to_cl<ActT>(mel, B, c.num_mels, T, v.mel, c.num_mels, (long long)T * c.num_mels, 1.0f, none, s)));
   int C = c.upsample_initial_channel;
@@ -196,12 +246,14 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
     C = Cin / 2;
     L = Lin * c.upsample_rates[i];
     const long long bs = L * C;
+    ctx->rag.rows_per_frame = (int)(Lin / T);   // the transposed conv's GEMM rows are its input rows
     {  // x = ups[i](leaky_relu(x)) -> fp32 residual stream x0 and its activated operand copy
       Epilogue e; e.out_f32 = v.x0; e.f32_ld = C; e.f32_bs = bs; e.act = ACT_LRELU; e.slope = kSlope;
       e.out_act = v.x0a; e.act_ld = C; e.act_bs = bs;
       EV_TRY(run_conv<ActT>(ctx, h.ups[i], v.stage_in, Cin, Lin * Cin, B, (int)Lin, e, s));
     }
     const bool last_stage = (i == c.n_ups - 1);
+    ctx->rag.rows_per_frame = (int)(L / T);
     for (int j = 0; j < c.n_kernels; ++j) {
       if constexpr (std::is_same<ActT, bf16>::value) {
         // fused ResBlock: six convs in one kernel, residual stream resident in TMEM (resblock_tc.cu)
@@ -222,7 +274,8 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
             snprintf(nm, sizeof nm, "resblock_tc/voc c%d k%d", C, rk);
             LaunchScope ls(ctx, s, ctx->prof_detail ? nm : "resblock_tc/voc", fl, (double)B * L * C * (4.0 + (mode ? 8.0 : 4.0)));
             ce = resblock_tc_launch(C, rk, c1p, c2p, bp, v.x0, v.sum, (last_branch && !last_stage) ? v.stage_in : nullptr, B, (int)L, mode,
-                                    1.0f / (float)c.n_kernels, kSlope, last_stage ? 1 : 0, s, &msg);
+                                    1.0f / (float)c.n_kernels, kSlope, last_stage ? 1 : 0, s, &msg,
+                                    ctx->rag.active() ? &ctx->rag : nullptr);
           }
           if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "resblock_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
           continue;
@@ -252,7 +305,7 @@ int vocode_impl(ev_ctx* ctx, const float* mel, int B, int T, float* wav, void* w
     }
   }
   EV_LAUNCH(ctx, s, "conv_post_tanh", 2.0 * B * (double)L * C * 7, (double)B * L * (4.0 * C + 4.0),
-            conv_post_tanh(v.sum, B, (int)L, C, h.post_w, h.post_b, wav, s));
+            conv_post_tanh(v.sum, B, (int)L, C, h.post_w, h.post_b, wav, lens32, h.total_up, s));
   return 0;
 }
 }  // namespace
@@ -265,14 +318,20 @@ extern "C" size_t ev_vocode_workspace_bytes(const ev_ctx* ctx, int B, int T) {
   return w.off + 256;
 }
 
-extern "C" int ev_vocode(ev_ctx* ctx, const float* mel, int B, int T, int precision, float* wav, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+extern "C" int ev_vocode_ragged(ev_ctx* ctx, const float* mel, const int64_t* mel_lengths, int B, int T, int precision, float* wav,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   if (!ctx) return EV_ERR_INVALID;
   if (!ctx->hifigan.loaded) return fail(ctx, EV_ERR_STATE, "ev_vocode: hifigan weights not loaded");
   if (!mel || !wav || B <= 0 || T <= 0) return fail(ctx, EV_ERR_INVALID, "ev_vocode: null argument or empty shape");
   EV_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t s = as_stream(stream);
-  if (precision == EV_PREC_FP32) return vocode_impl<float>(ctx, mel, B, T, wav, workspace, workspace_bytes, s);
-  if (precision == EV_PREC_BF16) return vocode_impl<bf16>(ctx, mel, B, T, wav, workspace, workspace_bytes, s);
+  const long long* ml = reinterpret_cast<const long long*>(mel_lengths);
+  if (precision == EV_PREC_FP32) return vocode_impl<float>(ctx, mel, ml, B, T, wav, workspace, workspace_bytes, s);
+  if (precision == EV_PREC_BF16) return vocode_impl<bf16>(ctx, mel, ml, B, T, wav, workspace, workspace_bytes, s);
   return fail(ctx, EV_ERR_INVALID, "ev_vocode: unknown precision");
+}
+
+extern "C" int ev_vocode(ev_ctx* ctx, const float* mel, int B, int T, int precision, float* wav, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  return ev_vocode_ragged(ctx, mel, nullptr, B, T, precision, wav, workspace, workspace_bytes, stream);
 }

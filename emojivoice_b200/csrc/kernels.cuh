@@ -102,7 +102,8 @@ template <typename ActT> cudaError_t group_norm_apply(const GnApplyArgs& a, cuda
 
 // ---- vocoder tail ---------------------------------------------------------------------------------------------------
 // hifigan/models.py:193-195 + to_waveform clamp: wav[b,t] = clamp(tanh(bias + sum_{j,c} w[j,c]*lrelu(x[b,t+j-3,c],0.01)))
+// lens (device [B], frames) != nullptr: samples t >= lens[b]*hop are written as 0 without reading x (ragged batch)
 cudaError_t conv_post_tanh(const float* x, int B, int L, int C, const float* w /*[7][C]*/, const float* bias, float* wav,
-                           cudaStream_t s);
+                           const int* lens, int hop, cudaStream_t s);
 
 }  // namespace ev

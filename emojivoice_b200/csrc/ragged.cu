@@ -1,0 +1,53 @@
+// Compact tile lists for ragged batches (see RaggedPlanner in conv.cuh): one small kernel per distinct tile geometry
+// turns the per-item lengths into the list of (item, m-tile) pairs that hold rows an utterance's valid audio depends on.
+#include "conv.cuh"
+
+namespace ev {
+namespace {
+
+__global__ void __launch_bounds__(256) ragged_table_kernel(const int* __restrict__ lens, int B, int margin, int rpf, int tile_rows,
+                                                           int M, int* __restrict__ table) {
+  __shared__ int start[kRaggedMaxB + 1];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const long long need = min((long long)M, ((long long)max(lens[b], 0) + margin) * rpf);
+    start[b + 1] = (int)((need + tile_rows - 1) / tile_rows);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    start[0] = 0;
+    for (int b = 0; b < B; ++b) start[b + 1] += start[b];
+    table[0] = start[B];
+  }
+  __syncthreads();
+  const int total = start[B];
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int lo = 0, hi = B - 1;              // last b with start[b] <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (start[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    table[1 + i] = (lo << 16) | (i - start[lo]);
+  }
+}
+
+}  // namespace
+
+const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
+  if (!lens || !arena || B <= 0 || B > kRaggedMaxB || B >= 32768 || tile_rows <= 0) return nullptr;
+  const int m_tiles = ceil_div(M, tile_rows);
+  if (m_tiles >= 65536) return nullptr;
+  for (int i = 0; i < n_cache; ++i)
+    if (cache[i].rpf == rows_per_frame && cache[i].tile_rows == tile_rows && cache[i].M == M) return cache[i].table;
+  const size_t ints = align_up((size_t)B * m_tiles + 1, 64);
+  if (n_cache >= 32 || arena_off + ints > arena_ints) return nullptr;
+  int* t = arena + arena_off;
+  // an ordinary launch (no programmatic serialization): every later kernel of the stream sees the finished table
+  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, tile_rows, M, t);
+  if (cudaGetLastError() != cudaSuccess) return nullptr;
+  arena_off += ints;
+  if (launch_counter) ++*launch_counter;
+  cache[n_cache++] = Entry{rows_per_frame, tile_rows, M, t};
+  return t;
+}
+
+}  // namespace ev

@@ -50,6 +50,7 @@ struct RbParams {
   int tiles_per_item, total_tiles, Wv, H;
   int w_slots;
   int resident;                        // all 6*k weight tiles stay in shared memory (C = 32): no per-tap barrier traffic
+  const int* rag;                      // ragged batch: compact (item, window) list (RaggedPlanner, conv.cuh) or nullptr = dense
 };
 
 template <int C> struct RbCfg {
@@ -145,6 +146,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_smem;
   pdl_trigger();
   pdl_wait();        // prologue (barriers, TMEM, zeroed operand buffer) overlapped the previous kernel's tail
+  const int total_tiles = p.rag ? __ldg(p.rag) : p.total_tiles;   // ragged batch: only windows that hold needed rows
   const uint32_t acc_x = tmem_base, acc_mid = tmem_base + (uint32_t)(MB * C);
   const int k = p.k, half_k = (p.k - 1) / 2;
 
@@ -159,7 +161,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           for (int j = 0; j < k; ++j)
             tma_load_3d(w_s + (uint32_t)((ci * k + j) * G::W_TILE), &maps.m[ci], &w_full[0], 0, 0, j);
       }
-      for (int tile = blockIdx.x; tile < p.total_tiles && !p.resident; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles && !p.resident; tile += gridDim.x) {
         for (int ci = 0; ci < 6; ++ci)
           for (int kc = 0; kc < KC; ++kc)
             for (int j = 0; j < k; ++j) {
@@ -183,7 +185,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       mbar_wait(&w_full[0], 0);
       tcgen05_fence_after();
       uint32_t cn = 0;                      // convs issued so far: epi_done_mb[*] completion number to wait for
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
 #pragma unroll 1
         for (int ci = 0; ci < 6; ++ci, ++cn) {
           const int l = ci >> 1, second = ci & 1;
@@ -234,7 +236,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     const uint64_t d_ones = ((uint64_t)hi_ns << 32) | (((ones_s & 0x3FFFFu) >> 4) | (8u << 16));
     const uint32_t bias_lo0 = ((bias_s & 0x3FFFFu) >> 4) | (8u << 16);
     if (resident) { mbar_wait(&w_full[0], 0); tcgen05_fence_after(); }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int ci = 0; ci < 6; ++ci) {
         const int l = ci >> 1, second = ci & 1;
         const int d = second ? 1 : p.dil[l];
@@ -361,8 +363,10 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     };
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.tiles_per_item, ti = tile - b * p.tiles_per_item;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int b, ti;
+      if (p.rag) { const int pair = __ldg(p.rag + 1 + tile); b = pair >> 16; ti = pair & 0xffff; }
+      else { b = tile / p.tiles_per_item; ti = tile - b * p.tiles_per_item; }
       const int w0 = ti * p.Wv - H;
       const bool interior = w0 >= 0 && w0 + W <= L;    // no row of this window lies outside the sequence: no zero-padding fix-ups
       const float* xb = p.x + b * p.x_bs;
@@ -521,8 +525,9 @@ int g_rb_wave = 0;       // EV_RB_WAVE=1: m-block wavefront schedule instead of 
                          // bound by shared-memory bandwidth -- MMA operand fetch alone takes 32 + N/4 of every 40-48 clk)
 
 template <int C>
-cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s) {
+cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, RaggedPlanner* ragged) {
   using G = RbCfg<C>;
+  p.rag = ragged ? ragged->table(G::W - 2 * 6 * (p.k - 1), p.L, s) : nullptr;   // windows of Wv output rows
   if constexpr (C == 32) {
     if (g_rb_occ2) {
       p.H = 6 * (p.k - 1);
@@ -613,7 +618,7 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
 // biases (device, [C]).  x, sum: fp32 (B, L, C); act_out: bf16 (B, L, C) or nullptr.
 cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
                                const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
-                               int write_f32, cudaStream_t s, std::string* err) {
+                               int write_f32, cudaStream_t s, std::string* err, RaggedPlanner* ragged) {
   { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0);
                                            v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0);
                                            v = getenv("EV_RB_WAVE"); g_rb_wave = v && atoi(v) != 0; once = true; } }
@@ -642,9 +647,9 @@ cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], con
   p.act_out = act_out; p.act_bs = (long long)L * C;
   p.L = L; p.k = k; p.mode = mode; p.inv_n = inv_n; p.slope_out = slope_out; p.write_f32 = write_f32;
   switch (C) {
-    case 32: return launch_rb<32>(maps, p, B, s);
-    case 64: return launch_rb<64>(maps, p, B, s);
-    default: return launch_rb<128>(maps, p, B, s);
+    case 32: return launch_rb<32>(maps, p, B, s, ragged);
+    case 64: return launch_rb<64>(maps, p, B, s, ragged);
+    default: return launch_rb<128>(maps, p, B, s, ragged);
   }
 }
 

@@ -18,7 +18,7 @@ LaunchScope::LaunchScope(ev_ctx* c, cudaStream_t st, const char* name, double fl
   for (size_t i = 0; i < ctx->kernel_names.size(); ++i)
     if (ctx->kernel_names[i] == name) { kid = (int)i; break; }
   if (kid < 0) { kid = (int)ctx->kernel_names.size(); ctx->kernel_names.push_back(name); }
-  ProfRecord r{kid, flops, bytes, nullptr, nullptr};
+  ProfRecord r{kid, flops * ctx->prof_scale, bytes * ctx->prof_scale, nullptr, nullptr};
   for (cudaEvent_t* e : {&r.e0, &r.e1}) {
     if (!ctx->event_pool.empty()) { *e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
     else if (cudaEventCreate(e) != cudaSuccess) return;
@@ -257,7 +257,7 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
       snprintf(buf, sizeof buf, " c%d n%d k%d d%d m%d", w.C_in, w.N, w.taps, w.dilation, g.M);
       nm += buf;
     }
-    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, 0, w, e, s, &msg); }
+    { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, x, x_ld, x_bs, 0, w, e, s, &msg, ctx->rag.active() ? &ctx->rag : nullptr); }
     if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch: " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   }
   return 0;

@@ -79,8 +79,13 @@ class Generator:
         self._ctx.check(rc, "ev_load_hifigan")
 
     @torch.inference_mode()
-    def __call__(self, mel, dtype=None):
-        """mel (B, num_mels, T) -> wav (B, 1, T*hop); tanh output already clamped to [-1, 1]."""
+    def __call__(self, mel, dtype=None, lengths=None):
+        """mel (B, num_mels, T) -> wav (B, 1, T*hop); tanh output already clamped to [-1, 1].
+
+        lengths (B,) int, optional: valid mel frames per item (the `mel_lengths` of synthesise) of a padded batch.  The
+        waveform of item b is then bit-identical on [: lengths[b]*hop] -- all the reference's batched caller keeps
+        (cli.py:307-311) -- and zero beyond; time tiles further than the generator's receptive field past an utterance's
+        end are never computed (ev_vocode_ragged)."""
         self._materialise()
         ctx, L = self._ctx, _lib.lib()
         dev = ctx.device
@@ -91,23 +96,30 @@ class Generator:
             B, _, T = mel.shape
             prec = _lib.PREC[dtype if dtype is not None else self.precision]
             nb = L.ev_vocode_workspace_bytes(ctx.handle, B, T)
+            if lengths is not None:
+                lengths = torch.as_tensor(lengths).reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+                if lengths.numel() != B:
+                    raise ValueError(f"lengths has {lengths.numel()} entries for a batch of {B}")
 
-            def call(mel_, wav_, ws_):
-                ctx.check(L.ev_vocode(ctx.handle, _lib.ptr(mel_), B, T, prec, _lib.ptr(wav_), _lib.ptr(ws_), ws_.numel(),
-                                      _lib.stream_ptr()), "ev_vocode")
+            def call(mel_, wav_, ws_, len_=None):
+                ctx.check(L.ev_vocode_ragged(ctx.handle, _lib.ptr(mel_), _lib.ptr(len_) if len_ is not None else None, B, T, prec,
+                                             _lib.ptr(wav_), _lib.ptr(ws_), ws_.numel(), _lib.stream_ptr()), "ev_vocode")
 
-            key = (B, T, prec)
+            key = (B, T, prec, lengths is not None)
             ws_shared = ctx.workspace(nb)                   # (may grow the workspace: do it before looking graphs up)
             ent = self._graphs.get(key, ctx.ws_version) if self.cuda_graphs else None
             if ent is None and self.cuda_graphs and self._graphs.should_capture(key):
-                ent = dict(mel=mel.clone(), wav=torch.empty(B, 1, T * self.hop, device=dev), ws=ws_shared, ws_version=ctx.ws_version)
-                ent["graph"], ent["launches"] = _lib.capture(ctx, lambda: call(ent["mel"], ent["wav"], ent["ws"]))
+                ent = dict(mel=mel.clone(), wav=torch.empty(B, 1, T * self.hop, device=dev), ws=ws_shared, ws_version=ctx.ws_version,
+                           len=lengths.clone() if lengths is not None else None)
+                ent["graph"], ent["launches"] = _lib.capture(ctx, lambda: call(ent["mel"], ent["wav"], ent["ws"], ent["len"]))
                 self._graphs.put(key, ent)
             if ent is None:
                 wav = torch.empty(B, 1, T * self.hop, device=dev)
-                call(mel, wav, ws_shared)
+                call(mel, wav, ws_shared, lengths)
             else:
                 ent["mel"].copy_(mel)
+                if lengths is not None:
+                    ent["len"].copy_(lengths)
                 ent["graph"].replay()
                 self._replayed_launches += ent["launches"]
                 wav = ent["wav"].clone()
@@ -159,9 +171,11 @@ class Denoiser:
 
 
 @torch.inference_mode()
-def to_waveform(mel, vocoder, denoiser=None, strength=0.00025):
-    """feel_me.py:181-187: vocoder(mel).clamp(-1, 1) -> optional denoiser -> .cpu().squeeze()."""
-    audio = vocoder(mel).clamp(-1, 1)
+def to_waveform(mel, vocoder, denoiser=None, strength=0.00025, lengths=None):
+    """feel_me.py:181-187: vocoder(mel).clamp(-1, 1) -> optional denoiser -> .cpu().squeeze().
+
+    lengths: optional valid frames per item of a padded batch (see Generator.__call__)."""
+    audio = (vocoder(mel, lengths=lengths) if lengths is not None else vocoder(mel)).clamp(-1, 1)
     if denoiser is not None:
         audio = denoiser(audio.squeeze(1), strength=strength)
     return audio.cpu().squeeze()

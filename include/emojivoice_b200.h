@@ -124,6 +124,14 @@ EV_API int ev_decode(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, c
 EV_API size_t ev_vocode_workspace_bytes(const ev_ctx* ctx, int B, int T);
 EV_API int ev_vocode(ev_ctx* ctx, const float* mel, int B, int T, int precision, float* wav, void* workspace,
               size_t workspace_bytes, void* stream);
+/* Ragged batch: the same generator for a padded batch whose item b holds mel_lengths[b] valid frames (device int64, the
+ * `mel_lengths` synthesise returns; NULL = ev_vocode).  Replaces the pair "vocoder(mel) on the padded batch, then crop
+ * each waveform to [: length * hop]" of the reference's batched caller (Matcha-TTS/matcha/cli.py:291-317): wav[b] is
+ * bit-identical to ev_vocode's on [0, mel_lengths[b]*hop) and ZERO beyond (the reference leaves vocoded prior noise there,
+ * which every caller crops away).  The generator is convolutional with a finite receptive field, so time tiles that start
+ * more than that field past an utterance's end are not computed at all. */
+EV_API int ev_vocode_ragged(ev_ctx* ctx, const float* mel, const int64_t* mel_lengths, int B, int T, int precision,
+              float* wav, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- bias denoiser -----------------------------------------------------------------------------------------
  * Replaces Denoiser.forward (hifigan/denoiser.py:58-64): centred hann STFT(1024, hop 256) -> magnitude minus

@@ -295,6 +295,60 @@ def test_vocoder_is_linear_in_batch_and_time_tiling_free():
     assert torch.equal(full[2:3], solo)
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_ragged_vocoder_equals_dense_on_valid_samples_and_is_zero_beyond(vocoders, prec):
+    """ev_vocode_ragged: item b's waveform is BIT-identical to the dense generator on [: len_b * 256] (what the reference's
+    batched caller keeps, cli.py:307-311) and exactly zero beyond; lengths 0, 1, T and > T, eager and graph replay, and
+    replays of one graph with different lengths."""
+    gen, sd = vocoders["hifigan_gain1"]
+    B, T = 6, 300
+    mel = synthetic.synthetic_mel(B, T, seed=77)
+    dense = gen(mel, dtype=prec)
+    for lens in ([300, 0, 1, 137, 299, 512], [17, 300, 300, 64, 2, 250], [100] * 6):
+        for _ in range(3):                               # eager, capture, replay
+            wav = gen(mel, dtype=prec, lengths=torch.tensor(lens))
+            assert wav.shape == dense.shape
+            for b, n in enumerate(lens):
+                n = min(n, T) * 256
+                assert torch.equal(wav[b, :, :n], dense[b, :, :n]), (lens, b)
+                assert float(wav[b, :, n:].abs().max() if n < T * 256 else 0.0) == 0.0
+    # the valid part also matches the oracle's (reference's) cropped waveform
+    ref = ho.generator(sd, HIFIGAN_V1, mel)
+    wav = gen(mel, dtype=prec, lengths=torch.tensor([137] * B))
+    assert rel_l2(wav[:, :, : 137 * 256].cpu(), ref[:, :, : 137 * 256]) < TOL[prec]
+    # a short batch (layer-by-layer ResBlocks below 1024 samples per stage) and a lone long item
+    mel_s = synthetic.synthetic_mel(3, 20, seed=78)
+    d_s, r_s = gen(mel_s, dtype=prec), gen(mel_s, dtype=prec, lengths=[20, 3, 11])
+    for b, n in enumerate([20, 3, 11]):
+        assert torch.equal(r_s[b, :, : n * 256], d_s[b, :, : n * 256]) and float(r_s[b, :, n * 256:].abs().sum()) == 0.0
+
+
+def test_ragged_vocoder_full_size_batch(matcha, matcha_sd, vocoders):
+    """BASELINE config 2 shape (32 x ~600 frames, mixed lengths) through synthesise -> ragged vocoder: valid samples equal
+    the dense path bit for bit, the corpus driver's cropped waveforms are unchanged by `ragged`."""
+    gen, _ = vocoders["hifigan_gain1"]
+    x, xl, spks = synthetic.phoneme_batch(32, 60, 90, seed=2000)
+    out = matcha.synthesise(x, xl, 2, 0.667, spks, 0.8)
+    dense = gen(out["mel"])
+    rag = gen(out["mel"], lengths=out["mel_lengths"])
+    ml = out["mel_lengths"].cpu().tolist()
+    assert min(ml) < max(ml)
+    for b, n in enumerate(ml):
+        assert torch.equal(rag[b, :, : n * 256], dense[b, :, : n * 256])
+        assert float(rag[b, :, n * 256:].abs().sum()) == 0.0
+    utts = [(x[i, : int(xl[i])].tolist(), int(spks[i])) for i in range(8)]
+    zs = {}
+
+    def z_fn(mb, model, x_, xl_, spks_):
+        probe = model.synthesise(x_, xl_, 1, 0.667, spks_, 1.0)
+        return zs.setdefault(tuple(mb.items), synthetic.prior_noise(len(mb.items), 80, probe["t_pad"], seed=3))
+
+    r0, _ = ev.synthesise_corpus(matcha, gen, utts, batch_size=4, n_timesteps=2, z_fn=z_fn, ragged=False)
+    r1, _ = ev.synthesise_corpus(matcha, gen, utts, batch_size=4, n_timesteps=2, z_fn=z_fn, ragged=True)
+    for i in r0:
+        assert torch.equal(r0[i]["waveform"], r1[i]["waveform"])
+
+
 def test_end_to_end_emoji_text_to_waveform(matcha, matcha_sd, vocoders):
     gen, hsd = vocoders["hifigan_gain1"]
     text, spk = ev.emoji_to_spk("that is wonderful \U0001F60D")
