@@ -235,6 +235,55 @@ extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y
   return EV_OK;
 }
 
+// Fused transformer feed-forward alone (ff_tc.cu): x (B, T, 256) CHANNEL-LAST fp32; w1 (inner, 256), w2 (256, inner) as
+// nn.Linear stores them; snake_a = exp(alpha), snake_invb = 1 / (exp(beta) + 1e-9); out (B, T, 256) fp32 (the kernel's
+// bf16 result widened).  y_lengths (B) int64 or NULL: rows with (t << len_shift) >= y_lengths[b] come out as zero.
+extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
+                                const float* snake_a, const float* snake_invb, const float* w2, const float* b2,
+                                const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, void* stream) {
+  if (!ctx || !x || !ln_g || !ln_b || !w1 || !b1 || !snake_a || !snake_invb || !w2 || !b2 || !out || B <= 0 || T <= 0 || inner <= 0)
+    return EV_ERR_INVALID;
+  cudaStream_t s = as_stream(stream);
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = 256;
+  const size_t mark = ctx->owned.size();
+  auto release = [&]() {
+    cudaStreamSynchronize(s);
+    for (size_t i = mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+    ctx->owned.resize(mark);
+  };
+  ev_tensor t1{}, t2{}, tb1{}, tb2{};
+  t1.name = "w1"; t1.data = w1; t1.ndim = 3; t1.shape[0] = inner; t1.shape[1] = D; t1.shape[2] = 1;
+  t2.name = "w2"; t2.data = w2; t2.ndim = 3; t2.shape[0] = D; t2.shape[1] = inner; t2.shape[2] = 1;
+  tb1.name = "b1"; tb1.data = b1; tb1.ndim = 1; tb1.shape[0] = inner;
+  tb2.name = "b2"; tb2.data = b2; tb2.ndim = 1; tb2.shape[0] = D;
+  ev_tensor list[4] = {t1, t2, tb1, tb2};
+  WeightStore ws(ctx, list, 4, s);
+  ConvWeights c1, c2;
+  int rc = make_conv(ctx, ws, {"w1"}, {"b1"}, inner, D, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c1);
+  if (!rc) rc = make_conv(ctx, ws, {"w2"}, {"b2"}, D, inner, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c2);
+  if (!rc && !ff_tc_supported(c1, c2)) rc = fail(ctx, EV_ERR_INVALID, "ev_test_ff_block: shape not served by the fused kernel");
+  void *yo = nullptr, *li = nullptr;
+  if (!rc) rc = device_alloc(ctx, (size_t)B * T * D * 2, &yo, false, s);
+  if (!rc) rc = device_alloc(ctx, (size_t)B * 4, &li, false, s);
+  if (rc) { release(); return rc; }
+  cudaError_t ce = cudaSuccess;
+  int* lens = nullptr;
+  if (y_lengths) { lens = reinterpret_cast<int*>(li); ce = i64_to_i32(reinterpret_cast<const long long*>(y_lengths), lens, B, s); }
+  FfTcArgs fa;
+  fa.x = x; fa.ln_g = ln_g; fa.ln_b = ln_b; fa.eps = 1e-5f; fa.ff1 = &c1; fa.ff2 = &c2; fa.snake_a = snake_a; fa.snake_invb = snake_invb;
+  fa.out = reinterpret_cast<bf16*>(yo); fa.out_ld = D; fa.out_bs = (long long)T * D; fa.lens = lens; fa.len_shift = len_shift;
+  fa.B = B; fa.T = T;
+  std::string err;
+  if (ce == cudaSuccess) ce = ff_tc_launch(fa, s, &err);
+  const long long n = (long long)B * T * D;
+  if (ce == cudaSuccess) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(yo), out, n); ce = cudaGetLastError(); }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  release();
+  if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ev_test_ff_block") : fail(ctx, EV_ERR_CUDA, err);
+  return EV_OK;
+}
+
 // diagnostic (EV_TC_TRACE=1): per-CTA clock stamps [n_cta][16] of the most recent conv_tc launch, host buffer
 extern "C" int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
   if (!ctx || !out_host || n <= 0) return EV_ERR_INVALID;

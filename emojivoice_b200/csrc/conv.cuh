@@ -136,4 +136,17 @@ cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], con
                                int write_f32, cudaStream_t s, std::string* err, RaggedPlanner* ragged = nullptr);
 int conv_tc_pick_bn(int N);
 
+// ff_tc.cu: LayerNorm -> Linear(256 -> inner) -> SnakeBeta -> Linear(inner -> 256) -> + residual -> * mask, one kernel
+struct FfTcArgs {
+  const float* x = nullptr;             // fp32 residual stream (b, t, 256), dense
+  const float* ln_g = nullptr; const float* ln_b = nullptr; float eps = 1e-5f;
+  const ConvWeights* ff1 = nullptr; const ConvWeights* ff2 = nullptr;
+  const float* snake_a = nullptr; const float* snake_invb = nullptr;
+  bf16* out = nullptr; long long out_ld = 0, out_bs = 0;   // (b, t, 256) bf16 operand of the next conv, masked
+  const int* lens = nullptr; int len_shift = 0;
+  int B = 0, T = 0;
+};
+bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2);
+cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err);
+
 }  // namespace ev

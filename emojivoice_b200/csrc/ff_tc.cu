@@ -1,0 +1,371 @@
+// Fused feed-forward of the decoder's BasicTransformerBlock (transformer.py:296-316 with the SnakeBeta activation,
+// transformer.py:13-83) on tcgen05: per 128-row tile ONE kernel does
+//     n = LayerNorm3(x);  h = SnakeBeta(n W1^T + b1);  y = (x + h W2^T + b2) * mask   -> bf16 operand of the next conv
+// The 1024-wide hidden activation never leaves the SM: it is produced 128 channels at a time into TMEM (double-buffered
+// accumulator), activated by the epilogue warps into a bf16 K-major operand tile in shared memory, and consumed by the
+// second GEMM, whose 256-wide accumulator stays in TMEM for the whole tile.  Replaces three launches (layer_norm,
+// conv_tc ff1, conv_tc ff2) and the 2 x 2 KB per row HBM round trip of the hidden tensor.
+//
+// Per CTA (persistent over 128-row tiles, one per SM):
+//   shared memory  A  [4 planes x 128 rows x 128 B]  LN output, bf16, 128B-swizzled K-major (written by hand)     64 KB
+//                  P  [2 buffers x 2 planes x 128 rows x 128 B]  SnakeBeta output of one 128-channel chunk          64 KB
+//                  W  ring of 6 x 16 KB weight tiles (TMA, box 64 k x 128 n): W1 chunk = 4 tiles, W2 chunk = 4 tiles  96 KB
+//   TMEM           acc1 [2 x 128 columns] (hidden chunk c in buffer c & 1), acc2 [256 columns]
+//   warp 0  : TMA producer -- weights only, which no kernel of the stream writes: it does NOT wait for the programmatic
+//             dependency, so the first six weight tiles land while the previous kernel is still draining
+//   warp 1  : MMA issuer (owns TMEM).  Order  G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(6) | G2(7): the tensor pipe
+//             always has the next chunk's first GEMM to run while the epilogue warps activate the current one
+//   warps 2-17 : LayerNorm prologue (warp = row), per-chunk activation (thread = row, 32 channels), final epilogue.
+// Work per tile: 2 x 128 x 256 x 1024 MACs = 16.4 k clk of tcgen05 at N = 128 (64 clk per MMA); weight stream 1 MB per
+// tile from L2.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdlib>
+
+#include "conv.cuh"
+#include "tc_ptx.cuh"
+
+namespace ev {
+using namespace tc;
+namespace {
+
+constexpr int FF_D = 256;                   // model width (K of GEMM 1, N of GEMM 2)
+constexpr int FF_CHUNK = 128;               // hidden channels per chunk
+constexpr int FF_SLOTS = 6;
+constexpr int FF_PLANE = 128 * 128;         // 128 rows x 64 bf16
+constexpr int FF_A_BYTES = 4 * FF_PLANE;
+constexpr int FF_P_BYTES = 2 * FF_PLANE;
+constexpr int FF_W_TILE = FF_PLANE;
+constexpr int FF_SMEM = FF_A_BYTES + 2 * FF_P_BYTES + FF_SLOTS * FF_W_TILE + 1024;
+constexpr int FF_EPI_WARPS = 16;
+constexpr int FF_THREADS = 32 * (2 + FF_EPI_WARPS);
+
+struct FfMaps { CUtensorMap w1, w2; };
+
+struct FfParams {
+  const float* x; long long x_bs;           // fp32 residual stream (b, t, 256), dense rows
+  const float* ln_g; const float* ln_b; float eps;
+  const float* b1; const float* snake_a; const float* snake_invb;   // [n_chunks * 128]
+  const float* b2;                          // [256]
+  bf16* out; long long out_ld, out_bs;
+  const int* lens; int len_shift;
+  int T, m_tiles, total_tiles, n_chunks;
+};
+
+__device__ __forceinline__ uint32_t d_hi(uint32_t sbo, uint32_t layout) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
+__device__ __forceinline__ uint32_t d_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t d_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+__global__ void __launch_bounds__(FF_THREADS, 1)
+ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t w_full[FF_SLOTS], w_empty[FF_SLOTS];
+  __shared__ __align__(8) uint64_t a_ready, a_free, acc1_full[2], p_ready[2], p_free[2], acc2_full, acc2_empty;
+  __shared__ uint32_t tmem_base_smem;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t a_s = base, p_s = base + FF_A_BYTES, w_s = p_s + 2 * FF_P_BYTES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = p.n_chunks;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w2) : "memory");
+    for (int s = 0; s < FF_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(&a_ready, FF_EPI_WARPS); mbar_init(&a_free, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&p_ready[s], FF_EPI_WARPS); mbar_init(&p_free[s], 1); }
+    mbar_init(&acc2_full, 1); mbar_init(&acc2_empty, FF_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t acc1 = tmem_base, acc2 = tmem_base + 256u;
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- weight producer (no dependency on the previous kernel: weights are constant)
+      int sl = 0;
+      uint32_t ph = 1;
+      auto load_w1 = [&](int c) {
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait(&w_empty[sl], ph);
+          mbar_expect_tx(&w_full[sl], (uint32_t)FF_W_TILE);
+          tma_load_3d(w_s + (uint32_t)(sl * FF_W_TILE), &maps.w1, &w_full[sl], kc * 64, c * FF_CHUNK, 0);
+          if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; }
+        }
+      };
+      auto load_w2 = [&](int c) {
+        for (int kc = 0; kc < 2; ++kc)
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_empty[sl], ph);
+            mbar_expect_tx(&w_full[sl], (uint32_t)FF_W_TILE);
+            tma_load_3d(w_s + (uint32_t)(sl * FF_W_TILE), &maps.w2, &w_full[sl], c * FF_CHUNK + kc * 64, nh * 128, 0);
+            if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; }
+          }
+      };
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        load_w1(0);
+        if (n_chunks > 1) load_w1(1);
+        for (int c = 0; c < n_chunks; ++c) {
+          load_w2(c);
+          if (c + 2 < n_chunks) load_w1(c + 2);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: warp-uniform control flow, one elected lane issues
+    constexpr uint32_t idesc = make_idesc(128, 128);
+    const uint32_t hi = d_hi(1024u, 2u);
+    const uint32_t a_lo0 = d_lo(a_s), p_lo0 = d_lo(p_s), w_lo0 = d_lo(w_s);
+    constexpr uint32_t plane16 = (uint32_t)FF_PLANE >> 4, pbuf16 = (uint32_t)FF_P_BYTES >> 4;
+    int sl = 0;
+    uint32_t wph = 0;
+    int it = 0;
+    auto gemm1 = [&](int c, bool last) {      // acc1[c & 1] = A (128 x 256) x W1[c]^T
+      const uint32_t d = acc1 + (uint32_t)((c & 1) * FF_CHUNK);
+      for (int kc = 0; kc < 4; ++kc) {
+        mbar_wait(&w_full[sl], wph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)kc * plane16, b_lo = w_lo0 + (uint32_t)sl * plane16;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_bf16(d, d_join(hi, a_lo + 2u * ks), d_join(hi, b_lo + 2u * ks), idesc, (kc | ks) ? 1u : 0u);
+          umma_commit(&w_empty[sl]);
+          if (kc == 3) {
+            umma_commit(&acc1_full[c & 1]);
+            if (last) umma_commit(&a_free);   // every GEMM-1 MMA of the tile has read A: the next tile's LayerNorm may overwrite it
+          }
+        }
+        __syncwarp();
+        if (++sl == FF_SLOTS) { sl = 0; wph ^= 1u; }
+      }
+    };
+    auto gemm2 = [&](int c, bool last) {      // acc2 (128 x 256) += P[c & 1] (128 x 128) x W2[:, chunk c]^T
+      const uint32_t pb = p_lo0 + (uint32_t)(c & 1) * pbuf16;
+      for (int kc = 0; kc < 2; ++kc)
+        for (int nh = 0; nh < 2; ++nh) {
+          mbar_wait(&w_full[sl], wph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = pb + (uint32_t)kc * plane16, b_lo = w_lo0 + (uint32_t)sl * plane16;
+            const uint32_t d = acc2 + (uint32_t)(nh * 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_bf16(d, d_join(hi, a_lo + 2u * ks), d_join(hi, b_lo + 2u * ks), idesc, (c | kc | ks) ? 1u : 0u);
+            umma_commit(&w_empty[sl]);
+            if (kc == 1 && nh == 1) {
+              umma_commit(&p_free[c & 1]);
+              if (last) umma_commit(&acc2_full);
+            }
+          }
+          __syncwarp();
+          if (++sl == FF_SLOTS) { sl = 0; wph ^= 1u; }
+        }
+    };
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(&a_ready, (uint32_t)it & 1u);
+      tcgen05_fence_after();
+      const int half = (n_chunks + 1) >> 1;   // uses of each acc1 / P buffer per tile
+      gemm1(0, n_chunks == 1);
+      if (n_chunks > 1) gemm1(1, n_chunks == 2);
+      for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t u = (uint32_t)(it * half + (c >> 1));
+        mbar_wait(&p_ready[c & 1], u & 1u);
+        if (c == 0) mbar_wait(&acc2_empty, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's output has left acc2
+        tcgen05_fence_after();
+        gemm2(c, c == n_chunks - 1);
+        if (c + 2 < n_chunks) gemm1(c + 2, c + 3 == n_chunks);
+      }
+    }
+  } else {
+    // ---------------- 16 worker warps
+    const int ew = warp - 2, q = warp & 3, j = ew >> 2;   // TMEM lane quadrant q, 32-column slot j of a 128-column chunk
+    const uint32_t lane_q = (uint32_t)(q * 32) << 16;
+    uint8_t* a_gen = base_gen;
+    uint8_t* p_gen = base_gen + FF_A_BYTES;
+    pdl_wait();                                            // x is the previous kernel's output
+    // LayerNorm affine parameters of this lane's 8 channels (4 at 4*lane, 4 at 128 + 4*lane)
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 32 + lane);
+    const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + lane), be1 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 32 + lane);
+    const int half = (n_chunks + 1) >> 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * 128;
+      const float* xb = p.x + b * p.x_bs;
+      // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7 of the tile into the swizzled bf16 operand A
+      {
+#pragma unroll 1
+        for (int hb4 = 0; hb4 < 8; hb4 += 4) {
+        float4 v0[4], v1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = m0 + ew * 8 + hb4 + i;
+          if (t < p.T) {
+            const float4* row = reinterpret_cast<const float4*>(xb + (long long)t * FF_D);
+            v0[i] = row[lane]; v1[i] = row[32 + lane];
+          } else { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
+        }
+        if (hb4 == 0) mbar_wait(&a_free, ((uint32_t)it & 1u) ^ 1u);      // the previous tile's GEMM 1 has finished reading A
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = ew * 8 + hb4 + i;
+          const float4 a = v0[i], c = v1[i];
+          const float mean = warp_sum((a.x + a.y) + (a.z + a.w) + (c.x + c.y) + (c.z + c.w)) * (1.0f / FF_D);
+          const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+          const float d4 = c.x - mean, d5 = c.y - mean, d6 = c.z - mean, d7 = c.w - mean;
+          const float var = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7)) * (1.0f / FF_D);
+          const float rstd = (m0 + r < p.T) ? 1.0f / sqrtf(var + p.eps) : 0.0f;
+          const float k = (m0 + r < p.T) ? 1.0f : 0.0f;    // rows past the sequence: exact zeros (their outputs are never stored)
+          __nv_bfloat162 l0 = __floats2bfloat162_rn((d0 * rstd * g0.x + be0.x) * k, (d1 * rstd * g0.y + be0.y) * k);
+          __nv_bfloat162 l1 = __floats2bfloat162_rn((d2 * rstd * g0.z + be0.z) * k, (d3 * rstd * g0.w + be0.w) * k);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn((d4 * rstd * g1.x + be1.x) * k, (d5 * rstd * g1.y + be1.y) * k);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn((d6 * rstd * g1.z + be1.z) * k, (d7 * rstd * g1.w + be1.w) * k);
+          // channel ch = 4*lane (+128): plane ch/64, 16-byte chunk (ch%64)/8, 8-byte half (lane & 1)
+          const int plane = lane >> 4, c16 = (lane & 15) >> 1, hb = (lane & 1) * 8;
+          const uint32_t off = (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4) + hb);
+          uint2 lo2, hi2;
+          lo2.x = *reinterpret_cast<uint32_t*>(&l0); lo2.y = *reinterpret_cast<uint32_t*>(&l1);
+          hi2.x = *reinterpret_cast<uint32_t*>(&h0); hi2.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(a_gen + plane * FF_PLANE + off) = lo2;
+          *reinterpret_cast<uint2*>(a_gen + (plane + 2) * FF_PLANE + off) = hi2;
+        }
+        }
+        fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready);
+      }
+      // ---- per chunk: acc1 -> + b1 -> SnakeBeta -> bf16 operand P
+      const int row = q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        const uint32_t u = (uint32_t)(it * half + (c >> 1));
+        mbar_wait(&acc1_full[buf], u & 1u);
+        tcgen05_fence_after();
+        uint32_t raw[32];
+        tmem_ld32(acc1 + lane_q + (uint32_t)(buf * FF_CHUNK + j * 32), raw);
+        const int ch0 = c * FF_CHUNK + j * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + ch0 + i));
+          const float4 sa = __ldg(reinterpret_cast<const float4*>(p.snake_a + ch0 + i));
+          const float4 sb = __ldg(reinterpret_cast<const float4*>(p.snake_invb + ch0 + i));
+          float v0 = __uint_as_float(raw[i]) + bb.x, v1 = __uint_as_float(raw[i + 1]) + bb.y;
+          float v2 = __uint_as_float(raw[i + 2]) + bb.z, v3 = __uint_as_float(raw[i + 3]) + bb.w;
+          const float s0 = __sinf(v0 * sa.x), s1 = __sinf(v1 * sa.y), s2 = __sinf(v2 * sa.z), s3 = __sinf(v3 * sa.w);
+          v0 = fmaf(sb.x, s0 * s0, v0); v1 = fmaf(sb.y, s1 * s1, v1); v2 = fmaf(sb.z, s2 * s2, v2); v3 = fmaf(sb.w, s3 * s3, v3);
+          __nv_bfloat162 e0 = __floats2bfloat162_rn(v0, v1), e1 = __floats2bfloat162_rn(v2, v3);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&e0);
+          pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&e1);
+        }
+        mbar_wait(&p_free[buf], (u & 1u) ^ 1u);            // GEMM 2 of chunk c-2 has finished reading this buffer
+        {
+          uint8_t* rp = p_gen + buf * FF_P_BYTES + (j >> 1) * FF_PLANE + row * 128;
+          const int c16 = (j & 1) * 4, sw = row & 7;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(rp + (((c16 + i) ^ sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        tcgen05_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[buf]);
+      }
+      // ---- output: y = (x + acc2 + b2) * mask -> bf16; each warp owns two 32-column blocks (j and j + 4) of its rows
+      mbar_wait(&acc2_full, (uint32_t)it & 1u);
+      tcgen05_fence_after();
+      const int t = m0 + row;
+      const bool row_ok = t < p.T;
+      const float mv = (p.lens == nullptr || (t << p.len_shift) < __ldg(p.lens + b)) ? 1.0f : 0.0f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int col = (j + 4 * h) * 32;
+        uint32_t raw[32];
+        tmem_ld32(acc2 + lane_q + (uint32_t)col, raw);
+        if (h == 1) {                                      // last TMEM read of the tile: hand acc2 back to the issuer
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc2_empty);
+        }
+        if (row_ok) {
+          const float4* xr = reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + b * p.out_bs + (long long)t * p.out_ld + col);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const float4 x0 = xr[i >> 2], x1 = xr[(i >> 2) + 1];
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + i)), c1 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + i + 4));
+            const float y0 = (__uint_as_float(raw[i]) + c0.x + x0.x) * mv, y1 = (__uint_as_float(raw[i + 1]) + c0.y + x0.y) * mv;
+            const float y2 = (__uint_as_float(raw[i + 2]) + c0.z + x0.z) * mv, y3 = (__uint_as_float(raw[i + 3]) + c0.w + x0.w) * mv;
+            const float y4 = (__uint_as_float(raw[i + 4]) + c1.x + x1.x) * mv, y5 = (__uint_as_float(raw[i + 5]) + c1.y + x1.y) * mv;
+            const float y6 = (__uint_as_float(raw[i + 6]) + c1.z + x1.z) * mv, y7 = (__uint_as_float(raw[i + 7]) + c1.w + x1.w) * mv;
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(y0, y1), o1 = __floats2bfloat162_rn(y2, y3);
+            __nv_bfloat162 o2 = __floats2bfloat162_rn(y4, y5), o3 = __floats2bfloat162_rn(y6, y7);
+            dst[i >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1),
+                                     *reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2) {
+  static const int mode = []() { const char* v = getenv("EV_FF_FUSE"); return v ? atoi(v) : 1; }();   // EV_FF_FUSE=0: three launches
+  return mode != 0 && ff1.w_bf16 && ff2.w_bf16 && ff1.taps == 1 && ff2.taps == 1 && ff1.C_in == FF_D && ff2.N == FF_D &&
+         ff1.N == ff2.C_in && ff1.N % (2 * FF_CHUNK) == 0 && ff1.K_pad == FF_D && ff2.K_pad == ff1.N &&
+         ff1.N_pad_tc == ff1.N && ff2.N_pad_tc == FF_D && ff1.bias && ff2.bias;
+}
+
+cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err) {
+  const ConvWeights& w1 = *a.ff1;
+  const ConvWeights& w2 = *a.ff2;
+  if (!ff_tc_supported(w1, w2) || (a.out_ld & 7) || (a.out_bs & 7) || (reinterpret_cast<uintptr_t>(a.out) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.x) & 15)) {
+    if (err) *err = "ff_tc: unsupported layer shape or alignment";
+    return cudaErrorInvalidValue;
+  }
+  FfMaps maps;
+  if (!tc_encode_bf16_map(&maps.w1, w1.w_bf16, (uint64_t)w1.K_pad, (uint64_t)w1.N_pad_tc, 1, (uint64_t)w1.K_pad * 2,
+                          (uint64_t)w1.K_pad * w1.N_pad_tc * 2, 64u, 128u, 128, err))
+    return cudaErrorInvalidValue;
+  if (!tc_encode_bf16_map(&maps.w2, w2.w_bf16, (uint64_t)w2.K_pad, (uint64_t)w2.N_pad_tc, 1, (uint64_t)w2.K_pad * 2,
+                          (uint64_t)w2.K_pad * w2.N_pad_tc * 2, 64u, 128u, 128, err))
+    return cudaErrorInvalidValue;
+  FfParams p{};
+  p.x = a.x; p.x_bs = (long long)a.T * FF_D;
+  p.ln_g = a.ln_g; p.ln_b = a.ln_b; p.eps = a.eps;
+  p.b1 = w1.bias; p.snake_a = a.snake_a; p.snake_invb = a.snake_invb; p.b2 = w2.bias;
+  p.out = a.out; p.out_ld = a.out_ld; p.out_bs = a.out_bs;
+  p.lens = a.lens; p.len_shift = a.len_shift;
+  p.T = a.T; p.m_tiles = ceil_div(a.T, 128); p.total_tiles = p.m_tiles * a.B; p.n_chunks = w1.N / FF_CHUNK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(ff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
+    if (ce != cudaSuccess) return ce;
+    configured = true;
+  }
+  const int grid = std::min(p.total_tiles, tc_sm_count());
+  return launch_pdl(ff_tc_kernel, dim3(grid), dim3(FF_THREADS), (size_t)FF_SMEM, s, maps, p);
+}
+
+}  // namespace ev

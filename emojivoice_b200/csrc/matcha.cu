@@ -478,6 +478,22 @@ struct Decoder {
     }
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
     EV_TRY(run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s));
+    if constexpr (std::is_same<ActT, bf16>::value) {
+      // LayerNorm3 + ff1 + SnakeBeta + ff2 + residual + mask as ONE kernel: the 1024-wide hidden tensor stays on the SM (ff_tc.cu)
+      if (D == 256 && !(dbg_skip & 3) && ff_tc_supported(w.ff1, w.ff2)) {
+        FfTcArgs fa;
+        fa.x = d.xr; fa.ln_g = w.ln3_g; fa.ln_b = w.ln3_b; fa.eps = 1e-5f; fa.ff1 = &w.ff1; fa.ff2 = &w.ff2;
+        fa.snake_a = w.snake_a; fa.snake_invb = w.snake_invb;
+        fa.out = out; fa.out_ld = out_ld; fa.out_bs = (long long)Tl * out_ld; fa.lens = d.ylen32; fa.len_shift = shift;
+        fa.B = B; fa.T = Tl;
+        std::string err;
+        cudaError_t ce;
+        { LaunchScope ls(ctx, s, "ff_tc", 4.0 * B * (double)Tl * D * w.ff1.N, (double)B * Tl * D * 10.0 + 4.0 * D * w.ff1.N);
+          ce = ff_tc_launch(fa, s, &err); }
+        if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ff_tc") : fail(ctx, EV_ERR_CUDA, err);
+        return 0;
+      }
+    }
     LnArgs ln;
     ln.x = d.xr; ln.x_ld = D; ln.gamma = w.ln3_g; ln.beta = w.ln3_b; ln.eps = 1e-5f; ln.out_act = d.n; ln.act_ld = D;
     ln.B = B; ln.T = Tl; ln.C = D;

@@ -181,6 +181,12 @@ EV_API int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const flo
 EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_lengths, int B, int T, int H, int len_shift,
                       int precision, float* out, void* stream);
 /* The float32 Euler times/steps of flow_matching.py:52,68-83 as the library computes them (pure host code). */
+/* Fused LayerNorm + feed-forward of one decoder transformer block (transformer.py:296-316): x (B,T,256) CHANNEL-LAST,
+ * w1 (inner,256), w2 (256,inner), snake_a = exp(alpha), snake_invb = 1/(exp(beta)+1e-9); out (B,T,256) channel-last,
+ * out = (x + W2 snake(W1 LN(x) + b1) + b2) * mask, computed with bf16 tensor-core operands. */
+EV_API int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
+              const float* snake_a, const float* snake_invb, const float* w2, const float* b2, const int64_t* y_lengths,
+              int B, int T, int inner, int len_shift, float* out, void* stream);
 EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
 /* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */
 EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream);

@@ -131,6 +131,35 @@ def test_decoder_attention_matches_torch_sdpa(ctx, case, prec):
     assert rel_l2(out.cpu(), ref) < (2e-6 if prec == "fp32" else 6e-3)    # bf16: P and the output are rounded to bf16
 
 
+@pytest.mark.parametrize("case", [(2, 200, 0), (3, 129, 1), (1, 1, 0), (32, 334, 1), (5, 668, 0)])
+def test_fused_feed_forward_block_matches_torch(ctx, case):
+    """ff_tc.cu: LayerNorm -> Linear -> SnakeBeta -> Linear -> + residual -> * mask in one kernel, against fp64 torch."""
+    B, T, shift = case
+    D, inner = 256, 1024
+    g = torch.Generator().manual_seed(1000 + T)
+    x = torch.randn(B, T, D, generator=g) * 1.5 + 0.3
+    ln_g, ln_b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    w1, b1 = torch.randn(inner, D, generator=g) / 16, 0.1 * torch.randn(inner, generator=g)
+    w2, b2 = torch.randn(D, inner, generator=g) / 32, 0.1 * torch.randn(D, generator=g)
+    sa, sb = torch.exp(0.3 * torch.randn(inner, generator=g)), 1 / (torch.exp(0.3 * torch.randn(inner, generator=g)) + 1e-9)
+    lens = torch.randint(1, (T << shift) + 1, (B,), generator=g)
+    lens[0] = T << shift
+    dev = [t.cuda().contiguous() for t in (x, ln_g, ln_b, w1, b1, sa, sb, w2, b2)]
+    lens_d = lens.cuda()
+    out = torch.empty(B, T, D, device="cuda")
+    ctx.check(_lib.lib().ev_test_ff_block(ctx.handle, *[_lib.ptr(t) for t in dev], _lib.ptr(lens_d), B, T, inner, shift,
+                                          _lib.ptr(out), _lib.stream_ptr()), "ev_test_ff_block")
+    xd = x.double()
+    n = F.layer_norm(xd, (D,), ln_g.double(), ln_b.double(), 1e-5)
+    h = n @ w1.double().T + b1.double()
+    h = h + sb.double() * torch.sin(h * sa.double()) ** 2
+    y = xd + h @ w2.double().T + b2.double()
+    mask = ((torch.arange(T)[None, :] << shift) < lens[:, None]).double()[:, :, None]
+    ref = y * mask
+    assert rel_l2(out.cpu(), ref) < 6e-3
+    assert float(out.cpu()[mask.expand_as(ref) == 0].abs().sum()) == 0.0
+
+
 def test_length_sum_follows_aten_cpu_order(ctx):
     rng = np.random.default_rng(0)
     for n in (1, 3, 7, 8, 9, 17, 151, 333, 513, 1100, 2100):
