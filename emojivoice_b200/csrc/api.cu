@@ -240,7 +240,8 @@ extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y
 // bf16 result widened).  y_lengths (B) int64 or NULL: rows with (t << len_shift) >= y_lengths[b] come out as zero.
 extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
                                 const float* snake_a, const float* snake_invb, const float* w2, const float* b2,
-                                const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, void* stream) {
+                                const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, int repeat,
+                                float* avg_us_host, void* stream) {
   if (!ctx || !x || !ln_g || !ln_b || !w1 || !b1 || !snake_a || !snake_invb || !w2 || !b2 || !out || B <= 0 || T <= 0 || inner <= 0)
     return EV_ERR_INVALID;
   cudaStream_t s = as_stream(stream);
@@ -263,19 +264,41 @@ extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, 
   int rc = make_conv(ctx, ws, {"w1"}, {"b1"}, inner, D, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c1);
   if (!rc) rc = make_conv(ctx, ws, {"w2"}, {"b2"}, D, inner, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c2);
   if (!rc && !ff_tc_supported(c1, c2)) rc = fail(ctx, EV_ERR_INVALID, "ev_test_ff_block: shape not served by the fused kernel");
-  void *yo = nullptr, *li = nullptr;
+  void *yo = nullptr, *li = nullptr, *tb = nullptr;
   if (!rc) rc = device_alloc(ctx, (size_t)B * T * D * 2, &yo, false, s);
   if (!rc) rc = device_alloc(ctx, (size_t)B * 4, &li, false, s);
+  if (!rc) rc = device_alloc(ctx, ((size_t)B * ceil_div(T, 128) + 64) * 4, &tb, false, s);
   if (rc) { release(); return rc; }
-  cudaError_t ce = cudaSuccess;
+  cudaError_t ce = cudaMemsetAsync(yo, 0xff, (size_t)B * T * D * 2, s);   // NaN patterns: every output row must be written
   int* lens = nullptr;
-  if (y_lengths) { lens = reinterpret_cast<int*>(li); ce = i64_to_i32(reinterpret_cast<const long long*>(y_lengths), lens, B, s); }
+  const int* tiles = nullptr;
+  if (ce == cudaSuccess && y_lengths) {
+    lens = reinterpret_cast<int*>(li);
+    ce = i64_to_i32(reinterpret_cast<const long long*>(y_lengths), lens, B, s);
+    const char* v = getenv("EV_FF_RAGGED");
+    if (ce == cudaSuccess && !(v && atoi(v) == 0) && B <= kRaggedMaxB) {   // as the decoder does: only tiles with a valid row are computed
+      ce = ragged_build_table(lens, B, 0, 1, len_shift, 128, T, reinterpret_cast<int*>(tb), s);
+      tiles = reinterpret_cast<int*>(tb);
+    }
+  }
   FfTcArgs fa;
   fa.x = x; fa.ln_g = ln_g; fa.ln_b = ln_b; fa.eps = 1e-5f; fa.ff1 = &c1; fa.ff2 = &c2; fa.snake_a = snake_a; fa.snake_invb = snake_invb;
   fa.out = reinterpret_cast<bf16*>(yo); fa.out_ld = D; fa.out_bs = (long long)T * D; fa.lens = lens; fa.len_shift = len_shift;
-  fa.B = B; fa.T = T;
+  fa.B = B; fa.T = T; fa.tiles = tiles;
   std::string err;
   if (ce == cudaSuccess) ce = ff_tc_launch(fa, s, &err);
+  if (ce == cudaSuccess && repeat > 0 && avg_us_host) {   // timing aid: `repeat` more back-to-back launches between two events
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < repeat && ce == cudaSuccess; ++i) ce = ff_tc_launch(fa, s, &err);
+    cudaEventRecord(e1, s);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us_host = ms * 1e3f / (float)repeat;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   const long long n = (long long)B * T * D;
   if (ce == cudaSuccess) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(yo), out, n); ce = cudaGetLastError(); }
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
@@ -290,6 +313,14 @@ extern "C" int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
   EV_CUDA(ctx, cudaSetDevice(ctx->device));
   EV_CUDA(ctx, cudaDeviceSynchronize());
   EV_CUDA(ctx, conv_tc_read_trace(reinterpret_cast<unsigned long long*>(out_host), n));
+  return EV_OK;
+}
+
+extern "C" int ev_test_ff_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
+  if (!ctx || !out_host || n <= 0) return EV_ERR_INVALID;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, cudaDeviceSynchronize());
+  EV_CUDA(ctx, ff_tc_read_trace(reinterpret_cast<unsigned long long*>(out_host), n));
   return EV_OK;
 }
 

@@ -113,6 +113,10 @@ struct RaggedPlanner {
   const int* table(int tile_rows, int M, cudaStream_t s);
 };
 constexpr int kRaggedMaxB = 2048;
+// one table, built directly: item b needs rows [0, min(M, (ceil(lens[b] / 2^len_shift) + margin) * rows_per_frame)); `table`
+// holds B * ceil(M / tile_rows) + 1 ints
+cudaError_t ragged_build_table(const int* lens, int B, int margin, int rows_per_frame, int len_shift, int tile_rows, int M, int* table,
+                               cudaStream_t s);
 
 // conv_simt.cu
 cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, long long x_bs, const ConvWeights& w,
@@ -145,8 +149,12 @@ struct FfTcArgs {
   bf16* out = nullptr; long long out_ld = 0, out_bs = 0;   // (b, t, 256) bf16 operand of the next conv, masked
   const int* lens = nullptr; int len_shift = 0;
   int B = 0, T = 0;
+  // optional compact list of the 128-row tiles that hold at least one valid row (ragged_build_table, margin 0): the output
+  // of a padded row is zero whatever its input, so tiles without a valid row are not computed, only zero-filled
+  const int* tiles = nullptr;
 };
 bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2);
 cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err);
+cudaError_t ff_tc_read_trace(unsigned long long* host, int n);   // diagnostic (EV_FF_DEBUG & 16)
 
 }  // namespace ev

@@ -13,7 +13,7 @@
 //   TMEM           acc1 [2 x 128 columns] (hidden chunk c in buffer c & 1), acc2 [256 columns]
 //   warp 0  : TMA producer -- weights only, which no kernel of the stream writes: it does NOT wait for the programmatic
 //             dependency, so the first six weight tiles land while the previous kernel is still draining
-//   warp 1  : MMA issuer (owns TMEM).  Order  G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(6) | G2(7): the tensor pipe
+//   warp 1  : MMA issuer (owns TMEM).  Order  G1(0) G1(1) | G1(2) G2(0) | G1(3) G2(1) | ... | G2(6) | G2(7): the tensor pipe
 //             always has the next chunk's first GEMM to run while the epilogue warps activate the current one
 //   warps 2-17 : LayerNorm prologue (warp = row), per-chunk activation (thread = row, 32 channels), final epilogue.
 // Work per tile: 2 x 128 x 256 x 1024 MACs = 16.4 k clk of tcgen05 at N = 128 (64 clk per MMA); weight stream 1 MB per
@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "conv.cuh"
@@ -50,18 +51,25 @@ struct FfParams {
   const float* b2;                          // [256]
   bf16* out; long long out_ld, out_bs;
   const int* lens; int len_shift;
-  int T, m_tiles, total_tiles, n_chunks;
+  const int* tiles;                         // compact (item, m-tile) list or nullptr = dense grid
+  int B, T, m_tiles, total_tiles, n_chunks;
+  int debug;                                // EV_FF_DEBUG (timing experiments only, results are wrong): 1 no SnakeBeta math, 2 no weight
+                                            // loads, 4 no LayerNorm loads, 8 no output pass
 };
 
 __device__ __forceinline__ uint32_t d_hi(uint32_t sbo, uint32_t layout) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
 __device__ __forceinline__ uint32_t d_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t d_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
+// EV_FF_DEBUG & 16: clock64 stamps of CTA 0's first tile (issuer: slots 0.., worker warp 0: slots 64..), read by ev_test_ff_trace
+__device__ unsigned long long g_ff_trace[192];
+#define FF_TR(i) do { if ((p.debug & 16) && blockIdx.x == 0 && lane == 0 && it == 0) g_ff_trace[(i)] = (unsigned long long)clock64(); } while (0)
+
 __global__ void __launch_bounds__(FF_THREADS, 1)
 ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full[FF_SLOTS], w_empty[FF_SLOTS];
-  __shared__ __align__(8) uint64_t a_ready, a_free, acc1_full[2], p_ready[2], p_free[2], acc2_full, acc2_empty;
+  __shared__ __align__(8) uint64_t a_ready, a_free, acc1_full[2], acc1_free[2], p_ready[2], p_free[2], acc2_full, acc2_empty;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,7 +83,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w2) : "memory");
     for (int s = 0; s < FF_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(&a_ready, FF_EPI_WARPS); mbar_init(&a_free, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&p_ready[s], FF_EPI_WARPS); mbar_init(&p_free[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc1_free[s], FF_EPI_WARPS); mbar_init(&p_ready[s], FF_EPI_WARPS); mbar_init(&p_free[s], 1); }
     mbar_init(&acc2_full, 1); mbar_init(&acc2_empty, FF_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -98,6 +106,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
       auto load_w1 = [&](int c) {
         for (int kc = 0; kc < 4; ++kc) {
           mbar_wait(&w_empty[sl], ph);
+          if (p.debug & 2) { mbar_arrive(&w_full[sl]); if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; } continue; }
           mbar_expect_tx(&w_full[sl], (uint32_t)FF_W_TILE);
           tma_load_3d(w_s + (uint32_t)(sl * FF_W_TILE), &maps.w1, &w_full[sl], kc * 64, c * FF_CHUNK, 0);
           if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; }
@@ -107,17 +116,22 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
         for (int kc = 0; kc < 2; ++kc)
           for (int nh = 0; nh < 2; ++nh) {
             mbar_wait(&w_empty[sl], ph);
+            if (p.debug & 2) { mbar_arrive(&w_full[sl]); if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; } continue; }
             mbar_expect_tx(&w_full[sl], (uint32_t)FF_W_TILE);
             tma_load_3d(w_s + (uint32_t)(sl * FF_W_TILE), &maps.w2, &w_full[sl], c * FF_CHUNK + kc * 64, nh * 128, 0);
             if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; }
           }
       };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      // weights are constants, so the dense grid does not wait for the previous kernel at all; a tile list is data of the
+      // stream and is read behind the programmatic dependency
+      if (p.tiles) pdl_wait();
+      const int total_tiles = p.tiles ? __ldg(p.tiles) : p.total_tiles;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         load_w1(0);
         if (n_chunks > 1) load_w1(1);
         for (int c = 0; c < n_chunks; ++c) {
-          load_w2(c);
           if (c + 2 < n_chunks) load_w1(c + 2);
+          load_w2(c);
         }
       }
     }
@@ -133,6 +147,9 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
     int it = 0;
     auto gemm1 = [&](int c, bool last) {      // acc1[c & 1] = A (128 x 256) x W1[c]^T
       const uint32_t d = acc1 + (uint32_t)((c & 1) * FF_CHUNK);
+      // the workers have read this buffer's previous contents (chunk c - 2, or the previous tile's last chunks)
+      mbar_wait(&acc1_free[c & 1], ((uint32_t)(it * (n_chunks >> 1) + (c >> 1)) & 1u) ^ 1u);
+      tcgen05_fence_after();
       for (int kc = 0; kc < 4; ++kc) {
         mbar_wait(&w_full[sl], wph);
         tcgen05_fence_after();
@@ -173,19 +190,29 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
           if (++sl == FF_SLOTS) { sl = 0; wph ^= 1u; }
         }
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    if (p.tiles) pdl_wait();
+    const int total_tiles = p.tiles ? __ldg(p.tiles) : p.total_tiles;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      FF_TR(0);
       mbar_wait(&a_ready, (uint32_t)it & 1u);
       tcgen05_fence_after();
+      FF_TR(1);
       const int half = (n_chunks + 1) >> 1;   // uses of each acc1 / P buffer per tile
       gemm1(0, n_chunks == 1);
+      FF_TR(2);
       if (n_chunks > 1) gemm1(1, n_chunks == 2);
+      FF_TR(3);
       for (int c = 0; c < n_chunks; ++c) {
+        // G1(c+2) only needs chunk c's accumulator to have been READ: it runs under the workers' activation of chunk c
+        if (c + 2 < n_chunks) gemm1(c + 2, c + 3 == n_chunks);
+        FF_TR(10 + 4 * c);
         const uint32_t u = (uint32_t)(it * half + (c >> 1));
         mbar_wait(&p_ready[c & 1], u & 1u);
         if (c == 0) mbar_wait(&acc2_empty, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's output has left acc2
         tcgen05_fence_after();
+        FF_TR(8 + 4 * c);
         gemm2(c, c == n_chunks - 1);
-        if (c + 2 < n_chunks) gemm1(c + 2, c + 3 == n_chunks);
+        FF_TR(9 + 4 * c);
       }
     }
   } else {
@@ -194,14 +221,37 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
     const uint32_t lane_q = (uint32_t)(q * 32) << 16;
     uint8_t* a_gen = base_gen;
     uint8_t* p_gen = base_gen + FF_A_BYTES;
-    pdl_wait();                                            // x is the previous kernel's output
-    // LayerNorm affine parameters of this lane's 8 channels (4 at 4*lane, 4 at 128 + 4*lane)
+    // LayerNorm affine parameters of this lane's 8 channels (4 at 4*lane, 4 at 128 + 4*lane): constants, fetched before the
+    // programmatic-dependency wait
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + lane), g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 32 + lane);
     const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + lane), be1 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 32 + lane);
+    // b1 / snake parameters of chunk c are three 128-byte lines per warp; lanes 0-2 pull the next chunk's lines into L1 while
+    // the current chunk is processed (a cold miss per chunk otherwise sits on the workers' critical path)
+    auto prefetch_params = [&](int c) {
+      if (lane < 3) {
+        const float* base_p = lane == 0 ? p.b1 : (lane == 1 ? p.snake_a : p.snake_invb);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base_p + c * FF_CHUNK + j * 32));
+      }
+    };
+    prefetch_params(0);
+    pdl_wait();                                            // x is the previous kernel's output
+    { const int it = 0; if (ew == 0) FF_TR(64); }
     const int half = (n_chunks + 1) >> 1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / p.m_tiles, m0 = (tile - b * p.m_tiles) * 128;
+    const int total_tiles = p.tiles ? __ldg(p.tiles) : p.total_tiles;
+    if (p.tiles) {
+      // tiles without a valid row are not in the list: their output rows are zero (y * mask); warp per row, 16 B per lane
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const int frames = (__ldg(p.lens + b) + (1 << p.len_shift) - 1) >> p.len_shift;
+        const int first = ((min(max(frames, 0), p.T) + 127) >> 7) << 7;
+        for (int t = first + ew; t < p.T; t += FF_EPI_WARPS)
+          reinterpret_cast<uint4*>(p.out + b * p.out_bs + (long long)t * p.out_ld)[lane] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int b, m0;
+      if (p.tiles) { const int pair = __ldg(p.tiles + 1 + tile); b = pair >> 16; m0 = (pair & 0xffff) * 128; }
+      else { b = tile / p.m_tiles; m0 = (tile - b * p.m_tiles) * 128; }
       const float* xb = p.x + b * p.x_bs;
       // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7 of the tile into the swizzled bf16 operand A
       {
@@ -211,12 +261,13 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int t = m0 + ew * 8 + hb4 + i;
-          if (t < p.T) {
+          if (t < p.T && !(p.debug & 4)) {
             const float4* row = reinterpret_cast<const float4*>(xb + (long long)t * FF_D);
             v0[i] = row[lane]; v1[i] = row[32 + lane];
           } else { v0[i] = make_float4(0.f, 0.f, 0.f, 0.f); v1[i] = v0[i]; }
         }
         if (hb4 == 0) mbar_wait(&a_free, ((uint32_t)it & 1u) ^ 1u);      // the previous tile's GEMM 1 has finished reading A
+        if (ew == 0) FF_TR(hb4 == 0 ? 65 : 67);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = ew * 8 + hb4 + i;
@@ -244,6 +295,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
         fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready);
+        if (ew == 0) FF_TR(66);
       }
       // ---- per chunk: acc1 -> + b1 -> SnakeBeta -> bf16 operand P
       const int row = q * 32 + lane;
@@ -251,10 +303,16 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
       for (int c = 0; c < n_chunks; ++c) {
         const int buf = c & 1;
         const uint32_t u = (uint32_t)(it * half + (c >> 1));
+        prefetch_params(c + 1 < n_chunks ? c + 1 : 0);
         mbar_wait(&acc1_full[buf], u & 1u);
         tcgen05_fence_after();
+        if (ew == 0) FF_TR(72 + 6 * c);
         uint32_t raw[32];
         tmem_ld32(acc1 + lane_q + (uint32_t)(buf * FF_CHUNK + j * 32), raw);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc1_free[buf]);       // the issuer may start chunk c+2's first GEMM into this buffer
+        if (ew == 0) FF_TR(73 + 6 * c);
         const int ch0 = c * FF_CHUNK + j * 32;
         uint32_t pk[16];
 #pragma unroll
@@ -264,13 +322,17 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
           const float4 sb = __ldg(reinterpret_cast<const float4*>(p.snake_invb + ch0 + i));
           float v0 = __uint_as_float(raw[i]) + bb.x, v1 = __uint_as_float(raw[i + 1]) + bb.y;
           float v2 = __uint_as_float(raw[i + 2]) + bb.z, v3 = __uint_as_float(raw[i + 3]) + bb.w;
+          if (!(p.debug & 1)) {
           const float s0 = __sinf(v0 * sa.x), s1 = __sinf(v1 * sa.y), s2 = __sinf(v2 * sa.z), s3 = __sinf(v3 * sa.w);
           v0 = fmaf(sb.x, s0 * s0, v0); v1 = fmaf(sb.y, s1 * s1, v1); v2 = fmaf(sb.z, s2 * s2, v2); v3 = fmaf(sb.w, s3 * s3, v3);
+          }
           __nv_bfloat162 e0 = __floats2bfloat162_rn(v0, v1), e1 = __floats2bfloat162_rn(v2, v3);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&e0);
           pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&e1);
         }
+        if (ew == 0) FF_TR(74 + 6 * c);
         mbar_wait(&p_free[buf], (u & 1u) ^ 1u);            // GEMM 2 of chunk c-2 has finished reading this buffer
+        if (ew == 0) FF_TR(75 + 6 * c);
         {
           uint8_t* rp = p_gen + buf * FF_P_BYTES + (j >> 1) * FF_PLANE + row * 128;
           const int c16 = (j & 1) * 4, sw = row & 7;
@@ -282,41 +344,57 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[buf]);
+        if (ew == 0) FF_TR(76 + 6 * c);
       }
       // ---- output: y = (x + acc2 + b2) * mask -> bf16; each warp owns two 32-column blocks (j and j + 4) of its rows
       mbar_wait(&acc2_full, (uint32_t)it & 1u);
       tcgen05_fence_after();
-      const int t = m0 + row;
-      const bool row_ok = t < p.T;
-      const float mv = (p.lens == nullptr || (t << p.len_shift) < __ldg(p.lens + b)) ? 1.0f : 0.0f;
+      if (ew == 0) FF_TR(130);
+      {
+        // Each warp owns two 32 x 32 blocks (columns (j + 4h) * 32).  thread = row after tcgen05.ld; a private 4 KB tile in
+        // the idle P region (XOR-swizzled 16-byte chunks: conflict-free both ways) turns that into a row-wise pass: 8 lanes x
+        // float4 per row, so the residual reads (128 B per row) and the bf16 stores (64 B per row) are coalesced.
+        uint8_t* stg = p_gen + ew * 4096;
+        const int sub = lane >> 3, cl = lane & 7;
+        const int len_b = p.lens ? __ldg(p.lens + b) : 0x7fffffff;
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int col = (j + 4 * h) * 32;
-        uint32_t raw[32];
-        tmem_ld32(acc2 + lane_q + (uint32_t)col, raw);
-        if (h == 1) {                                      // last TMEM read of the tile: hand acc2 back to the issuer
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc2_empty);
-        }
-        if (row_ok) {
-          const float4* xr = reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col);
-          uint4* dst = reinterpret_cast<uint4*>(p.out + b * p.out_bs + (long long)t * p.out_ld + col);
+        for (int h = 0; h < 2; ++h) {
+          const int col = (j + 4 * h) * 32 + cl * 4;
+          float4 rr[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const float4 x0 = xr[i >> 2], x1 = xr[(i >> 2) + 1];
-            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + i)), c1 = __ldg(reinterpret_cast<const float4*>(p.b2 + col + i + 4));
-            const float y0 = (__uint_as_float(raw[i]) + c0.x + x0.x) * mv, y1 = (__uint_as_float(raw[i + 1]) + c0.y + x0.y) * mv;
-            const float y2 = (__uint_as_float(raw[i + 2]) + c0.z + x0.z) * mv, y3 = (__uint_as_float(raw[i + 3]) + c0.w + x0.w) * mv;
-            const float y4 = (__uint_as_float(raw[i + 4]) + c1.x + x1.x) * mv, y5 = (__uint_as_float(raw[i + 5]) + c1.y + x1.y) * mv;
-            const float y6 = (__uint_as_float(raw[i + 6]) + c1.z + x1.z) * mv, y7 = (__uint_as_float(raw[i + 7]) + c1.w + x1.w) * mv;
-            __nv_bfloat162 o0 = __floats2bfloat162_rn(y0, y1), o1 = __floats2bfloat162_rn(y2, y3);
-            __nv_bfloat162 o2 = __floats2bfloat162_rn(y4, y5), o3 = __floats2bfloat162_rn(y6, y7);
-            dst[i >> 3] = make_uint4(*reinterpret_cast<uint32_t*>(&o0), *reinterpret_cast<uint32_t*>(&o1),
-                                     *reinterpret_cast<uint32_t*>(&o2), *reinterpret_cast<uint32_t*>(&o3));
+          for (int u = 0; u < 8; ++u) {                      // residual loads fly while the accumulator is fetched and staged
+            const int t = m0 + q * 32 + u * 4 + sub;
+            rr[u] = (t < p.T && !(p.debug & 8)) ? *reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          const float4 bias = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
+          uint32_t raw[32];
+          tmem_ld32(acc2 + lane_q + (uint32_t)((j + 4 * h) * 32), raw);
+          if (h == 1) {                                      // last TMEM read of the tile: hand acc2 back to the issuer
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc2_empty);
+          }
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = make_uint4(raw[4 * c8], raw[4 * c8 + 1], raw[4 * c8 + 2], raw[4 * c8 + 3]);
+          __syncwarp();
+          bf16* dst = p.out + b * p.out_bs + col;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rl = u * 4 + sub, t = m0 + q * 32 + rl;
+            if (t >= p.T || (p.debug & 8)) continue;
+            const float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cl ^ (rl & 7)) << 4));
+            const bool valid = (t << p.len_shift) < len_b;     // a select, not a multiply: padded rows may hold anything
+            __nv_bfloat162 o0 = __floats2bfloat162_rn(a.x + bias.x + rr[u].x, a.y + bias.y + rr[u].y);
+            __nv_bfloat162 o1 = __floats2bfloat162_rn(a.z + bias.z + rr[u].z, a.w + bias.w + rr[u].w);
+            uint2 pk2;
+            pk2.x = valid ? *reinterpret_cast<uint32_t*>(&o0) : 0u; pk2.y = valid ? *reinterpret_cast<uint32_t*>(&o1) : 0u;
+            *reinterpret_cast<uint2*>(dst + (long long)t * p.out_ld) = pk2;
+          }
+          __syncwarp();                                      // the staging tile is rewritten by the next block
         }
       }
+      if (ew == 0) FF_TR(131);
     }
   }
   tcgen05_fence_before();
@@ -328,6 +406,10 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
 }
 
 }  // namespace
+
+cudaError_t ff_tc_read_trace(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_ff_trace, sizeof(unsigned long long) * std::min(n, 192));
+}
 
 bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2) {
   static const int mode = []() { const char* v = getenv("EV_FF_FUSE"); return v ? atoi(v) : 1; }();   // EV_FF_FUSE=0: three launches
@@ -357,6 +439,8 @@ cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err) {
   p.b1 = w1.bias; p.snake_a = a.snake_a; p.snake_invb = a.snake_invb; p.b2 = w2.bias;
   p.out = a.out; p.out_ld = a.out_ld; p.out_bs = a.out_bs;
   p.lens = a.lens; p.len_shift = a.len_shift;
+  p.tiles = a.lens ? a.tiles : nullptr; p.B = a.B;
+  { static const int dbg = []() { const char* v = getenv("EV_FF_DEBUG"); return v ? atoi(v) : 0; }(); p.debug = dbg; }
   p.T = a.T; p.m_tiles = ceil_div(a.T, 128); p.total_tiles = p.m_tiles * a.B; p.n_chunks = w1.N / FF_CHUNK;
   static bool configured = false;
   if (!configured) {

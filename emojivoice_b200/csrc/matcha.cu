@@ -347,6 +347,7 @@ struct DecBuffers {
   float* xstate; ActT* xin; ActT* cat0; ActT* cat1; ActT* din;
   float* h; float* r; float* xr; ActT* a; ActT* n; float* qkv; ActT* att; ActT* ff; double* gn_partial;
   double* gn_fused; size_t gn_fused_count;   // [n_steps][13][B][8][2] sums written by the conv epilogues (bf16 path)
+  int* ff_tiles[2];                          // compact lists of the 128-row tiles with a valid row, at T and T/2 (ff_tc.cu)
 };
 
 template <typename ActT>
@@ -376,6 +377,8 @@ void plan_decode(const ev_matcha_cfg& c, int B, int T, int n_steps, Workspace& w
   d->gn_partial = w.take<double>((size_t)B * ceil_div(T, 32) * 8 * 2);
   d->gn_fused_count = (size_t)n_steps * 13 * B * 8 * 2;
   d->gn_fused = w.take<double>(d->gn_fused_count);
+  d->ff_tiles[0] = w.take<int>((size_t)B * ceil_div(T, 128) + 64);
+  d->ff_tiles[1] = w.take<int>((size_t)B * ceil_div(T / 2, 128) + 64);
 }
 
 // Fixed-step Euler times exactly as flow_matching.py:52,68-83 computes them in float32 (t_span = linspace(0,1,n+1),
@@ -408,6 +411,7 @@ template <typename ActT>
 struct Decoder {
   ev_ctx* ctx; const MatchaW& m; DecBuffers<ActT>& d; int B, T; cudaStream_t s; int D, inner;
   int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
+  bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
   // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
@@ -486,6 +490,7 @@ struct Decoder {
         fa.snake_a = w.snake_a; fa.snake_invb = w.snake_invb;
         fa.out = out; fa.out_ld = out_ld; fa.out_bs = (long long)Tl * out_ld; fa.lens = d.ylen32; fa.len_shift = shift;
         fa.B = B; fa.T = Tl;
+        fa.tiles = use_ff_tiles ? d.ff_tiles[shift] : nullptr;
         std::string err;
         cudaError_t ce;
         { LaunchScope ls(ctx, s, "ff_tc", 4.0 * B * (double)Tl * D * w.ff1.N, (double)B * Tl * D * 10.0 + 4.0 * D * w.ff1.N);
@@ -619,6 +624,14 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
               (decoder_pack_input<ActT>(z + b0 * item, mu_y + b0 * item, spk_emb ? spk_emb + (long long)b0 * S : nullptr, nb, F, S, T,
                                         temperature, mask0, q.xstate, q.xin, dec_in, ls[l])));
     dec.push_back(Decoder<ActT>{ctx, m, q, nb, T, ls[l], D, c.dec_heads * c.dec_head_dim});
+    if (std::is_same<ActT, bf16>::value && nb <= kRaggedMaxB) {
+      static const bool on = []() { const char* v = getenv("EV_FF_RAGGED"); return !(v && atoi(v) == 0); }();
+      if (on) {
+        EV_LAUNCH(ctx, ls[l], "ragged_table", 0, 8.0 * nb, ragged_build_table(q.ylen32, nb, 0, 1, 0, 128, T, q.ff_tiles[0], ls[l]));
+        EV_LAUNCH(ctx, ls[l], "ragged_table", 0, 8.0 * nb, ragged_build_table(q.ylen32, nb, 0, 1, 1, 128, T / 2, q.ff_tiles[1], ls[l]));
+        dec.back().use_ff_tiles = true;
+      }
+    }
     if (dec.back().fuse_gn()) EV_CUDA(ctx, cudaMemsetAsync(q.gn_fused, 0, q.gn_fused_count * sizeof(double), ls[l]));
   }
   // launches interleave across lanes step by step so that eager (un-captured) calls overlap as well

@@ -5,11 +5,13 @@
 namespace ev {
 namespace {
 
-__global__ void __launch_bounds__(256) ragged_table_kernel(const int* __restrict__ lens, int B, int margin, int rpf, int tile_rows,
-                                                           int M, int* __restrict__ table) {
+__global__ void __launch_bounds__(256) ragged_table_kernel(const int* __restrict__ lens, int B, int margin, int rpf, int shift,
+                                                           int tile_rows, int M, int* __restrict__ table) {
   __shared__ int start[kRaggedMaxB + 1];
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
-    const long long need = min((long long)M, ((long long)max(lens[b], 0) + margin) * rpf);
+    // frames valid at this level: t with (t << shift) < len  (the decoder's half-rate mask is mask[:, :, ::2])
+    const long long frames = ((long long)max(lens[b], 0) + (1 << shift) - 1) >> shift;
+    const long long need = min((long long)M, (frames + margin) * rpf);
     start[b + 1] = (int)((need + tile_rows - 1) / tile_rows);
   }
   __syncthreads();
@@ -42,12 +44,19 @@ const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
   if (n_cache >= 32 || arena_off + ints > arena_ints) return nullptr;
   int* t = arena + arena_off;
   // an ordinary launch (no programmatic serialization): every later kernel of the stream sees the finished table
-  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, tile_rows, M, t);
+  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, 0, tile_rows, M, t);
   if (cudaGetLastError() != cudaSuccess) return nullptr;
   arena_off += ints;
   if (launch_counter) ++*launch_counter;
   cache[n_cache++] = Entry{rows_per_frame, tile_rows, M, t};
   return t;
+}
+
+cudaError_t ragged_build_table(const int* lens, int B, int margin, int rows_per_frame, int len_shift, int tile_rows, int M, int* table,
+                               cudaStream_t s) {
+  if (B <= 0 || B > kRaggedMaxB || B >= 32768 || ceil_div(M, tile_rows) >= 65536) return cudaErrorInvalidValue;
+  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, len_shift, tile_rows, M, table);
+  return cudaGetLastError();
 }
 
 }  // namespace ev

@@ -183,10 +183,11 @@ EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_len
 /* The float32 Euler times/steps of flow_matching.py:52,68-83 as the library computes them (pure host code). */
 /* Fused LayerNorm + feed-forward of one decoder transformer block (transformer.py:296-316): x (B,T,256) CHANNEL-LAST,
  * w1 (inner,256), w2 (256,inner), snake_a = exp(alpha), snake_invb = 1/(exp(beta)+1e-9); out (B,T,256) channel-last,
- * out = (x + W2 snake(W1 LN(x) + b1) + b2) * mask, computed with bf16 tensor-core operands. */
+ * out = (x + W2 snake(W1 LN(x) + b1) + b2) * mask, computed with bf16 tensor-core operands.  repeat > 0 and avg_us_host
+ * != NULL: the launch is repeated and its average duration (us, CUDA events) written to the host float. */
 EV_API int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
               const float* snake_a, const float* snake_invb, const float* w2, const float* b2, const int64_t* y_lengths,
-              int B, int T, int inner, int len_shift, float* out, void* stream);
+              int B, int T, int inner, int len_shift, float* out, int repeat, float* avg_us_host, void* stream);
 EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
 /* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */
 EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream);
@@ -194,6 +195,8 @@ EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* ou
  * (0 entry, 1 prologue done, 2 after griddepcontrol.wait, 3 first TMA issued, 4 first operands landed, 5 first tile's MMAs
  * committed, 6 last commit, 7 first accumulator seen by the epilogue, 8 first tile stored, 9 last tile stored, 10 exit,
  * 11 %globaltimer at entry); synchronises the device.  scripts/conv_trace.py prints the medians. */
+/* EV_FF_DEBUG & 16: clock64 stamps [192] of the first tile of CTA 0 of the most recent ff_tc launch (host buffer). */
+EV_API int ev_test_ff_trace(ev_ctx* ctx, uint64_t* out_host, int n);
 EV_API int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n);
 
 #ifdef __cplusplus
