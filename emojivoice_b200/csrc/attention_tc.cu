@@ -32,6 +32,7 @@ struct Params {
   float c1, c2;            // scale*log2(e), log2(e)
   const int* lens; int len_shift;
   bf16* out; long long out_ld, out_bs;
+  int skip_padded_queries;   // query blocks without a valid row are left unwritten (the caller never reads those rows)
 };
 
 __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_constant__ CUtensorMap tm, const Params p) {
@@ -62,8 +63,11 @@ __global__ void __launch_bounds__(THREADS, 2) attn_tc_kernel(const __grid_consta
   const uint32_t tmem_base = tmem_base_smem;
   pdl_trigger();
   pdl_wait();
+  // CTA-uniform: the whole query block lies in the padding and its output is not wanted
+  const bool skip = p.skip_padded_queries && p.lens && (q0 << p.len_shift) >= __ldg(p.lens + b);
 
-  if (warp == 4) {
+  if (skip) {
+  } else if (warp == 4) {
     if (lane == 0) {
       // ---------------- TMA producer: Q once, then K (pass 1) and K+V (pass 2) through a 3-stage ring
       mbar_expect_tx(&q_full, Q_BYTES);
@@ -238,6 +242,7 @@ cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err) 
   p.c1 = a.scale * 1.4426950408889634f; p.c2 = 1.4426950408889634f;
   p.lens = a.lens; p.len_shift = a.len_shift;
   p.out = a.out; p.out_ld = a.out_ld; p.out_bs = a.out_bs;
+  p.skip_padded_queries = a.skip_padded_queries;
   dim3 grid(ceil_div(a.T, BQ), a.H, a.B);
   return launch_pdl(attn_tc_kernel, grid, dim3(THREADS), (size_t)SMEM_BYTES, s, tm, p);
 }

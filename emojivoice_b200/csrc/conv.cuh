@@ -102,9 +102,10 @@ struct RaggedPlanner {
   const int* lens = nullptr;      // device [B], valid frames per item; nullptr = dense batch
   int B = 0, margin = 0;          // margin in frames (>= the generator's receptive field, see hifigan.cu)
   int rows_per_frame = 1;         // GEMM rows per frame of the launches that follow (set by the caller per stage)
+  int len_shift = 0;              // frames valid at this level = ceil(lens[b] / 2^len_shift) (decoder half-rate levels)
   int* arena = nullptr;           // table storage (caller's workspace)
   size_t arena_ints = 0, arena_off = 0;
-  struct Entry { int rpf, tile_rows, M; const int* table; };
+  struct Entry { int rpf, shift, tile_rows, M; const int* table; };
   Entry cache[32];
   int n_cache = 0;
   long long* launch_counter = nullptr;   // bumped once per table kernel (the context's launch statistics)

@@ -62,6 +62,7 @@ struct AttnTcArgs {
   float scale = 1.0f;
   const int* lens = nullptr; int len_shift = 0;
   bf16* out = nullptr; long long out_ld = 0, out_bs = 0;
+  int skip_padded_queries = 0;   // 1: blocks of 128 queries that lie wholly in the padding are not computed (rows left unwritten)
 };
 cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err);
 cudaError_t rope_tables(float* cos_t, float* sin_t, int T, int rope_dim, float base, cudaStream_t s);

@@ -348,6 +348,7 @@ struct DecBuffers {
   float* h; float* r; float* xr; ActT* a; ActT* n; float* qkv; ActT* att; ActT* ff; double* gn_partial;
   double* gn_fused; size_t gn_fused_count;   // [n_steps][13][B][8][2] sums written by the conv epilogues (bf16 path)
   int* ff_tiles[2];                          // compact lists of the 128-row tiles with a valid row, at T and T/2 (ff_tc.cu)
+  int* rag_arena; size_t rag_ints;           // tile lists of the convs whose padded output rows nobody reads (out-projection)
 };
 
 template <typename ActT>
@@ -379,6 +380,8 @@ void plan_decode(const ev_matcha_cfg& c, int B, int T, int n_steps, Workspace& w
   d->gn_fused = w.take<double>(d->gn_fused_count);
   d->ff_tiles[0] = w.take<int>((size_t)B * ceil_div(T, 128) + 64);
   d->ff_tiles[1] = w.take<int>((size_t)B * ceil_div(T / 2, 128) + 64);
+  d->rag_ints = (size_t)8 * ((size_t)B * ceil_div(T, 128) + 64);
+  d->rag_arena = w.take<int>(d->rag_ints);
 }
 
 // Fixed-step Euler times exactly as flow_matching.py:52,68-83 computes them in float32 (t_span = linspace(0,1,n+1),
@@ -412,6 +415,7 @@ struct Decoder {
   ev_ctx* ctx; const MatchaW& m; DecBuffers<ActT>& d; int B, T; cudaStream_t s; int D, inner;
   int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
   bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
+  RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
   // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
@@ -465,6 +469,9 @@ struct Decoder {
       at.B = B; at.T = Tl; at.H = Hh; at.D = hd; at.inner = inner; at.scale = 1.0f / sqrtf((float)hd);
       at.lens = d.ylen32; at.len_shift = shift;
       at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
+      // Queries in the padding: their attention output only feeds rows of the residual stream that the block's masked
+      // output discards, so whole padded query blocks are skipped (keys / values of padded frames still take part, H1)
+      at.skip_padded_queries = use_ff_tiles ? 1 : 0;
       std::string err;
       cudaError_t ce;
       if (dbg_skip & 4) ce = cudaSuccess; else
@@ -481,7 +488,13 @@ struct Decoder {
       EV_LAUNCH(ctx, s, "attention_dec", attn_flops, (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
     }
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
-    EV_TRY(run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s));
+    if (use_ff_tiles) {   // out-projection: tiles without a valid row are skipped (same argument; the planner caches one table per level)
+      rag.rows_per_frame = 1; rag.len_shift = shift;
+      ctx->rag = rag;
+    }
+    const int rc_out = run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s);
+    if (use_ff_tiles) { rag = ctx->rag; ctx->rag = RaggedPlanner(); }
+    EV_TRY(rc_out);
     if constexpr (std::is_same<ActT, bf16>::value) {
       // LayerNorm3 + ff1 + SnakeBeta + ff2 + residual + mask as ONE kernel: the 1024-wide hidden tensor stays on the SM (ff_tc.cu)
       if (D == 256 && !(dbg_skip & 3) && ff_tc_supported(w.ff1, w.ff2)) {
@@ -630,6 +643,8 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
         EV_LAUNCH(ctx, ls[l], "ragged_table", 0, 8.0 * nb, ragged_build_table(q.ylen32, nb, 0, 1, 0, 128, T, q.ff_tiles[0], ls[l]));
         EV_LAUNCH(ctx, ls[l], "ragged_table", 0, 8.0 * nb, ragged_build_table(q.ylen32, nb, 0, 1, 1, 128, T / 2, q.ff_tiles[1], ls[l]));
         dec.back().use_ff_tiles = true;
+        RaggedPlanner& r = dec.back().rag;
+        r.lens = q.ylen32; r.B = nb; r.margin = 0; r.arena = q.rag_arena; r.arena_ints = q.rag_ints; r.launch_counter = &ctx->launches;
       }
     }
     if (dec.back().fuse_gn()) EV_CUDA(ctx, cudaMemsetAsync(q.gn_fused, 0, q.gn_fused_count * sizeof(double), ls[l]));

@@ -39,16 +39,16 @@ const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
   const int m_tiles = ceil_div(M, tile_rows);
   if (m_tiles >= 65536) return nullptr;
   for (int i = 0; i < n_cache; ++i)
-    if (cache[i].rpf == rows_per_frame && cache[i].tile_rows == tile_rows && cache[i].M == M) return cache[i].table;
+    if (cache[i].rpf == rows_per_frame && cache[i].shift == len_shift && cache[i].tile_rows == tile_rows && cache[i].M == M) return cache[i].table;
   const size_t ints = align_up((size_t)B * m_tiles + 1, 64);
   if (n_cache >= 32 || arena_off + ints > arena_ints) return nullptr;
   int* t = arena + arena_off;
   // an ordinary launch (no programmatic serialization): every later kernel of the stream sees the finished table
-  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, 0, tile_rows, M, t);
+  ragged_table_kernel<<<1, 256, 0, s>>>(lens, B, margin, rows_per_frame, len_shift, tile_rows, M, t);
   if (cudaGetLastError() != cudaSuccess) return nullptr;
   arena_off += ints;
   if (launch_counter) ++*launch_counter;
-  cache[n_cache++] = Entry{rows_per_frame, tile_rows, M, t};
+  cache[n_cache++] = Entry{rows_per_frame, len_shift, tile_rows, M, t};
   return t;
 }
 
