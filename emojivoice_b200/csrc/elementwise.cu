@@ -1,5 +1,8 @@
 // Coalesced / vectorised / warp-shuffle kernels around the GEMMs: layout glue, embeddings, LayerNorm, GroupNorm,
 // Mish, the decoder input pack, the sinusoidal time embedding and HiFi-GAN's conv_post+tanh tail.
+#include <cstdlib>
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace ev {
@@ -326,6 +329,118 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
   }
 }
 
+// Specialised bf16-operand variant for the decoder's width (C = 256, 8 groups of 32 channels): one compile-time MODE per
+// call site instead of runtime feature tests, constants fetched before the programmatic-dependency wait, two rows of a warp
+// in flight at a time, padded rows never read from x, four blocks per SM.  The generic kernel above spent ~58 issued
+// instructions per element at 27 % occupancy (ncu, profiles/r01_ncu_full_gn_apply_v22.txt).
+//   MODE 0: block1 of a ResNet block   y = (Mish(GN(x)) * m + temb) * m            -> bf16 operand
+//   MODE 1: block2 + residual + pre-LN y = Mish(GN(x)) * m + res -> fp32 stream;  LN(y) -> bf16 operand
+//   MODE 2: final block                y = Mish(GN(x)) * m                         -> bf16 operand
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) gn_apply256_kernel(GnApplyArgs a) {
+  constexpr int C = 256;
+  __shared__ float stat[16];
+  pdl_trigger();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int c0 = 4 * lane, c1 = 128 + 4 * lane;          // this lane's two float4 channel groups (groups lane/8 and 4 + lane/8)
+  // weights: not written by any kernel of the stream
+  const float4 ga0 = __ldg(reinterpret_cast<const float4*>(a.gamma + c0)), ga1 = __ldg(reinterpret_cast<const float4*>(a.gamma + c1));
+  const float4 be0 = __ldg(reinterpret_cast<const float4*>(a.beta + c0)), be1 = __ldg(reinterpret_cast<const float4*>(a.beta + c1));
+  float4 lg0, lg1, lb0, lb1;
+  if (MODE == 1) {
+    lg0 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + c0)); lg1 = __ldg(reinterpret_cast<const float4*>(a.ln_gamma + c1));
+    lb0 = __ldg(reinterpret_cast<const float4*>(a.ln_beta + c0)); lb1 = __ldg(reinterpret_cast<const float4*>(a.ln_beta + c1));
+  }
+  pdl_wait();
+  if (threadIdx.x < 8) {
+    double s = 0.0, q = 0.0;
+    for (int ch = 0; ch < a.n_chunks; ++ch) {
+      const double* p = a.partial + (((long long)b * a.n_chunks + ch) * 8 + threadIdx.x) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    const double n = 32.0 * (double)a.T;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stat[2 * threadIdx.x] = (float)mean;
+    stat[2 * threadIdx.x + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  const int len_b = a.mask.lens ? __ldg(a.mask.lens + b) : 0x7fffffff;
+  const int t_base = (blockIdx.x * 8 + warp) * GN_APPLY_ROWS;
+  float4 te0, te1;
+  if (MODE == 0) { te0 = *reinterpret_cast<const float4*>(a.temb + c0); te1 = *reinterpret_cast<const float4*>(a.temb + c1); }
+  __syncthreads();
+  float4 sc0, sc1, sh0, sh1;
+  {
+    const float m0 = stat[2 * (lane >> 3)], r0 = stat[2 * (lane >> 3) + 1], m1 = stat[8 + 2 * (lane >> 3)], r1 = stat[9 + 2 * (lane >> 3)];
+    sc0 = make_float4(r0 * ga0.x, r0 * ga0.y, r0 * ga0.z, r0 * ga0.w);
+    sc1 = make_float4(r1 * ga1.x, r1 * ga1.y, r1 * ga1.z, r1 * ga1.w);
+    sh0 = make_float4(be0.x - m0 * sc0.x, be0.y - m0 * sc0.y, be0.z - m0 * sc0.z, be0.w - m0 * sc0.w);
+    sh1 = make_float4(be1.x - m1 * sc1.x, be1.y - m1 * sc1.y, be1.z - m1 * sc1.z, be1.w - m1 * sc1.w);
+  }
+  auto mish4 = [](float4 x, float4 sc, float4 sh) {
+    return make_float4(mish_sel<bf16>(fmaf(x.x, sc.x, sh.x)), mish_sel<bf16>(fmaf(x.y, sc.y, sh.y)),
+                       mish_sel<bf16>(fmaf(x.z, sc.z, sh.z)), mish_sel<bf16>(fmaf(x.w, sc.w, sh.w)));
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int pair = 0; pair < GN_APPLY_ROWS; pair += 2) {
+    float4 x0[2], x1[2], r0[2], r1[2];
+    bool valid[2], live[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {                          // both rows' loads are issued before any arithmetic
+      const int t = t_base + pair + k;
+      live[k] = t < a.T;
+      valid[k] = live[k] && (t << a.mask.shift) < len_b;
+      const long long row = (long long)b * a.T + t;
+      x0[k] = x1[k] = r0[k] = r1[k] = zero4;
+      if (valid[k]) {                                      // a padded row is Mish(.) * 0: x is not read
+        x0[k] = *reinterpret_cast<const float4*>(a.x + row * C + c0);
+        x1[k] = *reinterpret_cast<const float4*>(a.x + row * C + c1);
+      }
+      if (MODE == 1 && live[k]) {
+        r0[k] = *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c0);
+        r1[k] = *reinterpret_cast<const float4*>(a.res + row * a.res_ld + c1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!live[k]) continue;
+      const long long row = (long long)b * a.T + t_base + pair + k;
+      float4 v0 = zero4, v1 = zero4;
+      if (valid[k]) {
+        v0 = mish4(x0[k], sc0, sh0); v1 = mish4(x1[k], sc1, sh1);
+        if (MODE == 0) {
+          v0.x += te0.x; v0.y += te0.y; v0.z += te0.z; v0.w += te0.w;
+          v1.x += te1.x; v1.y += te1.y; v1.z += te1.z; v1.w += te1.w;
+        }
+      }
+      if (MODE != 1) {
+        bf16* o = reinterpret_cast<bf16*>(a.out_act) + row * a.act_ld;
+        store_act4<bf16>(o + c0, v0);
+        store_act4<bf16>(o + c1, v1);
+      } else {
+        v0.x += r0[k].x; v0.y += r0[k].y; v0.z += r0[k].z; v0.w += r0[k].w;
+        v1.x += r1[k].x; v1.y += r1[k].y; v1.z += r1[k].z; v1.w += r1[k].w;
+        float* of = a.out_f32 + row * a.f32_ld;
+        *reinterpret_cast<float4*>(of + c0) = v0;
+        *reinterpret_cast<float4*>(of + c1) = v1;
+        // fused pre-LN of the transformer block that follows (transformer.py:262), eps 1e-5
+        const float mean = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w)) * (1.0f / C);
+        const float d0 = v0.x - mean, d1 = v0.y - mean, d2 = v0.z - mean, d3 = v0.w - mean;
+        const float d4 = v1.x - mean, d5 = v1.y - mean, d6 = v1.z - mean, d7 = v1.w - mean;
+        const float var = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7)) * (1.0f / C);
+        const float rstd = 1.0f / sqrtf(var + 1e-5f);
+        bf16* o = reinterpret_cast<bf16*>(a.out_ln) + row * a.ln_ld;
+        store_act4<bf16>(o + c0, make_float4(d0 * rstd * lg0.x + lb0.x, d1 * rstd * lg0.y + lb0.y, d2 * rstd * lg0.z + lb0.z, d3 * rstd * lg0.w + lb0.w));
+        store_act4<bf16>(o + c1, make_float4(d4 * rstd * lg1.x + lb1.x, d5 * rstd * lg1.y + lb1.y, d6 * rstd * lg1.z + lb1.z, d7 * rstd * lg1.w + lb1.w));
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- vocoder tail
 template <int C>
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, int L, const float* __restrict__ w,
@@ -458,6 +573,19 @@ cudaError_t group_norm_apply(const GnApplyArgs& a, cudaStream_t s) {
   if ((a.C & 3) || (cpg & 3) || (a.res_ld & 3) || (a.f32_ld & 3) || (a.act_ld & 3) || (a.ln_ld & 3)) return cudaErrorInvalidValue;
   const int v4 = ceil_div(a.C, 128);
   dim3 grid(ceil_div(a.T, 8 * GN_APPLY_ROWS), a.B);
+  if constexpr (std::is_same<ActT, bf16>::value) {
+    static const bool fast = []() { const char* v = getenv("EV_GN_FAST"); return !(v && atoi(v) == 0); }();   // EV_GN_FAST=0: generic kernel
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (fast && a.C == 256 && a.groups == 8 && al16(a.x) && al16(a.gamma) && al16(a.beta)) {
+      const bool m0 = a.temb && !a.res && !a.out_f32 && !a.out_ln && a.out_act && al16(a.temb) && al16(a.out_act);
+      const bool m1 = !a.temb && a.res && a.out_f32 && a.out_ln && !a.out_act && al16(a.res) && al16(a.out_f32) && al16(a.out_ln) &&
+                      al16(a.ln_gamma) && al16(a.ln_beta);
+      const bool m2 = !a.temb && !a.res && !a.out_f32 && !a.out_ln && a.out_act && al16(a.out_act);
+      if (m0) return launch_pdl(gn_apply256_kernel<0>, grid, dim3(256), 0, s, a);
+      if (m1) return launch_pdl(gn_apply256_kernel<1>, grid, dim3(256), 0, s, a);
+      if (m2) return launch_pdl(gn_apply256_kernel<2>, grid, dim3(256), 0, s, a);
+    }
+  }
   const size_t sh = (size_t)a.groups * 2 * sizeof(float);
   if (v4 <= 2) return launch_pdl(gn_apply_kernel<ActT, 2>, grid, dim3(256), sh, s, a);
   if (v4 <= 8) return launch_pdl(gn_apply_kernel<ActT, 8>, grid, dim3(256), sh, s, a);
