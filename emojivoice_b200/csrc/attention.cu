@@ -11,13 +11,52 @@ namespace {
 
 constexpr int QPW = 4, NW = 8, BQ = QPW * NW, BKT = 32;
 
-__device__ __forceinline__ float load_rope(const float* row, int d, int t, const AttnArgs& a) {
-  const float x = row[d];
-  if (d >= a.rope_dim) return x;
+// text_encoder.py:147-169 (rotate-half pairing): out[d] = x[d]*cos + partner*sin, partner = -x[d + half] for d < half, x[d - half] above
+__device__ __forceinline__ float rope_mix(float x, float partner, float c, float s) { return x * c + partner * s; }
+
+// Stage `rows` rows (starting at t0) of D features into shared memory (row pitch `pitch` floats), RoPE applied to the first
+// rope_dim features.  Work items are float4 groups: for d < rope_dim/2 one item loads the group at d AND its partner group at
+// d + rope_dim/2 and writes both rotated outputs; features >= rope_dim are plain copies.  All loads of a thread are issued
+// before the first use (the loops are fully unrolled).
+template <int D>
+__device__ __forceinline__ void load_tile_rope(const float* base, int t0, int rows, int pitch, float* dst, const AttnArgs& a) {
   const int half = a.rope_dim >> 1;
-  const int i = d < half ? d : d - half;
-  const float partner = d < half ? -row[d + half] : row[d - half];
-  return x * a.rope_cos[t * half + i] + partner * a.rope_sin[t * half + i];
+  const int pair_items = half >> 2, plain_items = (D - a.rope_dim) >> 2, per_row = pair_items + plain_items;
+  const int total = rows * per_row;
+  constexpr int MAX_IT = (BQ * (D / 4) + NW * 32 - 1) / (NW * 32);
+  float4 x[MAX_IT], y[MAX_IT];
+#pragma unroll
+  for (int it = 0; it < MAX_IT; ++it) {
+    const int idx = threadIdx.x + it * NW * 32;
+    x[it] = y[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < total) {
+      const int r = idx / per_row, i = idx - r * per_row, t = t0 + r;
+      if (t < a.T) {
+        const float* row = base + (long long)t * a.ld;
+        if (i < pair_items) { x[it] = *reinterpret_cast<const float4*>(row + 4 * i); y[it] = *reinterpret_cast<const float4*>(row + half + 4 * i); }
+        else x[it] = *reinterpret_cast<const float4*>(row + a.rope_dim + 4 * (i - pair_items));
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < MAX_IT; ++it) {
+    const int idx = threadIdx.x + it * NW * 32;
+    if (idx >= total) continue;
+    const int r = idx / per_row, i = idx - r * per_row, t = t0 + r;
+    float* o = dst + r * pitch;
+    if (i < pair_items) {
+      float4 c4 = make_float4(1.f, 1.f, 1.f, 1.f), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < a.T) { c4 = *reinterpret_cast<const float4*>(a.rope_cos + t * half + 4 * i); s4 = *reinterpret_cast<const float4*>(a.rope_sin + t * half + 4 * i); }
+      const int d = 4 * i;
+      o[d] = rope_mix(x[it].x, -y[it].x, c4.x, s4.x); o[d + 1] = rope_mix(x[it].y, -y[it].y, c4.y, s4.y);
+      o[d + 2] = rope_mix(x[it].z, -y[it].z, c4.z, s4.z); o[d + 3] = rope_mix(x[it].w, -y[it].w, c4.w, s4.w);
+      o[d + half] = rope_mix(y[it].x, x[it].x, c4.x, s4.x); o[d + half + 1] = rope_mix(y[it].y, x[it].y, c4.y, s4.y);
+      o[d + half + 2] = rope_mix(y[it].z, x[it].z, c4.z, s4.z); o[d + half + 3] = rope_mix(y[it].w, x[it].w, c4.w, s4.w);
+    } else {
+      const int d = a.rope_dim + 4 * (i - pair_items);
+      o[d] = x[it].x; o[d + 1] = x[it].y; o[d + 2] = x[it].z; o[d + 3] = x[it].w;
+    }
+  }
 }
 
 template <typename ActT, int D>
@@ -35,10 +74,9 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnArgs a) {
   const float* kb = a.k + b * a.bs + h * D;
   const float* vb = a.v + b * a.bs + h * D;
 
-  for (int idx = threadIdx.x; idx < BQ * D; idx += blockDim.x) {
-    const int qi = idx / D, d = idx - qi * D, t = q0 + qi;
-    Qs[idx] = t < a.T ? load_rope(qb + (long long)t * a.ld, d, t, a) : 0.0f;
-  }
+  // q, k, v tiles are staged float4 by float4 with every load of a thread in flight at once (the element-wise version
+  // spent most of the kernel in serial, latency-bound global loads); RoPE pairs (d, d + rope_dim/2) are rotated together
+  load_tile_rope<D>(qb, q0, BQ, D, Qs, a);
   float m_run[QPW], l_run[QPW], o[QPW][DPL];
   bool qvalid[QPW];
 #pragma unroll
@@ -53,15 +91,13 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(AttnArgs a) {
 
   for (int k0 = 0; k0 < a.T; k0 += BKT) {
     __syncthreads();
-    for (int idx = threadIdx.x; idx < BKT * D; idx += blockDim.x) {
-      const int kj = idx / D, d = idx - kj * D, t = k0 + kj;
-      float kv = 0.0f, vv = 0.0f;
-      if (t < a.T) {
-        kv = load_rope(kb + (long long)t * a.ld, d, t, a);
-        vv = vb[(long long)t * a.ld + d];
-      }
-      Ks[kj * (D + 1) + d] = kv;
-      Vs[kj * D + d] = vv;
+    load_tile_rope<D>(kb, k0, BKT, D + 1, Ks, a);
+#pragma unroll
+    for (int it = 0; it < (BKT * D / 4) / (NW * 32); ++it) {
+      const int idx = threadIdx.x + it * NW * 32, kj = idx / (D / 4), d = (idx - kj * (D / 4)) * 4, t = k0 + kj;
+      float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < a.T) vv = *reinterpret_cast<const float4*>(vb + (long long)t * a.ld + d);
+      *reinterpret_cast<float4*>(Vs + kj * D + d) = vv;
     }
     __syncthreads();
     const int tk = k0 + lane;
@@ -146,6 +182,7 @@ cudaError_t launch_attn(const AttnArgs& a, cudaStream_t s) {
     if (ce != cudaSuccess) return ce;
     configured = true;
   }
+  if ((a.rope_dim & 7) || ((D - a.rope_dim) & 3) || (a.ld & 3) || (a.bs & 3)) return cudaErrorInvalidValue;   // float4 staging
   dim3 grid(ceil_div(a.T, BQ), a.H, a.B);
   attn_kernel<ActT, D><<<grid, NW * 32, sh, s>>>(a);
   return cudaGetLastError();
