@@ -409,7 +409,7 @@ def main():
                        t_pad=t_pad, l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
                        "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
                        launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up)",
-                       vocoder=("ragged: time tiles past each utterance's own length (+ the generator's 14-frame receptive field) are "
+                       vocoder=("ragged: time tiles past each utterance's own length (+ the receptive field behind each layer: 13 frames at conv_pre ... 2 at the last stage) are "
                                 "not computed; waveform bit-identical to the dense generator on [: mel_length*256] and zero beyond "
                                 "-- the part the reference's batched caller crops away (cli.py:307-311); `padded_vocoder` is the "
                                 "same run with the padded frames vocoded too") if not args.dense_vocoder else "dense (padded frames vocoded too)"),

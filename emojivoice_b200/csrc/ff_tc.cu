@@ -367,8 +367,10 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
             rr[u] = (t < p.T && !(p.debug & 8)) ? *reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           const float4 bias = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
+          if (ew == 0) FF_TR(132 + 4 * h);
           uint32_t raw[32];
           tmem_ld32(acc2 + lane_q + (uint32_t)((j + 4 * h) * 32), raw);
+          if (ew == 0) FF_TR(133 + 4 * h);
           if (h == 1) {                                      // last TMEM read of the tile: hand acc2 back to the issuer
             tcgen05_fence_before();
             __syncwarp();
@@ -378,6 +380,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
           for (int c8 = 0; c8 < 8; ++c8)
             *reinterpret_cast<uint4*>(stg + lane * 128 + ((c8 ^ (lane & 7)) << 4)) = make_uint4(raw[4 * c8], raw[4 * c8 + 1], raw[4 * c8 + 2], raw[4 * c8 + 3]);
           __syncwarp();
+          if (ew == 0) FF_TR(134 + 4 * h);
           bf16* dst = p.out + b * p.out_bs + col;
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -392,6 +395,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
             *reinterpret_cast<uint2*>(dst + (long long)t * p.out_ld) = pk2;
           }
           __syncwarp();                                      // the staging tile is rewritten by the next block
+          if (ew == 0) FF_TR(135 + 4 * h);
         }
       }
       if (ew == 0) FF_TR(131);

@@ -154,24 +154,32 @@ struct VocBuffers {
   int* lens32; int* rag_arena; size_t rag_ints;
 };
 
-// Receptive field of the generator behind the first upsampler, in mel frames: how many frames past an utterance's end
-// its last valid sample can still see.  Walks the stages backwards in samples of each stage's rate: conv_post (k = 7),
-// the widest ResBlock1 of the stage (sum over l of (k-1)/2 * (d_l + 1)), then the transposed conv (output t reads
-// inputs floor((t + p) / s) and the (k/s - 1) before it).
-int vocoder_margin_frames(const ev_hifigan_cfg& c) {
+// How far past an utterance's end each layer must still be correct for the last valid sample to be exact, per stage, in mel
+// frames.  Walks the generator backwards in samples of each stage's rate: conv_post looks 3 samples ahead; the widest
+// ResBlock1 of a stage sum_l (k-1)/2 * (d_l + 1); a transposed conv output t reads inputs floor((t + p) / s) and the
+// (k/s - 1) before it (bounded by ceil(h / s) + ceil(k / s)).  One spare frame is added everywhere.
+struct VocMargins { int stage[8]; int up[8]; int pre; };
+VocMargins vocoder_margins(const ev_hifigan_cfg& c) {
+  VocMargins m{};
+  long long rate[8], r = 1;
+  for (int i = 0; i < c.n_ups; ++i) { r *= c.upsample_rates[i]; rate[i] = r; }
   long long h = 3;
   for (int i = c.n_ups - 1; i >= 0; --i) {
     long long rb = 0;
     for (int j = 0; j < c.n_kernels; ++j) {
-      long long r = 0;
-      for (int l = 0; l < 3; ++l) r += (long long)(c.resblock_kernel_sizes[j] - 1) / 2 * (c.resblock_dilation_sizes[j][l] + 1);
-      rb = std::max(rb, r);
+      long long q = 0;
+      for (int l = 0; l < 3; ++l) q += (long long)(c.resblock_kernel_sizes[j] - 1) / 2 * (c.resblock_dilation_sizes[j][l] + 1);
+      rb = std::max(rb, q);
     }
-    h += rb;
+    h += rb;                                                   // rows of the stage's input (= upsampler output) still needed
+    m.stage[i] = (int)((h + rate[i] - 1) / rate[i]) + 1;       // safe for every conv inside the stage
     const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
-    h = (h + u - 1) / u + (k + u - 1) / u;
+    h = (h + u - 1) / u + (k + u - 1) / u;                     // rows of the upsampler's input
+    const long long rin = i > 0 ? rate[i - 1] : 1;
+    m.up[i] = (int)((h + rin - 1) / rin) + 1;
   }
-  return (int)h + 2;
+  m.pre = (int)h + 1;
+  return m;
 }
 
 template <typename ActT>
@@ -215,12 +223,13 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
     ~RagGuard() { c->rag = RaggedPlanner(); c->prof_scale = 1.0; }
   } guard{ctx};
   const int* lens32 = nullptr;
+  const VocMargins margins = vocoder_margins(c);
   if (mel_lengths) {
     EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(mel_lengths, v.lens32, B, s));
     lens32 = v.lens32;
     RaggedPlanner& r = ctx->rag;
     r = RaggedPlanner();
-    r.lens = lens32; r.B = B; r.margin = vocoder_margin_frames(c);
+    r.lens = lens32; r.B = B; r.margin = margins.pre;
     r.arena = v.rag_arena; r.arena_ints = v.rag_ints;
     r.launch_counter = &ctx->launches;
     if (ctx->profiling) {   // algorithmic work = the valid frames only (instrumented eager step: a host copy is fine here)
@@ -247,6 +256,7 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
     L = Lin * c.upsample_rates[i];
     const long long bs = L * C;
     ctx->rag.rows_per_frame = (int)(Lin / T);   // the transposed conv's GEMM rows are its input rows
+    ctx->rag.margin = margins.up[i];
     {  // x = ups[i](leaky_relu(x)) -> fp32 residual stream x0 and its activated operand copy
       Epilogue e; e.out_f32 = v.x0; e.f32_ld = C; e.f32_bs = bs; e.act = ACT_LRELU; e.slope = kSlope;
       e.out_act = v.x0a; e.act_ld = C; e.act_bs = bs;
@@ -254,6 +264,7 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
     }
     const bool last_stage = (i == c.n_ups - 1);
     ctx->rag.rows_per_frame = (int)(L / T);
+    ctx->rag.margin = margins.stage[i];
     for (int j = 0; j < c.n_kernels; ++j) {
       if constexpr (std::is_same<ActT, bf16>::value) {
         // fused ResBlock: six convs in one kernel, residual stream resident in TMEM (resblock_tc.cu)

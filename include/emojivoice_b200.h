@@ -129,7 +129,7 @@ EV_API int ev_vocode(ev_ctx* ctx, const float* mel, int B, int T, int precision,
  * each waveform to [: length * hop]" of the reference's batched caller (Matcha-TTS/matcha/cli.py:291-317): wav[b] is
  * bit-identical to ev_vocode's on [0, mel_lengths[b]*hop) and ZERO beyond (the reference leaves vocoded prior noise there,
  * which every caller crops away).  The generator is convolutional with a finite receptive field, so time tiles that start
- * more than that field past an utterance's end are not computed at all. */
+ * more than that field (computed per layer from the configuration) past an utterance's end are not computed at all. */
 EV_API int ev_vocode_ragged(ev_ctx* ctx, const float* mel, const int64_t* mel_lengths, int B, int T, int precision,
               float* wav, void* workspace, size_t workspace_bytes, void* stream);
 

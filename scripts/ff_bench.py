@@ -42,3 +42,5 @@ if int(os.environ.get("EV_FF_DEBUG", "0")) & 16:
         print(f"chunk {c}: worker acc1_full {rel(72 + 6 * c)} ld {rel(73 + 6 * c)} math {rel(74 + 6 * c)} p_free {rel(75 + 6 * c)} arrive {rel(76 + 6 * c)}"
               f" | issuer p_ready {rel(8 + 4 * c)} G2 issued {rel(9 + 4 * c)} G1(c+2) issued {rel(10 + 4 * c)}")
     print("acc2_full", rel(130), "output done", rel(131))
+    for h in range(2):
+        print(f"output block {h}: loads issued {rel(132 + 4 * h)} tmem_ld {rel(133 + 4 * h)} staged {rel(134 + 4 * h)} rows stored {rel(135 + 4 * h)}")
