@@ -63,6 +63,9 @@ struct TcParams {
   int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
   int tf32;                     // operands are 32-bit (3xTF32 split path): K-chunks walk the sections [hi | hi | lo] of A
   int kch1;                     // K-chunks per section (== kchunks unless tf32)
+  int tf32_share;               // 3xTF32 with operand sharing: per 32-channel chunk c the steps (x_hi, w_lo) (x_hi, w_hi) (x_lo, w_hi)
+                                // run back to back, the activation tile of step 0 is reused by step 1 and the weight tiles of
+                                // step 1 by step 2: 2 + 2*taps tile loads per chunk instead of 3 + 3*taps (the path is L2->SM bound)
   int sec_off[3];               // column offset of each A section
   int debug_nob;                // EV_TC_DEBUG_NOB bit 0 / 1 / 2: skip weight loads / activation loads / lean-path stores.  Timing
                                 // experiments only (results are wrong): they showed the MMA-bound layers are issue-bound, not memory-bound
@@ -222,6 +225,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (tile == (int)blockIdx.x) EV_TR(13);
         for (int kc = 0; kc < kchunks; ++kc) {
           for (int g = 0; g < n_groups; ++g) {
+            const int sh_c = kc / 3, sh_s = kc - 3 * sh_c;       // operand-sharing walk (tf32_share): chunk, step
+            if (p.tf32_share) {
+              if (sh_s != 1) {     // step 1 reuses step 0's activation tile
+                mbar_wait(&a_empty[sa], pa);
+                mbar_expect_tx(&a_full[sa], a_bytes);
+                const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
+                const int col = p.grp_col0[0] + (sh_s == 2 ? p.sec_off[2] : 0) + sh_c * p.bk, row = m0 + p.grp_row0[0];
+                tma_load_3d(dst, &tmA, &a_full[sa], col, row, b);
+                if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, &tmA, &a_full[sa], col, row + p.a_box_rows, b);
+                if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+              }
+              if (sh_s != 2) {     // step 2 reuses step 1's weight tiles; sections of the packed weights are [hi | lo | hi]
+                const int wcol = (sh_s == 0 ? p.kch1 * p.bk : 0) + sh_c * p.bk;
+                for (int j = 0; j < grp_taps; ++j) {
+                  mbar_wait(&b_empty[sb], pb);
+                  mbar_expect_tx(&b_full[sb], (uint32_t)p.b_tile_bytes);
+                  tma_load_3d(b_base + (uint32_t)(sb * p.b_tile_bytes), &tmB, &b_full[sb], wcol, n0, j);
+                  if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
+                }
+              }
+              continue;
+            }
             { EV_TW_BEGIN(); mbar_wait(&a_empty[sa], pa); EV_TW_END(tw_a); }
             if (tile == (int)blockIdx.x && kc == 0 && g == 0) EV_TR(14);
             if (p.debug_nob & 2) { mbar_arrive(&a_full[sa]); if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; } if (resident) continue; goto b_loads; }
@@ -273,6 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int sa = 0, sb = 0, vt = 0;     // vt counts accumulator-set uses: one per tile, or one per flush group (3xTF32)
     long long tw_a = 0, tw_b = 0;
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
+    int sh_sb = 0; uint32_t sh_pb = 0;   // tf32_share: ring position of the weight tiles that step 2 reuses
     const int flush_kc = p.flush_kc;
     if (resident) { mbar_wait(&b_full[0], 0); tcgen05_fence_after(); }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -291,6 +317,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           d_tmem = tmem_base + (uint32_t)buf * acc_stride;
           acc = 0;
         }
+        if (p.tf32_share) {
+          // operand-sharing walk (one issuer, one m-block, one tap group): see TcParams::tf32_share
+          const int sh_s = kc % 3;
+          if (sh_s != 1) { mbar_wait(&a_full[sa], pa); tcgen05_fence_after(); }     // step 1 reads step 0's tile again
+          const uint32_t a_lo_s = a_lo0 + (uint32_t)sa * a_step16 + p.tap_first16;
+          if (sh_s == 1) { sh_sb = sb; sh_pb = pb; }                                  // step 2 walks step 1's weight slots again
+          if (sh_s == 2) { sb = sh_sb; pb = sh_pb; }
+          uint32_t a_lo = a_lo_s;
+          for (int j = 0; j < grp_taps; ++j) {
+            if (sh_s != 2) { mbar_wait(&b_full[sb], pb); tcgen05_fence_after(); }
+            const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step16;
+            if (elect_one()) {     // both issuer warps keep the barrier protocol; only the one that owns a valid m-block issues
+              if (my_mb < vmb) issue_tap<4, true>(d_tmem + (uint32_t)(my_mb * BN), hi, a_lo + (uint32_t)my_mb * mb_step16, b_lo, idesc, acc);
+              if (sh_s != 1) umma_commit(&b_empty[sb]);                              // step 1's weight tiles stay for step 2
+            }
+            __syncwarp();
+            acc = 1;
+            a_lo += tap_step16;
+            if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
+          }
+          if (sh_s != 0) {                                                            // step 0's activation tile stays for step 1
+            if (elect_one()) umma_commit(&a_empty[sa]);
+            __syncwarp();
+            if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
+          }
+        } else
         for (int g = 0; g < n_groups; ++g) {
           { EV_TW_BEGIN(); mbar_wait(&a_full[sa], pa); EV_TW_END(tw_a); }
           tcgen05_fence_after();
@@ -617,6 +669,7 @@ int g_cta2_mode = 1;       // EV_TC_CTA2=0 keeps one CTA per SM
 int g_wide_mode = 1;       // EV_TC_WIDE=0 keeps 8 epilogue warps
 int g_lean_mode = 1;       // EV_TC_LEAN=0 disables the activation-only epilogue path
 int g_min_b2 = 4;          // EV_TC_MINB2: fewest weight-ring slots accepted for the two-CTAs-per-SM configuration
+int g_tf32_share = 1;      // EV_TF32_SHARE=0: every one of the three products loads its own operand tiles
 int g_tf32_flush = 1;      // EV_TF32_FLUSH=0: 3xTF32 without two-level accumulation (shows the tensor core's truncation error)
 
 // Shared-memory plan of one launch for `k` CTAs per SM with `epi_warps` epilogue warps; false when the rings do not fit.
@@ -684,6 +737,8 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
     configured = true;
   }
   p.n_issuers = threads == NUM_THREADS_WIDE ? 2 : 1;
+  // the sharing walk needs one tap group (haloed tile or a 1x1 conv), streamed weights and room for a step's weight tiles
+  if (p.tf32_share && (p.n_groups != 1 || p.resident || p.b_slots < p.g.taps + 1 || p.a_slots < 2 || p.kchunks % 3 != 0)) p.tf32_share = 0;
   const int grid = std::min(p.total_tiles, k * g_sm_count);
   return launch_pdl(conv_tc_kernel<BN>, dim3(grid), dim3(threads), (size_t)smem, stream, tmA, tmB, p);
 }
@@ -742,6 +797,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     g_wide_mode = env_int("EV_TC_WIDE", 1);
     g_lean_mode = env_int("EV_TC_LEAN", 1);
     g_tf32_flush = env_int("EV_TF32_FLUSH", 1);
+    g_tf32_share = env_int("EV_TF32_SHARE", 1);
     g_min_b2 = env_int("EV_TC_MINB2", 4);
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
@@ -762,7 +818,9 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     p.idesc = make_idesc_tf32(BM, BN);
     p.flush_kc = std::max(1, 16 / (g.taps * p.ksteps));    // <= 16 truncating tensor-core accumulations per partial sum
     if (g_tf32_flush == 0) p.flush_kc = p.kchunks;
+    p.tf32_share = g_tf32_share;
   } else {
+    p.tf32_share = 0;
     p.bk = (g_bk32_mode && g.C_in <= 32) ? 32 : 64;
     p.row_bytes = p.bk * 2;
     p.ksteps = p.bk / UMMA_K;
