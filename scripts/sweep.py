@@ -45,7 +45,7 @@ def main():
 
     def step(x, xl, spk, n=10, ls=0.8):
         out = model.synthesise(x, xl, n, 0.667, spk, ls)
-        return out, voc(out["mel"]).clamp(-1, 1)
+        return out, voc(out["mel"], lengths=out["mel_lengths"]).clamp(-1, 1)
 
     print("# config 1: one utterance, Tx=151, n_timesteps=10, length_scale 0.8 (feel_me.py operating point)")
     x, xl, _ = synthetic.phoneme_batch(1, 75, 75, seed=1)

@@ -357,6 +357,16 @@ def test_ragged_vocoder_equals_dense_on_valid_samples_and_is_zero_beyond(vocoder
         assert torch.equal(r_s[b, :, : n * 256], d_s[b, :, : n * 256]) and float(r_s[b, :, n * 256:].abs().sum()) == 0.0
 
 
+def test_ragged_vocoder_long_segments(vocoders):
+    """BASELINE config 5 shape (tens of seconds per segment): thousands of tiles per item in the last stages."""
+    gen, _ = vocoders["hifigan_gain1"]
+    mel = synthetic.synthetic_mel(2, 2000, seed=79)
+    dense = gen(mel)
+    rag = gen(mel, lengths=[2000, 700])
+    assert torch.equal(rag[0], dense[0])
+    assert torch.equal(rag[1, :, : 700 * 256], dense[1, :, : 700 * 256]) and float(rag[1, :, 700 * 256:].abs().sum()) == 0.0
+
+
 def test_ragged_vocoder_full_size_batch(matcha, matcha_sd, vocoders):
     """BASELINE config 2 shape (32 x ~600 frames, mixed lengths) through synthesise -> ragged vocoder: valid samples equal
     the dense path bit for bit, the corpus driver's cropped waveforms are unchanged by `ragged`."""
