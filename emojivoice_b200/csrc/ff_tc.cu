@@ -11,8 +11,9 @@
 //                  P  [2 buffers x 2 planes x 128 rows x 128 B]  SnakeBeta output of one 128-channel chunk          64 KB
 //                  W  ring of 6 x 16 KB weight tiles (TMA, box 64 k x 128 n): W1 chunk = 4 tiles, W2 chunk = 4 tiles  96 KB
 //   TMEM           acc1 [2 x 128 columns] (hidden chunk c in buffer c & 1), acc2 [256 columns]
-//   warp 0  : TMA producer -- weights only, which no kernel of the stream writes: it does NOT wait for the programmatic
-//             dependency, so the first six weight tiles land while the previous kernel is still draining
+//   warp 0  : TMA producer -- weights only, which no kernel of the stream writes: with the dense grid it does NOT wait for the
+//             programmatic dependency, so the first six weight tiles land while the previous kernel is still draining (with a
+//             tile list, which is data of the stream, it waits like everybody else)
 //   warp 1  : MMA issuer (owns TMEM).  Order  G1(0) G1(1) | G1(2) G2(0) | G1(3) G2(1) | ... | G2(6) | G2(7): the tensor pipe
 //             always has the next chunk's first GEMM to run while the epilogue warps activate the current one
 //   warps 2-17 : LayerNorm prologue (warp = row), per-chunk activation (thread = row, 32 channels), final epilogue.
