@@ -529,8 +529,9 @@ def test_full_size_batch_properties_and_anchor_items(matcha, matcha_sd, vocoders
 
 # ------------------------------------------------------------------------------------------------ scheduling knobs
 def test_scheduling_knobs_do_not_change_results():
-    """Decoder batch lanes on forked streams, the ResBlock wavefront schedule, one vs two CTAs per SM and programmatic
-    dependent launch only reorder work: mel and waveform must be bit-identical to the default schedule."""
+    """Decoder batch lanes on forked streams, the ResBlock wavefront schedule, one vs two CTAs per SM, programmatic
+    dependent launch and the ragged tile lists of the decoder only reorder or skip dead work: mel and waveform must be
+    bit-identical to the default schedule."""
     import os
     import subprocess
     import sys
@@ -548,6 +549,9 @@ def test_scheduling_knobs_do_not_change_results():
     assert run(EV_RB_WAVE=1) == base
     assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
     assert run(EV_PDL=0) == base
+    # skipping the padded rows of the decoder's masked per-row work (feed-forward tiles, attention query blocks, out-projection
+    # tiles) must not change a single bit either: those rows never reach an output that survives the mask
+    assert run(EV_FF_RAGGED=0) == base
 
 
 def test_long_utterance_matches_oracle(matcha, matcha_sd, vocoders):
