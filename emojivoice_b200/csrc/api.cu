@@ -49,7 +49,10 @@ extern "C" int ev_create(ev_ctx** out, int device) {
   { const char* v = getenv("EV_ENC_TC"); ctx->enc_tc = !(v && atoi(v) == 0); }
   { const char* v = getenv("EV_DEC_LANES"); if (v) ctx->dec_lanes = std::min(std::max(atoi(v), 1), (int)ev_ctx::kMaxLanes); }
   // lane streams / events are created here: stream creation is not allowed while a caller captures a CUDA graph
+  { const char* v = getenv("EV_DEC_SIDE"); ctx->dec_side = !(v && atoi(v) == 0); }
   ce = cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->side_join, cudaEventDisableTiming);
   for (int i = 0; i < ev_ctx::kMaxLanes - 1 && ce == cudaSuccess; ++i) {
     ce = cudaStreamCreateWithFlags(&ctx->lane_stream[i], cudaStreamNonBlocking);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ctx->lane_join[i], cudaEventDisableTiming);
@@ -69,6 +72,8 @@ extern "C" int ev_destroy(ev_ctx* ctx) {
     if (ctx->lane_join[i]) cudaEventDestroy(ctx->lane_join[i]);
   }
   if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+  if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+  if (ctx->side_join) cudaEventDestroy(ctx->side_join);
   delete ctx;
   return EV_OK;
 }

@@ -104,6 +104,10 @@ struct ev_ctx {
   double prof_scale = 1.0;      // profiling: algorithmic FLOPs/bytes of the launches are scaled by the valid-row fraction
   cudaStream_t lane_stream[kMaxLanes - 1] = {};
   cudaEvent_t lane_fork = nullptr, lane_join[kMaxLanes - 1] = {};
+  // side branch of a ResNet block: res_conv(x) only depends on the block's input, so it runs on the last lane stream next to
+  // conv1 -> GroupNorm -> conv2 and is joined before the residual add (EV_DEC_SIDE=0: serial).  Single-lane decoding only.
+  bool dec_side = true;
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
 };
 
 namespace ev {

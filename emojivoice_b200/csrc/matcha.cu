@@ -416,6 +416,7 @@ struct Decoder {
   int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
   bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
   RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
+  cudaStream_t side_stream = nullptr;   // side branch for res_conv (single-lane decoding), see resnet()
   // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
@@ -429,6 +430,19 @@ struct Decoder {
     Epilogue e1; e1.out_f32 = d.h; e1.f32_ld = D; e1.f32_bs = bsD;
     const double* part = d.gn_partial;
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); e1.gn_groups = 8; part = e1.gn_sum; }
+    // res_conv(x * mask) depends only on the block's input: it runs as a side branch (a parallel branch of a captured graph),
+    // filling the SMs that conv1 -> GroupNorm -> conv2 leave idle, and is joined before the residual add
+    const bool side = side_stream != nullptr && !ctx->profiling;
+    cudaStream_t sr = side ? side_stream : s;
+    if (side) {
+      EV_CUDA(ctx, cudaEventRecord(ctx->side_fork, s));
+      EV_CUDA(ctx, cudaStreamWaitEvent(sr, ctx->side_fork, 0));
+    }
+    {
+      Epilogue er; er.out_f32 = d.r; er.f32_ld = D; er.f32_bs = bsD;
+      EV_TRY(run_conv<ActT>(ctx, w.res, in, in_ld, in_bs, B, Tl, er, sr));
+    }
+    if (side) EV_CUDA(ctx, cudaEventRecord(ctx->side_join, sr));
     EV_TRY(run_conv<ActT>(ctx, w.conv1, in, in_ld, in_bs, B, Tl, e1, s));
     int chunks = 1;
     const double RD = (double)B * Tl * D;
@@ -440,8 +454,7 @@ struct Decoder {
     if (!(dbg_skip & 8)) EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); part = e1.gn_sum; }
     EV_TRY(run_conv<ActT>(ctx, w.conv2, d.a, D, bsD, B, Tl, e1, s));
-    Epilogue er; er.out_f32 = d.r; er.f32_ld = D; er.f32_bs = bsD;
-    EV_TRY(run_conv<ActT>(ctx, w.res, in, in_ld, in_bs, B, Tl, er, s));
+    if (side) EV_CUDA(ctx, cudaStreamWaitEvent(s, ctx->side_join, 0));      // r is needed from here on
     if (!fuse_gn()) EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g2;
     g2.x = d.h; g2.partial = part; g2.n_chunks = chunks; g2.gamma = w.gn2_g; g2.beta = w.gn2_b;
@@ -637,6 +650,7 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
               (decoder_pack_input<ActT>(z + b0 * item, mu_y + b0 * item, spk_emb ? spk_emb + (long long)b0 * S : nullptr, nb, F, S, T,
                                         temperature, mask0, q.xstate, q.xin, dec_in, ls[l])));
     dec.push_back(Decoder<ActT>{ctx, m, q, nb, T, ls[l], D, c.dec_heads * c.dec_head_dim});
+    if (n_lanes == 1 && ctx->dec_side && std::is_same<ActT, bf16>::value) dec.back().side_stream = ctx->lane_stream[ev_ctx::kMaxLanes - 2];
     if (std::is_same<ActT, bf16>::value && nb <= kRaggedMaxB) {
       static const bool on = []() { const char* v = getenv("EV_FF_RAGGED"); return !(v && atoi(v) == 0); }();
       if (on) {

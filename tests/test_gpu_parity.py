@@ -552,6 +552,7 @@ def test_scheduling_knobs_do_not_change_results():
     # skipping the padded rows of the decoder's masked per-row work (feed-forward tiles, attention query blocks, out-projection
     # tiles) must not change a single bit either: those rows never reach an output that survives the mask
     assert run(EV_FF_RAGGED=0) == base
+    assert run(EV_DEC_SIDE=0) == base          # res_conv on a side branch of the graph vs in line
 
 
 def test_long_utterance_matches_oracle(matcha, matcha_sd, vocoders):
