@@ -109,6 +109,11 @@ struct RaggedPlanner {
   Entry cache[32];
   int n_cache = 0;
   long long* launch_counter = nullptr;   // bumped once per table kernel (the context's launch statistics)
+  // optional side branch: table kernels only depend on the lengths, so they are issued on `side` (which the caller has made
+  // wait for the lengths) and the consumer's stream waits for `ready` -- in a captured graph every table is then built at the
+  // very beginning, next to the first layers, instead of sitting in front of its first consumer
+  cudaStream_t side = nullptr;
+  cudaEvent_t ready = nullptr;
   bool active() const { return lens != nullptr; }
   // compact tile list for tiles of `tile_rows` GEMM rows over M rows per item; nullptr -> run dense (always correct)
   const int* table(int tile_rows, int M, cudaStream_t s);

@@ -232,6 +232,11 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
     r.lens = lens32; r.B = B; r.margin = margins.pre;
     r.arena = v.rag_arena; r.arena_ints = v.rag_ints;
     r.launch_counter = &ctx->launches;
+    if (ctx->dec_side && !ctx->profiling && std::is_same<ActT, bf16>::value) {   // tile lists are built on a side branch as soon as the lengths are there
+      r.side = ctx->lane_stream[ev_ctx::kMaxLanes - 2]; r.ready = ctx->side_join;
+      EV_CUDA(ctx, cudaEventRecord(ctx->side_fork, s));
+      EV_CUDA(ctx, cudaStreamWaitEvent(r.side, ctx->side_fork, 0));
+    }
     if (ctx->profiling) {   // algorithmic work = the valid frames only (instrumented eager step: a host copy is fine here)
       std::vector<long long> hl(B);
       EV_CUDA(ctx, cudaMemcpyAsync(hl.data(), mel_lengths, sizeof(long long) * B, cudaMemcpyDeviceToHost, s));
@@ -314,6 +319,10 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
         in_act = v.xba;
       }
     }
+  }
+  if (ctx->rag.side) {   // join the side branch whatever happened on it (a captured graph must not end with unjoined work)
+    EV_CUDA(ctx, cudaEventRecord(ctx->rag.ready, ctx->rag.side));
+    EV_CUDA(ctx, cudaStreamWaitEvent(s, ctx->rag.ready, 0));
   }
   EV_LAUNCH(ctx, s, "conv_post_tanh", 2.0 * B * (double)L * C * 7, (double)B * L * (4.0 * C + 4.0),
             conv_post_tanh(v.sum, B, (int)L, C, h.post_w, h.post_b, wav, lens32, h.total_up, s));

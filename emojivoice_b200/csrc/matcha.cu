@@ -417,6 +417,7 @@ struct Decoder {
   bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
   RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
   cudaStream_t side_stream = nullptr;   // side branch for res_conv (single-lane decoding), see resnet()
+  cudaEvent_t temb_event = nullptr;     // time embeddings are produced on another side branch: waited for at their first use
   // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
@@ -451,6 +452,7 @@ struct Decoder {
     g1.x = d.h; g1.partial = part; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
     g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.out_act = d.a; g1.act_ld = D;
     static const int dbg_skip = []() { const char* v = getenv("EV_DEC_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
+    if (temb_event) { EV_CUDA(ctx, cudaStreamWaitEvent(s, temb_event, 0)); temb_event = nullptr; }
     if (!(dbg_skip & 8)) EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); part = e1.gn_sum; }
     EV_TRY(run_conv<ActT>(ctx, w.conv2, d.a, D, bsD, B, Tl, e1, s));
@@ -621,15 +623,24 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
   // then Mish -> the six resnet mlp Linears stacked along N (decoder.py:381-382, :49,58)
   std::vector<float> ts, dts;
   euler_schedule(n_steps, &ts, &dts);
-  EV_LAUNCH(ctx, s, "upload_floats", 0, 4.0 * n_steps, upload_floats(d.t_steps, ts.data(), n_steps, s));
+  // The time-embedding chain depends on nothing but n_steps: with one lane it runs as a side branch (second lane stream) next
+  // to the input packing and the first ResNet conv, and is joined where the first time embedding is consumed.
+  const bool temb_side = n_lanes == 1 && ctx->dec_side && !ctx->profiling && std::is_same<ActT, bf16>::value;
+  cudaStream_t st = temb_side ? ctx->lane_stream[1] : s;
+  if (temb_side) {
+    EV_CUDA(ctx, cudaEventRecord(ctx->lane_fork, s));
+    EV_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lane_fork, 0));
+  }
+  EV_LAUNCH(ctx, st, "upload_floats", 0, 4.0 * n_steps, upload_floats(d.t_steps, ts.data(), n_steps, st));
   ctx->launches += ceil_div(n_steps, 32) - 1;
-  EV_LAUNCH(ctx, s, "time_sinusoid", 0, 4.0 * n_steps * dec_in, time_sinusoid(d.t_steps, n_steps, dec_in, d.sinus, s));
+  EV_LAUNCH(ctx, st, "time_sinusoid", 0, 4.0 * n_steps * dec_in, time_sinusoid(d.t_steps, n_steps, dec_in, d.sinus, st));
   { Epilogue e; e.act = ACT_SILU; e.out_act = d.th1; e.act_ld = 4 * D; e.act_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.time1, d.sinus, dec_in, 0, 1, n_steps, e, s)); }
+    EV_TRY(run_conv<float>(ctx, m.time1, d.sinus, dec_in, 0, 1, n_steps, e, st)); }
   { Epilogue e; e.act = ACT_MISH; e.out_act = d.th2; e.act_ld = 4 * D; e.act_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_steps, e, s)); }
+    EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_steps, e, st)); }
   { Epilogue e; e.out_f32 = d.tproj; e.f32_ld = 6 * D; e.f32_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_steps, e, s)); }
+    EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_steps, e, st)); }
+  if (temb_side) EV_CUDA(ctx, cudaEventRecord(ctx->lane_join[1], st));
   // fork: lane 0 stays on the caller's stream, the others wait for the time embeddings on their own streams
   cudaStream_t ls[ev_ctx::kMaxLanes];
   ls[0] = s;
@@ -651,6 +662,7 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
                                         temperature, mask0, q.xstate, q.xin, dec_in, ls[l])));
     dec.push_back(Decoder<ActT>{ctx, m, q, nb, T, ls[l], D, c.dec_heads * c.dec_head_dim});
     if (n_lanes == 1 && ctx->dec_side && std::is_same<ActT, bf16>::value) dec.back().side_stream = ctx->lane_stream[ev_ctx::kMaxLanes - 2];
+    if (temb_side) dec.back().temb_event = ctx->lane_join[1];
     if (std::is_same<ActT, bf16>::value && nb <= kRaggedMaxB) {
       static const bool on = []() { const char* v = getenv("EV_FF_RAGGED"); return !(v && atoi(v) == 0); }();
       if (on) {

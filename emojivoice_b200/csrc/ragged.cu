@@ -54,8 +54,10 @@ const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
   if (n_cache >= 32 || arena_off + ints > arena_ints) return nullptr;
   int* t = arena + arena_off;
   // an ordinary launch (no programmatic serialization): every later kernel of the stream sees the finished table
-  ragged_table_kernel<<<std::max(1, std::min(64, ceil_div(B * m_tiles, 2048))), 256, 0, s>>>(lens, B, margin, rows_per_frame, len_shift, tile_rows, M, t);
+  cudaStream_t ts = (side && ready) ? side : s;
+  ragged_table_kernel<<<std::max(1, std::min(64, ceil_div(B * m_tiles, 2048))), 256, 0, ts>>>(lens, B, margin, rows_per_frame, len_shift, tile_rows, M, t);
   if (cudaGetLastError() != cudaSuccess) return nullptr;
+  if (ts != s && (cudaEventRecord(ready, ts) != cudaSuccess || cudaStreamWaitEvent(s, ready, 0) != cudaSuccess)) return nullptr;
   arena_off += ints;
   if (launch_counter) ++*launch_counter;
   cache[n_cache++] = Entry{rows_per_frame, len_shift, tile_rows, M, t};
