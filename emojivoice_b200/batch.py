@@ -31,7 +31,22 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
     lens = [len(u[0]) for u in utterances]
     plan = sharding.shard(lens, batch_size, rank, world_size, n_timesteps=n_timesteps, sort=sort)
     results, stats = {}, sharding.ShardStats()
-    for mb in plan:
+    copy_stream = torch.cuda.Stream()
+    pinned = {}                      # two pinned staging buffers (grown on demand), used alternately
+    pending = None                   # the previous micro-batch: its read-back and crops overlap this one's GPU work
+
+    def finish(p):
+        p["done"].synchronize()
+        mel_len = p["len_host"].tolist()
+        stats.add(mel_len, p["xl"], n_timesteps, p["e0"].elapsed_time(p["e1"]) / 1e3)
+        for j, i in enumerate(p["items"]):
+            n = int(mel_len[j])
+            rec = {"waveform": p["wav_host"][j, 0, : n * 256].clone(), "mel_length": n}     # cli.py:308-309 crop
+            if keep_mel:
+                rec["mel"] = p["mel"][j, :, :n].cpu()
+            results[i] = rec
+
+    for k, mb in enumerate(plan):
         x, xl, spks = collate(utterances, mb.items)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -44,13 +59,27 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
         if denoiser is not None:
             wav = denoiser(wav.squeeze(1), strength=denoiser_strength).unsqueeze(1)
         e1.record()
-        wav_cpu, mel_len = wav.cpu(), out["mel_lengths"].cpu()
-        e1.synchronize()
-        stats.add(mel_len.tolist(), xl.tolist(), n_timesteps, e0.elapsed_time(e1) / 1e3)
-        for j, i in enumerate(mb.items):
-            n = int(mel_len[j])
-            rec = {"waveform": wav_cpu[j, 0, : n * 256].clone(), "mel_length": n}     # cli.py:308-309 crop
-            if keep_mel:
-                rec["mel"] = out["mel"][j, :, :n].cpu()
-            results[i] = rec
+        # read-back on a copy stream into pinned memory (the `.cpu()` of to_waveform): the host crops the PREVIOUS micro-batch
+        # while this one's copy -- and the next one's kernels -- are in flight
+        slot = pinned.setdefault(k & 1, {})
+        if "wav" not in slot or slot["wav"].numel() < wav.numel():
+            slot["wav"] = torch.empty(wav.numel(), dtype=wav.dtype).pin_memory()
+        if "len" not in slot or slot["len"].numel() < len(mb.items):
+            slot["len"] = torch.empty(len(mb.items), dtype=torch.int64).pin_memory()
+        wav_host = slot["wav"][: wav.numel()].view(wav.shape)
+        len_host = slot["len"][: len(mb.items)]
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(copy_stream):
+            wav_host.copy_(wav, non_blocking=True)
+            len_host.copy_(out["mel_lengths"], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        wav.record_stream(copy_stream)
+        cur = dict(done=done, e0=e0, e1=e1, wav_host=wav_host, len_host=len_host, xl=xl.tolist(), items=mb.items,
+                   mel=out["mel"] if keep_mel else None)
+        if pending is not None:
+            finish(pending)
+        pending = cur
+    if pending is not None:
+        finish(pending)
     return results, stats
