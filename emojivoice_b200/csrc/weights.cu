@@ -294,7 +294,12 @@ int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x
   }
   std::string msg;
   cudaError_t ce;
-  const std::string nm = std::string("conv_tc_tf32x3") + ctx->prof_tag;
+  std::string nm = std::string("conv_tc_tf32x3") + ctx->prof_tag;
+  if (ctx->profiling && ctx->prof_detail) {   // EV_PROF_DETAIL=1: one class per layer shape
+    char buf[64];
+    snprintf(buf, sizeof buf, " c%d n%d k%d m%d", w.C_in, w.N, w.taps, g.M);
+    nm += buf;
+  }
   { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, scratch, 2LL * w.C_in, (long long)T_in * 2 * w.C_in, 1, w, e, s, &msg); }
   if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch(tf32x3): " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   return 0;
