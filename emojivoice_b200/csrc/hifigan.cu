@@ -330,6 +330,15 @@ int vocode_impl(ev_ctx* ctx, const float* mel, const long long* mel_lengths, int
 }
 }  // namespace
 
+// host-only: the per-layer margins (mel frames) ev_vocode_ragged uses for this configuration; stage[i] / up[i] for i < n_ups
+extern "C" int ev_test_vocoder_margins(const ev_hifigan_cfg* cfg, int32_t* stage, int32_t* up, int32_t* pre) {
+  if (!cfg || !stage || !up || !pre || cfg->n_ups <= 0 || cfg->n_ups > 8 || cfg->n_kernels <= 0 || cfg->n_kernels > 4) return EV_ERR_INVALID;
+  const VocMargins m = vocoder_margins(*cfg);
+  for (int i = 0; i < cfg->n_ups; ++i) { stage[i] = m.stage[i]; up[i] = m.up[i]; }
+  *pre = m.pre;
+  return EV_OK;
+}
+
 extern "C" size_t ev_vocode_workspace_bytes(const ev_ctx* ctx, int B, int T) {
   if (!ctx || !ctx->hifigan.loaded || B <= 0 || T <= 0) return 0;
   Workspace w(nullptr, 0);

@@ -188,6 +188,9 @@ EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_len
 EV_API int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
               const float* snake_a, const float* snake_invb, const float* w2, const float* b2, const int64_t* y_lengths,
               int B, int T, int inner, int len_shift, float* out, int repeat, float* avg_us_host, void* stream);
+/* Host-only: how many mel frames past an utterance's end ev_vocode_ragged still computes in front of conv_pre (pre), of
+ * upsampler i (up[i]) and inside stage i (stage[i]), i < n_ups -- upper bounds of the generator's look-ahead. */
+EV_API int ev_test_vocoder_margins(const ev_hifigan_cfg* cfg, int32_t* stage, int32_t* up, int32_t* pre);
 EV_API int ev_test_euler_schedule(int n_timesteps, float* t_host, float* dt_host);
 /* y_lengths of torch.sum order: sums (B,Tx) fp32 rows exactly as ATen's CPU float32 reduction does. */
 EV_API int ev_test_row_sum(ev_ctx* ctx, const float* x, int B, int Tx, float* out, void* stream);

@@ -88,3 +88,41 @@ def test_aten_sum_order_restatement_matches_torch():
             w[rng.integers(0, n + 1):] = 0.0
             want = float(torch.sum(torch.from_numpy(w).view(1, 1, n), [1, 2])[0])
             assert sum_f32(w) == want, (n, ls)
+
+
+def test_ragged_vocoder_margins_cover_the_generators_look_ahead():
+    """ev_vocode_ragged computes item b only up to (len_b + margin) frames per layer.  The margins come from the configuration
+    (hifigan.cu: vocoder_margins); here they are pinned against the ORACLE generator's real receptive field: perturbing the
+    mel from frame f on must not change any sample before (f - look_ahead) * 256, and the look-ahead measured that way must
+    not exceed what the first layers keep (margin - 1 spare frame)."""
+    from emojivoice_b200.config import HIFIGAN_V1
+    from oracle import hifigan_oracle as ho
+
+    h = HIFIGAN_V1
+    cfg = _lib.EvHifiganCfg()
+    cfg.num_mels, cfg.upsample_initial_channel = 80, int(h["upsample_initial_channel"])
+    cfg.n_ups, cfg.n_kernels = len(h["upsample_rates"]), len(h["resblock_kernel_sizes"])
+    for i, (u, k) in enumerate(zip(h["upsample_rates"], h["upsample_kernel_sizes"])):
+        cfg.upsample_rates[i], cfg.upsample_kernel_sizes[i] = int(u), int(k)
+    for j, (k, dil) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
+        cfg.resblock_kernel_sizes[j] = int(k)
+        for l in range(3):
+            cfg.resblock_dilation_sizes[j][l] = int(dil[l])
+    stage, up, pre = (C.c_int32 * 8)(), (C.c_int32 * 8)(), C.c_int32(0)
+    assert _lib.lib().ev_test_vocoder_margins(C.byref(cfg), stage, up, C.byref(pre)) == 0
+    n = cfg.n_ups
+    assert list(stage)[:n] == [11, 3, 2, 2] and list(up)[:n] == [13, 3, 2, 2] and pre.value == 13      # HiFi-GAN v1
+    # measured look-ahead of the oracle: first output sample that reacts to a change of the frames >= f
+    sd = synthetic.hifigan_state_dict(h, seed=4321, gain=1.0)
+    T, f = 48, 32
+    mel = synthetic.synthetic_mel(1, T, seed=3)
+    mel2 = mel.clone()
+    mel2[:, :, f:] += torch.randn(1, 80, T - f, generator=torch.Generator().manual_seed(1))
+    a, b = ho.generator(sd, h, mel)[0, 0], ho.generator(sd, h, mel2)[0, 0]
+    first = int((a != b).nonzero()[0])
+    look_ahead_frames = (f * 256 - first + 255) // 256        # measured on the mel INPUT: 13 frames for v1
+    # conv_pre (k = 7) itself reaches 3 frames ahead and reads the dense mel, so its OUTPUT rows must be right up to
+    # look_ahead - 3 frames past the end; the margin keeps one spare frame on top of its own (conservative) bound
+    assert 5 < look_ahead_frames - 3 <= pre.value - 1, look_ahead_frames
+    # stage by stage the margins shrink with the remaining depth of the generator and never drop below one spare frame
+    assert all(stage[i] >= stage[i + 1] >= 2 for i in range(n - 1)) and all(up[i] >= stage[i] for i in range(n))
