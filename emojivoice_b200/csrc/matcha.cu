@@ -257,7 +257,10 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     const EncLayerW& L = m.enc[i];
     Epilogue ep;
     ep.out_f32 = e.qkv; ep.f32_ld = 3 * H; ep.f32_bs = (long long)Tx * 3 * H;
-    EV_TRY(run_conv_tf32(ctx, L.qkv, e.X, H, bsH, B, Tx, ep, e.split, s));
+    // 1x1 convs without a mask in the epilogue see the batch as ONE sequence of B*Tx rows (the tensors are dense): 128-row
+    // tiles then straddle utterances instead of leaving every utterance's last tile mostly empty (Tx = 177: 45 m-tiles, not 64).
+    // Row-wise the arithmetic is unchanged, so the results are bit-identical.
+    EV_TRY(run_conv_tf32(ctx, L.qkv, e.X, H, bsH * B, 1, B * Tx, ep, e.split, s));
     AttnArgs at;
     at.q = e.qkv; at.k = e.qkv + H; at.v = e.qkv + 2 * H; at.ld = 3 * H; at.bs = (long long)Tx * 3 * H;
     at.B = B; at.T = Tx; at.H = c.enc_heads; at.D = hd; at.scale = 1.0f / sqrtf((float)hd);
@@ -267,7 +270,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
     Epilogue eo;  // x + y
     eo.res = e.X; eo.res_ld = H; eo.res_bs = bsH; eo.out_f32 = e.tmp; eo.f32_ld = H; eo.f32_bs = bsH;
-    EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH, B, Tx, eo, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH * B, 1, B * Tx, eo, e.split, s));
     LnArgs l1;
     l1.x = e.tmp; l1.x_ld = H; l1.gamma = L.ln1_g; l1.beta = L.ln1_b; l1.eps = 1e-4f; l1.mask = mask;
     l1.out_f32 = e.X1; l1.f32_ld = H; l1.B = B; l1.T = Tx; l1.C = H;
