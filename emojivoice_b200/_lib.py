@@ -47,7 +47,7 @@ SIGNATURES = {
     "ev_load_matcha": (_I, [_P, C.POINTER(EvTensor), _I, C.POINTER(EvMatchaCfg), _P]),
     "ev_load_hifigan": (_I, [_P, C.POINTER(EvTensor), _I, C.POINTER(EvHifiganCfg), _P]),
     "ev_encode_workspace_bytes": (_SZ, [_P, _I, _I]),
-    "ev_encode": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "ev_encode": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "ev_align_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "ev_align": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "ev_decode_workspace_bytes": (_SZ, [_P, _I, _I, _I]),

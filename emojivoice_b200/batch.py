@@ -74,7 +74,8 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
             len_host.copy_(out["mel_lengths"], non_blocking=True)
             done = torch.cuda.Event()
             done.record()
-        wav.record_stream(copy_stream)
+        wav.record_stream(copy_stream)                        # both sources are read by the copy stream after this iteration
+        out["mel_lengths"].record_stream(copy_stream)         # rebinds `out`: the allocator must not recycle them early
         cur = dict(done=done, e0=e0, e1=e1, wav_host=wav_host, len_host=len_host, xl=xl.tolist(), items=mb.items,
                    mel=out["mel"] if keep_mel else None)
         if pending is not None:

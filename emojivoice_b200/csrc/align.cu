@@ -8,7 +8,8 @@ namespace {
 
 // one thread per utterance: the row is short (Tx tokens) and the summation ORDER is the contract
 __global__ void durations_kernel(const float* __restrict__ logw, const int* __restrict__ x_lens, int B, int Tx,
-                                 float length_scale, float* __restrict__ w_ceil, long long* __restrict__ y_lengths) {
+                                 float length_scale, float* __restrict__ w_ceil, long long* __restrict__ y_lengths,
+                                 long long* __restrict__ y_max) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float* lw = logw + (long long)b * Tx;
@@ -20,7 +21,9 @@ __global__ void durations_kernel(const float* __restrict__ logw, const int* __re
     wc[i] = __fmul_rn(ceilf(w), length_scale);                 // w_ceil = ceil(w) * length_scale
   }
   const float s = evsum::sum_f32(wc, Tx);                      // torch.sum(w_ceil, [1, 2]) in ATen's CPU order
-  y_lengths[b] = (long long)fmaxf(s, 1.0f);                    // clamp_min(.., 1).long() truncates
+  const long long y = (long long)fmaxf(s, 1.0f);               // clamp_min(.., 1).long() truncates
+  y_lengths[b] = y;
+  if (y_max) atomicMax(y_max, y);                              // y_lengths.max(): the host's one read-back (utils/model.py:18)
 }
 
 __global__ void row_sum_kernel(const float* x, int B, int Tx, float* out) {
@@ -77,8 +80,8 @@ __global__ void gather_mu_kernel(const float* __restrict__ mu_x, const int* __re
 }  // namespace
 
 cudaError_t durations(const float* logw, const int* x_lens, int B, int Tx, float length_scale, float* w_ceil,
-                      long long* y_lengths, cudaStream_t s) {
-  durations_kernel<<<ceil_div(B, 32), 32, 0, s>>>(logw, x_lens, B, Tx, length_scale, w_ceil, y_lengths);
+                      long long* y_lengths, long long* y_max, cudaStream_t s) {
+  durations_kernel<<<ceil_div(B, 32), 32, 0, s>>>(logw, x_lens, B, Tx, length_scale, w_ceil, y_lengths, y_max);
   return cudaGetLastError();
 }
 cudaError_t row_sum_aten(const float* x, int B, int Tx, float* out, cudaStream_t s) {

@@ -176,12 +176,9 @@ __global__ void rope_tables_kernel(float* cos_t, float* sin_t, int T, int rope_d
 template <typename ActT, int D>
 cudaError_t launch_attn(const AttnArgs& a, cudaStream_t s) {
   const size_t sh = (size_t)(BQ * D + BKT * (D + 1) + BKT * D + NW * QPW * BKT) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(attn_kernel<ActT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-    if (ce != cudaSuccess) return ce;
-    configured = true;
-  }
+  static DeviceOnce once;
+  cudaError_t ce = once.run([&]() { return cudaFuncSetAttribute(attn_kernel<ActT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); });
+  if (ce != cudaSuccess) return ce;
   if ((a.rope_dim & 7) || ((D - a.rope_dim) & 3) || (a.ld & 3) || (a.bs & 3)) return cudaErrorInvalidValue;   // float4 staging
   dim3 grid(ceil_div(a.T, BQ), a.H, a.B);
   attn_kernel<ActT, D><<<grid, NW * 32, sh, s>>>(a);

@@ -231,12 +231,9 @@ cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err) 
   if (!tc_encode_bf16_map(&tm, a.qkv, (uint64_t)(3 * a.inner), (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.ld * 2, (uint64_t)a.bs * 2,
                           HD, BKV, 128, err))
     return cudaErrorInvalidValue;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (ce != cudaSuccess) return ce;
-    configured = true;
-  }
+  static DeviceOnce once;
+  cudaError_t ce_attr = once.run([&]() { return cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); });
+  if (ce_attr != cudaSuccess) return ce_attr;
   Params p;
   p.T = a.T; p.H = a.H; p.inner = a.inner;
   p.c1 = a.scale * 1.4426950408889634f; p.c2 = 1.4426950408889634f;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 
 #if defined(__CUDA_ARCH__) && !defined(__CUDA_ARCH_FEAT_SM100_ALL) && !defined(__CUDA_ARCH_FEAT_SM103_ALL)
@@ -77,6 +78,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+
+// Host: one-time per-DEVICE setup (cudaFuncSetAttribute is a per-device property; a process may hold contexts on several
+// devices, and several host threads may race here: the setter runs until it has succeeded once for the current device).
+struct DeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  template <typename F> cudaError_t run(F&& setter) {
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return ce;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    ce = setter();
+    if (ce == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return ce;
+  }
+};
 
 // Host: launch `kernel` allowing programmatic stream serialization (only for kernels that call pdl_wait()).
 bool pdl_enabled();

@@ -64,7 +64,7 @@ __device__ __forceinline__ bool ep_coord(const Epilogue& e, int r, int n, int& t
 
 __device__ __forceinline__ float ep_value(const Epilogue& e, int b, int t, int co, float acc, float maskv) {
   float v = acc + (e.bias ? __ldg(e.bias + co) : 0.0f);
-  if (e.mask_pre) v *= maskv;
+  if (e.mask_pre && maskv == 0.0f) v = 0.0f;   // select: a padded row may hold a non-finite value
   v *= e.alpha;
   if (e.res) v += e.res[b * e.res_bs + (long long)t * e.res_ld + co];
   if (e.res2) v += e.res2[b * e.res2_bs + (long long)t * e.res2_ld + co];
@@ -76,7 +76,7 @@ __device__ __forceinline__ float ep_act(const Epilogue& e, int co, float v, floa
   float sa = 0.0f, sb = 0.0f;
   if (e.act == ACT_SNAKE) { sa = __ldg(e.snake_a + co); sb = __ldg(e.snake_invb + co); }
   float w = apply_act(v, e.act, e.slope, sa, sb);
-  if (e.mask_act) w *= maskv;
+  if (e.mask_act && maskv == 0.0f) w = 0.0f;
   return w;
 }
 
@@ -97,7 +97,7 @@ struct ConvWeights {
 // len_b + (receptive field); tiles that start beyond (len_b + margin) * rows_per_frame are never computed.  The tile
 // kernels walk a COMPACT list of (item, m-tile) pairs instead of the dense B x m_tiles grid:
 //     table[0] = number of pairs,  table[1 + i] = (b << 16) | m_tile      (built on the device from the lengths, so a
-// captured CUDA graph follows the lengths of each replay).  Tables are cached per (rows_per_frame, tile_rows, M).
+// captured CUDA graph follows the lengths of each replay).  Tables are cached per (rows_per_frame, len_shift, tile_rows, M, margin).
 struct RaggedPlanner {
   const int* lens = nullptr;      // device [B], valid frames per item; nullptr = dense batch
   int B = 0, margin = 0;          // margin in frames (>= the generator's receptive field, see hifigan.cu)
@@ -105,7 +105,7 @@ struct RaggedPlanner {
   int len_shift = 0;              // frames valid at this level = ceil(lens[b] / 2^len_shift) (decoder half-rate levels)
   int* arena = nullptr;           // table storage (caller's workspace)
   size_t arena_ints = 0, arena_off = 0;
-  struct Entry { int rpf, shift, tile_rows, M; const int* table; };
+  struct Entry { int rpf, shift, tile_rows, M, margin; const int* table; };
   Entry cache[32];
   int n_cache = 0;
   long long* launch_counter = nullptr;   // bumped once per table kernel (the context's launch statistics)

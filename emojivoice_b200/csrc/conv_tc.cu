@@ -468,10 +468,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const float sa[8] = {sa0.x, sa0.y, sa0.z, sa0.w, sa1.x, sa1.y, sa1.z, sa1.w};
               const float sb[8] = {sb0.x, sb0.y, sb0.z, sb0.w, sb1.x, sb1.y, sb1.z, sb1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { const float sn = __sinf(v[i] * sa[i]); v[i] = fmaf(sb[i], sn * sn, v[i]) * mv; }
+              for (int i = 0; i < 8; ++i) { const float sn = __sinf(v[i] * sa[i]); v[i] = mv != 0.0f ? fmaf(sb[i], sn * sn, v[i]) : 0.0f; }
             } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], v[i] * slope) * mv;
+              for (int i = 0; i < 8; ++i) v[i] = mv != 0.0f ? fmaxf(v[i], v[i] * slope) : 0.0f;
             }
             uint32_t w[4];
 #pragma unroll
@@ -572,7 +572,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float4 a4 = *reinterpret_cast<const float4*>(srow_r + u * 4 * STAGE_LD);
             float v0 = a4.x + bias4.x, v1 = a4.y + bias4.y, v2 = a4.z + bias4.z, v3 = a4.w + bias4.w;
             const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
-            if (mask_pre) { v0 *= mv; v1 *= mv; v2 *= mv; v3 *= mv; }
+            if (mask_pre && mv == 0.0f) { v0 = v1 = v2 = v3 = 0.0f; }   // a select, not a multiply: a padded row may hold anything
             if (use_alpha) { v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha; }
             if (has_res) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
             if (has_res2) {
@@ -590,7 +590,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               } else {       // LeakyReLU(slope) for slope in [0,1]: max(v, v*slope); slope = 1 is the identity
                 a0 = fmaxf(v0, v0 * slope); a1 = fmaxf(v1, v1 * slope); a2 = fmaxf(v2, v2 * slope); a3 = fmaxf(v3, v3 * slope);
               }
-              if (mask_act) { a0 *= mv; a1 *= mv; a2 *= mv; a3 *= mv; }
+              if (mask_act && mv == 0.0f) { a0 = a1 = a2 = a3 = 0.0f; }
               if (f32_act) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(a0, a1, a2, a3);
               if (has_act) {
                 __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
@@ -661,7 +661,15 @@ bool encode_map(CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, ui
   return true;
 }
 
-int g_sm_count = 0;
+thread_local int g_sm_count = 0;     // SM count of the device of the launch being planned (refreshed per launch, see sm_count_now)
+int g_sm_by_dev[64] = {};
+int sm_count_now() {    // per-device (a process may drive several GPUs), cached after the first query
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& c = g_sm_by_dev[dev & 63];
+  if (c <= 0) { int v = 0; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); c = v > 0 ? v : 148; }
+  return c;
+}
 int g_resident_mode = 1;   // EV_TC_RESIDENT=0 disables the weights-resident variant (debugging)
 int g_mb_mode = 0;         // EV_TC_MB=1|2 forces the m-blocks per tile (0 = heuristic)
 int g_bk32_mode = 1;       // EV_TC_BK32=0 disables the 64-byte-swizzle path for C_in <= 32
@@ -730,12 +738,9 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& 
   // never let more CTAs become co-resident than TMEM can serve (tcgen05.alloc would spin forever)
   const int min_smem = (228 * 1024) / (k_tmem + 1) + 1;
   if (smem < min_smem && k_tmem < 8) smem = std::min(min_smem, SMEM_LIMIT);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (ce != cudaSuccess) return ce;
-    configured = true;
-  }
+  static DeviceOnce once;
+  cudaError_t ce_attr = once.run([&]() { return cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT); });
+  if (ce_attr != cudaSuccess) return ce_attr;
   p.n_issuers = threads == NUM_THREADS_WIDE ? 2 : 1;
   // the sharing walk needs one tap group (haloed tile or a 1x1 conv), streamed weights and room for a step's weight tiles
   if (p.tf32_share && (p.n_groups != 1 || p.resident || p.b_slots < p.g.taps + 1 || p.a_slots < 2 || p.kchunks % 3 != 0)) p.tf32_share = 0;
@@ -750,7 +755,7 @@ bool tc_encode_bf16_map(::CUtensorMap_st* map, const void* base, uint64_t d0, ui
   if (!g_encode && !conv_tc_init(err)) return false;
   return encode_map(map, base, d0, d1, d2, s1_bytes, s2_bytes, b0, b1, err, swizzle_bytes);
 }
-int tc_sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
+int tc_sm_count() { return sm_count_now(); }
 cudaError_t conv_tc_read_trace(unsigned long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_trace, sizeof(unsigned long long) * std::min(n, 512 * 24));
 }
@@ -772,10 +777,7 @@ bool conv_tc_init(std::string* err) {
     return false;
   }
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-  if (g_sm_count <= 0) g_sm_count = 148;
+  g_sm_count = sm_count_now();
   return true;
 }
 
@@ -802,6 +804,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     g_halo_mode = env_int("EV_TC_HALO", 1);
   }
   const int BN = conv_tc_pick_bn(g.N);
+  g_sm_count = sm_count_now();
   TcParams p;
   p.g = g;
   p.e = e;

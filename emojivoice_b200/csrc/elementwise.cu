@@ -54,17 +54,20 @@ __global__ void upload_kernel(float* dst, Vals32 vals, int n) {
 
 // ---------------------------------------------------------------------------------------------- embeddings
 __global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ emb, int Tx, int C,
-                                    int n_vocab, float scale, RowMask mask, float* __restrict__ out, long long out_ld) {
+                                    int n_vocab, float scale, RowMask mask, float* __restrict__ out, long long out_ld,
+                                    long long* flags) {
   const int row = blockIdx.x, b = row / Tx, t = row - b * Tx;
   long long id = ids[row];
-  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
   const float m = mask.at(b, t);
+  if ((id < 0 || id >= n_vocab) && flags && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned long long*>(flags), 1ull);
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
   for (int c = threadIdx.x; c < C; c += blockDim.x) out[(long long)row * out_ld + c] = emb[id * C + c] * scale * m;
 }
 
-__global__ void embed_speakers_kernel(const long long* ids, const float* table, int dim, int n_spks, float* out) {
+__global__ void embed_speakers_kernel(const long long* ids, const float* table, int dim, int n_spks, float* out, long long* flags) {
   const int b = blockIdx.x;
   long long id = ids[b];
+  if ((id < 0 || id >= n_spks) && flags && threadIdx.x == 0) atomicOr(reinterpret_cast<unsigned long long*>(flags), 2ull);
   id = id < 0 ? 0 : (id >= n_spks ? n_spks - 1 : id);
   for (int c = threadIdx.x; c < dim; c += blockDim.x) out[b * dim + c] = table[id * dim + c];
 }
@@ -514,12 +517,12 @@ cudaError_t upload_floats(float* dst, const float* vals_host, int n, cudaStream_
 }
 
 cudaError_t embed_tokens(const long long* ids, const float* emb, int B, int Tx, int C, int n_vocab, float scale,
-                         RowMask mask, float* out, long long out_ld, cudaStream_t s) {
-  embed_tokens_kernel<<<B * Tx, 64, 0, s>>>(ids, emb, Tx, C, n_vocab, scale, mask, out, out_ld);
+                         RowMask mask, float* out, long long out_ld, long long* flags, cudaStream_t s) {
+  embed_tokens_kernel<<<B * Tx, 64, 0, s>>>(ids, emb, Tx, C, n_vocab, scale, mask, out, out_ld, flags);
   return cudaGetLastError();
 }
-cudaError_t embed_speakers(const long long* ids, const float* table, int B, int dim, int n_spks, float* out, cudaStream_t s) {
-  embed_speakers_kernel<<<B, 64, 0, s>>>(ids, table, dim, n_spks, out);
+cudaError_t embed_speakers(const long long* ids, const float* table, int B, int dim, int n_spks, float* out, long long* flags, cudaStream_t s) {
+  embed_speakers_kernel<<<B, 64, 0, s>>>(ids, table, dim, n_spks, out, flags);
   return cudaGetLastError();
 }
 cudaError_t fill_speaker_channels(const float* spk, int B, int T, int dim, RowMask mask, float* buf, long long ld, int c0,

@@ -447,12 +447,9 @@ cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err) {
   p.tiles = a.lens ? a.tiles : nullptr; p.B = a.B;
   { static const int dbg = []() { const char* v = getenv("EV_FF_DEBUG"); return v ? atoi(v) : 0; }(); p.debug = dbg; }
   p.T = a.T; p.m_tiles = ceil_div(a.T, 128); p.total_tiles = p.m_tiles * a.B; p.n_chunks = w1.N / FF_CHUNK;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(ff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM);
-    if (ce != cudaSuccess) return ce;
-    configured = true;
-  }
+  static DeviceOnce once;
+  cudaError_t ce_attr = once.run([&]() { return cudaFuncSetAttribute(ff_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM); });
+  if (ce_attr != cudaSuccess) return ce_attr;
   const int grid = std::min(p.total_tiles, tc_sm_count());
   return launch_pdl(ff_tc_kernel, dim3(grid), dim3(FF_THREADS), (size_t)FF_SMEM, s, maps, p);
 }

@@ -19,10 +19,13 @@ cudaError_t upload_floats(float* dst, const float* vals_host, int n, cudaStream_
 
 // ---- text encoder --------------------------------------------------------------------------------------------
 // text_encoder.py:397: out[b,t,:] = emb[ids[b,t]] * scale, zero on padded rows
+// ids outside [0, n_vocab) (valid rows only) are clamped for the lookup and reported as bit 0 of *flags (nullable):
+// nn.Embedding raises IndexError there, and so does the python layer once it reads the flags
 cudaError_t embed_tokens(const long long* ids, const float* emb, int B, int Tx, int C, int n_vocab, float scale,
-                         RowMask mask, float* out, long long out_ld, cudaStream_t s);
+                         RowMask mask, float* out, long long out_ld, long long* flags, cudaStream_t s);
 // matcha_tts.py:118: out[b,:] = table[clamp(ids[b])]
-cudaError_t embed_speakers(const long long* ids, const float* table, int B, int dim, int n_spks, float* out, cudaStream_t s);
+cudaError_t embed_speakers(const long long* ids, const float* table, int B, int dim, int n_spks, float* out, long long* flags /* bit 1 */,
+                           cudaStream_t s);
 // text_encoder.py:402-403: buf[b,t,c0:c0+dim] = spk[b,:] (masked rows -> 0)
 cudaError_t fill_speaker_channels(const float* spk, int B, int T, int dim, RowMask mask, float* buf, long long ld,
                                   int c0, cudaStream_t s);
@@ -68,8 +71,9 @@ cudaError_t attention_tc(const AttnTcArgs& a, cudaStream_t s, std::string* err);
 cudaError_t rope_tables(float* cos_t, float* sin_t, int T, int rope_dim, float base, cudaStream_t s);
 
 // ---- duration / alignment (integer, bit-exact) -------------------------------------------------------------------
+// y_max (nullable): atomicMax of the lengths (zeroed by the caller) -- the one scalar the host reads back (utils/model.py:18)
 cudaError_t durations(const float* logw, const int* x_lens, int B, int Tx, float length_scale, float* w_ceil,
-                      long long* y_lengths, cudaStream_t s);
+                      long long* y_lengths, long long* y_max, cudaStream_t s);
 cudaError_t row_sum_aten(const float* x, int B, int Tx, float* out, cudaStream_t s);
 cudaError_t generate_path(const float* w_ceil, const int* x_lens, const int* y_lens, int B, int Tx, int T_pad,
                           float* attn, int* frame_token, cudaStream_t s);

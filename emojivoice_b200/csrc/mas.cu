@@ -90,8 +90,8 @@ extern "C" int ev_maximum_path(ev_ctx* ctx, const float* value, const int32_t* t
     return fail(ctx, EV_ERR_STATE, "ev_maximum_path: workspace too small");
   if (base > (size_t)200 * 1024) return fail(ctx, EV_ERR_INVALID, "ev_maximum_path: t_x / t_y too large");
   const size_t smem = bits_in_smem ? with_bits : base;
-  static bool configured = false;
-  if (!configured) { EV_CUDA(ctx, cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+  static DeviceOnce once;
+  EV_CUDA(ctx, once.run([&]() { return cudaFuncSetAttribute(mas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
   EV_CUDA(ctx, cudaMemsetAsync(path, 0, (size_t)B * Tx * Ty * sizeof(int32_t), s));
   const int threads = std::min(MAS_THREADS, ((Tx + 31) / 32) * 32);
   EV_LAUNCH(ctx, s, "maximum_path", 0, (double)B * Tx * Ty * 8.0,

@@ -200,7 +200,7 @@ extern "C" size_t ev_encode_workspace_bytes(const ev_ctx* ctx, int B, int Tx) {
 
 extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths, const int64_t* spks, int B, int Tx,
                          float length_scale, float* spk_emb, float* mu_x, float* logw, float* w_ceil, int64_t* y_lengths,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         int64_t* summary, void* workspace, size_t workspace_bytes, void* stream) {
   if (!ctx) return EV_ERR_INVALID;
   if (!ctx->matcha.loaded) return fail(ctx, EV_ERR_STATE, "ev_encode: matcha weights not loaded");
   if (!x || !x_lengths || !mu_x || !logw || !w_ceil || !y_lengths || B <= 0 || Tx <= 0)
@@ -221,11 +221,13 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
   const double R = (double)B * Tx;
   EV_LAUNCH(ctx, s, "i64_to_i32", 0, 12.0 * B, i64_to_i32(reinterpret_cast<const long long*>(x_lengths), e.xlen32, B, s));
   const RowMask mask{e.xlen32, 0};
+  long long* summ = reinterpret_cast<long long*>(summary);      // [0] max(y_lengths), [1] id-range flags
+  if (summ) EV_CUDA(ctx, cudaMemsetAsync(summ, 0, 2 * sizeof(long long), s));
   if (c.n_spks > 1)
     EV_LAUNCH(ctx, s, "embed_speakers", 0, 8.0 * B * c.spk_emb_dim,
-              embed_speakers(reinterpret_cast<const long long*>(spks), m.spk_table, B, c.spk_emb_dim, c.n_spks, spk_emb, s));
+              embed_speakers(reinterpret_cast<const long long*>(spks), m.spk_table, B, c.spk_emb_dim, c.n_spks, spk_emb, summ ? summ + 1 : nullptr, s));
   EV_LAUNCH(ctx, s, "embed_tokens", 0, R * (8 + 8.0 * C),
-            embed_tokens(reinterpret_cast<const long long*>(x), m.tok_emb, B, Tx, C, c.n_vocab, sqrtf((float)C), mask, e.h0, C, s));
+            embed_tokens(reinterpret_cast<const long long*>(x), m.tok_emb, B, Tx, C, c.n_vocab, sqrtf((float)C), mask, e.h0, C, summ ? summ + 1 : nullptr, s));
   if (c.enc_prenet) {
     // ConvReluNorm (text_encoder.py:60-67): 3 x [conv5(x*mask) -> LN -> ReLU], 1x1 proj, + x_org, * mask
     const float* cur = e.h0;
@@ -309,7 +311,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     Epilogue el;
     el.mask = mask; el.mask_pre = 1; el.out_f32 = logw; el.f32_ld = 1; el.f32_bs = Tx;
     EV_TRY(run_conv_tf32(ctx, m.dp_proj, e.D2, Fd, bsF, B, Tx, el, e.split, s));
-    EV_LAUNCH(ctx, s, "durations", 0, R * 8.0, durations(logw, e.xlen32, B, Tx, length_scale, w_ceil, reinterpret_cast<long long*>(y_lengths), s));
+    EV_LAUNCH(ctx, s, "durations", 0, R * 8.0, durations(logw, e.xlen32, B, Tx, length_scale, w_ceil, reinterpret_cast<long long*>(y_lengths), summ, s));
   }
   return 0;
 }
@@ -477,6 +479,9 @@ struct Decoder {
     const long long bsD = (long long)Tl * D;
     const int Hh = m.cfg.dec_heads, hd = m.cfg.dec_head_dim;
     const double attn_flops = 4.0 * B * Hh * (double)Tl * Tl * hd;
+    // rows that the skips below leave unwritten are only safe behind the fused feed-forward, which masks with selects and
+    // zero-fills the tiles it does not compute; the unfused fallback (D != 256) computes every row
+    const bool ff_fused = std::is_same<ActT, bf16>::value && D == 256 && !(dbg_skip & 3) && ff_tc_supported(w.ff1, w.ff2);
     if constexpr (std::is_same<ActT, bf16>::value) {
       // bf16 q|k|v straight from the projection epilogue -> tcgen05 attention (attention_tc.cu)
       bf16* qkv16 = reinterpret_cast<bf16*>(d.qkv);
@@ -489,7 +494,7 @@ struct Decoder {
       at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
       // Queries in the padding: their attention output only feeds rows of the residual stream that the block's masked
       // output discards, so whole padded query blocks are skipped (keys / values of padded frames still take part, H1)
-      at.skip_padded_queries = use_ff_tiles ? 1 : 0;
+      at.skip_padded_queries = (use_ff_tiles && ff_fused) ? 1 : 0;
       std::string err;
       cudaError_t ce;
       if (dbg_skip & 4) ce = cudaSuccess; else
@@ -506,16 +511,16 @@ struct Decoder {
       EV_LAUNCH(ctx, s, "attention_dec", attn_flops, (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
     }
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
-    if (use_ff_tiles) {   // out-projection: tiles without a valid row are skipped (same argument; the planner caches one table per level)
+    if (use_ff_tiles && ff_fused) {   // out-projection: tiles without a valid row are skipped (same argument; the planner caches one table per level)
       rag.rows_per_frame = 1; rag.len_shift = shift;
       ctx->rag = rag;
     }
     const int rc_out = run_conv<ActT>(ctx, w.out, d.att, inner, (long long)Tl * inner, B, Tl, eo, s);
-    if (use_ff_tiles) { rag = ctx->rag; ctx->rag = RaggedPlanner(); }
+    if (use_ff_tiles && ff_fused) { rag = ctx->rag; ctx->rag = RaggedPlanner(); }
     EV_TRY(rc_out);
     if constexpr (std::is_same<ActT, bf16>::value) {
       // LayerNorm3 + ff1 + SnakeBeta + ff2 + residual + mask as ONE kernel: the 1024-wide hidden tensor stays on the SM (ff_tc.cu)
-      if (D == 256 && !(dbg_skip & 3) && ff_tc_supported(w.ff1, w.ff2)) {
+      if (ff_fused) {
         FfTcArgs fa;
         fa.x = d.xr; fa.ln_g = w.ln3_g; fa.ln_b = w.ln3_b; fa.eps = 1e-5f; fa.ff1 = &w.ff1; fa.ff2 = &w.ff2;
         fa.snake_a = w.snake_a; fa.snake_invb = w.snake_invb;

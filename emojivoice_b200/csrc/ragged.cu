@@ -49,7 +49,7 @@ const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
   const int m_tiles = ceil_div(M, tile_rows);
   if (m_tiles >= 65536) return nullptr;
   for (int i = 0; i < n_cache; ++i)
-    if (cache[i].rpf == rows_per_frame && cache[i].shift == len_shift && cache[i].tile_rows == tile_rows && cache[i].M == M) return cache[i].table;
+    if (cache[i].rpf == rows_per_frame && cache[i].shift == len_shift && cache[i].tile_rows == tile_rows && cache[i].M == M && cache[i].margin == margin) return cache[i].table;
   const size_t ints = align_up((size_t)B * m_tiles + 1, 64);
   if (n_cache >= 32 || arena_off + ints > arena_ints) return nullptr;
   int* t = arena + arena_off;
@@ -60,7 +60,7 @@ const int* RaggedPlanner::table(int tile_rows, int M, cudaStream_t s) {
   if (ts != s && (cudaEventRecord(ready, ts) != cudaSuccess || cudaStreamWaitEvent(s, ready, 0) != cudaSuccess)) return nullptr;
   arena_off += ints;
   if (launch_counter) ++*launch_counter;
-  cache[n_cache++] = Entry{rows_per_frame, len_shift, tile_rows, M, t};
+  cache[n_cache++] = Entry{rows_per_frame, len_shift, tile_rows, M, margin, t};
   return t;
 }
 

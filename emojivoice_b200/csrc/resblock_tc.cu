@@ -545,13 +545,13 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, Ra
         smem = fixed8 + p.w_slots * G::W_TILE;
       }
       if (p.w_slots >= 1 && (p.resident || p.w_slots >= 4)) {
-        static bool configured2 = false;
-        if (!configured2) {
+        static DeviceOnce once2;
+        cudaError_t ce2 = once2.run([&]() {
           cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
           if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
-          if (ce != cudaSuccess) return ce;
-          configured2 = true;
-        }
+          return ce;
+        });
+        if (ce2 != cudaSuccess) return ce2;
         const int grid = std::min(p.total_tiles, 2 * tc_sm_count());
         // at least a third of the SM's shared memory: a third CTA would not find TMEM columns (2 x 256 are taken)
         if (p.resident && g_rb_wave) return launch_pdl(resblock_tc_kernel<C, 2, true>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
@@ -577,13 +577,13 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, Ra
     smem = fixed16 + slots * G::W_TILE;
   }
   if (p.resident) p.w_slots = 1;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  cudaError_t ce1 = once.run([&]() {
     cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (ce == cudaSuccess && G::BIAS_MMA && G::KC == 1) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-    if (ce != cudaSuccess) return ce;
-    configured = true;
-  }
+    return ce;
+  });
+  if (ce1 != cudaSuccess) return ce1;
   const int grid = std::min(p.total_tiles, tc_sm_count());
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
   if (G::BIAS_MMA && G::KC == 1 && p.resident && g_rb_wave)

@@ -118,17 +118,24 @@ class MatchaTTS:
             def encode(i, o, ws):
                 ctx.check(L.ev_encode(ctx.handle, _lib.ptr(i["x"]), _lib.ptr(i["x_lengths"]), _lib.ptr(i["spks"]), B, Tx,
                                       float(length_scale), _lib.ptr(o.get("spk_emb")), _lib.ptr(o["mu_x"]), _lib.ptr(o["logw"]),
-                                      _lib.ptr(o["w_ceil"]), _lib.ptr(o["y_lengths"]), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                                      _lib.ptr(o["w_ceil"]), _lib.ptr(o["y_lengths"]), _lib.ptr(o["summary"]), _lib.ptr(ws), ws.numel(),
+                                      _lib.stream_ptr()),
                           "ev_encode")
 
             f32, i64 = torch.float32, torch.int64
-            enc_out = {"mu_x": ((B, F, Tx), f32), "logw": ((B, 1, Tx), f32), "w_ceil": ((B, 1, Tx), f32), "y_lengths": ((B,), i64)}
+            enc_out = {"mu_x": ((B, F, Tx), f32), "logw": ((B, 1, Tx), f32), "w_ceil": ((B, 1, Tx), f32), "y_lengths": ((B,), i64),
+                       "summary": ((2,), i64)}
             if S:
                 enc_out["spk_emb"] = ((B, S), f32)
             e = self._run("encode", (B, Tx, float(length_scale)), L.ev_encode_workspace_bytes(ctx.handle, B, Tx),
                           {"x": x, "x_lengths": x_lengths, "spks": spks}, enc_out, encode)
             mu_x, logw, w_ceil, y_lengths, spk_emb = e["mu_x"], e["logw"], e["w_ceil"], e["y_lengths"], e.get("spk_emb")
-            y_max_length = int(y_lengths.max().item())                    # the reference's one host sync (utils/model.py:18)
+            # the reference's one host sync (y_lengths.max(), utils/model.py:18): the library reduced it on the device, together
+            # with the id-range flags (nn.Embedding raises IndexError where the kernels clamp)
+            y_max_length, bad_ids = (int(v) for v in e["summary"].tolist())
+            if bad_ids:
+                raise IndexError("index out of range in self: " + " and ".join(
+                    n for bit, n in ((1, f"token id outside [0, {self.n_vocab})"), (2, f"speaker id outside [0, {self.n_spks})")) if bad_ids & bit))
             T_pad = self.fix_len_compatibility(y_max_length)
             if z is None:
                 z = torch.randn(B, F, T_pad, device=dev)                 # flow_matching.py:51

@@ -92,11 +92,15 @@ EV_API int ev_load_hifigan(ev_ctx* ctx, const ev_tensor* weights, int n_weights,
  * Replaces matcha_tts.py:116-124: spk_emb lookup, TextEncoder.forward (text_encoder.py:378-410),
  * w = exp(logw)*mask, w_ceil = ceil(w)*length_scale, y_lengths = trunc(max(sum(w_ceil),1)).
  *   x (B,Tx) int64, x_lengths (B) int64, spks (B) int64 (ignored when n_spks == 1)
- *   out: spk_emb (B,spk_emb_dim), mu_x (B,n_feats,Tx), logw (B,1,Tx), w_ceil (B,1,Tx), y_lengths (B) int64 */
+ *   out: spk_emb (B,spk_emb_dim), mu_x (B,n_feats,Tx), logw (B,1,Tx), w_ceil (B,1,Tx), y_lengths (B) int64
+ *        summary (2) int64, nullable: [0] = max(y_lengths) -- the one scalar the host reads back to size the
+ *        decoder (y_lengths.max(), utils/model.py:18); [1] = id-range flags (bit 0: a token id of a valid
+ *        position outside [0, n_vocab); bit 1: a speaker id outside [0, n_spks)) -- nn.Embedding raises
+ *        IndexError for those (matcha_tts.py:118, text_encoder.py:397); the library clamps and reports. */
 EV_API size_t ev_encode_workspace_bytes(const ev_ctx* ctx, int B, int Tx);
 EV_API int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths, const int64_t* spks, int B, int Tx,
               float length_scale, float* spk_emb, float* mu_x, float* logw, float* w_ceil, int64_t* y_lengths,
-              void* workspace, size_t workspace_bytes, void* stream);
+              int64_t* summary, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- alignment / length regulator (integer, bit-exact) -----------------------------------------------
  * Replaces matcha_tts.py:129-135: sequence_mask, generate_path (utils/model.py:29-41) and

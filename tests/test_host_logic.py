@@ -60,6 +60,24 @@ def test_emoji_front_end():
     assert ev.emoji_to_spk(txt, order="mapping", default=12)[1] == 107
     assert ev.emoji_to_spk("plain", order="mapping", default=12)[1] == 12
     assert ev.emoji_to_spk("x \U0001F60E", mapping=ev.EMOJI_MAPPING_MALE)[1] == 6
+
+
+def test_emoji_recognition_follows_the_unicode_emoji_property():
+    """`emoji.is_emoji` / `emoji.replace_emoji` semantics (feel_me.py:298-312): plain arrows, maths and technical symbols, digits
+    and stand-alone joiners are NOT emoji and stay in the text; whole sequences (ZWJ families, flags, keycaps, skin tones,
+    text-presentation emoji with VS16) are removed as one unit."""
+    from emojivoice_b200.emoji_frontend import is_emoji, replace_emoji
+
+    for ch in "\u2192\u2191\u2193\u2200\u2211\u2318\u23000123456789#*\u200d\ufe0f\u20e3\U0001F1E8a ":
+        assert not is_emoji(ch), hex(ord(ch))
+    for ch in "\u2194\u21a9\u00a9\u00ae\u2122\u231a\u2600\u2764\u2b50\u3030\U0001F600\U0001F984\U0001F3FD\U0001FAE0":
+        assert is_emoji(ch), hex(ord(ch))
+    assert all(is_emoji(k) for k in list(ev.EMOJI_MAPPING_FEMALE) + list(ev.EMOJI_MAPPING_MALE))
+    assert not is_emoji("\U0001F600\U0001F600")                      # the apps pass single characters
+    txt = "a \u2192 b \U0001F468\u200d\U0001F469\u200d\U0001F467 c 5\ufe0f\u20e3 d \u20e3 e \U0001F1E8\U0001F1E6 f \U0001F44D\U0001F3FD g\ufe0f \u2639\ufe0f 7"
+    assert replace_emoji(txt) == "a \u2192 b  c  d \u20e3 e  f  g\ufe0f  7"
+    assert replace_emoji("x\U0001F600y", "_") == "x_y"
+    assert ev.emoji_to_spk("go \u2192 there \U0001F60D")[0] == "go \u2192 there "
     assert ev.intersperse([5, 6, 7]) == [0, 5, 0, 6, 0, 7, 0]
 
 
