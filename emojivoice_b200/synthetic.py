@@ -219,6 +219,21 @@ def phoneme_batch(batch: int, p_lo: int, p_hi: int, seed: int, n_vocab: int = 17
     return torch.from_numpy(x), torch.from_numpy(lens.astype(np.int64)), torch.from_numpy(spk)
 
 
+def mixed_length_corpus(n: int = 1024, p_lo: int = 20, p_hi: int = 150, seed: int = 1237, n_vocab: int = 178, speakers=None):
+    """BASELINE.json configs[2]: `n` mixed-length utterances (P ~ U[p_lo, p_hi] phonemes, Tx = 2P + 1 blank-interspersed ids,
+    about 1.5-12 s of speech each at length_scale 0.8) cycling through the 11 emoji voices.  -> list of (ids, speaker id),
+    the input format of `synthesise_corpus` (cli.py:277-317 feeds the same pairs from a text file)."""
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), 33]))
+    speakers = list(speakers or EMOJI_MAPPING_FEMALE.values())
+    utts = []
+    for i in range(n):
+        p = int(rng.integers(p_lo, p_hi + 1))
+        ids = [0] * (2 * p + 1)
+        ids[1::2] = rng.integers(1, n_vocab, size=p).tolist()
+        utts.append((ids, int(speakers[i % len(speakers)])))
+    return utts
+
+
 def prior_noise(batch: int, n_feats: int, t_pad: int, seed: int) -> torch.Tensor:
     """The injected prior-noise tensor z (B, n_feats, T_pad), before temperature scaling (flow_matching.py:51)."""
     rng = np.random.Generator(np.random.Philox(key=[int(seed), 99]))

@@ -184,11 +184,10 @@ def _near_tie_tokens(ref):
 
 
 def _check_synthesise(out, ref, tol):
-    if not torch.equal(out["w_ceil"].cpu(), ref["w_ceil"]):
-        # ceil(exp(logw)) may only flip where the oracle's own duration sits within 1e-4 of an integer
-        diff = out["w_ceil"].cpu() != ref["w_ceil"]
-        assert bool((diff & ~_near_tie_tokens(ref)).sum() == 0), "duration mismatch away from a near-tie"
-        pytest.skip("near-tie duration flip: batch composition differs from the oracle's, compare another seed")
+    # durations are bit-exact.  (ceil(exp(logw)) could only flip where the oracle's own duration sits within 1e-4 of an
+    # integer; none of the fixtures / seeds used here holds such a token -- a mismatch is a failure, not a skip.)
+    assert torch.equal(out["w_ceil"].cpu(), ref["w_ceil"]), \
+        f"duration mismatch ({int((out['w_ceil'].cpu() != ref['w_ceil']).sum())} tokens, {int(_near_tie_tokens(ref).sum())} near-ties in the batch)"
     assert out["mel_lengths"].cpu().tolist() == ref["mel_lengths"].tolist()
     assert torch.equal(out["attn"].cpu(), ref["attn"])
     assert rel_l2(out["encoder_outputs"].cpu(), ref["encoder_outputs"]) < 2e-5
@@ -240,13 +239,17 @@ def test_bf16_mel_cepstral_distortion_is_reported_and_small(matcha, matcha_sd, c
 
 @pytest.mark.parametrize("ls", [0.8, 0.9, 1.0, 1.1, 1.2])
 def test_durations_and_alignment_bit_exact_over_length_scales(matcha, matcha_sd, ls):
-    x, xl, spk = synthetic.phoneme_batch(8, 2, 60, seed=int(ls * 100))
-    ref = mo.synthesise(matcha_sd, VCTK, x, xl, 1, 0.667, spk, ls)
+    # A batch whose oracle durations hold a near-tie token (|w - round(w)| < 1e-4, SURVEY H2a: the one place where a last-ulp
+    # difference of exp() may legitimately flip a ceil) is replaced by the next seed instead of being skipped.
+    for seed in range(int(ls * 100), int(ls * 100) + 5000, 1000):
+        x, xl, spk = synthetic.phoneme_batch(8, 2, 60, seed=seed)
+        ref = mo.synthesise(matcha_sd, VCTK, x, xl, 1, 0.667, spk, ls)
+        if not bool(_near_tie_tokens(ref).any()):
+            break
+    else:
+        raise AssertionError("no near-tie-free batch among 5 seeds")
     out = matcha.synthesise(x, xl, 1, 0.667, spk, ls, z=torch.zeros(8, 80, ref["t_pad"]), dtype="fp32")
-    if not torch.equal(out["w_ceil"].cpu(), ref["w_ceil"]):
-        diff = out["w_ceil"].cpu() != ref["w_ceil"]
-        assert bool((diff & ~_near_tie_tokens(ref)).sum() == 0)
-        pytest.skip("near-tie duration flip")
+    assert torch.equal(out["w_ceil"].cpu(), ref["w_ceil"])
     assert out["mel_lengths"].cpu().tolist() == ref["mel_lengths"].tolist()
     assert out["t_pad"] == ref["t_pad"]
     assert torch.equal(out["attn"].cpu(), ref["attn"])
@@ -433,7 +436,7 @@ def test_end_to_end_emoji_text_to_waveform(matcha, matcha_sd, vocoders):
         finally:
             gen.precision = "bf16"
         assert wav.shape == ref_wav.shape
-        assert rel_l2(wav, ref_wav) < 2 * TOL[prec]
+        assert rel_l2(wav, ref_wav) < TOL[prec]
 
 
 def test_corpus_driver_matches_oracle_on_identical_microbatches(matcha_sd, vocoders):
@@ -522,7 +525,7 @@ def test_full_size_batch_properties_and_anchor_items(matcha, matcha_sd, vocoders
     wavs = [gen(out32["mel"], dtype="bf16") for _ in range(3)]
     assert torch.equal(wavs[0], wavs[2])
     assert wav32.shape == (32, 1, 256 * out32["mel"].shape[2])
-    assert rel_l2(wavs[2].cpu(), wav32.cpu()) < 2 * TOL["bf16"]
+    assert rel_l2(wavs[2].cpu(), wav32.cpu()) < TOL["bf16"]
     ref_wav = ho.generator(hsd, HIFIGAN_V1, out32["mel"].cpu()[sel[:1]])
     assert rel_l2(wav32.cpu()[sel[:1]], ref_wav) < 1e-4
 
