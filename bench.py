@@ -7,12 +7,15 @@ A "step" is one pass of the hot path over one batch: MatchaTTS.synthesise(x, x_l
 temperature=0.667, spks=emoji ids, length_scale=0.8) followed by vocoder(mel).clamp(-1, 1), on BASELINE.json
 configs[1] (batch 32 emoji-tagged utterances of ~5 s, bf16, random-init VCTK Matcha-TTS + HiFi-GAN v1).
 For N > 1 the driver launches one rank per GPU with torch.distributed.run; utterances shard by batch, every
-rank synthesises its own 32 utterances (weak scaling), no collective on the data path.
+rank synthesises the same 32-utterance batch (weak scaling: identical work per GPU), no collective on the data path.
 
 One JSON line is printed by rank 0 (see the task contract): `value` is measured with the inputs resident in HBM,
 `e2e` through the same public API with pinned HOST inputs and the waveform read back, `roofline` for the dominant
-kernel from a CUDA-event-instrumented step, `cpu_baseline` = the CPU oracle (a port of the reference's PyTorch
-path) timed on this box's host cores on a bounded sample.
+kernel class (plus `rooflines` per stage) from a CUDA-event-instrumented step, `cpu_baseline` = the reference's own CPU
+PyTorch path (the unmodified files staged under baseline/_ref, else the oracle port) timed on this box's host cores on a
+bounded sample.  Further blocks: `padded_vocoder` (the reference's literal work list, with its own e2e), `denoiser`,
+`config3` (BASELINE configs[2]: 1024 mixed-length utterances sharded over the N ranks through synthesise_corpus, strong
+scaling, wall clock incl. D2H + crop, cold = never-seen shapes and warm) and `config5` (vocoder only, 60-s segments).
 """
 from __future__ import annotations
 
@@ -33,7 +36,7 @@ if ROOT not in sys.path:
 SR, HOP = 22050, 256
 N_TIMESTEPS, TEMPERATURE, LENGTH_SCALE = 10, 0.667, 0.8      # feel_me.py:71-77 (the operating point of every app)
 BATCH, P_LO, P_HI = 32, 60, 90                                # Tx = 2P+1 in [121, 181]
-CPU_SAMPLE = 8                                                # utterances of the batch the CPU baseline synthesises (~3 s of CPU work per pass)
+CPU_SAMPLE = 8                                                # utterances the `cpu_baseline` leg / reference warm-up synthesise (~4.5 s per pass)
 
 
 def load_peaks():
@@ -90,12 +93,19 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
+TRAFFIC_FILE = ["r02_launch_summary.json"]
+
+
 def measured_traffic(kernel_class: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu launch list of this same command
-    (profiles/r01_launch_summary.json, written by scripts/ncu_launch_summary.py); None when no capture is committed."""
+    """DRAM bytes per launch of a kernel function from the committed ncu launch list of this same command
+    (profiles/r02_launch_summary.json -- r01 when this round's capture is not there yet -- written by
+    scripts/ncu_launch_summary.py); None when no capture is committed."""
     import re
 
-    path = os.path.join(ROOT, "profiles", "r01_launch_summary.json")
+    path = os.path.join(ROOT, "profiles", TRAFFIC_FILE[0])
+    if not os.path.exists(path):
+        TRAFFIC_FILE[0] = "r01_launch_summary.json"
+        path = os.path.join(ROOT, "profiles", TRAFFIC_FILE[0])
     if not os.path.exists(path):
         return None, None
     k = json.load(open(path))["kernels"]
@@ -115,53 +125,75 @@ def audio_seconds(mel_lengths) -> float:
     return float(mel_lengths.sum()) * HOP / SR
 
 
-def cpu_oracle_rate(x, xl, spks, n_utts, repeats=2):
-    """The reference's CPU PyTorch path (restated in oracle/) on the first n_utts utterances, all host threads."""
-    from emojivoice_b200 import synthetic
-    from emojivoice_b200.config import HIFIGAN_V1, VCTK
-    from oracle import hifigan_oracle as ho
-    from oracle import matcha_oracle as mo
+class CpuArm:
+    """The reference's CPU PyTorch implementation of the path on this box's host cores, all host threads:
+    kind "reference" = the reference's UNMODIFIED files (staged under baseline/_ref by scripts/install_reference.py, or
+    /root/reference in the build container) driven through oracle/reference_shim.py -- MatchaTTS.synthesise(...) then
+    Generator(mel).clamp(-1, 1) exactly as feel_me.py:193-200,183 calls them; kind "port" = the oracle's restatement, only
+    when no copy of the reference travelled."""
 
-    torch.set_num_threads(os.cpu_count() or 1)
-    sd = synthetic.matcha_state_dict(VCTK, seed=1234)
-    hsd = synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321)
-    n = min(n_utts, x.shape[0])
-    xs, ls, ss = x[:n, : int(xl[:n].max())].contiguous(), xl[:n], spks[:n]
+    def __init__(self):
+        from emojivoice_b200 import synthetic
+        from emojivoice_b200.config import HIFIGAN_V1, VCTK
+        from oracle import reference_shim as shim
 
-    def once():
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        sd = synthetic.matcha_state_dict(VCTK, seed=1234)
+        hsd = synthetic.hifigan_state_dict(HIFIGAN_V1, seed=4321)
+        if shim.available():
+            self.kind, self.src = "reference", shim.REFERENCE_ROOT
+            self.model, self.voc = shim.build_matcha(VCTK, sd), shim.build_hifigan(HIFIGAN_V1, hsd)
+        else:
+            from oracle import hifigan_oracle as ho
+            from oracle import matcha_oracle as mo
+
+            self.kind, self.src = "port", "oracle/"
+            self.model = lambda x, xl, n, t, s, ls: mo.synthesise(sd, VCTK, x, xl, n, t, s, ls)
+            self.voc = lambda mel: ho.generator(hsd, HIFIGAN_V1, mel)
+
+    @torch.inference_mode()
+    def once(self, x, xl, spks, n_utts=None):
+        """One pass over the first n_utts utterances (all when None) -> (audio seconds, wall seconds)."""
+        n = x.shape[0] if n_utts is None else min(n_utts, x.shape[0])
+        xs, ls, ss = x[:n, : int(xl[:n].max())].contiguous(), xl[:n], spks[:n]
         t0 = time.perf_counter()
-        out = mo.synthesise(sd, VCTK, xs, ls, N_TIMESTEPS, TEMPERATURE, ss, LENGTH_SCALE)
-        wav = ho.generator(hsd, HIFIGAN_V1, out["mel"]).clamp(-1, 1)
+        if self.kind == "reference":
+            out = self.model.synthesise(xs, ls, n_timesteps=N_TIMESTEPS, temperature=TEMPERATURE, spks=ss, length_scale=LENGTH_SCALE)
+        else:
+            out = self.model(xs, ls, N_TIMESTEPS, TEMPERATURE, ss, LENGTH_SCALE)
+        wav = self.voc(out["mel"]).clamp(-1, 1)
         dt = time.perf_counter() - t0
-        return audio_seconds(out["mel_lengths"]), dt, wav
-
-    return once, n
+        assert wav.shape[-1] == out["mel"].shape[-1] * HOP
+        return audio_seconds(out["mel_lengths"]), dt
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the python reference cannot
-    travel to the GPU box), all host threads, each step a bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU implementation of the path, all host threads, on the SAME workload as our arm:
+    every timed step synthesises the whole 32-utterance batch (about 19 s of CPU work); the W warm-up steps run the first
+    CPU_SAMPLE utterances only, so the default K = 20 finishes in about 6.5 minutes."""
     if rank != 0:
         return
     from emojivoice_b200 import synthetic
 
     x, xl, spks = synthetic.phoneme_batch(BATCH, P_LO, P_HI, seed=2000)
-    once, n = cpu_oracle_rate(x, xl, spks, CPU_SAMPLE)
+    arm = CpuArm()
     for _ in range(args.warmup):
-        once()
+        arm.once(x, xl, spks, CPU_SAMPLE)
     t0 = time.perf_counter()
     secs = 0.0
     for _ in range(args.steps):
-        a, _, _ = once()
+        a, _ = arm.once(x, xl, spks)
         secs += a
     dt = time.perf_counter() - t0
     val = secs / dt
-    sample = f"first {n} utterances of the batch per step ({secs / args.steps:.1f} audio-s), fp32, torch CPU"
+    sample = (f"all {BATCH} utterances of the batch per timed step ({secs / args.steps:.1f} audio-s), fp32 torch CPU, "
+              f"{arm.kind} ({arm.src}); warm-up steps: first {CPU_SAMPLE} utterances")
     print(json.dumps({
         "impl": "reference", "metric": "audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(),
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "rtf": 1.0 / val}))
 
@@ -173,6 +205,23 @@ def workload_config():
             "tokens_per_utt": f"2P+1, P~U[{P_LO},{P_HI}]", "speakers": "11 emoji voices (feel_me.py:84-96)"}
 
 
+def roofline_of(a, peaks, ksum):
+    """Roofline entry of one kernel class of the instrumented step (algorithmic FLOPs / bytes of the valid, un-padded work)."""
+    sec = a["total_ms"] / 1e3
+    ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+    ai = a["flops"] / max(a["bytes"], 1.0)
+    if a["flops"] > 0 and ai >= ridge:
+        ach, peak, unit, bound = a["flops"] / sec / 1e12, peaks["tflops"], "TFLOP/s", "tensor"
+    else:
+        ach, peak, unit, bound = a["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+    n = max(a["launches"], 1)
+    return {"kernel": a["name"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit, "frac": round(ach / peak, 4),
+            "traffic": None, "launches": a["launches"], "algorithmic_bytes_per_launch": round(a["bytes"] / n),
+            "algorithmic_flops_per_launch": round(a["flops"] / n), "avg_launch_us": round(a["total_ms"] * 1e3 / n, 2),
+            "share_of_step": round(a["total_ms"] / ksum, 4), "arith_intensity": round(ai, 1),
+            "tflops": round(a["flops"] / sec / 1e12, 2) if sec else 0.0}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,6 +230,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config5 / denoiser blocks (headline numbers only)")
     ap.add_argument("--dense-vocoder", action="store_true",
                     help="vocode the padded frames of every utterance too (the default skips the time tiles past each utterance's "
                          "own length: identical waveform on [: length*256], zero beyond -- what cli.py:307-311 crops away)")
@@ -193,8 +243,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.warmup < 3:
-        args.warmup = 3
+    n_warm_min = max(args.warmup, 3)                             # the contract's floor; the JSON line echoes the requested value
 
     import torch.distributed as dist
 
@@ -215,6 +264,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return t.tolist()
+
+    MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM)
+
     model = ev.MatchaTTS(**VCTK.constructor_kwargs(), device=dev, precision=args.precision).eval()
     model.load_state_dict(synthetic.matcha_state_dict(VCTK, seed=1234))
     voc = ev.Generator(HIFIGAN_V1, device=dev, precision=args.precision)
@@ -222,8 +279,9 @@ def main():
     voc.eval()
     voc.remove_weight_norm()
 
-    # every rank synthesises its own batch (weak scaling); same distribution, different seed
-    x, xl, spks = synthetic.phoneme_batch(BATCH, P_LO, P_HI, seed=2000 + rank)
+    # weak scaling: every rank synthesises the SAME 32-utterance batch (identical work per GPU, so the per-N values are
+    # comparable; round 1 drew a different batch per rank and rank 0's happened to be the heaviest)
+    x, xl, spks = synthetic.phoneme_batch(BATCH, P_LO, P_HI, seed=2000)
     x_pin, xl_pin, spk_pin = x.pin_memory(), xl.pin_memory(), spks.pin_memory()
     x_dev, xl_dev, spk_dev = x.to(dev), xl.to(dev), spks.to(dev)
 
@@ -253,20 +311,33 @@ def main():
         torch.cuda.current_stream().synchronize()
         return out, wav
 
-    # warm-up: W steps at least (graphs are captured on the second sight of a shape), then keep stepping until the
-    # per-step wall time has settled (a freshly booted box stalls the host for 100s of ms now and then) or 15 s passed
-    t_w0, recent = time.perf_counter(), []
-    n_warm = 0
-    while True:
-        t_s = time.perf_counter()
-        out, wav = step_resident()
-        torch.cuda.synchronize()
-        recent.append(time.perf_counter() - t_s)
-        n_warm += 1
-        if n_warm >= max(args.warmup, 4):
-            last = recent[-6:]
-            if (len(last) >= 6 and max(last) < 1.15 * min(last)) or time.perf_counter() - t_w0 > 15.0:
-                break
+    def settle(fn, floor, window, cap_s=15.0, cap_n=60):
+        """Run fn until the last `window` per-step wall times agree within 15 % (a freshly booted box stalls the host for
+        100s of ms now and then), at least `floor` times."""
+        t0, recent = time.perf_counter(), []
+        while True:
+            t_s = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            recent.append(time.perf_counter() - t_s)
+            last = recent[-window:]
+            if len(recent) >= floor and ((len(last) >= window and max(last) < 1.15 * min(last)) or
+                                         time.perf_counter() - t0 > cap_s or len(recent) >= cap_n):
+                return res, len(recent)
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream -> ms (this rank)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # warm-up: W steps at least (graphs are captured on the second sight of a shape), then until the step time has settled
+    (out, wav), n_warm = settle(step_resident, max(n_warm_min, 4), 6)
     secs_per_step = audio_seconds(out["mel_lengths"].cpu())
     frames = int(out["mel_lengths"].sum())
     t_pad = int(out["t_pad"])
@@ -286,68 +357,52 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     model.launch_count(reset=True); voc.launch_count(reset=True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(step_resident, args.steps)
     launches = model.launch_count() + voc.launch_count()
     clocks = sampler.stop()
 
-    # ---------------- the same K steps with the padded frames vocoded too (reference-identical waveform everywhere)
-    ms_dense = None
+    # ---------------- e2e: same steps through the public API with pinned host inputs and the waveform read back
+    settle(step_e2e, 4, 4, cap_n=40)
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # ---------------- the same with the padded frames vocoded too: the reference's literal work list (vocoder(mel), no kwarg)
+    ms_dense = ms_e2e_dense = None
     if ragged[0]:
         ragged[0] = False
         for _ in range(3):
             step_resident()
-        barrier()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        d0.record()
-        for _ in range(args.steps):
-            step_resident()
-        d1.record()
-        barrier()
-        ms_dense = d0.elapsed_time(d1)
+        ms_dense = timed(step_resident, args.steps)
+        settle(step_e2e, 3, 3, cap_n=20)
+        ms_e2e_dense = timed(step_e2e, args.steps)
         ragged[0] = True
 
-    # ---------------- e2e: same steps through the public API with pinned host inputs and the waveform read back
-    recent = []
-    while True:                                                  # settle like the warm-up above
-        t_s = time.perf_counter()
-        step_e2e()
-        recent.append(time.perf_counter() - t_s)
-        last = recent[-4:]
-        if (len(recent) >= 4 and max(last) < 1.15 * min(last)) or len(recent) >= 40:
-            break
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
-        step_e2e()
-    f1.record()
-    barrier()
-    ms_e2e = f0.elapsed_time(f1)
-
-    tt = torch.tensor([ms, ms_e2e, -secs_per_step, ms_dense or 0.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)                # slowest rank bounds the job
-        tot = torch.tensor([secs_per_step, float(launches)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        total_secs, launches = float(tot[0]), int(tot[1])
-    else:
-        total_secs = secs_per_step
-    ms, ms_e2e = float(tt[0]), float(tt[1])
-    ms_dense = float(tt[3]) if ms_dense is not None else None
-    value = total_secs * args.steps / (ms / 1e3)
-    value_e2e = total_secs * args.steps / (ms_e2e / 1e3)
+    red = reduce([ms, ms_e2e, ms_dense or 0.0, ms_e2e_dense or 0.0], MAX)        # the slowest rank bounds the job
+    ms, ms_e2e = red[0], red[1]
+    ms_dense, ms_e2e_dense = (red[2], red[3]) if ms_dense is not None else (None, None)
+    total_secs, launches = reduce([secs_per_step, float(launches)], SUM)
+    launches = int(launches)
+    per_s = lambda t_ms: total_secs * args.steps / (t_ms / 1e3)
+    value, value_e2e = per_s(ms), per_s(ms_e2e)
     h2d = x.numel() * 8 + xl.numel() * 8 + spks.numel() * 8
     d2h = int(wav.numel()) * 4 + BATCH * 8
-
-    # ---------------- roofline of the dominant kernel: one more step with CUDA events around every launch
     peaks = load_peaks()
+
+    # ---------------- denoiser (hifigan/denoiser.py:59-64; every app calls it after the vocoder, feel_me.py:183-185)
+    denoiser_block = None
+    if not args.no_extras:
+        den = ev.Denoiser(voc, mode="zeros")
+        wav_d = voc(out["mel"]).clamp(-1, 1).squeeze(1)          # the denoiser needs the dense waveform (STFT windows reach into the padding)
+        for _ in range(3):
+            den(wav_d, strength=0.00025)
+        ms_den = reduce([timed(lambda: den(wav_d, strength=0.00025), args.steps)], MAX)[0] / args.steps
+        den_bytes = 8.0 * wav_d.numel()                          # algorithmic: read the waveform once, write it once
+        denoiser_block = {"ms_per_step": round(ms_den, 3), "samples": int(wav_d.numel()), "algorithmic_bytes": int(den_bytes),
+                          "gbs": round(den_bytes / (ms_den / 1e3) / 1e9, 1), "frac_of_hbm_peak": round(den_bytes / (ms_den / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
+                          "share_of_step": round(ms_den / (ms_dense / args.steps + ms_den), 4) if ms_dense else None,
+                          "what": "Denoiser(vocoder)(audio, 0.00025) on the batch's dense waveform: STFT (1024/256 hann) -> magnitude - bias*strength -> ISTFT"}
+        del wav_d
+
+    # ---------------- roofline: one more step with CUDA events around every launch
     model.cuda_graphs = voc.cuda_graphs = False                  # per-launch events need eager launches, not a graph replay
     model._ctx.profile_begin(); voc._ctx.profile_begin()
     step_resident()
@@ -361,79 +416,105 @@ def main():
     klist = sorted(agg.values(), key=lambda a: -a["total_ms"])
     ksum = sum(a["total_ms"] for a in klist) or 1.0
     table = []
-    for a in klist[:10]:
+    for a in klist[:12]:
         sec = a["total_ms"] / 1e3
         table.append({"name": a["name"], "launches": a["launches"], "ms": round(a["total_ms"], 3),
                       "share": round(a["total_ms"] / ksum, 4), "tflops": round(a["flops"] / sec / 1e12, 2) if sec else 0,
                       "gbs": round(a["bytes"] / sec / 1e9, 1) if sec else 0})
-    # dominant kernel = the __global__ function with the largest share of the step (classes "fn/stage" share a function)
-    byfn = {}
-    for a in klist:
-        f = byfn.setdefault(a["name"].split("/")[0], dict(name=a["name"].split("/")[0], launches=0, total_ms=0.0, flops=0.0, bytes=0.0))
-        for k in ("launches", "total_ms", "flops", "bytes"):
-            f[k] += a[k]
-    top = max(byfn.values(), key=lambda a: a["total_ms"])
-    sec = top["total_ms"] / 1e3
-    ridge = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
-    ai = top["flops"] / max(top["bytes"], 1.0)
-    if top["flops"] > 0 and ai >= ridge:
-        ach, peak, unit, bound = top["flops"] / sec / 1e12, peaks["tflops"], "TFLOP/s", "tensor"
-    else:
-        ach, peak, unit, bound = top["bytes"] / sec / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
-    roofline = {"kernel": top["name"], "bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
-                "frac": round(ach / peak, 4), "traffic": None, "launches": top["launches"],
-                "algorithmic_bytes_per_launch": round(top["bytes"] / max(top["launches"], 1)),
-                "algorithmic_flops_per_launch": round(top["flops"] / max(top["launches"], 1)),
-                "avg_launch_us": round(top["total_ms"] * 1e3 / max(top["launches"], 1), 2),
-                "share_of_step": round(top["total_ms"] / ksum, 4), "arith_intensity": round(ai, 1),
-                "peak_source": peaks["source"], "how": "CUDA events around every launch on the launching stream, one "
-                "instrumented step right after the timed region; algorithmic FLOPs/bytes (valid un-padded work)"}
-    tr, tr_fn = measured_traffic(top["name"])
-    if tr is not None:
-        roofline["traffic"] = round(tr)
-        roofline["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of %s, averaged over the launches of one "
-                                      "bench step (profiles/r01_launch_summary.json, ncu --clock-control none)" % tr_fn)
+    # one roofline per kernel CLASS = (__global__ function, stage): the decoder's and the vocoder's launches of the same conv
+    # function are different populations (small latency-bound tiles vs long MMA-bound ones) and are reported separately;
+    # `roofline` is the class with the largest share of the step
+    rooflines = [roofline_of(a, peaks, ksum) for a in klist if a["total_ms"] / ksum >= 0.02]
+    how = ("CUDA events around every launch on the launching stream, one instrumented (eager) step right after the timed region; "
+           "algorithmic FLOPs/bytes (valid un-padded work)")
+    for r in rooflines:
+        tr, tr_fn = measured_traffic(r["kernel"])
+        if tr is not None:
+            r["traffic"] = round(tr)
+            r["traffic_source"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch of %s, averaged over its launches in one bench step "
+                                   "(profiles/%s, ncu --clock-control none)" % (tr_fn, TRAFFIC_FILE[0]))
+    roofline = dict(rooflines[0], peak_source=peaks["source"], how=how)
     # whole-path algorithmic FLOPs as a fraction of the tensor roofline
     tx = xl.double()
     flops_step = float((tx * (19309056 + 6144 * tx)).sum()) + 0.0
     ml = out["mel_lengths"].double().cpu()
     flops_step += float((N_TIMESTEPS * ml * (11116544 + 1536 * ml)).sum()) + float((ml * 614105088).sum())
-    path_tflops = flops_step * args.steps / (ms / 1e3) / 1e12 * (world if world > 1 else 1)
+    path_tflops = flops_step * args.steps / (ms / 1e3) / 1e12 * world
+
+    # ---------------- BASELINE configs[2]: 1024 mixed-length utterances, sharded over the ranks (strong scaling)
+    config3 = config5 = None
+    if not args.no_extras:
+        utts = synthetic.mixed_length_corpus(1024)
+        passes = []
+        for rep in range(4):
+            barrier()
+            t0 = time.perf_counter()
+            res, st = ev.synthesise_corpus(model, voc, utts, batch_size=32, n_timesteps=N_TIMESTEPS, temperature=TEMPERATURE,
+                                           length_scale=LENGTH_SCALE, rank=rank, world_size=world)
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            wall_max, dev_max = reduce([wall, st.seconds], MAX)
+            secs3, n3 = reduce([st.audio_seconds, float(len(res))], SUM)
+            passes.append({"pass": rep, "wall_s": round(wall_max, 3), "audio_s_per_s_wall": round(secs3 / wall_max, 1),
+                           "audio_s_per_s_device": round(secs3 / dev_max, 1)})
+            del res
+        config3 = {"workload": "BASELINE.json configs[2]: 1024 mixed-length utterances (P~U[20,150]), 11 emoji voices, micro-batches of 32 "
+                               "sorted by length, dealt to the ranks by estimated FLOPs (sharding.shard), synthesise_corpus: "
+                               "collate -> synthesise -> ragged vocoder -> pinned D2H on a copy stream -> per-utterance crop",
+                   "scaling": "strong", "utterances": int(n3), "audio_seconds": round(secs3, 1), "n_gpus": world,
+                   "timing": "host wall clock around the whole call incl. D2H + crop, max over ranks (pass 0 = shapes never seen before)",
+                   "passes": passes, "value_first_pass": passes[0]["audio_s_per_s_wall"], "value_warm": passes[-1]["audio_s_per_s_wall"]}
+        # ---------------- BASELINE configs[4]: vocoder only, 60-second segments (T = 5168 frames), 4 segments per GPU
+        T5 = int(round(60 * SR / HOP))
+        mel5 = synthetic.synthetic_mel(4, T5, seed=5).to(dev)
+        for _ in range(3):
+            voc(mel5)
+        ms5 = reduce([timed(lambda: voc(mel5), 10)], MAX)[0] / 10
+        secs5 = 4 * T5 * HOP / SR
+        config5 = {"workload": "BASELINE.json configs[4]: HiFi-GAN only, synthetic 80-bin mel, 4 x 60-s segments per GPU (T = 5168)",
+                   "scaling": "weak", "n_gpus": world, "ms_per_step": round(ms5, 3), "value": round(world * secs5 / (ms5 / 1e3), 1),
+                   "unit": "audio-s/s", "tflops_per_gpu": round(4 * T5 * 614105088 / (ms5 / 1e3) / 1e12, 1)}
+        del mel5
 
     result = {
         "metric": "audio_seconds_per_second", "value": round(value, 2), "unit": "audio-s/s", "n_gpus": world,
-        "steps": args.steps, "warmup": n_warm, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
         "data": "synthetic",
-        "config": dict(workload_config(), audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames,
-                       t_pad=t_pad, l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
-                       "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
-                       launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up)",
-                       vocoder=("ragged: time tiles past each utterance's own length (+ the receptive field behind each layer: 13 frames at conv_pre ... 2 at the last stage) are "
-                                "not computed; waveform bit-identical to the dense generator on [: mel_length*256] and zero beyond "
-                                "-- the part the reference's batched caller crops away (cli.py:307-311); `padded_vocoder` is the "
-                                "same run with the padded frames vocoded too") if not args.dense_vocoder else "dense (padded frames vocoded too)"),
+        "config": workload_config(),
+        "details": dict(audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames, t_pad=t_pad,
+                        warmup_steps_run=n_warm, per_rank_batch="identical on every rank (seed 2000)",
+                        l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
+                        "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
+                        launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up)",
+                        vocoder=("ragged: time tiles past each utterance's own length (+ the receptive field behind each layer: 13 frames at conv_pre ... 2 at the last stage) are "
+                                 "not computed; waveform bit-identical to the dense generator on [: mel_length*256] and zero beyond "
+                                 "-- the part the reference's batched caller crops away (cli.py:307-311); `padded_vocoder` is the "
+                                 "same run with the padded frames vocoded too") if not args.dense_vocoder else "dense (padded frames vocoded too)"),
         "rtf": round(1.0 / value, 8), "x_realtime": round(value, 1),
         "clocks": clocks,
         "e2e": {"value": round(value_e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
-        "padded_vocoder": ({"value": round(total_secs * args.steps / (ms_dense / 1e3), 2), "unit": "audio-s/s",
-                            "ms_per_step": round(ms_dense / args.steps, 3)} if ms_dense else None),
-        "roofline": roofline,
+        "padded_vocoder": ({"value": round(per_s(ms_dense), 2), "unit": "audio-s/s", "ms_per_step": round(ms_dense / args.steps, 3),
+                            "e2e": {"value": round(per_s(ms_e2e_dense), 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e_dense / args.steps, 3)},
+                            "what": "vocoder(mel) without the `lengths` kwarg: the reference's literal work list (padded frames vocoded, cropped afterwards)"}
+                           if ms_dense else None),
+        "roofline": roofline, "rooflines": rooflines,
         "path_tflops": round(path_tflops, 2), "path_frac_of_tensor_peak": round(path_tflops / (peaks["tflops"] * world), 4),
-        "kernels": table,
+        "kernels": table, "denoiser": denoiser_block, "config3": config3, "config5": config5,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        once, n = cpu_oracle_rate(x, xl, spks, CPU_SAMPLE)
-        once()
+        arm = CpuArm()
+        arm.once(x, xl, spks, CPU_SAMPLE)
         best = None
         for _ in range(3):
-            a, dt, _ = once()
+            a, dt = arm.once(x, xl, spks, CPU_SAMPLE)
             best = (a, dt) if best is None or dt < best[1] else best
-        result["cpu_baseline"] = {"value": round(best[0] / best[1], 3), "unit": "audio-s/s", "cores": torch.get_num_threads(),
-                                  "kind": "port", "sample": f"first {n} utterances of the batch ({best[0]:.1f} audio-s), fp32 "
-                                  f"torch CPU oracle, warm-up 1, best of 3, {os.cpu_count()} host cpus"}
+        result["cpu_baseline"] = {"value": round(best[0] / best[1], 3), "unit": "audio-s/s", "cores": arm.cores, "kind": arm.kind,
+                                  "sample": f"first {CPU_SAMPLE} utterances of the batch ({best[0]:.1f} audio-s), fp32 torch CPU, "
+                                  f"{arm.kind} ({arm.src}), warm-up 1, best of 3, {os.cpu_count()} host cpus"}
     elif rank == 0:
         result["cpu_baseline"] = None
     if rank == 0:

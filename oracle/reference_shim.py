@@ -4,8 +4,9 @@ Test infrastructure only.  The reference cannot be imported as-is: it pulls ligh
 conformer, matplotlib, phonemizer ... none of which are installed.  This module installs
 inert stand-ins for those packages in `sys.modules` -- plus a restatement of the four diffusers==0.25.0
 symbols the hot path touches -- and then imports `matcha.models.matcha_tts`, `matcha.hifigan.*` from where
-they lie.  Nothing is copied into this repository.  It is used by scripts/make_golden.py (which writes
-tests/golden/) and tests/test_oracle_vs_reference.py; both skip when /root/reference is absent (GPU box).
+they lie.  Nothing is copied into this repository's history.  It is used by scripts/make_golden.py (which writes
+tests/golden/), tests/test_oracle_vs_reference.py and the CPU arms of bench.py (`--impl reference`, `cpu_baseline`), which
+on the GPU box find the staged copy of the same files under baseline/_ref/ (scripts/install_reference.py).
 """
 from __future__ import annotations
 
@@ -18,7 +19,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("EMOJIVOICE_REFERENCE", "/root/reference")
+def _find_root():
+    """EMOJIVOICE_REFERENCE, else the read-only tree of the build container, else the staged copy of the path's files that
+    scripts/install_reference.py puts under baseline/_ref/ (git-ignored; it travels to the GPU box with gpurun)."""
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    for cand in (os.environ.get("EMOJIVOICE_REFERENCE"), "/root/reference", staged):
+        if cand and os.path.isdir(os.path.join(cand, "Matcha-TTS", "matcha", "models")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _MATCHA_ROOT = os.path.join(REFERENCE_ROOT, "Matcha-TTS")
 
 
