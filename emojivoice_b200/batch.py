@@ -20,14 +20,16 @@ def collate(utterances, items):
 @torch.inference_mode()
 def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10, temperature=0.667, length_scale=1.0,
                       rank=0, world_size=1, denoiser=None, denoiser_strength=0.00025, sort=True, keep_mel=False, z_fn=None,
-                      ragged=True):
+                      ragged=True, cuda_graphs=False):
     """Synthesise this rank's share of `utterances` (list of (phoneme ids, speaker id)).
 
     -> (results, stats): results maps utterance index -> dict(waveform (L,) cpu float32, mel_length, [mel]), stats is a
     sharding.ShardStats with this rank's device time.  `z_fn(mb, shape)` may supply the prior noise per micro-batch
     (parity runs share it with the oracle).  ragged: the vocoder skips the time tiles past each utterance's own length
     (identical cropped waveforms, see Generator.__call__); ignored with a denoiser, whose STFT windows at an utterance's
-    end reach into the padded region."""
+    end reach into the padded region.  cuda_graphs: a corpus hardly ever repeats a (B, Tx, T_pad) shape, so by default the
+    stages are launched eagerly -- measured within 2 % of a graph replay (the host enqueues a step in 5 ms of the GPU's 29),
+    whereas capturing costs ~250 ms per new shape (profiles/r02_host_cost.txt); True restores capture-on-second-sight."""
     lens = [len(u[0]) for u in utterances]
     plan = sharding.shard(lens, batch_size, rank, world_size, n_timesteps=n_timesteps, sort=sort)
     results, stats = {}, sharding.ShardStats()
@@ -46,6 +48,11 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
                 rec["mel"] = p["mel"][j, :, :n].cpu()
             results[i] = rec
 
+    saved_graphs = (getattr(model, "cuda_graphs", None), getattr(vocoder, "cuda_graphs", None))
+    if not cuda_graphs:
+        model.cuda_graphs = vocoder.cuda_graphs = False
+    # largest micro-batch first: the workspace and the caching allocator's blocks are sized once, every later batch fits
+    plan = sorted(plan, key=lambda m: -m.cost)
     for k, mb in enumerate(plan):
         x, xl, spks = collate(utterances, mb.items)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -83,4 +90,5 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
         pending = cur
     if pending is not None:
         finish(pending)
+    model.cuda_graphs, vocoder.cuda_graphs = saved_graphs
     return results, stats

@@ -312,6 +312,104 @@ extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, 
   return EV_OK;
 }
 
+// Fused ResnetBlock1D (+ pre-LN) alone (resnet_tc.cu).  `weights`: conv1.weight (256, C_in, 3), conv1.bias, gn1.weight, gn1.bias,
+// and -- for the full block -- temb (256), conv2.weight (256, 256, 3), conv2.bias, gn2.weight, gn2.bias, res.weight (256, C_in, 1),
+// res.bias, ln.weight, ln.bias, named like that.  x (B, C_in, T) channel-first fp32 (masked and rounded to bf16 inside).
+// full != 0: out_a = conv2's operand, out_xr = the block's fp32 output, out_n = LayerNorm(out_xr), all (B, T, 256) channel-last
+// fp32 (bf16 results widened); full == 0: conv -> GN -> Mish -> mask only, result in out_a.
+extern "C" int ev_test_resnet_block(ev_ctx* ctx, const ev_tensor* weights, int n_weights, const float* x, const int64_t* y_lengths,
+                                    int B, int T, int C_in, int len_shift, int full, float* out_a, float* out_xr, float* out_n,
+                                    int repeat, float* avg_us_host, void* stream) {
+  if (!ctx || !weights || !x || !out_a || B <= 0 || T <= 0 || C_in <= 0 || (full && (!out_xr || !out_n))) return EV_ERR_INVALID;
+  cudaStream_t s = as_stream(stream);
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int D = 256;
+  const size_t mark = ctx->owned.size();
+  auto release = [&]() {
+    cudaStreamSynchronize(s);
+    for (size_t i = mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+    ctx->owned.resize(mark);
+  };
+  WeightStore ws(ctx, weights, n_weights, s);
+  ConvWeights c1, c2, cr;
+  float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr, *te = nullptr, *lg = nullptr, *lb = nullptr;
+  int rc = make_conv(ctx, ws, {"conv1.weight"}, {"conv1.bias"}, D, C_in, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &c1);
+  if (!rc) rc = ws.copy_vec("gn1.weight", D, &g1);
+  if (!rc) rc = ws.copy_vec("gn1.bias", D, &b1);
+  if (!rc && full) {
+    rc = make_conv(ctx, ws, {"conv2.weight"}, {"conv2.bias"}, D, D, 3, 1, 1, 1, CONV_NORMAL, TC_BF16, &c2);
+    if (!rc) rc = make_conv(ctx, ws, {"res.weight"}, {"res.bias"}, D, C_in, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &cr);
+    if (!rc) rc = ws.copy_vec("gn2.weight", D, &g2);
+    if (!rc) rc = ws.copy_vec("gn2.bias", D, &b2);
+    if (!rc) rc = ws.copy_vec("temb", D, &te);
+    if (!rc) rc = ws.copy_vec("ln.weight", D, &lg);
+    if (!rc) rc = ws.copy_vec("ln.bias", D, &lb);
+  }
+  if (!rc && !resnet_tc_supported(c1, full ? &c2 : nullptr, full ? &cr : nullptr, B, T))
+    rc = fail(ctx, EV_ERR_INVALID, "ev_test_resnet_block: shape not served by the fused kernel (too many tiles for one wave?)");
+  const int ld_in = (int)align_up((size_t)C_in, 8);
+  const size_t n = (size_t)B * T * D;
+  void *xin = nullptr, *ab = nullptr, *nb = nullptr, *li = nullptr, *zero = nullptr;
+  if (!rc) rc = device_alloc(ctx, (size_t)B * T * ld_in * 2, &xin, true, s);
+  if (!rc) rc = device_alloc(ctx, n * 2, &ab, false, s);
+  if (!rc) rc = device_alloc(ctx, n * 2, &nb, false, s);
+  if (!rc) rc = device_alloc(ctx, (size_t)B * 4, &li, false, s);
+  const size_t zero_bytes = (size_t)B * 8 * 2 * 2 * sizeof(double) + 64;
+  if (!rc) rc = device_alloc(ctx, zero_bytes, &zero, true, s);
+  if (rc) { release(); return rc; }
+  cudaError_t ce = cudaMemsetAsync(ab, 0xff, n * 2, s);      // NaN patterns: every output row must be written
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(nb, 0xff, n * 2, s);
+  if (ce == cudaSuccess && full) ce = cudaMemsetAsync(out_xr, 0xff, n * 4, s);
+  int* lens = nullptr;
+  if (ce == cudaSuccess && y_lengths) {
+    lens = reinterpret_cast<int*>(li);
+    ce = i64_to_i32(reinterpret_cast<const long long*>(y_lengths), lens, B, s);
+  }
+  if (ce == cudaSuccess) ce = cf_to_cl<bf16>(x, B, C_in, T, reinterpret_cast<bf16*>(xin), ld_in, (long long)T * ld_in, 1.0f, RowMask{lens, len_shift}, s);
+  ResnetTcArgs ra;
+  ra.x = reinterpret_cast<bf16*>(xin); ra.x_ld = ld_in; ra.x_bs = (long long)T * ld_in;
+  ra.conv1 = &c1; ra.gn_g1 = g1; ra.gn_b1 = b1;
+  if (full) { ra.conv2 = &c2; ra.res = &cr; ra.gn_g2 = g2; ra.gn_b2 = b2; ra.temb = te; ra.ln_g = lg; ra.ln_b = lb; }
+  ra.lens = lens; ra.len_shift = len_shift; ra.B = B; ra.T = T;
+  double* sums = reinterpret_cast<double*>(zero);
+  ra.gn_sum1 = sums; ra.gn_sum2 = sums + (size_t)B * 16;
+  ra.barriers = reinterpret_cast<unsigned int*>(sums + (size_t)B * 32);
+  ra.a_buf = reinterpret_cast<bf16*>(ab); ra.a_ld = D; ra.a_bs = (long long)T * D;
+  ra.xr = out_xr; ra.n_out = reinterpret_cast<bf16*>(nb);
+  std::string err;
+  auto once = [&]() {
+    cudaError_t e = cudaMemsetAsync(zero, 0, zero_bytes, s);
+    return e == cudaSuccess ? resnet_tc_launch(ra, s, &err) : e;
+  };
+  if (ce == cudaSuccess) ce = once();
+  if (ce == cudaSuccess && repeat > 0 && avg_us_host) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < repeat && ce == cudaSuccess; ++i) ce = once();
+    cudaEventRecord(e1, s);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us_host = ms * 1e3f / (float)repeat;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  if (ce == cudaSuccess) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(ab), out_a, (long long)n); ce = cudaGetLastError(); }
+  if (ce == cudaSuccess && full) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(nb), out_n, (long long)n); ce = cudaGetLastError(); }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  release();
+  if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ev_test_resnet_block") : fail(ctx, EV_ERR_CUDA, err);
+  return EV_OK;
+}
+
+extern "C" int ev_test_resnet_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
+  if (!ctx || !out_host || n <= 0) return EV_ERR_INVALID;
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  EV_CUDA(ctx, cudaDeviceSynchronize());
+  EV_CUDA(ctx, resnet_tc_read_trace(reinterpret_cast<unsigned long long*>(out_host), n));
+  return EV_OK;
+}
+
 // diagnostic (EV_TC_TRACE=1): per-CTA clock stamps [n_cta][16] of the most recent conv_tc launch, host buffer
 extern "C" int ev_test_conv_trace(ev_ctx* ctx, uint64_t* out_host, int n) {
   if (!ctx || !out_host || n <= 0) return EV_ERR_INVALID;

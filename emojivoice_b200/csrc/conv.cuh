@@ -163,4 +163,23 @@ bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2);
 cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err);
 cudaError_t ff_tc_read_trace(unsigned long long* host, int n);   // diagnostic (EV_FF_DEBUG & 16)
 
+// resnet_tc.cu: one whole ResnetBlock1D (+ the following pre-LayerNorm) per launch; conv2 == nullptr -> conv -> GN -> Mish -> mask only
+struct ResnetTcArgs {
+  const bf16* x = nullptr; long long x_ld = 0, x_bs = 0;   // masked bf16 block input (b, t, C_in)
+  const ConvWeights* conv1 = nullptr; const ConvWeights* conv2 = nullptr; const ConvWeights* res = nullptr;
+  const float *gn_g1 = nullptr, *gn_b1 = nullptr, *gn_g2 = nullptr, *gn_b2 = nullptr;
+  const float* temb = nullptr;                              // [256] time embedding of this block and step
+  const float *ln_g = nullptr, *ln_b = nullptr;
+  const int* lens = nullptr; int len_shift = 0;
+  int B = 0, T = 0;
+  double* gn_sum1 = nullptr; double* gn_sum2 = nullptr;     // [B][8][2] each, zeroed
+  unsigned int* barriers = nullptr;                         // 4 counters, zeroed
+  bf16* a_buf = nullptr; long long a_ld = 0, a_bs = 0;      // conv2 operand scratch, or the output when conv2 == nullptr
+  float* xr = nullptr; bf16* n_out = nullptr;               // (b, t, 256) dense outputs of the full block
+};
+int resnet_tc_plan(int B, int T);
+bool resnet_tc_supported(const ConvWeights& conv1, const ConvWeights* conv2, const ConvWeights* res, int B, int T);
+cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string* err);
+cudaError_t resnet_tc_read_trace(unsigned long long* host, int n);
+
 }  // namespace ev

@@ -176,7 +176,8 @@ def test_narrow_decoder_with_poisoned_workspace(capsys):
     z = synthetic.prior_noise(5, 80, probe["t_pad"], seed=79)
     ref = mo.synthesise(sd, cfg, x, xl, 3, 0.667, spk, 1.0, z=z)
     model.synthesise(x, xl, 3, 0.667, spk, 1.0, z=z)            # sizes the workspace
-    model._ctx._ws.fill_(0xFF)
+    with torch.inference_mode():
+        model._ctx._ws.fill_(0xFF)
     out = model.synthesise(x, xl, 3, 0.667, spk, 1.0, z=z)
     assert torch.isfinite(out["mel"]).all()
     _assert_alignment_exact(out, ref)

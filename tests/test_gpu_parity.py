@@ -166,6 +166,64 @@ def test_fused_feed_forward_block_matches_torch(ctx, case):
     assert float(out.cpu()[mask.expand_as(ref) == 0].abs().sum()) == 0.0
 
 
+def _mish(x):
+    return x * torch.tanh(F.softplus(x))
+
+
+# B, T, C_in, len_shift, full      (one tile per CTA; B * ceil(T / 128) <= 148 -> one m-block per CTA, else two)
+RESNET_CASES = [(2, 200, 256, 0, 1), (3, 129, 224, 1, 1), (1, 1, 256, 0, 1), (32, 334, 512, 1, 1), (32, 668, 224, 0, 1),
+                (5, 700, 512, 0, 1), (32, 668, 256, 0, 0), (2, 130, 256, 0, 0), (40, 500, 256, 0, 1)]
+
+
+@pytest.mark.parametrize("case", RESNET_CASES)
+def test_fused_resnet_block_matches_torch(ctx, case):
+    """resnet_tc.cu: conv3 -> GroupNorm(8) over the padded extent -> Mish -> mask -> + temb -> mask -> conv3 -> GroupNorm -> Mish ->
+    mask -> + res_conv(x) -> LayerNorm, one cooperative launch with three grid barriers, against fp64 torch on the same
+    bf16-rounded operands (decoder.py:32-61, transformer.py:262)."""
+    B, T, Cin, shift, full = case
+    D = 256
+    g = torch.Generator().manual_seed(B * 7919 + T * 31 + Cin)
+    x = torch.randn(B, Cin, T, generator=g) * 1.2
+    lens = torch.randint(1, (T << shift) + 1, (B,), generator=g)
+    lens[0] = T << shift
+    if B > 2:
+        lens[1], lens[2] = 1, max(1, (T << shift) // 3)
+    rnd = lambda *s, scale=1.0: torch.randn(*s, generator=g) * scale
+    w = {"conv1.weight": rnd(D, Cin, 3, scale=(2.0 / (3 * Cin)) ** 0.5), "conv1.bias": rnd(D, scale=0.1),
+         "gn1.weight": 1 + rnd(D, scale=0.1), "gn1.bias": rnd(D, scale=0.1)}
+    if full:
+        w.update({"temb": rnd(D, scale=0.5), "conv2.weight": rnd(D, D, 3, scale=(2.0 / (3 * D)) ** 0.5), "conv2.bias": rnd(D, scale=0.1),
+                  "gn2.weight": 1 + rnd(D, scale=0.1), "gn2.bias": rnd(D, scale=0.1), "res.weight": rnd(D, Cin, 1, scale=Cin ** -0.5),
+                  "res.bias": rnd(D, scale=0.1), "ln.weight": 1 + rnd(D, scale=0.1), "ln.bias": rnd(D, scale=0.1)})
+    arr, keep = _lib.tensor_list(w, ctx.device)
+    xd, ld = x.cuda(), lens.cuda()
+    out_a, out_xr, out_n = (torch.empty(B, T, D, device="cuda") for _ in range(3))
+    ctx.check(_lib.lib().ev_test_resnet_block(ctx.handle, arr, len(keep), _lib.ptr(xd), _lib.ptr(ld), B, T, Cin, shift, full,
+                                              _lib.ptr(out_a), _lib.ptr(out_xr), _lib.ptr(out_n), 0, None, _lib.stream_ptr()),
+              "ev_test_resnet_block")
+    # reference on the same bf16-rounded operands, fp64
+    bf = lambda t: t.bfloat16().double()
+    m = ((torch.arange(T)[None, :] << shift) < lens[:, None]).double()[:, None, :]          # (B, 1, T)
+    xm = bf(x * m.float())
+    h = F.conv1d(xm, bf(w["conv1.weight"]), w["conv1.bias"].double(), padding=1)
+    h = _mish(F.group_norm(h, 8, w["gn1.weight"].double(), w["gn1.bias"].double(), 1e-5)) * m
+    if not full:
+        assert torch.isfinite(out_a).all()
+        assert rel_l2(out_a.cpu(), h.transpose(1, 2)) < 4e-3
+        return
+    a_ref = (h + w["temb"].double()[None, :, None]) * m
+    h2 = F.conv1d(bf(a_ref.float()), bf(w["conv2.weight"]), w["conv2.bias"].double(), padding=1)
+    h2 = _mish(F.group_norm(h2, 8, w["gn2.weight"].double(), w["gn2.bias"].double(), 1e-5)) * m
+    xr_ref = h2 + F.conv1d(xm, bf(w["res.weight"]), w["res.bias"].double())
+    n_ref = F.layer_norm(xr_ref.transpose(1, 2), (D,), w["ln.weight"].double(), w["ln.bias"].double(), 1e-5)
+    for t in (out_a, out_xr, out_n):
+        assert torch.isfinite(t).all()
+    assert rel_l2(out_a.cpu(), a_ref.transpose(1, 2)) < 4e-3             # bf16 output
+    assert rel_l2(out_xr.cpu(), xr_ref.transpose(1, 2)) < 4e-3           # conv2 consumes the bf16-rounded `a` (1-ulp flips vs the reference's)
+    assert rel_l2(out_n.cpu(), n_ref) < 6e-3
+    assert float(out_a.cpu()[(m.transpose(1, 2) == 0).expand_as(out_a)].abs().sum()) == 0.0
+
+
 def test_length_sum_follows_aten_cpu_order(ctx):
     rng = np.random.default_rng(0)
     for n in (1, 3, 7, 8, 9, 17, 151, 333, 513, 1100, 2100):
@@ -548,14 +606,19 @@ def test_scheduling_knobs_do_not_change_results():
         return [l for l in r.stdout.splitlines() if l.startswith("HASH")][0]
 
     base = run()
-    assert run(EV_DEC_LANES=2) == base
+    # decoder lanes and the res_conv side branch belong to the layer-by-layer ResNet path (EV_RN_FUSE=0: five launches per block
+    # instead of the fused cooperative kernel, whose arithmetic order differs): compared among themselves
+    unfused = run(EV_RN_FUSE=0)
+    assert run(EV_RN_FUSE=0, EV_DEC_LANES=2) == unfused
+    assert run(EV_DEC_LANES=2) == unfused          # two lanes never run the cooperative kernel (co-residency)
+    assert run(EV_RN_FUSE=0, EV_DEC_SIDE=0) == unfused
+    assert run(EV_RN_COOP=0) == base               # plain launch of the same grid
     assert run(EV_RB_WAVE=1) == base
     assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
     assert run(EV_PDL=0) == base
     # skipping the padded rows of the decoder's masked per-row work (feed-forward tiles, attention query blocks, out-projection
     # tiles) must not change a single bit either: those rows never reach an output that survives the mask
     assert run(EV_FF_RAGGED=0) == base
-    assert run(EV_DEC_SIDE=0) == base          # res_conv on a side branch of the graph vs in line
 
 
 def test_long_utterance_matches_oracle(matcha, matcha_sd, vocoders):
