@@ -49,6 +49,7 @@ struct MatchaW {
 struct DenoiseBasis {          // windowed Fourier bases of the bias denoiser (denoiser.cu)
   ConvWeights fwd, inv;
   float* win_sq = nullptr;     // hann^2 [1024]
+  void* twiddle = nullptr;     // float2[1024] exp(-2 pi i n / 1024) for the FFT path
   bool ready = false;
 };
 
