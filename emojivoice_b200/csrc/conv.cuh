@@ -172,9 +172,7 @@ struct ResnetTcArgs {
   const float *ln_g = nullptr, *ln_b = nullptr;
   const int* lens = nullptr; int len_shift = 0;
   int B = 0, T = 0;
-  double* gn_sum1 = nullptr; double* gn_sum2 = nullptr;     // [B][8][2] each, zeroed
-  unsigned int* barriers = nullptr;                         // 4 counters, zeroed
-  bf16* a_buf = nullptr; long long a_ld = 0, a_bs = 0;      // conv2 operand scratch, or the output when conv2 == nullptr
+  bf16* a_buf = nullptr; long long a_ld = 0, a_bs = 0;      // the output when conv2 == nullptr; else an optional copy of conv2's operand (tests)
   float* xr = nullptr; bf16* n_out = nullptr;               // (b, t, 256) dense outputs of the full block
 };
 int resnet_tc_plan(int B, int T);

@@ -354,7 +354,6 @@ struct DecBuffers {
   double* gn_fused; size_t gn_fused_count;   // [n_steps][13][B][8][2] sums written by the conv epilogues (bf16 path)
   int* ff_tiles[2];                          // compact lists of the 128-row tiles with a valid row, at T and T/2 (ff_tc.cu)
   int* rag_arena; size_t rag_ints;           // tile lists of the convs whose padded output rows nobody reads (out-projection)
-  unsigned int* rn_bar; size_t rn_bar_count; // [n_steps][7][4] grid-barrier counters of the fused ResNet-block kernel (resnet_tc.cu), zeroed per call
 };
 
 template <typename ActT>
@@ -388,8 +387,6 @@ void plan_decode(const ev_matcha_cfg& c, int B, int T, int n_steps, Workspace& w
   d->ff_tiles[1] = w.take<int>((size_t)B * ceil_div(T / 2, 128) + 64);
   d->rag_ints = (size_t)8 * ((size_t)B * ceil_div(T, 128) + 64);
   d->rag_arena = w.take<int>(d->rag_ints);
-  d->rn_bar_count = (size_t)n_steps * 7 * 4;
-  d->rn_bar = w.take<unsigned int>(d->rn_bar_count);
 }
 
 // Fixed-step Euler times exactly as flow_matching.py:52,68-83 computes them in float32 (t_span = linspace(0,1,n+1),
@@ -430,12 +427,10 @@ struct Decoder {
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
   double* next_gn_slot() { double* p = d.gn_fused + (size_t)(gn_slot++) * B * 8 * 2; return p; }
-  int rn_slot = 0;   // next free group of 4 grid-barrier counters
-  bool single_lane = true;     // the fused ResNet kernel needs all its CTAs co-resident: never two of them at a time
   // One launch for the whole ResNet block + pre-LN (resnet_tc.cu) when every tile of the level fits one co-resident wave
   bool fuse_resnet(const ResnetW& w, int Tl) const {
     if constexpr (!std::is_same<ActT, bf16>::value) return false;
-    return D == 256 && single_lane && resnet_tc_supported(w.conv1, &w.conv2, &w.res, B, Tl);
+    return D == 256 && resnet_tc_supported(w.conv1, &w.conv2, &w.res, B, Tl);
   }
   int launch_resnet_tc(const ResnetTcArgs& ra, double flops, double bytes, const char* name) {
     std::string err;
@@ -459,9 +454,7 @@ struct Decoder {
         ra.gn_g1 = w.gn1_g; ra.gn_b1 = w.gn1_b; ra.gn_g2 = w.gn2_g; ra.gn_b2 = w.gn2_b; ra.temb = temb;
         ra.ln_g = m.tf[k].ln1_g; ra.ln_b = m.tf[k].ln1_b;
         ra.lens = d.ylen32; ra.len_shift = shift; ra.B = B; ra.T = Tl;
-        ra.gn_sum1 = next_gn_slot(); ra.gn_sum2 = next_gn_slot();
-        ra.barriers = d.rn_bar + (size_t)(rn_slot++) * 4;
-        ra.a_buf = d.a; ra.a_ld = D; ra.a_bs = bsD; ra.xr = d.xr; ra.n_out = d.n;
+        ra.xr = d.xr; ra.n_out = d.n;        // conv2's operand stays in shared memory
         const double rows = (double)B * Tl;
         return launch_resnet_tc(ra, 2.0 * rows * D * (4.0 * w.c_in + 3.0 * D), rows * (2.0 * w.c_in + 6.0 * D), "resnet_tc");
       }
@@ -614,12 +607,11 @@ struct Decoder {
     // final_block (conv3 -> GN -> Mish -> *mask), final_proj fused with the Euler update x += dt * (proj*mask)
     bool final_fused = false;
     if constexpr (std::is_same<ActT, bf16>::value) {
-      if (D == 256 && single_lane && resnet_tc_supported(m.final_conv, nullptr, nullptr, B, T)) {   // conv -> GN -> Mish -> mask in one launch
+      if (D == 256 && resnet_tc_supported(m.final_conv, nullptr, nullptr, B, T)) {   // conv -> GN -> Mish -> mask in one launch
         ResnetTcArgs ra;
         ra.x = d.n; ra.x_ld = D; ra.x_bs = (long long)T * D;
         ra.conv1 = &m.final_conv; ra.gn_g1 = m.final_g; ra.gn_b1 = m.final_b;
         ra.lens = d.ylen32; ra.len_shift = 0; ra.B = B; ra.T = T;
-        ra.gn_sum1 = next_gn_slot(); ra.barriers = d.rn_bar + (size_t)(rn_slot++) * 4;
         ra.a_buf = d.a; ra.a_ld = D; ra.a_bs = (long long)T * D;
         EV_TRY(launch_resnet_tc(ra, 2.0 * B * T * D * 3.0 * D, (double)B * T * 4.0 * D, "final_block_tc"));
         final_fused = true;
@@ -729,10 +721,8 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
         r.lens = q.ylen32; r.B = nb; r.margin = 0; r.arena = q.rag_arena; r.arena_ints = q.rag_ints; r.launch_counter = &ctx->launches;
       }
     }
-    dec.back().single_lane = n_lanes == 1;
     if (dec.back().fuse_gn()) {
       EV_CUDA(ctx, cudaMemsetAsync(q.gn_fused, 0, q.gn_fused_count * sizeof(double), ls[l]));
-      EV_CUDA(ctx, cudaMemsetAsync(q.rn_bar, 0, q.rn_bar_count * sizeof(unsigned int), ls[l]));
     }
   }
   // launches interleave across lanes step by step so that eager (un-captured) calls overlap as well

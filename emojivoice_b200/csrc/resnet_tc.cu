@@ -8,24 +8,32 @@
 //     n  = LayerNorm(xr)                                                    (bf16 operand of the QKV projection)
 //
 // Round 1 ran this as five launches (res_conv, conv1, gn_apply, conv2, gn_apply_ln), each ~15-20 us of which ~3 us were
-// tensor work: the decoder was launch / prologue / epilogue-drain bound ("Where a small decoder conv spends its
-// time").  Here every CTA owns ONE tile of mb x 128 frames x all 256 channels for the whole block:
-//   * the conv accumulators (mb x 256 fp32 columns) stay in TMEM across the GroupNorm: pass 1 reads them for the
-//     statistics (fp64 atomics per (item, group)), a GRID BARRIER makes the statistics of every CTA visible, pass 2 reads
-//     them again and normalises -- the fp32 conv output never touches HBM;
-//   * conv2's operand `a` goes through global memory (L2) because its taps need the neighbour tiles' rows: a second grid
-//     barrier, then TMA loads it back (generic-proxy stores -> fence.proxy.async -> barrier -> TMA);
-//   * Mish(GN2(h2)) * m is written back INTO the accumulator (tcgen05.st) and res_conv(x) is accumulated onto it by the
-//     tensor core (accumulate = 1), so the residual add costs nothing and `r` is never materialised;
-//   * LayerNorm statistics are taken per row from the same TMEM tile (thread = row), exchanged through shared memory.
-// All CTAs must be co-resident (grid = B * ceil(T / (128 mb)) <= SM count, one CTA per SM): the launch is cooperative.
-// `mode 1` stops after the first apply (final_block: conv -> GN -> Mish -> mask, decoder.py:431).
+// tensor work.  Here every CTA owns ONE tile of R = 128 * mb consecutive frames x all 256 channels for the whole block:
+//   * tiles overlap by two frames: tile row 0 and row R - 1 are HALO rows (the neighbour tiles own those frames), so conv2's
+//     operand `a` -- its taps reach one row to either side -- never leaves the SM: the epilogue warps write it, hand-swizzled,
+//     straight into the shared-memory K-major operand planes conv2's MMAs read.  No global round trip, no grid barrier there;
+//   * the tiles of one item form a THREAD-BLOCK CLUSTER (<= 8 CTAs).  The conv accumulators (R x 256 fp32) stay in TMEM across
+//     the GroupNorm: pass 1 reads them for the statistics of the OWNED rows (shared-memory atomics per group), every CTA then
+//     pushes its 16 partial sums into the shared memory of every CTA of the cluster (st.async + mbarrier complete_tx over
+//     DSMEM: one ~0.5 us hop instead of global atomics + a grid barrier), sums them in rank order (deterministic) and pass 2
+//     reads the accumulators again and normalises.  The fp32 conv outputs never touch HBM, nothing is zeroed beforehand,
+//     and the grid may be any number of clusters (no co-residency requirement);
+//   * normalisation constants are folded per channel once per CTA (scale = rstd * gamma, shift = beta + (bias - mean) * scale),
+//     so the per-element work of an apply pass is one FMA + Mish (ex2 + rcp) + one FMA;
+//   * Mish(GN2(h2)) * m + res_bias is written back INTO the accumulator (tcgen05.st) and res_conv(x) is accumulated onto it by
+//     the tensor core, per 128-column half: the MMAs of half 0 run under the apply pass of half 1, those of half 1 under the
+//     output pass of half 0;
+//   * with one m-block per CTA (mb = 1) conv2 accumulates into the spare 256 TMEM columns and starts on K-chunks 0-1 while the
+//     epilogue warps are still producing K-chunks 2-3 of `a`;
+//   * LayerNorm statistics are taken per row from the same TMEM tile (thread = row), combined through shared-memory atomics.
+// `mode 1` stops after the first apply (final_block: conv -> GN -> Mish -> mask, decoder.py:431) and writes bf16 to global.
 //
-// Warp roles (19 warps): 0 activation-tile TMA producer, 1 weight-tile TMA producer (weights are constants: it runs free),
-// 2 MMA issuer (owns TMEM), 3-18 sixteen epilogue warps (TMEM lane quadrant = warp & 3, four column slots per quadrant).
-// Shared memory: weight ring 4 x 32 KB ([64 k x 256 n] bf16, 128B swizzle), activation ring (2-4 haloed tiles) ALIASED
-// with the epilogue's transpose buffers (they are never live together: an epilogue phase starts when its GEMM's last MMA
-// has completed, and the next GEMM's activation loads wait for the grid barrier behind that epilogue phase).
+// Warp roles (20 warps): 0 activation-tile TMA producer, 1 weight-tile TMA producer (weights are constants: it runs free),
+// 2-3 MMA issuers, one per 128-column half of the accumulator (a weight tile only feeds 4-8 MMAs: one issuer's barrier
+// bookkeeping runs under the other's MMAs; warp 2 owns TMEM), 4-19 sixteen epilogue warps (TMEM lane quadrant = warp & 3,
+// column slot = (warp - 4) >> 2: a warp works on the 32-column blocks 4h + slot of both 128-column halves h).
+// Shared memory: weight ring (5-7 slots of [64 k x 128 n] bf16 = 16 KB, 128B swizzle), the A region (block-input tiles for
+// conv1, then the four operand planes of `a`, then block-input tiles for res_conv + the output transpose buffers), constants.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -41,31 +49,32 @@ namespace {
 
 constexpr int RN_C = 256;
 constexpr int RN_EPI_WARPS = 16;
-constexpr int RN_ROLE_WARPS = 3;
+constexpr int RN_ROLE_WARPS = 4;
 constexpr int RN_THREADS = 32 * (RN_ROLE_WARPS + RN_EPI_WARPS);
 constexpr int RN_EPI_THREADS = 32 * RN_EPI_WARPS;
-constexpr int RN_B_TILE = RN_C * 128;            // [64 k x 256 n] bf16
-constexpr int RN_B_SLOTS = 4;
-constexpr int RN_MAX_A_SLOTS = 4;
-constexpr int RN_STAGE_LD = 36;
-constexpr int RN_STAGE_WARP = 32 * RN_STAGE_LD * 4;
-constexpr int RN_AREGION = RN_EPI_WARPS * RN_STAGE_WARP;   // 73728 B: activation ring / transpose buffers
-constexpr int RN_ROWSTAT = 2 * 128 * 4 * 2 * 4;            // LayerNorm partial sums [m-block][row][slot][2]
-constexpr int RN_SMEM = 1024 + RN_B_SLOTS * RN_B_TILE + RN_AREGION + RN_ROWSTAT;
-constexpr int RN_ACT_PITCH = 80;                           // bytes per staged bf16 row (64 + 16: conflict-free 16-byte access)
+constexpr int RN_W_TILE = 128 * 128;             // [64 k x 128 n] bf16
+constexpr int RN_MAX_W_SLOTS = 8;
+constexpr int RN_X1_SLOTS = 3, RN_X3_SLOTS = 2;
+constexpr int RN_STAGE_WARP = 4096;              // 32 x 32 fp32 (XOR-swizzled) or 32 rows x 80 B of bf16
+constexpr int RN_STAGE = RN_EPI_WARPS * RN_STAGE_WARP;
+constexpr int RN_ACT_PITCH = 80;                 // bytes per staged bf16 row (64 + 16: conflict-free 16-byte access)
+constexpr int RN_MAX_CLUSTER = 8;
+// constants: scale, shift, extra (temb / res bias), conv bias, LN gamma, LN beta [256 each], row sums [256][2], group sums [8][2],
+// the cluster's partial group sums [2 GroupNorms][8 ranks][16]
+constexpr int RN_CONST_FLOATS = 6 * RN_C + 2 * 256 + 16 + 2 * RN_MAX_CLUSTER * 16;
+constexpr int RN_SMEM_LIMIT = 227 * 1024 - 1024; // dynamic + ~0.5 KB of static barriers must stay below 227 KB
 
-struct RnMaps { CUtensorMap x, a, w1, w2, wr; };
+struct RnMaps { CUtensorMap x1, x3, w1, w2, wr; };
 
 struct RnParams {
   int B, T, mb, m_tiles, n_cta;
   int kc_in;                                   // 64-channel K-chunks of the block input (conv1 and res_conv)
-  int a_boxes, a_box_rows, a_slot_bytes, a_slots;
+  int x1_boxes, x1_box_rows, x1_slot_bytes;    // conv1's haloed input tile: R + 2 rows from frame m0 - 2
+  int a_bytes, w_slots;
   int mode;
   const int* lens; int len_shift;
   const float *bias1, *bias2, *bias_r, *g1, *b1, *g2, *b2, *temb, *ln_g, *ln_b;
-  double* gn1; double* gn2;                    // [B][8][2] (sum, sum of squares), zeroed by the caller
-  unsigned int* bar;                           // three grid-barrier counters, zeroed by the caller
-  bf16* a_buf; long long a_ld, a_bs;           // conv2's operand (mode 0) / the block's output (mode 1)
+  bf16* a_buf; long long a_ld, a_bs;           // mode 1: the block's output; mode 0: optional copy of conv2's operand (tests)
   float* xr; bf16* n_out;                      // (b, t, 256) dense
   float eps_gn, eps_ln;
   int trace;
@@ -78,57 +87,73 @@ __device__ __forceinline__ uint32_t rd_hi(uint32_t sbo, uint32_t layout) { retur
 __device__ __forceinline__ uint32_t rd_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t rd_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-static __device__ __noinline__ void grid_barrier_timeout() {
-  printf("emojivoice_b200: resnet_tc grid barrier timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-  __trap();
-}
-// one thread per CTA: wait until `n` CTAs have arrived at `ctr` (a bug or a non-resident CTA must trap, not hang the device)
-__device__ __forceinline__ void grid_wait(const unsigned int* ctr, unsigned int n) {
-  const long long t0 = clock64();
-  while (ld_acquire_gpu(ctr) < n) {
-    __nanosleep(32);
-    if (clock64() - t0 > (2ll << 30)) grid_barrier_timeout();     // ~1 s
-  }
-}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RN_EPI_THREADS) : "memory"); }
 
-// x * tanh(softplus(x)) = x * w / (w + 2), w = e^x (e^x + 2)   (same formulation as gn_apply256, elementwise.cu)
-__device__ __forceinline__ float mish_fast(float x) {
-  const float n = __expf(fminf(x, 20.0f));
-  const float w = n * (n + 2.0f);
-  return x > 20.0f ? x : x * __fdividef(w, w + 2.0f);
+// x * tanh(softplus(x)) + add.  With n = e^x: tanh(log(1 + n)) = 1 - 2 / (n (n + 2) + 2); x is clamped at 20 inside the
+// exponential only (there the quotient is 1 to fp32 precision, torch's softplus threshold: decoder.py:38)
+__device__ __forceinline__ float mish_add(float x, float add) {
+  const float n = ex2f(fminf(x * 1.4426950408889634f, 28.853900817779268f));
+  const float d = fmaf(n, n + 2.0f, 2.0f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(x, fmaf(-2.0f, r, 1.0f), add);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+// 4 bytes into the shared memory of a CTA of the cluster; completes 4 bytes of transaction count on THAT CTA's mbarrier
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(__float_as_uint(v)), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void red_add_smem(float* addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(RN_THREADS, 1)
 resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ RnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t a_full[RN_MAX_A_SLOTS], a_empty[RN_MAX_A_SLOTS], b_full[RN_B_SLOTS], b_empty[RN_B_SLOTS];
-  __shared__ __align__(8) uint64_t acc_full, epi_done;
+  __shared__ __align__(8) uint64_t x1_full[RN_X1_SLOTS], x1_empty[RN_X1_SLOTS], x3_full[RN_X3_SLOTS], x3_empty[RN_X3_SLOTS];
+  __shared__ __align__(8) uint64_t w_full[RN_MAX_W_SLOTS], w_empty[RN_MAX_W_SLOTS];
+  __shared__ __align__(8) uint64_t acc_full, plane_ready[2], tm_ready[2], res_full[2], xch_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t b_s = base, a_s = base + RN_B_SLOTS * RN_B_TILE;
-  uint8_t* stage_gen = base_gen + RN_B_SLOTS * RN_B_TILE;                       // aliases the activation ring
-  float* rowstat = reinterpret_cast<float*>(base_gen + RN_B_SLOTS * RN_B_TILE + RN_AREGION);
+  const uint32_t w_s = base, a_s = base + (uint32_t)(p.w_slots * RN_W_TILE);
+  uint8_t* a_gen = base_gen + p.w_slots * RN_W_TILE;
+  uint8_t* stage_gen = a_gen + (p.a_bytes - RN_STAGE);                          // the last 64 KB of the A region
+  float* cst = reinterpret_cast<float*>(a_gen + p.a_bytes);
+  float *c_scale = cst, *c_shift = cst + RN_C, *c_extra = cst + 2 * RN_C, *c_bias = cst + 3 * RN_C, *c_lng = cst + 4 * RN_C, *c_lnb = cst + 5 * RN_C;
+  float* rowsum = cst + 6 * RN_C;                                               // [256 rows][2]
+  float* gsum = rowsum + 512;                                                   // [8 groups][2]
+  float* xch = gsum + 16;                                                       // [2][8 ranks][16]: partial sums pushed by the cluster's CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.mb * 128, U = R - 2;
   const int b = (int)blockIdx.x / p.m_tiles, mt = (int)blockIdx.x - b * p.m_tiles;
-  const int m0 = mt * p.mb * 128;
-  const int vmb = min(p.mb, (p.T - m0 + 127) >> 7);                             // m-blocks that hold a frame
+  const int m0 = mt * U;                                                        // first owned frame; tile row r holds frame m0 - 1 + r
+  const int vmb = min(p.mb, (p.T - m0 + 1 + 127) >> 7);                         // m-blocks that hold a frame < T
   const bool full = p.mode == 0;
+  const uint32_t acc2_col = (p.mb == 1 && full) ? 256u : 0u;                    // conv2 / res_conv / output accumulator columns
 
   if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.w1) : "memory");
-    for (int s = 0; s < RN_MAX_A_SLOTS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < RN_B_SLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(&acc_full, 1);
-    mbar_init(&epi_done, RN_EPI_WARPS);
+    for (int s = 0; s < RN_X1_SLOTS; ++s) { mbar_init(&x1_full[s], 1); mbar_init(&x1_empty[s], 2); }
+    for (int s = 0; s < RN_X3_SLOTS; ++s) { mbar_init(&x3_full[s], 1); mbar_init(&x3_empty[s], 1); }
+    for (int s = 0; s < RN_MAX_W_SLOTS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(&acc_full, 2);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(&plane_ready[h], RN_EPI_WARPS); mbar_init(&tm_ready[h], RN_EPI_WARPS); mbar_init(&res_full[h], 1); mbar_init(&xch_bar[h], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -136,7 +161,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();                             // every CTA's mbarriers exist before a peer pushes its sums at them
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_trigger();
@@ -144,334 +169,412 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
   RN_TR(0);
 
   if (warp == 0) {
-    // ---------------- activation tiles: conv1 reads x, conv2 reads `a` (behind grid barrier 2), res_conv reads x again
+    // ---------------- block-input tiles: conv1 reads R + 2 rows from frame m0 - 2; res_conv reads R rows from frame m0 - 1
     if (lane == 0) {
-      int sa = 0;
-      uint32_t pa = 1;
-      const uint32_t a_bytes = (uint32_t)(p.a_boxes * p.a_box_rows * 128), box_bytes = (uint32_t)(p.a_box_rows * 128);
-      auto load_a = [&](const CUtensorMap* map, int kc) {
-        mbar_wait(&a_empty[sa], pa);
-        mbar_expect_tx(&a_full[sa], a_bytes);
-        const uint32_t dst = a_s + (uint32_t)(sa * p.a_slot_bytes);
-        tma_load_3d(dst, map, &a_full[sa], kc * 64, m0 - 1, b);
-        if (p.a_boxes > 1) tma_load_3d(dst + box_bytes, map, &a_full[sa], kc * 64, m0 - 1 + p.a_box_rows, b);
-        if (++sa == p.a_slots) { sa = 0; pa ^= 1u; }
-      };
-      for (int kc = 0; kc < p.kc_in; ++kc) load_a(&maps.x, kc);
+      int sx = 0;
+      uint32_t px = 1;
+      const uint32_t x1_bytes = (uint32_t)(p.x1_boxes * p.x1_box_rows * 128), box_bytes = (uint32_t)(p.x1_box_rows * 128);
+      for (int kc = 0; kc < p.kc_in; ++kc) {
+        mbar_wait(&x1_empty[sx], px);
+        mbar_expect_tx(&x1_full[sx], x1_bytes);
+        const uint32_t dst = a_s + (uint32_t)(sx * p.x1_slot_bytes);
+        tma_load_3d(dst, &maps.x1, &x1_full[sx], kc * 64, m0 - 2, b);
+        if (p.x1_boxes > 1) tma_load_3d(dst + box_bytes, &maps.x1, &x1_full[sx], kc * 64, m0 - 2 + p.x1_box_rows, b);
+        if (++sx == RN_X1_SLOTS) { sx = 0; px ^= 1u; }
+      }
       if (full) {
-        // `a` of every CTA is complete (and this CTA's transpose buffers are idle) once all CTAs passed barrier 2
-        grid_wait(p.bar + 1, (unsigned)p.n_cta);
-        asm volatile("fence.proxy.async;" ::: "memory");      // generic-proxy stores of the other CTAs -> this thread's TMA reads
-        RN_TR(6);
-        for (int kc = 0; kc < RN_C / 64; ++kc) load_a(&maps.a, kc);
-        for (int kc = 0; kc < p.kc_in; ++kc) load_a(&maps.x, kc);
+        mbar_wait(&acc_full, 0);
+        mbar_wait(&acc_full, 1);                  // conv2's MMAs have completed: the operand planes are dead
+        sx = 0; px = 1;
+        const uint32_t x3_bytes = (uint32_t)(R * 128);
+        for (int h = 0; h < 2; ++h)
+          for (int kc = 0; kc < p.kc_in; ++kc) {
+            mbar_wait(&x3_empty[sx], px);
+            mbar_expect_tx(&x3_full[sx], x3_bytes);
+            const uint32_t dst = a_s + (uint32_t)sx * x3_bytes;
+            for (int j = 0; j < p.mb; ++j) tma_load_3d(dst + (uint32_t)(j * 128 * 128), &maps.x3, &x3_full[sx], kc * 64, m0 - 1 + j * 128, b);
+            if (++sx == RN_X3_SLOTS) { sx = 0; px ^= 1u; }
+          }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ---------------- weight tiles in the issuer's order (constants: no dependency on anything)
     if (lane == 0) {
-      int sb = 0;
-      uint32_t pb = 1;
-      auto load_b = [&](const CUtensorMap* map, int kc, int tap) {
-        mbar_wait(&b_empty[sb], pb);
-        mbar_expect_tx(&b_full[sb], (uint32_t)RN_B_TILE);
-        tma_load_3d(b_s + (uint32_t)(sb * RN_B_TILE), map, &b_full[sb], kc * 64, 0, tap);
-        if (++sb == RN_B_SLOTS) { sb = 0; pb ^= 1u; }
+      int sw = 0;
+      uint32_t pw = 1;
+      auto load_w = [&](const CUtensorMap* map, int kc, int h, int tap) {
+        mbar_wait(&w_empty[sw], pw);
+        mbar_expect_tx(&w_full[sw], (uint32_t)RN_W_TILE);
+        tma_load_3d(w_s + (uint32_t)(sw * RN_W_TILE), map, &w_full[sw], kc * 64, h * 128, tap);
+        if (++sw == p.w_slots) { sw = 0; pw ^= 1u; }
       };
       for (int kc = 0; kc < p.kc_in; ++kc)
-        for (int j = 0; j < 3; ++j) load_b(&maps.w1, kc, j);
+        for (int j = 0; j < 3; ++j)
+          for (int h = 0; h < 2; ++h) load_w(&maps.w1, kc, h, j);
       if (full) {
         for (int kc = 0; kc < RN_C / 64; ++kc)
-          for (int j = 0; j < 3; ++j) load_b(&maps.w2, kc, j);
-        for (int kc = 0; kc < p.kc_in; ++kc) load_b(&maps.wr, kc, 0);
+          for (int j = 0; j < 3; ++j)
+            for (int h = 0; h < 2; ++h) load_w(&maps.w2, kc, h, j);
+        for (int h = 0; h < 2; ++h)
+          for (int kc = 0; kc < p.kc_in; ++kc) load_w(&maps.wr, kc, h, 0);
       }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ---------------- MMA issuer: warp-uniform control flow, one elected lane issues.  M = 128, N = 256, K = 16.
-    constexpr uint32_t idesc = make_idesc(128, RN_C);
+  } else if (warp < RN_ROLE_WARPS) {
+    // ---------------- two MMA issuers, h = 0 / 1: the 128-column half of every accumulator.  Warp-uniform control flow, one
+    // elected lane issues.  M = 128, N = 128, K = 16.  Weight tiles are numbered in the producer's order; tile i sits in ring
+    // slot i % w_slots.  conv1 / conv2: tile 2 (3 kc + j) + h belongs to issuer h; res_conv: issuer 0 takes every tile.
+    const int h = warp - 2;
+    constexpr uint32_t idesc = make_idesc(128, 128);
     const uint32_t hi = rd_hi(1024u, 2u);
-    const uint32_t a_lo0 = rd_lo(a_s), b_lo0 = rd_lo(b_s);
-    const uint32_t a_step16 = (uint32_t)p.a_slot_bytes >> 4;
-    constexpr uint32_t b_step16 = (uint32_t)RN_B_TILE >> 4, mb_step16 = (128u * 128u) >> 4, row16 = 128u >> 4;
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
-    // one GEMM: `kchunks` activation tiles, `taps` weight tiles each; tap j reads the haloed tile from row `row0 + j` on
-    auto gemm = [&](int kchunks, int taps, int row0, uint32_t acc_first) {
-      uint32_t acc = acc_first;
-      for (int kc = 0; kc < kchunks; ++kc) {
-        mbar_wait(&a_full[sa], pa);
-        tcgen05_fence_after();
-        const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_step16 + (uint32_t)row0 * row16;
-        for (int j = 0; j < taps; ++j) {
-          mbar_wait(&b_full[sb], pb);
-          tcgen05_fence_after();
-          const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step16;
-          if (elect_one()) {
+    const uint32_t a_lo0 = rd_lo(a_s), w_lo0 = rd_lo(w_s);
+    constexpr uint32_t w_step16 = (uint32_t)RN_W_TILE >> 4, row16 = 128u >> 4;
+    int sw = h;
+    uint32_t pw = 0;
+    auto ring_advance = [&](int k) { sw += k; while (sw >= p.w_slots) { sw -= p.w_slots; pw ^= 1u; } };
+    // the MMAs of one weight tile: m-blocks j < vmb, A rows from `a_lo` + j * 128 rows, D columns d0 + j * 256
+    auto tile_mmas = [&](uint32_t a_lo, uint32_t d0, uint32_t acc) {
+      mbar_wait(&w_full[sw], pw);
+      tcgen05_fence_after();
+      const uint32_t w_lo = w_lo0 + (uint32_t)sw * w_step16;
+      if (elect_one()) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              if (m < vmb) {
-                const uint32_t d = tmem_base + (uint32_t)(m * RN_C), am = a_lo + (uint32_t)j * row16 + (uint32_t)m * mb_step16;
+        for (int m = 0; m < 2; ++m) {
+          if (m < vmb) {
+            const uint32_t d = d0 + (uint32_t)(m * RN_C), am = a_lo + (uint32_t)m * (128u * row16);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks)
-                  umma_bf16(d, rd_join(hi, am + 2u * ks), rd_join(hi, b_lo + 2u * ks), idesc, (acc | (uint32_t)ks) ? 1u : 0u);
-              }
-            }
-            umma_commit(&b_empty[sb]);
+            for (int ks = 0; ks < 4; ++ks) umma_bf16(d, rd_join(hi, am + 2u * ks), rd_join(hi, w_lo + 2u * ks), idesc, (acc | (uint32_t)ks) ? 1u : 0u);
           }
-          __syncwarp();
-          acc = 1;
-          if (++sb == RN_B_SLOTS) { sb = 0; pb ^= 1u; }
         }
-        if (elect_one()) umma_commit(&a_empty[sa]);
+        umma_commit(&w_empty[sw]);
+      }
+      __syncwarp();
+    };
+    {  // conv1: tap j of tile row r reads input-tile row r + j (input-tile row 0 = frame m0 - 2)
+      int sx = 0;
+      uint32_t px = 0;
+      for (int kc = 0; kc < p.kc_in; ++kc) {
+        mbar_wait(&x1_full[sx], px);
+        tcgen05_fence_after();
+        const uint32_t a_lo = a_lo0 + (uint32_t)(sx * p.x1_slot_bytes >> 4);
+        for (int j = 0; j < 3; ++j) {
+          tile_mmas(a_lo + (uint32_t)j * row16, tmem_base + (uint32_t)(h * 128), (kc | j) ? 1u : 0u);
+          ring_advance(2);
+        }
+        if (elect_one()) umma_commit(&x1_empty[sx]);
         __syncwarp();
-        if (++sa == p.a_slots) { sa = 0; pa ^= 1u; }
+        if (++sx == RN_X1_SLOTS) { sx = 0; px ^= 1u; }
       }
       if (elect_one()) umma_commit(&acc_full);
       __syncwarp();
-    };
-    gemm(p.kc_in, 3, 0, 0u);                       // conv1: taps at tile rows 0, 1, 2 (tile row 0 = frame m0 - 1)
-    RN_TR(1);
+    }
+    if (h == 0) RN_TR(1);
     if (full) {
-      mbar_wait(&epi_done, 0);                     // apply-1 has read the accumulator for the last time
+      // conv2: operand planes written by the epilogue warps; tap j of tile row r reads plane row r + j - 1 (rows -1 and R only
+      // feed the two halo rows of the output, which nobody reads).  K-chunks 0-1 are the channels of half 0, 2-3 of half 1.
+      // With two m-blocks conv2 overwrites conv1's accumulator: every apply-1 read must have happened (both halves ready).
+      const uint32_t plane16 = (uint32_t)(R * 128) >> 4;
+      mbar_wait(&plane_ready[0], 0);
+      if (p.mb == 2) mbar_wait(&plane_ready[1], 0);
       tcgen05_fence_after();
-      gemm(RN_C / 64, 3, 0, 0u);                   // conv2
-      RN_TR(7);
-      mbar_wait(&epi_done, 1);                     // Mish(GN2(h2)) * m sits in the accumulator
-      tcgen05_fence_after();
-      gemm(p.kc_in, 1, 1, 1u);                     // + res_conv(x): the centre row of the haloed tile, accumulated on top
-      RN_TR(10);
+      for (int kc = 0; kc < RN_C / 64; ++kc) {
+        if (kc == 2 && p.mb == 1) { mbar_wait(&plane_ready[1], 0); tcgen05_fence_after(); }
+        const uint32_t a_lo = a_lo0 + (uint32_t)kc * plane16;
+        for (int j = 0; j < 3; ++j) {
+          tile_mmas(a_lo + (uint32_t)j * row16 - row16, tmem_base + acc2_col + (uint32_t)(h * 128), (kc | j) ? 1u : 0u);
+          ring_advance(2);
+        }
+      }
+      if (elect_one()) umma_commit(&acc_full);
+      __syncwarp();
+      if (h == 0) RN_TR(7);
+      // res_conv, accumulated on top of Mish(GN2(h2)) * m + bias, half by half: input-tile row r = frame m0 - 1 + r.  One
+      // issuer does both halves (the other one would have to join the rings mid-sequence: mbarrier parities alias); the
+      // input tiles stream twice, in the order h = 0: kc = 0.., h = 1: kc = 0..
+      if (h == 0) {
+        int sx = 0;
+        uint32_t px = 0;
+        const uint32_t x3_16 = (uint32_t)(R * 128) >> 4;
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&tm_ready[hh], 0);
+          tcgen05_fence_after();
+          for (int kc = 0; kc < p.kc_in; ++kc) {
+            mbar_wait(&x3_full[sx], px);
+            tcgen05_fence_after();
+            tile_mmas(a_lo0 + (uint32_t)sx * x3_16, tmem_base + acc2_col + (uint32_t)(hh * 128), 1u);
+            ring_advance(1);
+            if (elect_one()) umma_commit(&x3_empty[sx]);
+            __syncwarp();
+            if (++sx == RN_X3_SLOTS) { sx = 0; px ^= 1u; }
+          }
+          if (elect_one()) umma_commit(&res_full[hh]);
+          __syncwarp();
+        }
+      }
+      if (h == 0) RN_TR(10);
     }
   } else {
     // ---------------- sixteen epilogue warps
-    const int ew = warp - RN_ROLE_WARPS, q = warp & 3, slot = ew >> 2;
+    const int ew = warp - RN_ROLE_WARPS, q = warp & 3, slot = ew >> 2, te = threadIdx.x - 32 * RN_ROLE_WARPS;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const int n_blk = vmb * 8;                                         // 32-column blocks of this lane quadrant
-    float* wstage = reinterpret_cast<float*>(stage_gen + ew * RN_STAGE_WARP);
+    uint8_t* wstage = stage_gen + ew * RN_STAGE_WARP;
     const int len_b = p.lens ? __ldg(p.lens + b) : 0x7fffffff;
-    const bool leader = ew == 0 && lane == 0;
     const double inv_n = 1.0 / (32.0 * (double)p.T);
+    const int rl = q * 32 + lane;                                      // row of this thread inside an m-block
 
-    // GroupNorm statistics of (accumulator + bias) over the tile's frames t < T: one fp64 atomic pair per warp and block
-    auto stats_pass = [&](const float* bias, double* gn) {
+    // constants that do not depend on a barrier
+    for (int i = te; i < 2 * 256 + 16; i += RN_EPI_THREADS) rowsum[i] = 0.0f;
+    if (te < RN_C) {
+      c_bias[te] = __ldg(p.bias1 + te);
+      if (full) { c_lng[te] = __ldg(p.ln_g + te); c_lnb[te] = __ldg(p.ln_b + te); }
+    }
+    epi_bar();
+
+    // GroupNorm statistics of (accumulator + bias) over the OWNED rows of the tile
+    auto stats_pass = [&](uint32_t col0) {
 #pragma unroll 1
-      for (int blk = slot; blk < n_blk; blk += 4) {
-        const int m = blk >> 3, cb = blk & 7;
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-        const bool ok = m0 + m * 128 + q * 32 + lane < p.T;
+      for (int h = 0; h < 2; ++h) {
+        const int cb = 4 * h + slot;
         float s = 0.0f, qq = 0.0f;
+#pragma unroll 1
+        for (int m = 0; m < vmb; ++m) {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + col0 + (uint32_t)(m * RN_C + cb * 32), raw);
+          const int r = m * 128 + rl;
+          const bool own = r >= 1 && r <= R - 2 && m0 - 1 + r < p.T;
+          float s1 = 0.0f, q1 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + cb * 32 + j));
-          const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
-          const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
-          s += (v0 + v1) + (v2 + v3);
-          qq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(c_bias + cb * 32 + j);
+            const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
+            const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
+            s1 += (v0 + v1) + (v2 + v3);
+            q1 = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, q1))));
+          }
+          if (own) { s += s1; qq += q1; }
         }
-        if (!ok) { s = 0.0f; qq = 0.0f; }
         s = warp_sum(s); qq = warp_sum(qq);
-        if (lane == 0) {
-          double* dst = gn + ((long long)b * 8 + cb) * 2;
-          atomicAdd(dst, (double)s);
-          atomicAdd(dst + 1, (double)qq);
+        if (lane == 0) { red_add_smem(gsum + cb * 2, s); red_add_smem(gsum + cb * 2 + 1, qq); }
+      }
+    };
+    // exchange k: push this CTA's 16 partial sums into slot `mt` of every CTA of the cluster (this one included); the
+    // receiving CTA's mbarrier counts the bytes, so nobody waits for anything but the data itself
+    auto exchange = [&](int k) {
+      epi_bar();                                                       // this CTA's shared-memory atomics have landed
+      if (ew == 0) {
+        if (lane == 0) mbar_expect_tx(&xch_bar[k], (uint32_t)(p.m_tiles * 64));
+        if (lane < 16) {
+          const float v = gsum[lane];
+          gsum[lane] = 0.0f;
+          const uint32_t slot_addr = smem_u32(xch + (k * RN_MAX_CLUSTER + mt) * 16 + lane), bar_addr = smem_u32(&xch_bar[k]);
+          for (int c = 0; c < p.m_tiles; ++c) st_async_f32(map_to_cta(slot_addr, (uint32_t)c), v, map_to_cta(bar_addr, (uint32_t)c));
         }
       }
+      mbar_wait(&xch_bar[k], 0);
     };
-    // every CTA has added its statistics once `ctr` reaches n_cta
-    auto grid_sync = [&](unsigned int* ctr) {
-      epi_bar();
-      if (leader) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        grid_wait(ctr, (unsigned)p.n_cta);
-        __threadfence();
+    // per-channel scale / shift of this item's GroupNorm (partial sums added in rank order, mean / variance in fp64), bias folded in
+    auto fold_consts = [&](int k, const float* gamma, const float* beta, const float* extra, const float* next_bias) {
+      if (te < RN_C) {
+        const float* part = xch + (k * RN_MAX_CLUSTER) * 16 + (te >> 5) * 2;
+        double s = 0.0, qq = 0.0;
+        for (int c = 0; c < p.m_tiles; ++c) { s += (double)part[c * 16]; qq += (double)part[c * 16 + 1]; }
+        const double mu = s * inv_n;
+        double var = qq * inv_n - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float mean = (float)mu, ve = (float)(var + (double)p.eps_gn);
+        float rstd = rsqrtf(ve);
+        rstd = rstd * fmaf(-0.5f * ve, rstd * rstd, 1.5f);             // one Newton step: fp32-exact to the last bit or two
+        const float sc = rstd * __ldg(gamma + te);
+        const float bias = c_bias[te];
+        c_scale[te] = sc;
+        c_shift[te] = fmaf(bias - mean, sc, __ldg(beta + te));
+        c_extra[te] = extra ? __ldg(extra + te) : 0.0f;
+        if (next_bias) c_bias[te] = __ldg(next_bias + te);
       }
       epi_bar();
     };
-    // mean / rstd of group `cb` of this item (same arithmetic as gn_apply256: fp64 sums -> fp32 mean, rstd)
-    auto group_stat = [&](const double* gn, int cb, float& mean, float& rstd) {
-      const double* src = gn + ((long long)b * 8 + cb) * 2;
-      const double s = __ldcg(src), qq = __ldcg(src + 1);
-      const double mu = s * inv_n;
-      double var = qq * inv_n - mu * mu;
-      if (var < 0.0) var = 0.0;
-      mean = (float)mu;
-      rstd = (float)(1.0 / sqrt(var + (double)p.eps_gn));
-    };
-    // 32 bf16 values per lane (thread = row) -> coalesced 16-byte stores of the 32 x 32 block at dst (row stride ld elements)
-    auto store_bf16_block = [&](const uint32_t (&pk)[16], bf16* dst, long long ld, int t0) {
-      uint8_t* brow = reinterpret_cast<uint8_t*>(wstage) + lane * RN_ACT_PITCH;
+    // 32 bf16 values per lane (thread = row) -> coalesced 16-byte stores of the owned rows of the 32 x 32 block
+    auto store_bf16_block = [&](const uint32_t (&pk)[16], bf16* dst, long long ld, int m) {
+      uint8_t* brow = wstage + lane * RN_ACT_PITCH;
 #pragma unroll
       for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(brow + i * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
       __syncwarp();
       const int rsub = lane >> 2, ch = lane & 3;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(wstage) + ch * 16;
+      const uint8_t* src = wstage + ch * 16;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
-        const int rl = rsub + it * 8, t = t0 + rl;
-        if (t < p.T) *reinterpret_cast<uint4*>(dst + (long long)t * ld + ch * 8) = *reinterpret_cast<const uint4*>(src + rl * RN_ACT_PITCH);
+        const int rr = rsub + it * 8, r = m * 128 + q * 32 + rr, t = m0 - 1 + r;
+        if (r >= 1 && r <= R - 2 && t < p.T) *reinterpret_cast<uint4*>(dst + (long long)t * ld + ch * 8) = *reinterpret_cast<const uint4*>(src + rr * RN_ACT_PITCH);
       }
       __syncwarp();
     };
 
-    // ======== conv1 done: statistics -> grid barrier 1 -> apply 1
+    // ======== conv1 done: statistics -> exchange within the cluster -> apply 1
     mbar_wait(&acc_full, 0);
     tcgen05_fence_after();
     if (ew == 0) RN_TR(2);
-    stats_pass(p.bias1, p.gn1);
-    grid_sync(p.bar + 0);
+    stats_pass(0u);
+    exchange(0);
     if (ew == 0) RN_TR(3);
+    fold_consts(0, p.g1, p.b1, full ? p.temb : nullptr, full ? p.bias2 : nullptr);
 #pragma unroll 1
-    for (int blk = slot; blk < n_blk; blk += 4) {
-      const int m = blk >> 3, cb = blk & 7;
-      float mean, rstd;
-      group_stat(p.gn1, cb, mean, rstd);
-      uint32_t raw[32];
-      tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-      const int t = m0 + m * 128 + q * 32 + lane;
-      const bool valid = t < p.T && (t << p.len_shift) < len_b;
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int c = cb * 32 + j;
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + c));
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g1 + c)), be = __ldg(reinterpret_cast<const float4*>(p.b1 + c));
-        float4 te = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (full) te = *reinterpret_cast<const float4*>(p.temb + c);
-        const float s0 = rstd * ga.x, s1 = rstd * ga.y, s2 = rstd * ga.z, s3 = rstd * ga.w;
-        float v0 = mish_fast(fmaf(__uint_as_float(raw[j]) + bv.x, s0, be.x - mean * s0)) + te.x;
-        float v1 = mish_fast(fmaf(__uint_as_float(raw[j + 1]) + bv.y, s1, be.y - mean * s1)) + te.y;
-        float v2 = mish_fast(fmaf(__uint_as_float(raw[j + 2]) + bv.z, s2, be.z - mean * s2)) + te.z;
-        float v3 = mish_fast(fmaf(__uint_as_float(raw[j + 3]) + bv.w, s3, be.w - mean * s3)) + te.w;
-        if (!valid) { v0 = v1 = v2 = v3 = 0.0f; }                      // (Mish * m + temb) * m: a select, the row may hold anything
-        __nv_bfloat162 lo2 = __floats2bfloat162_rn(v0, v1), hi2 = __floats2bfloat162_rn(v2, v3);
-        pk[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
-        pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hi2);
-      }
-      store_bf16_block(pk, p.a_buf + b * p.a_bs + cb * 32, p.a_ld, m0 + m * 128 + q * 32);
-    }
-    if (ew == 0) RN_TR(4);
-    if (!full) {                                                       // final_block: done
-      tcgen05_fence_before();
-    } else {
-      tcgen05_fence_before();
-      asm volatile("fence.proxy.async;" ::: "memory");                 // this thread's stores of `a` -> later TMA reads (any CTA)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&epi_done);                           // conv2 may overwrite the accumulator
-      // grid barrier 2 (arrive only): the activation producers wait for it before loading `a`
-      epi_bar();
-      if (leader) { __threadfence(); atomicAdd(p.bar + 1, 1u); }
-      if (ew == 0) RN_TR(5);
-
-      // ======== conv2 done: statistics -> grid barrier 3 -> Mish(GN2) * m back into the accumulator
-      mbar_wait(&acc_full, 1);
-      tcgen05_fence_after();
-      if (ew == 0) RN_TR(8);
-      stats_pass(p.bias2, p.gn2);
-      grid_sync(p.bar + 2);
+    for (int h = 0; h < 2; ++h) {
+      const int cb = 4 * h + slot;
 #pragma unroll 1
-      for (int blk = slot; blk < n_blk; blk += 4) {
-        const int m = blk >> 3, cb = blk & 7;
-        float mean, rstd;
-        group_stat(p.gn2, cb, mean, rstd);
+      for (int m = 0; m < p.mb; ++m) {
         uint32_t raw[32];
         tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-        const int t = m0 + m * 128 + q * 32 + lane;
-        const bool valid = t < p.T && (t << p.len_shift) < len_b;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = cb * 32 + j;
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + c));
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(p.g2 + c)), be = __ldg(reinterpret_cast<const float4*>(p.b2 + c));
-          const float s0 = rstd * ga.x, s1 = rstd * ga.y, s2 = rstd * ga.z, s3 = rstd * ga.w;
-          const float v0 = mish_fast(fmaf(__uint_as_float(raw[j]) + bv.x, s0, be.x - mean * s0));
-          const float v1 = mish_fast(fmaf(__uint_as_float(raw[j + 1]) + bv.y, s1, be.y - mean * s1));
-          const float v2 = mish_fast(fmaf(__uint_as_float(raw[j + 2]) + bv.z, s2, be.z - mean * s2));
-          const float v3 = mish_fast(fmaf(__uint_as_float(raw[j + 3]) + bv.w, s3, be.w - mean * s3));
-          raw[j] = valid ? __float_as_uint(v0) : 0u; raw[j + 1] = valid ? __float_as_uint(v1) : 0u;
-          raw[j + 2] = valid ? __float_as_uint(v2) : 0u; raw[j + 3] = valid ? __float_as_uint(v3) : 0u;
-        }
-        tmem_st32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-      }
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&epi_done);                           // res_conv may accumulate on top
-      if (ew == 0) RN_TR(9);
-
-      // ======== xr = accumulator + res bias -> fp32 stream (coalesced through the transpose buffer) + LayerNorm partial sums
-      mbar_wait(&acc_full, 0);
-      tcgen05_fence_after();
-      if (ew == 0) RN_TR(11);
-      const int sub = lane >> 3, cl = (lane & 7) * 4;
-      float ls[2] = {0.0f, 0.0f}, lq[2] = {0.0f, 0.0f};
-#pragma unroll 1
-      for (int blk = slot; blk < n_blk; blk += 4) {
-        const int m = blk >> 3, cb = blk & 7;
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-        float s = 0.0f, qq = 0.0f;
-        float* srow_w = wstage + lane * RN_STAGE_LD;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_r + cb * 32 + j));
-          const float v0 = __uint_as_float(raw[j]) + bv.x, v1 = __uint_as_float(raw[j + 1]) + bv.y;
-          const float v2 = __uint_as_float(raw[j + 2]) + bv.z, v3 = __uint_as_float(raw[j + 3]) + bv.w;
-          s += (v0 + v1) + (v2 + v3);
-          qq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3);
-          *reinterpret_cast<float4*>(srow_w + j) = make_float4(v0, v1, v2, v3);
-        }
-        if (m == 0) { ls[0] += s; lq[0] += qq; } else { ls[1] += s; lq[1] += qq; }
-        __syncwarp();
-        float* dst = p.xr + ((long long)b * p.T) * RN_C + cb * 32 + cl;
-        const int t0 = m0 + m * 128 + q * 32;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int rl = u * 4 + sub, t = t0 + rl;
-          if (t < p.T) *reinterpret_cast<float4*>(dst + (long long)t * RN_C) = *reinterpret_cast<const float4*>(wstage + rl * RN_STAGE_LD + cl);
-        }
-        __syncwarp();
-      }
-      for (int m = 0; m < vmb; ++m) {
-        float* rs = rowstat + (((m * 128) + q * 32 + lane) * 4 + slot) * 2;
-        rs[0] = ls[m]; rs[1] = lq[m];
-      }
-      epi_bar();
-      float mean_r[2], rstd_r[2];
-      for (int m = 0; m < vmb; ++m) {
-        const float4* rs = reinterpret_cast<const float4*>(rowstat + ((m * 128) + q * 32 + lane) * 8);
-        const float4 u0 = rs[0], u1 = rs[1];
-        const float mu = ((u0.x + u0.z) + (u1.x + u1.z)) * (1.0f / RN_C);
-        const float var = fmaxf(((u0.y + u0.w) + (u1.y + u1.w)) * (1.0f / RN_C) - mu * mu, 0.0f);
-        mean_r[m] = mu;
-        rstd_r[m] = 1.0f / sqrtf(var + p.eps_ln);
-      }
-      // ======== n = LayerNorm(xr) -> bf16 operand of the QKV projection
-#pragma unroll 1
-      for (int blk = slot; blk < n_blk; blk += 4) {
-        const int m = blk >> 3, cb = blk & 7;
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
-        const float mu = m == 0 ? mean_r[0] : mean_r[1], rs = m == 0 ? rstd_r[0] : rstd_r[1];
+        const int r = m * 128 + rl, t = m0 - 1 + r;
+        const bool valid = t >= 0 && t < p.T && (t << p.len_shift) < len_b;   // (Mish * m + temb) * m; rows outside [0, T) are conv2's zero padding
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int c = cb * 32 + j;
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias_r + c));
-          const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + c)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + c));
-          const float v0 = (__uint_as_float(raw[j]) + bv.x - mu) * rs * ga.x + be.x;
-          const float v1 = (__uint_as_float(raw[j + 1]) + bv.y - mu) * rs * ga.y + be.y;
-          const float v2 = (__uint_as_float(raw[j + 2]) + bv.z - mu) * rs * ga.z + be.z;
-          const float v3 = (__uint_as_float(raw[j + 3]) + bv.w - mu) * rs * ga.w + be.w;
-          __nv_bfloat162 lo2 = __floats2bfloat162_rn(v0, v1), hi2 = __floats2bfloat162_rn(v2, v3);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
-          pk[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&hi2);
+          const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
+          const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
+          const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
+          const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
+          const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
+          const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
+          pk[j >> 1] = valid ? pack_bf16(v0, v1) : 0u;                 // a select: the row may hold anything
+          pk[(j >> 1) + 1] = valid ? pack_bf16(v2, v3) : 0u;
         }
-        store_bf16_block(pk, p.n_out + ((long long)b * p.T) * RN_C + cb * 32, RN_C, m0 + m * 128 + q * 32);
+        if (full) {
+          // K-major operand plane (cb >> 1), row r, 16-byte chunks 4 (cb & 1) + i, 128B swizzle: chunk ^= r & 7
+          uint8_t* prow = a_gen + (cb >> 1) * (R * 128) + r * 128;
+          const int c0 = 4 * (cb & 1), x7 = r & 7;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(prow + (((c0 + i) ^ x7) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          if (p.a_buf && r >= 1 && r <= R - 2 && t < p.T) {            // tests only: a copy of the operand
+            uint4* dst = reinterpret_cast<uint4*>(p.a_buf + b * p.a_bs + (long long)t * p.a_ld + cb * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        } else {
+          store_bf16_block(pk, p.a_buf + b * p.a_bs + cb * 32, p.a_ld, m);
+        }
       }
-      tcgen05_fence_before();
+      if (full) {
+        tcgen05_fence_before();
+        fence_proxy_async();                                           // generic-proxy smem stores -> the MMAs' async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&plane_ready[h]);
+      }
+    }
+    if (ew == 0) RN_TR(4);
+    if (full) {
+      // ======== conv2 done: statistics -> exchange -> Mish(GN2(h2)) * m + res bias back into the accumulator
+      mbar_wait(&acc_full, 1);
+      tcgen05_fence_after();
+      if (ew == 0) RN_TR(8);
+      stats_pass(acc2_col);
+      exchange(1);
+      if (ew == 0) RN_TR(5);
+      fold_consts(1, p.g2, p.b2, p.bias_r, nullptr);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int cb = 4 * h + slot;
+#pragma unroll 1
+        for (int m = 0; m < vmb; ++m) {
+          uint32_t raw[32];
+          const uint32_t taddr = lane_addr + acc2_col + (uint32_t)(m * RN_C + cb * 32);
+          tmem_ld32(taddr, raw);
+          const int t = m0 - 1 + m * 128 + rl;
+          const bool valid = t >= 0 && t < p.T && (t << p.len_shift) < len_b;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int c = cb * 32 + j;
+            const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
+            const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
+            const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
+            const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
+            const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
+            const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
+            raw[j] = __float_as_uint(valid ? v0 : ex.x); raw[j + 1] = __float_as_uint(valid ? v1 : ex.y);
+            raw[j + 2] = __float_as_uint(valid ? v2 : ex.z); raw[j + 3] = __float_as_uint(valid ? v3 : ex.w);
+          }
+          tmem_st32(taddr, raw);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tm_ready[h]);                      // res_conv may accumulate on top of this half
+      }
+      if (ew == 0) RN_TR(9);
+
+      // ======== xr = accumulator -> fp32 stream (coalesced through the transpose buffer) + LayerNorm row sums
+      const int sub = lane >> 3, cl = lane & 7;
+      float ls[2] = {0.0f, 0.0f}, lq[2] = {0.0f, 0.0f};
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int cb = 4 * h + slot;
+        mbar_wait(&res_full[h], 0);
+        tcgen05_fence_after();
+        if (ew == 0 && h == 0) RN_TR(11);
+#pragma unroll 1
+        for (int m = 0; m < vmb; ++m) {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + acc2_col + (uint32_t)(m * RN_C + cb * 32), raw);
+          float s = 0.0f, qq = 0.0f;
+          uint8_t* srow = wstage + lane * 128;
+          const int x7 = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float v0 = __uint_as_float(raw[j]), v1 = __uint_as_float(raw[j + 1]), v2 = __uint_as_float(raw[j + 2]), v3 = __uint_as_float(raw[j + 3]);
+            s += (v0 + v1) + (v2 + v3);
+            qq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, qq))));
+            *reinterpret_cast<float4*>(srow + ((((j >> 2) ^ x7)) << 4)) = make_float4(v0, v1, v2, v3);
+          }
+          if (m == 0) { ls[0] += s; lq[0] += qq; } else { ls[1] += s; lq[1] += qq; }
+          __syncwarp();
+          float* dst = p.xr + ((long long)b * p.T) * RN_C + cb * 32 + cl * 4;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rr = u * 4 + sub, r = m * 128 + q * 32 + rr, t = m0 - 1 + r;
+            if (r >= 1 && r <= R - 2 && t < p.T)
+              *reinterpret_cast<float4*>(dst + (long long)t * RN_C) = *reinterpret_cast<const float4*>(wstage + rr * 128 + ((cl ^ (rr & 7)) << 4));
+          }
+          __syncwarp();
+        }
+      }
+      red_add_smem(rowsum + rl * 2, ls[0]);
+      red_add_smem(rowsum + rl * 2 + 1, lq[0]);
+      if (vmb > 1) {
+        red_add_smem(rowsum + (128 + rl) * 2, ls[1]);
+        red_add_smem(rowsum + (128 + rl) * 2 + 1, lq[1]);
+      }
+      epi_bar();
+      if (ew == 0) RN_TR(6);
+      // ======== n = LayerNorm(xr) -> bf16 operand of the QKV projection
+#pragma unroll 1
+      for (int m = 0; m < vmb; ++m) {
+        const float2 rs2 = *reinterpret_cast<const float2*>(rowsum + (m * 128 + rl) * 2);
+        const float mu = rs2.x * (1.0f / RN_C);
+        const float var = fmaxf(rs2.y * (1.0f / RN_C) - mu * mu, 0.0f);
+        const float rs = rsqrtf(var + p.eps_ln);
+        const float nmu = -mu * rs;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int cb = 4 * h + slot;
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + acc2_col + (uint32_t)(m * RN_C + cb * 32), raw);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int c = cb * 32 + j;
+            const float4 ga = *reinterpret_cast<const float4*>(c_lng + c), be = *reinterpret_cast<const float4*>(c_lnb + c);
+            const float v0 = fmaf(fmaf(__uint_as_float(raw[j]), rs, nmu), ga.x, be.x);
+            const float v1 = fmaf(fmaf(__uint_as_float(raw[j + 1]), rs, nmu), ga.y, be.y);
+            const float v2 = fmaf(fmaf(__uint_as_float(raw[j + 2]), rs, nmu), ga.z, be.z);
+            const float v3 = fmaf(fmaf(__uint_as_float(raw[j + 3]), rs, nmu), ga.w, be.w);
+            pk[j >> 1] = pack_bf16(v0, v1);
+            pk[(j >> 1) + 1] = pack_bf16(v2, v3);
+          }
+          store_bf16_block(pk, p.n_out + ((long long)b * p.T) * RN_C + cb * 32, RN_C, m);
+        }
+      }
       if (ew == 0) RN_TR(12);
     }
   }
@@ -484,7 +587,12 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
 }
 
 int g_rn_mode = -1;    // EV_RN_FUSE: 0 = five launches per ResNet block (round-1 path), 1 = fused (default)
-int g_rn_coop = 1;     // EV_RN_COOP=0: plain launch (co-residency then rests on grid <= SM count alone)
+
+// A region: conv1's input ring, the four operand planes, or res_conv's input ring + the 64 KB of transpose buffers
+int rn_a_bytes(int mb, int x1_slot_bytes) {
+  const int R = 128 * mb;
+  return (int)align_up((size_t)std::max({RN_X1_SLOTS * x1_slot_bytes, 4 * R * 128, RN_X3_SLOTS * R * 128 + RN_STAGE}), 1024);
+}
 
 }  // namespace
 
@@ -492,12 +600,57 @@ cudaError_t resnet_tc_read_trace(unsigned long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_rn_trace, sizeof(unsigned long long) * std::min(n, 32));
 }
 
-// m-blocks per CTA for B items of T frames, or 0 when the tiles cannot all be co-resident
+namespace {
+struct RnPlan { int mb, m_tiles, x1_boxes, x1_box_rows, x1_slot_bytes, a_bytes, w_slots, smem_bytes; };
+RnPlan rn_plan_for(int mb, int T) {
+  RnPlan q{};
+  q.mb = mb;
+  const int R = 128 * mb, x1_rows = R + 2;
+  q.m_tiles = ceil_div(T, R - 2);
+  q.x1_boxes = x1_rows > 256 ? 2 : 1;
+  q.x1_box_rows = (int)align_up((size_t)ceil_div(x1_rows, q.x1_boxes), 8);
+  q.x1_slot_bytes = (int)align_up((size_t)q.x1_boxes * q.x1_box_rows * 128, 1024);
+  q.a_bytes = rn_a_bytes(mb, q.x1_slot_bytes);
+  const int fixed = 1024 + q.a_bytes + RN_CONST_FLOATS * 4;
+  q.w_slots = std::min(RN_MAX_W_SLOTS, (RN_SMEM_LIMIT - fixed) / RN_W_TILE);
+  q.smem_bytes = fixed + q.w_slots * RN_W_TILE;
+  return q;
+}
+cudaError_t rn_set_attributes() {
+  static DeviceOnce once;
+  return once.run([&]() { return cudaFuncSetAttribute(resnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RN_SMEM_LIMIT); });
+}
+// CTAs of `cluster`-sized clusters (one m-block per CTA) the device holds at once; clusters do not straddle GPCs, so this
+// can be less than the SM count
+int rn_resident_ctas(int cluster) {
+  static std::atomic<int> cache[RN_MAX_CLUSTER + 1];
+  int v = cache[cluster].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  v = tc_sm_count() / cluster * cluster * 3 / 4;                     // conservative guess if the query is unavailable
+  if (rn_set_attributes() == cudaSuccess) {
+    const RnPlan q = rn_plan_for(1, 126 * cluster);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster * 64); cfg.blockDim = dim3(RN_THREADS); cfg.dynamicSmemBytes = q.smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, resnet_tc_kernel, &cfg) == cudaSuccess && n > 0) v = n * cluster;
+    else (void)cudaGetLastError();
+  }
+  cache[cluster].store(v, std::memory_order_relaxed);
+  return v;
+}
+}  // namespace
+
+// m-blocks per CTA for B items of T frames (a CTA owns 128 * mb - 2 frames; the tiles of an item form a cluster of <= 8 CTAs):
+// one m-block when the whole batch then fits one wave, else two; 0 when an item needs more than 8 tiles
 int resnet_tc_plan(int B, int T) {
-  const int sms = tc_sm_count();
   if (B <= 0 || T <= 0) return 0;
-  if ((long long)B * ceil_div(T, 128) <= sms) return 1;
-  if ((long long)B * ceil_div(T, 256) <= sms) return 2;
+  const int t1 = ceil_div(T, 126), t2 = ceil_div(T, 254);
+  if (t1 <= RN_MAX_CLUSTER && (long long)B * t1 <= rn_resident_ctas(t1)) return 1;
+  if (t2 <= RN_MAX_CLUSTER) return 2;
   return 0;
 }
 
@@ -505,8 +658,6 @@ bool resnet_tc_supported(const ConvWeights& conv1, const ConvWeights* conv2, con
   if (g_rn_mode < 0) {
     const char* v = getenv("EV_RN_FUSE");
     g_rn_mode = v ? atoi(v) : 1;
-    const char* c = getenv("EV_RN_COOP");
-    g_rn_coop = c ? atoi(c) : 1;
   }
   auto ok3 = [](const ConvWeights& w) {
     return w.w_bf16 && w.bias && w.taps == 3 && w.N == RN_C && w.N_pad_tc == RN_C && w.conv_stride == 1 && w.dilation == 1 && w.pad == 1 &&
@@ -525,62 +676,64 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
   const ConvWeights& w1 = *a.conv1;
   const bool full = a.conv2 != nullptr;
   if (!resnet_tc_supported(w1, a.conv2, a.res, a.B, a.T)) {
-    if (err) *err = "resnet_tc: unsupported layer shapes or too many tiles for one co-resident wave";
+    if (err) *err = "resnet_tc: unsupported layer shapes, or more than 8 tiles per item";
     return cudaErrorInvalidValue;
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if ((a.x_ld & 7) || (a.x_bs & 7) || (a.a_ld & 7) || (a.a_bs & 7) || !al16(a.x) || !al16(a.a_buf) || !al16(a.gn_g1) || !al16(a.gn_b1) ||
-      (full && (!al16(a.xr) || !al16(a.n_out) || !al16(a.temb) || !al16(a.gn_g2) || !al16(a.gn_b2) || !al16(a.ln_g) || !al16(a.ln_b)))) {
+  if ((a.x_ld & 7) || (a.x_bs & 7) || !al16(a.x) || (a.a_buf && ((a.a_ld & 7) || (a.a_bs & 7) || !al16(a.a_buf))) || (!full && !a.a_buf) ||
+      (full && (!al16(a.xr) || !al16(a.n_out) || !a.xr || !a.n_out || !a.temb || !a.ln_g || !a.ln_b))) {
     if (err) *err = "resnet_tc: tensors must be 16-byte aligned";
+    return cudaErrorInvalidValue;
+  }
+  const RnPlan plan = rn_plan_for(resnet_tc_plan(a.B, a.T), a.T);
+  if (plan.w_slots < 3) {
+    if (err) *err = "resnet_tc: shared-memory plan does not fit";
     return cudaErrorInvalidValue;
   }
   RnParams p{};
   p.B = a.B; p.T = a.T;
-  p.mb = resnet_tc_plan(a.B, a.T);
-  p.m_tiles = ceil_div(a.T, 128 * p.mb);
+  p.mb = plan.mb; p.m_tiles = plan.m_tiles;
   p.n_cta = a.B * p.m_tiles;
   p.kc_in = ceil_div(w1.C_in, 64);
-  const int a_rows = p.mb * 128 + 2;
-  p.a_boxes = a_rows > 256 ? 2 : 1;
-  p.a_box_rows = (int)align_up((size_t)ceil_div(a_rows, p.a_boxes), 8);
-  p.a_slot_bytes = (int)align_up((size_t)p.a_boxes * p.a_box_rows * 128, 1024);
-  p.a_slots = std::min(RN_MAX_A_SLOTS, RN_AREGION / p.a_slot_bytes);
+  p.x1_boxes = plan.x1_boxes; p.x1_box_rows = plan.x1_box_rows; p.x1_slot_bytes = plan.x1_slot_bytes;
+  p.a_bytes = plan.a_bytes; p.w_slots = plan.w_slots;
+  const int smem_bytes = plan.smem_bytes;
   p.mode = full ? 0 : 1;
   p.lens = a.lens; p.len_shift = a.len_shift;
   p.bias1 = w1.bias; p.g1 = a.gn_g1; p.b1 = a.gn_b1; p.temb = a.temb;
-  p.gn1 = a.gn_sum1; p.gn2 = a.gn_sum2; p.bar = a.barriers;
   p.a_buf = a.a_buf; p.a_ld = a.a_ld; p.a_bs = a.a_bs;
   p.eps_gn = 1e-5f; p.eps_ln = 1e-5f;
   { static const int tr = []() { const char* v = getenv("EV_RN_TRACE"); return v ? atoi(v) : 0; }(); p.trace = tr; }
   RnMaps maps;
-  bool ok = tc_encode_bf16_map(&maps.x, a.x, (uint64_t)w1.C_in, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.x_ld * 2, (uint64_t)a.x_bs * 2,
-                               64u, (uint32_t)p.a_box_rows, 128, err);
+  bool ok = tc_encode_bf16_map(&maps.x1, a.x, (uint64_t)w1.C_in, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.x_ld * 2, (uint64_t)a.x_bs * 2,
+                               64u, (uint32_t)p.x1_box_rows, 128, err);
   ok = ok && tc_encode_bf16_map(&maps.w1, w1.w_bf16, (uint64_t)w1.K_pad, (uint64_t)w1.N_pad_tc, 3, (uint64_t)w1.K_pad * 2,
-                                (uint64_t)w1.K_pad * w1.N_pad_tc * 2, 64u, (uint32_t)RN_C, 128, err);
+                                (uint64_t)w1.K_pad * w1.N_pad_tc * 2, 64u, 128u, 128, err);
   if (full) {
     const ConvWeights& w2 = *a.conv2;
     const ConvWeights& wr = *a.res;
     p.bias2 = w2.bias; p.bias_r = wr.bias; p.g2 = a.gn_g2; p.b2 = a.gn_b2; p.ln_g = a.ln_g; p.ln_b = a.ln_b;
     p.xr = a.xr; p.n_out = a.n_out;
-    ok = ok && tc_encode_bf16_map(&maps.a, a.a_buf, (uint64_t)RN_C, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.a_ld * 2, (uint64_t)a.a_bs * 2,
-                                  64u, (uint32_t)p.a_box_rows, 128, err);
+    ok = ok && tc_encode_bf16_map(&maps.x3, a.x, (uint64_t)w1.C_in, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.x_ld * 2, (uint64_t)a.x_bs * 2,
+                                  64u, 128u, 128, err);
     ok = ok && tc_encode_bf16_map(&maps.w2, w2.w_bf16, (uint64_t)w2.K_pad, (uint64_t)w2.N_pad_tc, 3, (uint64_t)w2.K_pad * 2,
-                                  (uint64_t)w2.K_pad * w2.N_pad_tc * 2, 64u, (uint32_t)RN_C, 128, err);
+                                  (uint64_t)w2.K_pad * w2.N_pad_tc * 2, 64u, 128u, 128, err);
     ok = ok && tc_encode_bf16_map(&maps.wr, wr.w_bf16, (uint64_t)wr.K_pad, (uint64_t)wr.N_pad_tc, 1, (uint64_t)wr.K_pad * 2,
-                                  (uint64_t)wr.K_pad * wr.N_pad_tc * 2, 64u, (uint32_t)RN_C, 128, err);
+                                  (uint64_t)wr.K_pad * wr.N_pad_tc * 2, 64u, 128u, 128, err);
   } else {
-    maps.a = maps.x; maps.w2 = maps.w1; maps.wr = maps.w1;
+    maps.x3 = maps.x1; maps.w2 = maps.w1; maps.wr = maps.w1;
   }
   if (!ok) return cudaErrorInvalidValue;
-  static DeviceOnce once;
-  cudaError_t ce = once.run([&]() { return cudaFuncSetAttribute(resnet_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RN_SMEM); });
+  cudaError_t ce = rn_set_attributes();
   if (ce != cudaSuccess) return ce;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(p.n_cta); cfg.blockDim = dim3(RN_THREADS); cfg.dynamicSmemBytes = RN_SMEM; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeCooperative;
-  at[0].val.cooperative = g_rn_coop ? 1 : 0;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  cfg.gridDim = dim3(p.n_cta); cfg.blockDim = dim3(RN_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;                      // one cluster = the tiles of one item
+  at[0].val.clusterDim.x = p.m_tiles; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, resnet_tc_kernel, maps, p);
 }
 

@@ -11,9 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from emojivoice_b200 import _lib  # noqa: E402
 
-NAMES = {0: "entry", 1: "conv1 issued", 2: "acc1 seen", 3: "barrier 1 passed", 4: "apply 1 done", 5: "barrier 2 arrived",
-         6: "barrier 2 passed (producer)", 7: "conv2 issued", 8: "acc2 seen", 9: "apply 2 -> TMEM done", 10: "res issued",
-         11: "acc3 seen", 12: "exit of epilogue"}
+NAMES = {0: "entry", 1: "conv1 issued", 2: "acc1 seen", 3: "barrier 1 passed", 4: "apply 1 done", 7: "conv2 issued", 8: "acc2 seen",
+         5: "barrier 2 passed", 9: "apply 2 -> TMEM done", 10: "res issued", 11: "res half 0 seen", 6: "xr stored", 12: "exit of epilogue"}
 
 
 def main():
@@ -40,7 +39,7 @@ def main():
             buf = (C.c_uint64 * 32)()
             ctx.check(L.ev_test_resnet_trace(ctx.handle, buf, 32), "trace")
             t0 = buf[0]
-            print("   trace (clk from entry, CTA 0): " + ", ".join(f"{NAMES[i]} {buf[i] - t0}" for i in range(1, 13) if buf[i] >= t0 and buf[i] != 0))
+            print("   trace (clk from entry, CTA 0): " + ", ".join(f"{NAMES[i]} {buf[i] - t0}" for i in (1, 2, 3, 4, 7, 8, 5, 9, 10, 11, 6, 12) if buf[i] >= t0 and buf[i] != 0))
 
 
 if __name__ == "__main__":

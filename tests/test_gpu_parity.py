@@ -170,15 +170,18 @@ def _mish(x):
     return x * torch.tanh(F.softplus(x))
 
 
-# B, T, C_in, len_shift, full      (one tile per CTA; B * ceil(T / 128) <= 148 -> one m-block per CTA, else two)
+# B, T, C_in, len_shift, full      (one tile per CTA, 126 owned frames per m-block + 2 halo rows; B * ceil(T / 126) <= 148 -> one
+# m-block per CTA, else two; (50, 300) ends in a tile whose second m-block is empty, 126 / 127 / 252 sit on tile boundaries)
 RESNET_CASES = [(2, 200, 256, 0, 1), (3, 129, 224, 1, 1), (1, 1, 256, 0, 1), (32, 334, 512, 1, 1), (32, 668, 224, 0, 1),
-                (5, 700, 512, 0, 1), (32, 668, 256, 0, 0), (2, 130, 256, 0, 0), (40, 500, 256, 0, 1)]
+                (5, 700, 512, 0, 1), (32, 668, 256, 0, 0), (2, 130, 256, 0, 0), (40, 500, 256, 0, 1), (50, 300, 256, 0, 1),
+                (3, 126, 256, 0, 1), (3, 127, 256, 0, 1), (2, 252, 256, 1, 1), (50, 254, 512, 0, 1), (50, 255, 256, 0, 0),
+                (200, 130, 256, 0, 1), (3, 1000, 256, 0, 1), (2, 1500, 224, 0, 1), (20, 1008, 256, 0, 0)]   # several waves; clusters of 8 and 6
 
 
 @pytest.mark.parametrize("case", RESNET_CASES)
 def test_fused_resnet_block_matches_torch(ctx, case):
     """resnet_tc.cu: conv3 -> GroupNorm(8) over the padded extent -> Mish -> mask -> + temb -> mask -> conv3 -> GroupNorm -> Mish ->
-    mask -> + res_conv(x) -> LayerNorm, one cooperative launch with three grid barriers, against fp64 torch on the same
+    mask -> + res_conv(x) -> LayerNorm, one launch, the tiles of an item exchanging GroupNorm sums inside a thread-block cluster, against fp64 torch on the same
     bf16-rounded operands (decoder.py:32-61, transformer.py:262)."""
     B, T, Cin, shift, full = case
     D = 256
