@@ -13,7 +13,7 @@
 //     operand `a` -- its taps reach one row to either side -- never leaves the SM: the epilogue warps write it, hand-swizzled,
 //     straight into the shared-memory K-major operand planes conv2's MMAs read.  No global round trip, no grid barrier there;
 //   * the tiles of one item form a THREAD-BLOCK CLUSTER (<= 8 CTAs).  The conv accumulators (R x 256 fp32) stay in TMEM across
-//     the GroupNorm: pass 1 reads them for the statistics of the OWNED rows (shared-memory atomics per group), every CTA then
+//     the GroupNorm: pass 1 reads them for the statistics of the OWNED rows, every CTA then
 //     pushes its 16 partial sums into the shared memory of every CTA of the cluster (st.async + mbarrier complete_tx over
 //     DSMEM: one ~0.5 us hop instead of global atomics + a grid barrier), sums them in rank order (deterministic) and pass 2
 //     reads the accumulators again and normalises.  The fp32 conv outputs never touch HBM, nothing is zeroed beforehand,
@@ -25,7 +25,7 @@
 //     output pass of half 0;
 //   * with one m-block per CTA (mb = 1) conv2 accumulates into the spare 256 TMEM columns and starts on K-chunks 0-1 while the
 //     epilogue warps are still producing K-chunks 2-3 of `a`;
-//   * LayerNorm statistics are taken per row from the same TMEM tile (thread = row), combined through shared-memory atomics.
+//   * LayerNorm statistics are taken per row from the same TMEM tile (thread = row), combined across the four column-slot warps through shared memory (one writer per partial sum, fixed order).
 // `mode 1` stops after the first apply (final_block: conv -> GN -> Mish -> mask, decoder.py:431) and writes bf16 to global.
 //
 // Warp roles (20 warps): 0 activation-tile TMA producer, 1 weight-tile TMA producer (weights are constants: it runs free),
@@ -59,9 +59,10 @@ constexpr int RN_STAGE_WARP = 4096;              // 32 x 32 fp32 (XOR-swizzled) 
 constexpr int RN_STAGE = RN_EPI_WARPS * RN_STAGE_WARP;
 constexpr int RN_ACT_PITCH = 80;                 // bytes per staged bf16 row (64 + 16: conflict-free 16-byte access)
 constexpr int RN_MAX_CLUSTER = 8;
-// constants: scale, shift, extra (temb / res bias), conv bias, LN gamma, LN beta [256 each], row sums [256][2], group sums [8][2],
-// the cluster's partial group sums [2 GroupNorms][8 ranks][16]
-constexpr int RN_CONST_FLOATS = 6 * RN_C + 2 * 256 + 16 + 2 * RN_MAX_CLUSTER * 16;
+// constants: scale, shift, extra (temb / res bias), conv bias, LN gamma, LN beta [256 each], LayerNorm partial row sums
+// [256 rows][4 column slots][2], GroupNorm partial sums [8 groups][4 lane quadrants][2], the cluster's group sums
+// [2 GroupNorms][8 ranks][16].  Every partial sum has ONE writer and is added in a fixed order: results are reproducible.
+constexpr int RN_CONST_FLOATS = 6 * RN_C + 256 * 8 + 64 + 2 * RN_MAX_CLUSTER * 16;
 constexpr int RN_SMEM_LIMIT = 227 * 1024 - 1024; // dynamic + ~0.5 KB of static barriers must stay below 227 KB
 
 struct RnMaps { CUtensorMap x1, x3, w1, w2, wr; };
@@ -86,6 +87,29 @@ __device__ unsigned long long g_rn_trace[32];
 __device__ __forceinline__ uint32_t rd_hi(uint32_t sbo, uint32_t layout) { return ((sbo >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29); }
 __device__ __forceinline__ uint32_t rd_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
 __device__ __forceinline__ uint64_t rd_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+static __device__ __noinline__ void rn_wait_timeout(int line) {
+  printf("emojivoice_b200: resnet_tc mbarrier wait at line %d timed out (block %d thread %d)\n", line, blockIdx.x, threadIdx.x);
+  __trap();
+}
+// mbar_wait with the source line in the diagnostic (a pipeline bug must trap, not hang the device)
+__device__ __forceinline__ void rn_wait_at(uint64_t* bar, uint32_t parity, int line) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) rn_wait_timeout(line);
+  }
+}
+#define RN_WAIT(bar, parity) rn_wait_at((bar), (parity), __LINE__)
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(RN_EPI_THREADS) : "memory"); }
 
@@ -114,10 +138,6 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void red_add_smem(float* addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(addr)), "f"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(RN_THREADS, 1)
 resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ RnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,9 +153,9 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
   uint8_t* stage_gen = a_gen + (p.a_bytes - RN_STAGE);                          // the last 64 KB of the A region
   float* cst = reinterpret_cast<float*>(a_gen + p.a_bytes);
   float *c_scale = cst, *c_shift = cst + RN_C, *c_extra = cst + 2 * RN_C, *c_bias = cst + 3 * RN_C, *c_lng = cst + 4 * RN_C, *c_lnb = cst + 5 * RN_C;
-  float* rowsum = cst + 6 * RN_C;                                               // [256 rows][2]
-  float* gsum = rowsum + 512;                                                   // [8 groups][2]
-  float* xch = gsum + 16;                                                       // [2][8 ranks][16]: partial sums pushed by the cluster's CTAs
+  float* rowsum = cst + 6 * RN_C;                                               // [256 rows][4 slots][2]
+  float* gsum = rowsum + 256 * 8;                                               // [8 groups][4 quadrants][2]
+  float* xch = gsum + 64;                                                       // [2][8 ranks][16]: partial sums pushed by the cluster's CTAs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.mb * 128, U = R - 2;
   const int b = (int)blockIdx.x / p.m_tiles, mt = (int)blockIdx.x - b * p.m_tiles;
@@ -175,7 +195,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       uint32_t px = 1;
       const uint32_t x1_bytes = (uint32_t)(p.x1_boxes * p.x1_box_rows * 128), box_bytes = (uint32_t)(p.x1_box_rows * 128);
       for (int kc = 0; kc < p.kc_in; ++kc) {
-        mbar_wait(&x1_empty[sx], px);
+        RN_WAIT(&x1_empty[sx], px);
         mbar_expect_tx(&x1_full[sx], x1_bytes);
         const uint32_t dst = a_s + (uint32_t)(sx * p.x1_slot_bytes);
         tma_load_3d(dst, &maps.x1, &x1_full[sx], kc * 64, m0 - 2, b);
@@ -183,13 +203,13 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
         if (++sx == RN_X1_SLOTS) { sx = 0; px ^= 1u; }
       }
       if (full) {
-        mbar_wait(&acc_full, 0);
-        mbar_wait(&acc_full, 1);                  // conv2's MMAs have completed: the operand planes are dead
+        RN_WAIT(&acc_full, 0);
+        RN_WAIT(&acc_full, 1);                  // conv2's MMAs have completed: the operand planes are dead
         sx = 0; px = 1;
         const uint32_t x3_bytes = (uint32_t)(R * 128);
         for (int h = 0; h < 2; ++h)
           for (int kc = 0; kc < p.kc_in; ++kc) {
-            mbar_wait(&x3_empty[sx], px);
+            RN_WAIT(&x3_empty[sx], px);
             mbar_expect_tx(&x3_full[sx], x3_bytes);
             const uint32_t dst = a_s + (uint32_t)sx * x3_bytes;
             for (int j = 0; j < p.mb; ++j) tma_load_3d(dst + (uint32_t)(j * 128 * 128), &maps.x3, &x3_full[sx], kc * 64, m0 - 1 + j * 128, b);
@@ -204,7 +224,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       int sw = 0;
       uint32_t pw = 1;
       auto load_w = [&](const CUtensorMap* map, int kc, int h, int tap) {
-        mbar_wait(&w_empty[sw], pw);
+        RN_WAIT(&w_empty[sw], pw);
         mbar_expect_tx(&w_full[sw], (uint32_t)RN_W_TILE);
         tma_load_3d(w_s + (uint32_t)(sw * RN_W_TILE), map, &w_full[sw], kc * 64, h * 128, tap);
         if (++sw == p.w_slots) { sw = 0; pw ^= 1u; }
@@ -234,8 +254,12 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     uint32_t pw = 0;
     auto ring_advance = [&](int k) { sw += k; while (sw >= p.w_slots) { sw -= p.w_slots; pw ^= 1u; } };
     // the MMAs of one weight tile: m-blocks j < vmb, A rows from `a_lo` + j * 128 rows, D columns d0 + j * 256
+    // The two issuers share the weight ring.  The slot count is EVEN, so every slot only ever holds tiles of one issuer: an
+    // issuer asks for fill k of a slot after it consumed fill k - 1 itself.  (With an odd count fill k - 1 would be the other
+    // issuer's tile, possibly still in flight -- weight tiles that miss L2 land out of order -- and a parity wait cannot tell
+    // fill k from fill k - 2: the ring protocol would break.)
     auto tile_mmas = [&](uint32_t a_lo, uint32_t d0, uint32_t acc) {
-      mbar_wait(&w_full[sw], pw);
+      RN_WAIT(&w_full[sw], pw);
       tcgen05_fence_after();
       const uint32_t w_lo = w_lo0 + (uint32_t)sw * w_step16;
       if (elect_one()) {
@@ -255,7 +279,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       int sx = 0;
       uint32_t px = 0;
       for (int kc = 0; kc < p.kc_in; ++kc) {
-        mbar_wait(&x1_full[sx], px);
+        RN_WAIT(&x1_full[sx], px);
         tcgen05_fence_after();
         const uint32_t a_lo = a_lo0 + (uint32_t)(sx * p.x1_slot_bytes >> 4);
         for (int j = 0; j < 3; ++j) {
@@ -275,11 +299,11 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       // feed the two halo rows of the output, which nobody reads).  K-chunks 0-1 are the channels of half 0, 2-3 of half 1.
       // With two m-blocks conv2 overwrites conv1's accumulator: every apply-1 read must have happened (both halves ready).
       const uint32_t plane16 = (uint32_t)(R * 128) >> 4;
-      mbar_wait(&plane_ready[0], 0);
-      if (p.mb == 2) mbar_wait(&plane_ready[1], 0);
+      RN_WAIT(&plane_ready[0], 0);
+      if (p.mb == 2) RN_WAIT(&plane_ready[1], 0);
       tcgen05_fence_after();
       for (int kc = 0; kc < RN_C / 64; ++kc) {
-        if (kc == 2 && p.mb == 1) { mbar_wait(&plane_ready[1], 0); tcgen05_fence_after(); }
+        if (kc == 2 && p.mb == 1) { RN_WAIT(&plane_ready[1], 0); tcgen05_fence_after(); }
         const uint32_t a_lo = a_lo0 + (uint32_t)kc * plane16;
         for (int j = 0; j < 3; ++j) {
           tile_mmas(a_lo + (uint32_t)j * row16 - row16, tmem_base + acc2_col + (uint32_t)(h * 128), (kc | j) ? 1u : 0u);
@@ -297,10 +321,10 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
         uint32_t px = 0;
         const uint32_t x3_16 = (uint32_t)(R * 128) >> 4;
         for (int hh = 0; hh < 2; ++hh) {
-          mbar_wait(&tm_ready[hh], 0);
+          RN_WAIT(&tm_ready[hh], 0);
           tcgen05_fence_after();
           for (int kc = 0; kc < p.kc_in; ++kc) {
-            mbar_wait(&x3_full[sx], px);
+            RN_WAIT(&x3_full[sx], px);
             tcgen05_fence_after();
             tile_mmas(a_lo0 + (uint32_t)sx * x3_16, tmem_base + acc2_col + (uint32_t)(hh * 128), 1u);
             ring_advance(1);
@@ -324,7 +348,6 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     const int rl = q * 32 + lane;                                      // row of this thread inside an m-block
 
     // constants that do not depend on a barrier
-    for (int i = te; i < 2 * 256 + 16; i += RN_EPI_THREADS) rowsum[i] = 0.0f;
     if (te < RN_C) {
       c_bias[te] = __ldg(p.bias1 + te);
       if (full) { c_lng[te] = __ldg(p.ln_g + te); c_lnb[te] = __ldg(p.ln_b + te); }
@@ -355,7 +378,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
           if (own) { s += s1; qq += q1; }
         }
         s = warp_sum(s); qq = warp_sum(qq);
-        if (lane == 0) { red_add_smem(gsum + cb * 2, s); red_add_smem(gsum + cb * 2 + 1, qq); }
+        if (lane == 0) *reinterpret_cast<float2*>(gsum + (cb * 4 + q) * 2) = make_float2(s, qq);
       }
     };
     // exchange k: push this CTA's 16 partial sums into slot `mt` of every CTA of the cluster (this one included); the
@@ -365,13 +388,13 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       if (ew == 0) {
         if (lane == 0) mbar_expect_tx(&xch_bar[k], (uint32_t)(p.m_tiles * 64));
         if (lane < 16) {
-          const float v = gsum[lane];
-          gsum[lane] = 0.0f;
+          const float* gp = gsum + (lane >> 1) * 8 + (lane & 1);        // group lane / 2, sum or sum of squares: quadrants in order
+          const float v = (gp[0] + gp[2]) + (gp[4] + gp[6]);
           const uint32_t slot_addr = smem_u32(xch + (k * RN_MAX_CLUSTER + mt) * 16 + lane), bar_addr = smem_u32(&xch_bar[k]);
           for (int c = 0; c < p.m_tiles; ++c) st_async_f32(map_to_cta(slot_addr, (uint32_t)c), v, map_to_cta(bar_addr, (uint32_t)c));
         }
       }
-      mbar_wait(&xch_bar[k], 0);
+      RN_WAIT(&xch_bar[k], 0);
     };
     // per-channel scale / shift of this item's GroupNorm (partial sums added in rank order, mean / variance in fp64), bias folded in
     auto fold_consts = [&](int k, const float* gamma, const float* beta, const float* extra, const float* next_bias) {
@@ -411,7 +434,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     };
 
     // ======== conv1 done: statistics -> exchange within the cluster -> apply 1
-    mbar_wait(&acc_full, 0);
+    RN_WAIT(&acc_full, 0);
     tcgen05_fence_after();
     if (ew == 0) RN_TR(2);
     stats_pass(0u);
@@ -466,7 +489,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     if (ew == 0) RN_TR(4);
     if (full) {
       // ======== conv2 done: statistics -> exchange -> Mish(GN2(h2)) * m + res bias back into the accumulator
-      mbar_wait(&acc_full, 1);
+      RN_WAIT(&acc_full, 1);
       tcgen05_fence_after();
       if (ew == 0) RN_TR(8);
       stats_pass(acc2_col);
@@ -510,7 +533,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int cb = 4 * h + slot;
-        mbar_wait(&res_full[h], 0);
+        RN_WAIT(&res_full[h], 0);
         tcgen05_fence_after();
         if (ew == 0 && h == 0) RN_TR(11);
 #pragma unroll 1
@@ -539,20 +562,16 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
           __syncwarp();
         }
       }
-      red_add_smem(rowsum + rl * 2, ls[0]);
-      red_add_smem(rowsum + rl * 2 + 1, lq[0]);
-      if (vmb > 1) {
-        red_add_smem(rowsum + (128 + rl) * 2, ls[1]);
-        red_add_smem(rowsum + (128 + rl) * 2 + 1, lq[1]);
-      }
+      *reinterpret_cast<float2*>(rowsum + (rl * 4 + slot) * 2) = make_float2(ls[0], lq[0]);
+      if (vmb > 1) *reinterpret_cast<float2*>(rowsum + ((128 + rl) * 4 + slot) * 2) = make_float2(ls[1], lq[1]);
       epi_bar();
       if (ew == 0) RN_TR(6);
       // ======== n = LayerNorm(xr) -> bf16 operand of the QKV projection
 #pragma unroll 1
       for (int m = 0; m < vmb; ++m) {
-        const float2 rs2 = *reinterpret_cast<const float2*>(rowsum + (m * 128 + rl) * 2);
-        const float mu = rs2.x * (1.0f / RN_C);
-        const float var = fmaxf(rs2.y * (1.0f / RN_C) - mu * mu, 0.0f);
+        const float4 ra = *reinterpret_cast<const float4*>(rowsum + (m * 128 + rl) * 8), rb = *reinterpret_cast<const float4*>(rowsum + (m * 128 + rl) * 8 + 4);
+        const float mu = ((ra.x + ra.z) + (rb.x + rb.z)) * (1.0f / RN_C);
+        const float var = fmaxf(((ra.y + ra.w) + (rb.y + rb.w)) * (1.0f / RN_C) - mu * mu, 0.0f);
         const float rs = rsqrtf(var + p.eps_ln);
         const float nmu = -mu * rs;
 #pragma unroll 1
@@ -612,7 +631,7 @@ RnPlan rn_plan_for(int mb, int T) {
   q.x1_slot_bytes = (int)align_up((size_t)q.x1_boxes * q.x1_box_rows * 128, 1024);
   q.a_bytes = rn_a_bytes(mb, q.x1_slot_bytes);
   const int fixed = 1024 + q.a_bytes + RN_CONST_FLOATS * 4;
-  q.w_slots = std::min(RN_MAX_W_SLOTS, (RN_SMEM_LIMIT - fixed) / RN_W_TILE);
+  q.w_slots = std::min(RN_MAX_W_SLOTS, (RN_SMEM_LIMIT - fixed) / RN_W_TILE) & ~1;   // even: see the issuers' ring protocol
   q.smem_bytes = fixed + q.w_slots * RN_W_TILE;
   return q;
 }
@@ -686,7 +705,7 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
     return cudaErrorInvalidValue;
   }
   const RnPlan plan = rn_plan_for(resnet_tc_plan(a.B, a.T), a.T);
-  if (plan.w_slots < 3) {
+  if (plan.w_slots < 4) {
     if (err) *err = "resnet_tc: shared-memory plan does not fit";
     return cudaErrorInvalidValue;
   }

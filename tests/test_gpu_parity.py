@@ -610,12 +610,12 @@ def test_scheduling_knobs_do_not_change_results():
 
     base = run()
     # decoder lanes and the res_conv side branch belong to the layer-by-layer ResNet path (EV_RN_FUSE=0: five launches per block
-    # instead of the fused cooperative kernel, whose arithmetic order differs): compared among themselves
+    # instead of the fused kernel, whose arithmetic order differs -- and depends on the tile plan, hence on the lane's batch
+    # size): compared among themselves
     unfused = run(EV_RN_FUSE=0)
     assert run(EV_RN_FUSE=0, EV_DEC_LANES=2) == unfused
-    assert run(EV_DEC_LANES=2) == unfused          # two lanes never run the cooperative kernel (co-residency)
     assert run(EV_RN_FUSE=0, EV_DEC_SIDE=0) == unfused
-    assert run(EV_RN_COOP=0) == base               # plain launch of the same grid
+    assert run() == base                            # the fused kernel's sums have one writer each and a fixed order: reproducible
     assert run(EV_RB_WAVE=1) == base
     assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
     assert run(EV_PDL=0) == base
