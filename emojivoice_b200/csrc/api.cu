@@ -185,6 +185,10 @@ extern "C" int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const
 }
 
 namespace {
+__global__ void f32_to_bf16_kernel(const float* in, bf16* out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
 __global__ void bf16_to_f32_kernel(const bf16* in, float* out, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
@@ -243,10 +247,35 @@ extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y
 // Fused transformer feed-forward alone (ff_tc.cu): x (B, T, 256) CHANNEL-LAST fp32; w1 (inner, 256), w2 (256, inner) as
 // nn.Linear stores them; snake_a = exp(alpha), snake_invb = 1 / (exp(beta) + 1e-9); out (B, T, 256) fp32 (the kernel's
 // bf16 result widened).  y_lengths (B) int64 or NULL: rows with (t << len_shift) >= y_lengths[b] come out as zero.
+static int test_ff_block(ev_ctx* ctx, const float* x, const float* att, const float* wo, const float* bo, const float* ln_g, const float* ln_b,
+                         const float* w1, const float* b1, const float* snake_a, const float* snake_invb, const float* w2, const float* b2,
+                         const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, int repeat, float* avg_us_host,
+                         void* stream);
+
 extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
                                 const float* snake_a, const float* snake_invb, const float* w2, const float* b2,
                                 const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, int repeat,
                                 float* avg_us_host, void* stream) {
+  return test_ff_block(ctx, x, nullptr, nullptr, nullptr, ln_g, ln_b, w1, b1, snake_a, snake_invb, w2, b2, y_lengths, B, T, inner, len_shift, out,
+                       repeat, avg_us_host, stream);
+}
+
+// ff_tc's attention tail mode alone: xr (B, 256, T) CHANNEL-FIRST fp32 residual stream, att (B, T, 128) channel-last fp32 (rounded
+// to bf16 inside), wo (256, 128) / bo (256) the out-projection; everything else as ev_test_ff_block.
+// out = (x + W2 snake(W1 LN(x) + b1) + b2) * mask with x = xr + att Wo^T + bo.
+extern "C" int ev_test_tf_tail(ev_ctx* ctx, const float* xr_cf, const float* att, const float* wo, const float* bo, const float* ln_g,
+                               const float* ln_b, const float* w1, const float* b1, const float* snake_a, const float* snake_invb,
+                               const float* w2, const float* b2, const int64_t* y_lengths, int B, int T, int inner, int len_shift,
+                               float* out, int repeat, float* avg_us_host, void* stream) {
+  if (!att || !wo || !bo) return EV_ERR_INVALID;
+  return test_ff_block(ctx, xr_cf, att, wo, bo, ln_g, ln_b, w1, b1, snake_a, snake_invb, w2, b2, y_lengths, B, T, inner, len_shift, out, repeat,
+                       avg_us_host, stream);
+}
+
+static int test_ff_block(ev_ctx* ctx, const float* x, const float* att, const float* wo, const float* bo, const float* ln_g, const float* ln_b,
+                         const float* w1, const float* b1, const float* snake_a, const float* snake_invb, const float* w2, const float* b2,
+                         const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, int repeat, float* avg_us_host,
+                         void* stream) {
   if (!ctx || !x || !ln_g || !ln_b || !w1 || !b1 || !snake_a || !snake_invb || !w2 || !b2 || !out || B <= 0 || T <= 0 || inner <= 0)
     return EV_ERR_INVALID;
   cudaStream_t s = as_stream(stream);
@@ -263,11 +292,18 @@ extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, 
   t2.name = "w2"; t2.data = w2; t2.ndim = 3; t2.shape[0] = D; t2.shape[1] = inner; t2.shape[2] = 1;
   tb1.name = "b1"; tb1.data = b1; tb1.ndim = 1; tb1.shape[0] = inner;
   tb2.name = "b2"; tb2.data = b2; tb2.ndim = 1; tb2.shape[0] = D;
-  ev_tensor list[4] = {t1, t2, tb1, tb2};
-  WeightStore ws(ctx, list, 4, s);
-  ConvWeights c1, c2;
+  ev_tensor two{}, tbo{};
+  two.name = "wo"; two.data = wo; two.ndim = 3; two.shape[0] = D; two.shape[1] = 128; two.shape[2] = 1;
+  tbo.name = "bo"; tbo.data = bo; tbo.ndim = 1; tbo.shape[0] = D;
+  ev_tensor list[6] = {t1, t2, tb1, tb2, two, tbo};
+  WeightStore ws(ctx, list, att ? 6 : 4, s);
+  ConvWeights c1, c2, co;
   int rc = make_conv(ctx, ws, {"w1"}, {"b1"}, inner, D, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c1);
   if (!rc) rc = make_conv(ctx, ws, {"w2"}, {"b2"}, D, inner, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &c2);
+  if (!rc && att) rc = make_conv(ctx, ws, {"wo"}, {"bo"}, D, 128, 1, 1, 0, 1, CONV_NORMAL, TC_BF16, &co);
+  if (!rc && att && !ff_tc_oproj_supported(co)) rc = fail(ctx, EV_ERR_INVALID, "ev_test_tf_tail: out-projection not served by the fused kernel");
+  void* att16 = nullptr;
+  if (!rc && att) rc = device_alloc(ctx, (size_t)B * T * 128 * 2, &att16, false, s);
   if (!rc && !ff_tc_supported(c1, c2)) rc = fail(ctx, EV_ERR_INVALID, "ev_test_ff_block: shape not served by the fused kernel");
   void *yo = nullptr, *li = nullptr, *tb = nullptr;
   if (!rc) rc = device_alloc(ctx, (size_t)B * T * D * 2, &yo, false, s);
@@ -287,7 +323,14 @@ extern "C" int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, 
     }
   }
   FfTcArgs fa;
-  fa.x = x; fa.ln_g = ln_g; fa.ln_b = ln_b; fa.eps = 1e-5f; fa.ff1 = &c1; fa.ff2 = &c2; fa.snake_a = snake_a; fa.snake_invb = snake_invb;
+  if (att) {
+    const long long na = (long long)B * T * 128;
+    if (ce == cudaSuccess) { f32_to_bf16_kernel<<<(unsigned)((na + 255) / 256), 256, 0, s>>>(att, reinterpret_cast<bf16*>(att16), na); ce = cudaGetLastError(); }
+    fa.att = reinterpret_cast<bf16*>(att16); fa.att_ld = 128; fa.att_bs = (long long)T * 128; fa.oproj = &co; fa.xr_cf = x;
+  } else {
+    fa.x = x;
+  }
+  fa.ln_g = ln_g; fa.ln_b = ln_b; fa.eps = 1e-5f; fa.ff1 = &c1; fa.ff2 = &c2; fa.snake_a = snake_a; fa.snake_invb = snake_invb;
   fa.out = reinterpret_cast<bf16*>(yo); fa.out_ld = D; fa.out_bs = (long long)T * D; fa.lens = lens; fa.len_shift = len_shift;
   fa.B = B; fa.T = T; fa.tiles = tiles;
   std::string err;
@@ -370,7 +413,16 @@ extern "C" int ev_test_resnet_block(ev_ctx* ctx, const ev_tensor* weights, int n
   if (full) { ra.conv2 = &c2; ra.res = &cr; ra.gn_g2 = g2; ra.gn_b2 = b2; ra.temb = te; ra.ln_g = lg; ra.ln_b = lb; }
   ra.lens = lens; ra.len_shift = len_shift; ra.B = B; ra.T = T;
   ra.a_buf = reinterpret_cast<bf16*>(ab); ra.a_ld = D; ra.a_bs = (long long)T * D;
-  ra.xr = out_xr; ra.n_out = reinterpret_cast<bf16*>(nb);
+  ra.n_out = reinterpret_cast<bf16*>(nb);
+  void* xcf = nullptr;
+  if (full == 2) {                       // the stream channel-first (what ff_tc's tail mode reads); handed back channel-last
+    rc = device_alloc(ctx, n * 4, &xcf, false, s);
+    if (rc) { release(); return rc; }
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(xcf, 0xff, n * 4, s);
+    ra.xr_cf = reinterpret_cast<float*>(xcf);
+  } else {
+    ra.xr = out_xr;
+  }
   std::string err;
   auto once = [&]() { return resnet_tc_launch(ra, s, &err); };
   if (ce == cudaSuccess) ce = once();
@@ -388,6 +440,7 @@ extern "C" int ev_test_resnet_block(ev_ctx* ctx, const ev_tensor* weights, int n
   }
   if (ce == cudaSuccess) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(ab), out_a, (long long)n); ce = cudaGetLastError(); }
   if (ce == cudaSuccess && full) { bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<bf16*>(nb), out_n, (long long)n); ce = cudaGetLastError(); }
+  if (ce == cudaSuccess && full == 2) ce = cf_to_cl<float>(reinterpret_cast<float*>(xcf), B, D, T, out_xr, D, (long long)T * D, 1.0f, RowMask{nullptr, 0}, s);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
   release();
   if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ev_test_resnet_block") : fail(ctx, EV_ERR_CUDA, err);

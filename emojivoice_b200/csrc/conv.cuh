@@ -149,6 +149,10 @@ int conv_tc_pick_bn(int N);
 // ff_tc.cu: LayerNorm -> Linear(256 -> inner) -> SnakeBeta -> Linear(inner -> 256) -> + residual -> * mask, one kernel
 struct FfTcArgs {
   const float* x = nullptr;             // fp32 residual stream (b, t, 256), dense
+  // attention tail mode (instead of x): x = xr_cf + att Wo^T + bo is formed in the kernel
+  const bf16* att = nullptr; long long att_ld = 0, att_bs = 0;   // attention output (b, t, 128) bf16
+  const ConvWeights* oproj = nullptr;                            // Linear(128 -> 256) + bias
+  const float* xr_cf = nullptr;                                  // fp32 residual stream, CHANNEL-FIRST (b, 256, t)
   const float* ln_g = nullptr; const float* ln_b = nullptr; float eps = 1e-5f;
   const ConvWeights* ff1 = nullptr; const ConvWeights* ff2 = nullptr;
   const float* snake_a = nullptr; const float* snake_invb = nullptr;
@@ -160,6 +164,7 @@ struct FfTcArgs {
   const int* tiles = nullptr;
 };
 bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2);
+bool ff_tc_oproj_supported(const ConvWeights& wo);
 cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err);
 cudaError_t ff_tc_read_trace(unsigned long long* host, int n);   // diagnostic (EV_FF_DEBUG & 16)
 
@@ -174,6 +179,7 @@ struct ResnetTcArgs {
   int B = 0, T = 0;
   bf16* a_buf = nullptr; long long a_ld = 0, a_bs = 0;      // the output when conv2 == nullptr; else an optional copy of conv2's operand (tests)
   float* xr = nullptr; bf16* n_out = nullptr;               // (b, t, 256) dense outputs of the full block
+  float* xr_cf = nullptr;                                   // instead of xr: the fp32 stream channel-first (b, 256, t)
 };
 int resnet_tc_plan(int B, int T);
 bool resnet_tc_supported(const ConvWeights& conv1, const ConvWeights* conv2, const ConvWeights* res, int B, int T);

@@ -19,6 +19,14 @@
 //   warps 2-17 : LayerNorm prologue (warp = row), per-chunk activation (thread = row, 32 channels), final epilogue.
 // Work per tile: 2 x 128 x 256 x 1024 MACs = 16.4 k clk of tcgen05 at N = 128 (64 clk per MMA); weight stream 1 MB per
 // tile from L2.
+//
+// Attention tail mode (FfTcArgs::att != nullptr): the attention's out-projection and its residual add (transformer.py:
+// 283-294) run in front, in the same launch:  x = xr + att Wo^T + bo.  The producer loads the tile's 128 x 128 bf16
+// attention output into the idle P[0] buffer, the issuer multiplies it with Wo (16 MMAs) INTO acc2, the workers add the
+// bias and the fp32 residual stream -- stored CHANNEL-FIRST by resnet_tc, so that thread = row reads of a column are
+// coalesced -- write x back into acc2 (tcgen05.st) and normalise it from there (thread = row, row sums combined across
+// the four column-slot warps through the idle P[1] buffer).  GEMM 2 then accumulates ON TOP of x, so the final residual
+// add is free and x is read from HBM once.  Replaces the out-projection launch and its fp32 read-modify-write of xr.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -43,10 +51,12 @@ constexpr int FF_SMEM = FF_A_BYTES + 2 * FF_P_BYTES + FF_SLOTS * FF_W_TILE + 102
 constexpr int FF_EPI_WARPS = 16;
 constexpr int FF_THREADS = 32 * (2 + FF_EPI_WARPS);
 
-struct FfMaps { CUtensorMap w1, w2; };
+struct FfMaps { CUtensorMap w1, w2, wo, att; };
 
 struct FfParams {
-  const float* x; long long x_bs;           // fp32 residual stream (b, t, 256), dense rows
+  const float* x; long long x_bs;           // fp32 residual stream (b, t, 256), dense rows (att_mode == 0)
+  const float* xr_cf; const float* bo;      // att_mode: fp32 residual stream (b, 256, t) channel-first, out-projection bias [256]
+  int att_mode;
   const float* ln_g; const float* ln_b; float eps;
   const float* b1; const float* snake_a; const float* snake_invb;   // [n_chunks * 128]
   const float* b2;                          // [256]
@@ -71,6 +81,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full[FF_SLOTS], w_empty[FF_SLOTS];
   __shared__ __align__(8) uint64_t a_ready, a_free, acc1_full[2], acc1_free[2], p_ready[2], p_free[2], acc2_full, acc2_empty;
+  __shared__ __align__(8) uint64_t att_full, att_free, oproj_full;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,6 +97,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
     mbar_init(&a_ready, FF_EPI_WARPS); mbar_init(&a_free, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc1_free[s], FF_EPI_WARPS); mbar_init(&p_ready[s], FF_EPI_WARPS); mbar_init(&p_free[s], 1); }
     mbar_init(&acc2_full, 1); mbar_init(&acc2_empty, FF_EPI_WARPS);
+    mbar_init(&att_full, 1); mbar_init(&att_free, 1); mbar_init(&oproj_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -125,9 +137,28 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
       };
       // weights are constants, so the dense grid does not wait for the previous kernel at all; a tile list is data of the
       // stream and is read behind the programmatic dependency
-      if (p.tiles) pdl_wait();
+      if (p.tiles || p.att_mode) pdl_wait();
       const int total_tiles = p.tiles ? __ldg(p.tiles) : p.total_tiles;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        if (p.att_mode) {
+          // the tile's attention output -> P[0] (free once the previous tile's last GEMM 2 on that buffer has completed),
+          // then the four out-projection weight tiles
+          int b, m0;
+          if (p.tiles) { const int pair = __ldg(p.tiles + 1 + tile); b = pair >> 16; m0 = (pair & 0xffff) * 128; }
+          else { b = tile / p.m_tiles; m0 = (tile - b * p.m_tiles) * 128; }
+          mbar_wait(&att_free, ((uint32_t)it & 1u) ^ 1u);
+          mbar_expect_tx(&att_full, (uint32_t)FF_P_BYTES);
+          tma_load_3d(p_s, &maps.att, &att_full, 0, m0, b);
+          tma_load_3d(p_s + (uint32_t)FF_PLANE, &maps.att, &att_full, 64, m0, b);
+          for (int kc = 0; kc < 2; ++kc)
+            for (int nh = 0; nh < 2; ++nh) {
+              mbar_wait(&w_empty[sl], ph);
+              mbar_expect_tx(&w_full[sl], (uint32_t)FF_W_TILE);
+              tma_load_3d(w_s + (uint32_t)(sl * FF_W_TILE), &maps.wo, &w_full[sl], kc * 64, nh * 128, 0);
+              if (++sl == FF_SLOTS) { sl = 0; ph ^= 1u; }
+            }
+        }
         load_w1(0);
         if (n_chunks > 1) load_w1(1);
         for (int c = 0; c < n_chunks; ++c) {
@@ -180,10 +211,11 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
             const uint32_t d = acc2 + (uint32_t)(nh * 128);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_bf16(d, d_join(hi, a_lo + 2u * ks), d_join(hi, b_lo + 2u * ks), idesc, (c | kc | ks) ? 1u : 0u);
+              umma_bf16(d, d_join(hi, a_lo + 2u * ks), d_join(hi, b_lo + 2u * ks), idesc, (p.att_mode | c | kc | ks) ? 1u : 0u);
             umma_commit(&w_empty[sl]);
             if (kc == 1 && nh == 1) {
               umma_commit(&p_free[c & 1]);
+              if (c + 2 == n_chunks || n_chunks == 1) umma_commit(&att_free);   // last use of P[0] in this tile
               if (last) umma_commit(&acc2_full);
             }
           }
@@ -195,6 +227,28 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
     const int total_tiles = p.tiles ? __ldg(p.tiles) : p.total_tiles;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       FF_TR(0);
+      if (p.att_mode) {
+        // acc2 = att (128 x 128, in P[0]) x Wo^T: the out-projection; GEMM 2 accumulates on top of it later
+        mbar_wait(&att_full, (uint32_t)it & 1u);
+        mbar_wait(&acc2_empty, ((uint32_t)it & 1u) ^ 1u);                // the previous tile's output has left acc2
+        tcgen05_fence_after();
+        for (int kc = 0; kc < 2; ++kc)
+          for (int nh = 0; nh < 2; ++nh) {
+            mbar_wait(&w_full[sl], wph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = p_lo0 + (uint32_t)kc * plane16, b_lo = w_lo0 + (uint32_t)sl * plane16;
+              const uint32_t d = acc2 + (uint32_t)(nh * 128);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_bf16(d, d_join(hi, a_lo + 2u * ks), d_join(hi, b_lo + 2u * ks), idesc, (kc | ks) ? 1u : 0u);
+              umma_commit(&w_empty[sl]);
+              if (kc == 1 && nh == 1) umma_commit(&oproj_full);
+            }
+            __syncwarp();
+            if (++sl == FF_SLOTS) { sl = 0; wph ^= 1u; }
+          }
+      }
       mbar_wait(&a_ready, (uint32_t)it & 1u);
       tcgen05_fence_after();
       FF_TR(1);
@@ -209,7 +263,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
         FF_TR(10 + 4 * c);
         const uint32_t u = (uint32_t)(it * half + (c >> 1));
         mbar_wait(&p_ready[c & 1], u & 1u);
-        if (c == 0) mbar_wait(&acc2_empty, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's output has left acc2
+        if (c == 0 && !p.att_mode) mbar_wait(&acc2_empty, ((uint32_t)it & 1u) ^ 1u);   // the previous tile's output has left acc2
         tcgen05_fence_after();
         FF_TR(8 + 4 * c);
         gemm2(c, c == n_chunks - 1);
@@ -254,6 +308,79 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
       if (p.tiles) { const int pair = __ldg(p.tiles + 1 + tile); b = pair >> 16; m0 = (pair & 0xffff) * 128; }
       else { b = tile / p.m_tiles; m0 = (tile - b * p.m_tiles) * 128; }
       const float* xb = p.x + b * p.x_bs;
+      if (p.att_mode) {
+        // ---- x = out-projection (acc2) + bo + residual stream -> back into acc2; LayerNorm3(x) -> operand A.  thread = row.
+        const int rowq = q * 32 + lane, t = m0 + rowq;
+        const bool in_seq = t < p.T;
+        const float* xcol = p.xr_cf + ((long long)b * FF_D) * p.T + t;
+        float* rpart = reinterpret_cast<float*>(p_gen + FF_P_BYTES);          // idle P[1]: [128 rows][4 slots][2]
+        mbar_wait(&oproj_full, (uint32_t)it & 1u);
+        tcgen05_fence_after();
+        float s = 0.0f, qq = 0.0f;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int col0 = (j + 4 * h) * 32;
+          float xv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xv[i] = in_seq ? xcol[(long long)(col0 + i) * p.T] : 0.0f;   // a column of 32 rows: 128 B per warp
+          uint32_t raw[32];
+          tmem_ld32(acc2 + lane_q + (uint32_t)col0, raw);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const int c = hh * 16 + i;
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bo + col0 + c));
+              const float v0 = __uint_as_float(raw[c]) + bb.x + xv[i], v1 = __uint_as_float(raw[c + 1]) + bb.y + xv[i + 1];
+              const float v2 = __uint_as_float(raw[c + 2]) + bb.z + xv[i + 2], v3 = __uint_as_float(raw[c + 3]) + bb.w + xv[i + 3];
+              s += (v0 + v1) + (v2 + v3);
+              qq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, qq))));
+              raw[c] = __float_as_uint(v0); raw[c + 1] = __float_as_uint(v1); raw[c + 2] = __float_as_uint(v2); raw[c + 3] = __float_as_uint(v3);
+            }
+            if (hh == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xv[i] = in_seq ? xcol[(long long)(col0 + 16 + i) * p.T] : 0.0f;
+            }
+          }
+          tmem_st32(acc2 + lane_q + (uint32_t)col0, raw);
+        }
+        *reinterpret_cast<float2*>(rpart + (rowq * 4 + j) * 2) = make_float2(s, qq);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * FF_EPI_WARPS) : "memory");
+        tcgen05_fence_after();
+        const float4 pa = *reinterpret_cast<const float4*>(rpart + rowq * 8), pb = *reinterpret_cast<const float4*>(rpart + rowq * 8 + 4);
+        const float mean = ((pa.x + pa.z) + (pb.x + pb.z)) * (1.0f / FF_D);
+        const float var = fmaxf(((pa.y + pa.w) + (pb.y + pb.w)) * (1.0f / FF_D) - mean * mean, 0.0f);
+        const float rstd = in_seq ? rsqrtf(var + p.eps) : 0.0f;             // rows past the sequence: finite values, never stored
+        const float nmu = -mean * rstd;
+        mbar_wait(&a_free, ((uint32_t)it & 1u) ^ 1u);                        // the previous tile's GEMM 1 has finished reading A
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int cb = j + 4 * h, col0 = cb * 32;
+          uint32_t raw[32];
+          tmem_ld32(acc2 + lane_q + (uint32_t)col0, raw);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_g + col0 + i)), be = __ldg(reinterpret_cast<const float4*>(p.ln_b + col0 + i));
+            const float v0 = fmaf(fmaf(__uint_as_float(raw[i]), rstd, nmu), ga.x, be.x), v1 = fmaf(fmaf(__uint_as_float(raw[i + 1]), rstd, nmu), ga.y, be.y);
+            const float v2 = fmaf(fmaf(__uint_as_float(raw[i + 2]), rstd, nmu), ga.z, be.z), v3 = fmaf(fmaf(__uint_as_float(raw[i + 3]), rstd, nmu), ga.w, be.w);
+            __nv_bfloat162 e0 = __floats2bfloat162_rn(v0, v1), e1 = __floats2bfloat162_rn(v2, v3);
+            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&e0);
+            pk[(i >> 1) + 1] = *reinterpret_cast<uint32_t*>(&e1);
+          }
+          uint8_t* rp = a_gen + (cb >> 1) * FF_PLANE + rowq * 128;
+          const int c16 = (cb & 1) * 4, sw = rowq & 7;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(rp + (((c16 + i) ^ sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        tcgen05_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready);
+      } else
       // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7 of the tile into the swizzled bf16 operand A
       {
 #pragma unroll 1
@@ -353,9 +480,11 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
       if (ew == 0) FF_TR(130);
       {
         // Each warp owns two 32 x 32 blocks (columns (j + 4h) * 32).  thread = row after tcgen05.ld; a private 4 KB tile in
-        // the idle P region (XOR-swizzled 16-byte chunks: conflict-free both ways) turns that into a row-wise pass: 8 lanes x
-        // float4 per row, so the residual reads (128 B per row) and the bf16 stores (64 B per row) are coalesced.
-        uint8_t* stg = p_gen + ew * 4096;
+        // the idle A region (every GEMM 1 of the tile has completed; the next tile's LayerNorm is these warps' own next step;
+        // P[0] may already hold the next tile's attention output) -- XOR-swizzled 16-byte chunks, conflict-free both ways --
+        // turns that into a row-wise pass: 8 lanes x float4 per row, so the residual reads (128 B per row) and the bf16
+        // stores (64 B per row) are coalesced.
+        uint8_t* stg = a_gen + ew * 4096;
         const int sub = lane >> 3, cl = lane & 7;
         const int len_b = p.lens ? __ldg(p.lens + b) : 0x7fffffff;
 #pragma unroll 1
@@ -365,7 +494,7 @@ ff_tc_kernel(const __grid_constant__ FfMaps maps, const __grid_constant__ FfPara
 #pragma unroll
           for (int u = 0; u < 8; ++u) {                      // residual loads fly while the accumulator is fetched and staged
             const int t = m0 + q * 32 + u * 4 + sub;
-            rr[u] = (t < p.T && !(p.debug & 8)) ? *reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = (t < p.T && !p.att_mode && !(p.debug & 8)) ? *reinterpret_cast<const float4*>(xb + (long long)t * FF_D + col) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           const float4 bias = __ldg(reinterpret_cast<const float4*>(p.b2 + col));
           if (ew == 0) FF_TR(132 + 4 * h);
@@ -423,11 +552,19 @@ bool ff_tc_supported(const ConvWeights& ff1, const ConvWeights& ff2) {
          ff1.N_pad_tc == ff1.N && ff2.N_pad_tc == FF_D && ff1.bias && ff2.bias;
 }
 
+// the attention out-projection the tail mode can run in front: Linear(128 -> 256) with a bias
+bool ff_tc_oproj_supported(const ConvWeights& wo) {
+  return wo.w_bf16 && wo.bias && wo.taps == 1 && wo.C_in == 128 && wo.K_pad == 128 && wo.N == FF_D && wo.N_pad_tc == FF_D;
+}
+
 cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err) {
   const ConvWeights& w1 = *a.ff1;
   const ConvWeights& w2 = *a.ff2;
+  const bool att_mode = a.att != nullptr;
   if (!ff_tc_supported(w1, w2) || (a.out_ld & 7) || (a.out_bs & 7) || (reinterpret_cast<uintptr_t>(a.out) & 15) ||
-      (reinterpret_cast<uintptr_t>(a.x) & 15)) {
+      (reinterpret_cast<uintptr_t>(a.x) & 15) || (!att_mode && !a.x) ||
+      (att_mode && (!a.oproj || !ff_tc_oproj_supported(*a.oproj) || !a.xr_cf || (a.att_ld & 7) || (a.att_bs & 7) ||
+                    (reinterpret_cast<uintptr_t>(a.att) & 15)))) {
     if (err) *err = "ff_tc: unsupported layer shape or alignment";
     return cudaErrorInvalidValue;
   }
@@ -438,8 +575,19 @@ cudaError_t ff_tc_launch(const FfTcArgs& a, cudaStream_t s, std::string* err) {
   if (!tc_encode_bf16_map(&maps.w2, w2.w_bf16, (uint64_t)w2.K_pad, (uint64_t)w2.N_pad_tc, 1, (uint64_t)w2.K_pad * 2,
                           (uint64_t)w2.K_pad * w2.N_pad_tc * 2, 64u, 128u, 128, err))
     return cudaErrorInvalidValue;
+  if (att_mode) {
+    const ConvWeights& wo = *a.oproj;
+    if (!tc_encode_bf16_map(&maps.wo, wo.w_bf16, (uint64_t)wo.K_pad, (uint64_t)wo.N_pad_tc, 1, (uint64_t)wo.K_pad * 2,
+                            (uint64_t)wo.K_pad * wo.N_pad_tc * 2, 64u, 128u, 128, err))
+      return cudaErrorInvalidValue;
+    if (!tc_encode_bf16_map(&maps.att, a.att, 128u, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.att_ld * 2, (uint64_t)a.att_bs * 2, 64u, 128u, 128, err))
+      return cudaErrorInvalidValue;
+  } else {
+    maps.wo = maps.w2; maps.att = maps.w2;
+  }
   FfParams p{};
   p.x = a.x; p.x_bs = (long long)a.T * FF_D;
+  p.att_mode = att_mode ? 1 : 0; p.xr_cf = a.xr_cf; p.bo = att_mode ? a.oproj->bias : nullptr;
   p.ln_g = a.ln_g; p.ln_b = a.ln_b; p.eps = a.eps;
   p.b1 = w1.bias; p.snake_a = a.snake_a; p.snake_invb = a.snake_invb; p.b2 = w2.bias;
   p.out = a.out; p.out_ld = a.out_ld; p.out_bs = a.out_bs;

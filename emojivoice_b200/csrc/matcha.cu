@@ -419,6 +419,7 @@ template <typename ActT>
 struct Decoder {
   ev_ctx* ctx; const MatchaW& m; DecBuffers<ActT>& d; int B, T; cudaStream_t s; int D, inner;
   int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
+  bool xr_is_cf = false;       // d.xr of the current block holds the residual stream channel-first (written by resnet_tc for ff_tc's tail mode)
   bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
   RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
   cudaStream_t side_stream = nullptr;   // side branch for res_conv (single-lane decoding), see resnet()
@@ -428,6 +429,15 @@ struct Decoder {
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
   double* next_gn_slot() { double* p = d.gn_fused + (size_t)(gn_slot++) * B * 8 * 2; return p; }
   // One launch for the whole ResNet block + pre-LN (resnet_tc.cu) when every tile of the level fits one co-resident wave
+  // ff_tc's attention tail mode (out-projection + residual + LayerNorm3 + feed-forward in one launch) reads the residual stream
+  // channel-first: it is used when the block's ResNet half is the fused kernel, which can write it that way
+  bool fuse_tail(int k) const {
+    if constexpr (!std::is_same<ActT, bf16>::value) return false;
+    static const bool on = []() { const char* v = getenv("EV_TAIL_FUSE"); return !(v && atoi(v) == 0); }();
+    static const int dbg_skip = []() { const char* v = getenv("EV_DEC_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
+    const TransformerW& w = m.tf[k];
+    return on && D == 256 && inner == 128 && !dbg_skip && ff_tc_supported(w.ff1, w.ff2) && ff_tc_oproj_supported(w.out);
+  }
   bool fuse_resnet(const ResnetW& w, int Tl) const {
     if constexpr (!std::is_same<ActT, bf16>::value) return false;
     return D == 256 && resnet_tc_supported(w.conv1, &w.conv2, &w.res, B, Tl);
@@ -454,11 +464,14 @@ struct Decoder {
         ra.gn_g1 = w.gn1_g; ra.gn_b1 = w.gn1_b; ra.gn_g2 = w.gn2_g; ra.gn_b2 = w.gn2_b; ra.temb = temb;
         ra.ln_g = m.tf[k].ln1_g; ra.ln_b = m.tf[k].ln1_b;
         ra.lens = d.ylen32; ra.len_shift = shift; ra.B = B; ra.T = Tl;
-        ra.xr = d.xr; ra.n_out = d.n;        // conv2's operand stays in shared memory
+        ra.n_out = d.n;                      // conv2's operand stays in shared memory
+        xr_is_cf = fuse_tail(k);
+        if (xr_is_cf) ra.xr_cf = d.xr; else ra.xr = d.xr;
         const double rows = (double)B * Tl;
         return launch_resnet_tc(ra, 2.0 * rows * D * (4.0 * w.c_in + 3.0 * D), rows * (2.0 * w.c_in + 6.0 * D), "resnet_tc");
       }
     }
+    xr_is_cf = false;
     Epilogue e1; e1.out_f32 = d.h; e1.f32_ld = D; e1.f32_bs = bsD;
     const double* part = d.gn_partial;
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); e1.gn_groups = 8; part = e1.gn_sum; }
@@ -535,6 +548,24 @@ struct Decoder {
       at.lens = d.ylen32; at.len_shift = shift; at.mode = 1;
       at.out = d.att; at.out_ld = inner; at.out_bs = (long long)Tl * inner;
       EV_LAUNCH(ctx, s, "attention_dec", attn_flops, (double)B * Tl * inner * (12.0 + sizeof(ActT)), attention_rows<ActT>(at, s));
+    }
+    if constexpr (std::is_same<ActT, bf16>::value) {
+      if (xr_is_cf) {
+        // out-projection + residual + LayerNorm3 + ff1 + SnakeBeta + ff2 + residual + mask: ONE launch (ff_tc.cu, tail mode)
+        FfTcArgs fa;
+        fa.att = d.att; fa.att_ld = inner; fa.att_bs = (long long)Tl * inner; fa.oproj = &w.out; fa.xr_cf = d.xr;
+        fa.ln_g = w.ln3_g; fa.ln_b = w.ln3_b; fa.eps = 1e-5f; fa.ff1 = &w.ff1; fa.ff2 = &w.ff2;
+        fa.snake_a = w.snake_a; fa.snake_invb = w.snake_invb;
+        fa.out = out; fa.out_ld = out_ld; fa.out_bs = (long long)Tl * out_ld; fa.lens = d.ylen32; fa.len_shift = shift;
+        fa.B = B; fa.T = Tl;
+        fa.tiles = use_ff_tiles ? d.ff_tiles[shift] : nullptr;
+        std::string err;
+        cudaError_t ce;
+        { LaunchScope ls(ctx, s, "ff_tc", 4.0 * B * (double)Tl * D * (w.ff1.N + inner / 2), (double)B * Tl * (D * 6.0 + inner * 2.0) + 4.0 * D * w.ff1.N);
+          ce = ff_tc_launch(fa, s, &err); }
+        if (ce != cudaSuccess) return err.empty() ? cuda_fail(ctx, ce, "ff_tc") : fail(ctx, EV_ERR_CUDA, err);
+        return 0;
+      }
     }
     Epilogue eo; eo.res = d.xr; eo.res_ld = D; eo.res_bs = bsD; eo.out_f32 = d.xr; eo.f32_ld = D; eo.f32_bs = bsD;
     if (use_ff_tiles && ff_fused) {   // out-projection: tiles without a valid row are skipped (same argument; the planner caches one table per level)

@@ -77,6 +77,7 @@ struct RnParams {
   const float *bias1, *bias2, *bias_r, *g1, *b1, *g2, *b2, *temb, *ln_g, *ln_b;
   bf16* a_buf; long long a_ld, a_bs;           // mode 1: the block's output; mode 0: optional copy of conv2's operand (tests)
   float* xr; bf16* n_out;                      // (b, t, 256) dense
+  float* xr_cf;                                // instead of xr: the same stream CHANNEL-FIRST (b, 256, t), for ff_tc's tail mode
   float eps_gn, eps_ln;
   int trace;
 };
@@ -541,6 +542,22 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
           uint32_t raw[32];
           tmem_ld32(lane_addr + acc2_col + (uint32_t)(m * RN_C + cb * 32), raw);
           float s = 0.0f, qq = 0.0f;
+          if (p.xr_cf) {
+            // channel-first stream: the 32 rows of a warp are consecutive addresses of one channel -- coalesced straight from
+            // the registers, no transpose (the consumer, ff_tc's tail mode, reads it thread = row as well)
+            const int r = m * 128 + rl, t = m0 - 1 + r;
+            const bool own = r >= 1 && r <= R - 2 && t < p.T;
+            float* dst = p.xr_cf + ((long long)b * RN_C + cb * 32) * p.T + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(raw[j]);
+              s += v;
+              qq = fmaf(v, v, qq);
+              if (own) dst[(long long)j * p.T] = v;
+            }
+            if (m == 0) { ls[0] += s; lq[0] += qq; } else { ls[1] += s; lq[1] += qq; }
+            continue;
+          }
           uint8_t* srow = wstage + lane * 128;
           const int x7 = lane & 7;
 #pragma unroll
@@ -700,7 +717,7 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if ((a.x_ld & 7) || (a.x_bs & 7) || !al16(a.x) || (a.a_buf && ((a.a_ld & 7) || (a.a_bs & 7) || !al16(a.a_buf))) || (!full && !a.a_buf) ||
-      (full && (!al16(a.xr) || !al16(a.n_out) || !a.xr || !a.n_out || !a.temb || !a.ln_g || !a.ln_b))) {
+      (full && (!al16(a.xr) || !al16(a.n_out) || (!a.xr && !a.xr_cf) || !a.n_out || !a.temb || !a.ln_g || !a.ln_b))) {
     if (err) *err = "resnet_tc: tensors must be 16-byte aligned";
     return cudaErrorInvalidValue;
   }
@@ -732,7 +749,7 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
     const ConvWeights& w2 = *a.conv2;
     const ConvWeights& wr = *a.res;
     p.bias2 = w2.bias; p.bias_r = wr.bias; p.g2 = a.gn_g2; p.b2 = a.gn_b2; p.ln_g = a.ln_g; p.ln_b = a.ln_b;
-    p.xr = a.xr; p.n_out = a.n_out;
+    p.xr = a.xr; p.n_out = a.n_out; p.xr_cf = a.xr_cf;
     ok = ok && tc_encode_bf16_map(&maps.x3, a.x, (uint64_t)w1.C_in, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.x_ld * 2, (uint64_t)a.x_bs * 2,
                                   64u, 128u, 128, err);
     ok = ok && tc_encode_bf16_map(&maps.w2, w2.w_bf16, (uint64_t)w2.K_pad, (uint64_t)w2.N_pad_tc, 3, (uint64_t)w2.K_pad * 2,

@@ -192,12 +192,20 @@ EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_len
 EV_API int ev_test_ff_block(ev_ctx* ctx, const float* x, const float* ln_g, const float* ln_b, const float* w1, const float* b1,
               const float* snake_a, const float* snake_invb, const float* w2, const float* b2, const int64_t* y_lengths,
               int B, int T, int inner, int len_shift, float* out, int repeat, float* avg_us_host, void* stream);
+/* ff_tc's attention tail mode alone (transformer.py:283-316): x = xr + att Wo^T + bo in front of the feed-forward above, one launch.
+ * xr_cf (B,256,T) CHANNEL-FIRST fp32 residual stream, att (B,T,128) channel-last fp32 (rounded to bf16 inside), wo (256,128), bo (256);
+ * the other arguments as ev_test_ff_block. */
+EV_API int ev_test_tf_tail(ev_ctx* ctx, const float* xr_cf, const float* att, const float* wo, const float* bo, const float* ln_g,
+              const float* ln_b, const float* w1, const float* b1, const float* snake_a, const float* snake_invb, const float* w2,
+              const float* b2, const int64_t* y_lengths, int B, int T, int inner, int len_shift, float* out, int repeat,
+              float* avg_us_host, void* stream);
 /* Fused ResnetBlock1D + pre-LayerNorm of one decoder level (decoder.py:32-61, transformer.py:262; resnet_tc.cu) alone.
  * weights: ev_tensor list named conv1.weight (256,C_in,3), conv1.bias, gn1.weight, gn1.bias and, when full != 0, temb (256),
  * conv2.weight (256,256,3), conv2.bias, gn2.weight, gn2.bias, res.weight (256,C_in,1), res.bias, ln.weight, ln.bias.
  * x (B,C_in,T) channel-first fp32 (masked + rounded to bf16 inside); outputs (B,T,256) channel-last fp32:
  * out_a = (Mish(GN1(conv1 x)) m + temb) m, out_xr = Mish(GN2(conv2 a)) m + res(x), out_n = LayerNorm(out_xr);
- * full == 0: out_a = Mish(GN1(conv1 x)) m only (the decoder's final_block).  repeat / avg_us_host as ev_test_ff_block. */
+ * full == 0: out_a = Mish(GN1(conv1 x)) m only (the decoder's final_block); full == 2: as 1, but the kernel writes the stream
+ * channel-first (the layout ff_tc's tail mode reads; handed back channel-last).  repeat / avg_us_host as ev_test_ff_block. */
 EV_API int ev_test_resnet_block(ev_ctx* ctx, const ev_tensor* weights, int n_weights, const float* x, const int64_t* y_lengths,
               int B, int T, int C_in, int len_shift, int full, float* out_a, float* out_xr, float* out_n, int repeat,
               float* avg_us_host, void* stream);

@@ -134,7 +134,7 @@ def test_decoder_attention_matches_torch_sdpa(ctx, case, prec):
     assert rel_l2(out.cpu(), ref) < (2e-6 if prec == "fp32" else 6e-3)    # bf16: P and the output are rounded to bf16
 
 
-@pytest.mark.parametrize("case", [(2, 200, 0), (3, 129, 1), (1, 1, 0), (32, 334, 1), (5, 668, 0)])
+@pytest.mark.parametrize("case", [(2, 200, 0), (3, 129, 1), (1, 1, 0), (32, 334, 1), (5, 668, 0), (40, 1100, 0)])   # the last: several tiles per CTA
 def test_fused_feed_forward_block_matches_torch(ctx, case):
     """ff_tc.cu: LayerNorm -> Linear -> SnakeBeta -> Linear -> + residual -> * mask in one kernel, against fp64 torch."""
     B, T, shift = case
@@ -166,6 +166,43 @@ def test_fused_feed_forward_block_matches_torch(ctx, case):
     assert float(out.cpu()[mask.expand_as(ref) == 0].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("case", [(2, 200, 0), (3, 129, 1), (1, 1, 0), (32, 334, 1), (5, 668, 0), (40, 300, 0), (40, 1100, 0), (64, 334, 1)])
+def test_fused_transformer_tail_matches_torch(ctx, case):
+    """ff_tc.cu, attention tail mode: x = xr + att Wo^T + bo (out-projection + residual, transformer.py:283-294) -> LayerNorm ->
+    Linear -> SnakeBeta -> Linear -> + x -> * mask in ONE kernel; the residual stream is read channel-first.  Against fp64 torch
+    on the same bf16-rounded attention operand."""
+    B, T, shift = case
+    D, inner, A = 256, 1024, 128
+    g = torch.Generator().manual_seed(2000 + T)
+    xr = torch.randn(B, D, T, generator=g) * 1.5 + 0.3                     # channel-first
+    att = torch.randn(B, T, A, generator=g)
+    wo, bo = torch.randn(D, A, generator=g) / 11, 0.1 * torch.randn(D, generator=g)
+    ln_g, ln_b = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
+    w1, b1 = torch.randn(inner, D, generator=g) / 16, 0.1 * torch.randn(inner, generator=g)
+    w2, b2 = torch.randn(D, inner, generator=g) / 32, 0.1 * torch.randn(D, generator=g)
+    sa, sb = torch.exp(0.3 * torch.randn(inner, generator=g)), 1 / (torch.exp(0.3 * torch.randn(inner, generator=g)) + 1e-9)
+    lens = torch.randint(1, (T << shift) + 1, (B,), generator=g)
+    lens[0] = T << shift
+    if B > 2:
+        lens[1], lens[2] = 1, max(1, (T << shift) // 3)     # whole tiles of padding: zero-filled, not computed
+    dev = [t.cuda().contiguous() for t in (xr, att, wo, bo, ln_g, ln_b, w1, b1, sa, sb, w2, b2)]
+    lens_d = lens.cuda()
+    out = torch.empty(B, T, D, device="cuda")
+    ctx.check(_lib.lib().ev_test_tf_tail(ctx.handle, *[_lib.ptr(t) for t in dev], _lib.ptr(lens_d), B, T, inner, shift,
+                                         _lib.ptr(out), 0, None, _lib.stream_ptr()), "ev_test_tf_tail")
+    bf = lambda t: t.bfloat16().double()
+    xd = xr.double().transpose(1, 2) + bf(att) @ bf(wo).T + bo.double()
+    n = F.layer_norm(xd, (D,), ln_g.double(), ln_b.double(), 1e-5)
+    h = n @ w1.double().T + b1.double()
+    h = h + sb.double() * torch.sin(h * sa.double()) ** 2
+    y = xd + h @ w2.double().T + b2.double()
+    mask = ((torch.arange(T)[None, :] << shift) < lens[:, None]).double()[:, :, None]
+    ref = y * mask
+    assert torch.isfinite(out).all()
+    assert rel_l2(out.cpu(), ref) < 6e-3
+    assert float(out.cpu()[mask.expand_as(ref) == 0].abs().sum()) == 0.0
+
+
 def _mish(x):
     return x * torch.tanh(F.softplus(x))
 
@@ -175,7 +212,8 @@ def _mish(x):
 RESNET_CASES = [(2, 200, 256, 0, 1), (3, 129, 224, 1, 1), (1, 1, 256, 0, 1), (32, 334, 512, 1, 1), (32, 668, 224, 0, 1),
                 (5, 700, 512, 0, 1), (32, 668, 256, 0, 0), (2, 130, 256, 0, 0), (40, 500, 256, 0, 1), (50, 300, 256, 0, 1),
                 (3, 126, 256, 0, 1), (3, 127, 256, 0, 1), (2, 252, 256, 1, 1), (50, 254, 512, 0, 1), (50, 255, 256, 0, 0),
-                (200, 130, 256, 0, 1), (3, 1000, 256, 0, 1), (2, 1500, 224, 0, 1), (20, 1008, 256, 0, 0)]   # several waves; clusters of 8 and 6
+                (200, 130, 256, 0, 1), (3, 1000, 256, 0, 1), (2, 1500, 224, 0, 1), (20, 1008, 256, 0, 0),   # several waves; clusters of 8 and 6
+                (32, 1100, 512, 0, 1), (32, 334, 256, 1, 2), (32, 668, 512, 0, 2), (3, 129, 224, 1, 2)]     # full = 2: channel-first stream
 
 
 @pytest.mark.parametrize("case", RESNET_CASES)
