@@ -92,3 +92,52 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
         finish(pending)
     model.cuda_graphs, vocoder.cuda_graphs = saved_graphs
     return results, stats
+
+
+def synthesise_file(model, vocoder, script, out_dir, *, phonemizer=None, cleaner="english_cleaners2", spk=None, emoji_mapping=None,
+                    default_spk: int = 12, batch_size: int = 32, n_timesteps: int = 10, temperature: float = 0.667,
+                    length_scale: float = 1.0, denoiser=None, denoiser_strength: float = 0.00025, rank: int = 0,
+                    world_size: int = 1):
+    """One call from a script file to audio on disk: the reference's batched file path composed end to end
+    (`matcha/cli.py:226-250` get_texts / `:277-317` batched_synthesis / `:129-135` save_to_folder).
+
+    script : path of a text file or an iterable of lines.  Three line formats, decided per line:
+               `text|speaker_id`   (cli.py:326-330)            -> that speaker
+               text with an emoji  (feel_me.py:298-312)         -> the emoji's voice from `emoji_mapping`, emoji stripped
+               plain text                                       -> `spk` if given, else `default_spk`
+    phonemizer : callable text -> phoneme string standing for espeak-ng (absent offline); the rule-based half of the cleaner
+                 (`text_cleaners`) runs in front of it.  None: the line must already be a phoneme string of the symbol table.
+    Writes `<out_dir>/utterance_{i:03d}_speaker_{spk:03d}.wav` (PCM_24, 22.05 kHz) + `.npy` (mel), i = line index, for the
+    lines this rank owns (`sharding.shard`).  -> (list of (index, wav_path, mel_length), ShardStats)"""
+    from . import audio_io, text_cleaners, text_frontend
+    from .emoji_frontend import emoji_to_spk
+    from .config import EMOJI_MAPPING_FEMALE
+
+    if isinstance(script, (str, bytes)) or hasattr(script, "__fspath__"):
+        with open(script, "r", encoding="utf-8") as f:
+            lines = f.read().splitlines()
+    else:
+        lines = list(script)
+    mapping = EMOJI_MAPPING_FEMALE if emoji_mapping is None else emoji_mapping
+    utterances, speakers = [], []
+    for ln in (l.strip() for l in lines):
+        if not ln:
+            continue
+        head, bar, tail = ln.rpartition("|")
+        if bar and head and tail.strip().lstrip("-").isdigit():
+            text, speaker = head.strip(), int(tail)
+        else:
+            text, speaker = emoji_to_spk(ln, mapping, default_spk if spk is None else int(spk))
+        g2p = (lambda t, _c=cleaner: text_cleaners.clean_text(t, [_c], phonemizer)) if phonemizer is not None else None
+        rec = text_frontend.process_text(text, g2p)
+        utterances.append((rec["x"][0].tolist(), speaker))
+        speakers.append(speaker)
+    results, stats = synthesise_corpus(model, vocoder, utterances, batch_size=batch_size, n_timesteps=n_timesteps, temperature=temperature,
+                                       length_scale=length_scale, rank=rank, world_size=world_size, denoiser=denoiser,
+                                       denoiser_strength=denoiser_strength, keep_mel=True)
+    written = []
+    for i in sorted(results):
+        name = f"utterance_{i:03d}_speaker_{speakers[i]:03d}"
+        path = audio_io.save_to_folder(name, {"mel": results[i]["mel"], "waveform": results[i]["waveform"]}, out_dir)
+        written.append((i, path, results[i]["mel_length"]))
+    return written, stats
