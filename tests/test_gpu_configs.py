@@ -198,13 +198,13 @@ def test_synthesise_file_script_to_wav_on_disk(matcha, matcha_sd, hifigan, tmp_p
     gen, hsd = hifigan
     fake_g2p = {"doctor who is here.": "dˈɑktɚ hˈuː ɪz hˈɪɹ.", "i am so happy today !": "aɪ æm sˈoʊ hˈæpi tədˈeɪ !", "plain line": "plˈeɪn lˈaɪn"}
     script = tmp_path / "script.txt"
-    script.write_text("Dr. Who is here.|107\n\nI am so happy today \U0001F603!\nPlain   line\n", encoding="utf-8")
+    script.write_text("Dr. Who is here.|107\n\nI am so happy today \U0001F601!\nPlain   line\n", encoding="utf-8")
     model = ev.MatchaTTS(**VCTK.constructor_kwargs(), precision="fp32")
     model.load_state_dict(matcha_sd)
     written, stats = ev.synthesise_file(model, gen, script, tmp_path / "out", phonemizer=lambda t: fake_g2p[" ".join(t.split())], n_timesteps=2,
                                         temperature=0.0, length_scale=1.0, batch_size=1, spk=12)   # batch of 1: the decoder is not padding-invariant (H1)
     assert [w[0] for w in written] == [0, 1, 2] and stats.utterances == 3
-    happy = ev.EMOJI_MAPPING_FEMALE["\U0001F603"]
+    happy = ev.EMOJI_MAPPING_FEMALE["\U0001F601"]
     names = ["utterance_000_speaker_107", f"utterance_001_speaker_{happy:03d}", "utterance_002_speaker_012"]
     for (i, path, n), name, spk, key in zip(written, names, (107, happy, 12), fake_g2p):
         assert path.endswith(name + ".wav")
@@ -214,6 +214,6 @@ def test_synthesise_file_script_to_wav_on_disk(matcha, matcha_sd, hifigan, tmp_p
         wav_ref = ho.generator(hsd, HIFIGAN_V1, ref["mel"][:, :, :n + 16])[0, 0, : n * 256].clamp(-1, 1)
         wav, sr = audio_io.read_wav_pcm24(path)
         assert sr == 22050 and wav.shape == (n * 256,)
-        assert rel_l2(torch.from_numpy(wav), wav_ref) < 2e-4                      # fp32 path + 24-bit quantisation
+        assert rel_l2(torch.from_numpy(wav), wav_ref) < TOL["bf16"]              # the vocoder fixture runs its default bf16 mode
         mel = torch.from_numpy(__import__("numpy").load(path[:-4] + ".npy"))
         assert mel.shape == (80, n) and rel_l2(mel, ref["mel"][0, :, :n]) < TOL["fp32"]
