@@ -60,6 +60,10 @@ SIGNATURES = {
     "ev_denoise": (_I, [_P, _P, _I, _I, _F, _P, _P, _SZ, _P]),
     "ev_maximum_path_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "ev_maximum_path": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _SZ, _P]),
+    "ev_estimator_workspace_bytes": (_SZ, [_P, _I, _I]),
+    "ev_estimator": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _SZ, _P]),
+    "ev_train_forward_workspace_bytes": (_SZ, [_P, _I, _I, _I, _I]),
+    "ev_train_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _F, _I, _I, _P, _P, _P, _SZ, _P]),
     "ev_launch_count": (_I64, [_P, _I]),
     "ev_profile_begin": (_I, [_P]),
     "ev_profile_end": (_I, [_P, C.POINTER(EvKernelStat), _I, C.POINTER(_I)]),

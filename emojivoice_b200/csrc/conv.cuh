@@ -174,6 +174,7 @@ struct ResnetTcArgs {
   const ConvWeights* conv1 = nullptr; const ConvWeights* conv2 = nullptr; const ConvWeights* res = nullptr;
   const float *gn_g1 = nullptr, *gn_b1 = nullptr, *gn_g2 = nullptr, *gn_b2 = nullptr;
   const float* temb = nullptr;                              // [256] time embedding of this block and step
+  long long temb_bs = 0;                                    // item stride of temb (0: shared by the batch)
   const float *ln_g = nullptr, *ln_b = nullptr;
   const int* lens = nullptr; int len_shift = 0;
   int B = 0, T = 0;

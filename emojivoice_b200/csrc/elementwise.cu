@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnApplyArgs a) {
       const float4 ga = *reinterpret_cast<const float4*>(a.gamma + c), be = *reinterpret_cast<const float4*>(a.beta + c);
       sc[i] = make_float4(rstd * ga.x, rstd * ga.y, rstd * ga.z, rstd * ga.w);
       sh[i] = make_float4(be.x - mean * sc[i].x, be.y - mean * sc[i].y, be.z - mean * sc[i].z, be.w - mean * sc[i].w);
-      if (a.temb) te[i] = *reinterpret_cast<const float4*>(a.temb + c);
+      if (a.temb) te[i] = *reinterpret_cast<const float4*>(a.temb + b * a.temb_bs + c);
       if (a.out_ln) { lg[i] = *reinterpret_cast<const float4*>(a.ln_gamma + c); lb[i] = *reinterpret_cast<const float4*>(a.ln_beta + c); }
     }
   }
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 3 : 4) gn_apply256_kernel(GnA
   const int len_b = a.mask.lens ? __ldg(a.mask.lens + b) : 0x7fffffff;
   const int t_base = (blockIdx.x * 8 + warp) * GN_APPLY_ROWS;
   float4 te0, te1;
-  if (MODE == 0) { te0 = *reinterpret_cast<const float4*>(a.temb + c0); te1 = *reinterpret_cast<const float4*>(a.temb + c1); }
+  if (MODE == 0) { te0 = *reinterpret_cast<const float4*>(a.temb + b * a.temb_bs + c0); te1 = *reinterpret_cast<const float4*>(a.temb + b * a.temb_bs + c1); }
   __syncthreads();
   float4 sc0, sc1, sh0, sh1;
   {

@@ -97,6 +97,7 @@ struct GnApplyArgs {
   int B = 0, T = 0, C = 0, groups = 8;
   RowMask mask = {nullptr, 0};
   const float* temb = nullptr;        // [C] added after Mish*mask (resnet block1), then masked again
+  long long temb_bs = 0;              // item stride of temb (0: one time step for the whole batch; training draws one t per item)
   const float* res = nullptr; long long res_ld = 0;      // + res (resnet output = h + res_conv(x))
   float* out_f32 = nullptr; long long f32_ld = 0;        // y (after res)
   void* out_act = nullptr; long long act_ld = 0;         // y as next conv operand

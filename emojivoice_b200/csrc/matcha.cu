@@ -424,6 +424,8 @@ struct Decoder {
   RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
   cudaStream_t side_stream = nullptr;   // side branch for res_conv (single-lane decoding), see resnet()
   cudaEvent_t temb_event = nullptr;     // time embeddings are produced on another side branch: waited for at their first use
+  long long temb_bs = 0;                // item stride of the time embeddings (0: one t for the batch; ev_estimator: one t per item)
+  bool estimator_only = false;          // ev_estimator: the final projection writes v * mask instead of the Euler update
   // GroupNorm statistics: fused into the producing conv's epilogue on the tensor-core path (32 channels per group),
   // a separate reduction kernel otherwise.  Returns the (partial, n_chunks) pair gn_apply reads.
   bool fuse_gn() const { return std::is_same<ActT, bf16>::value && D == 256; }
@@ -461,7 +463,7 @@ struct Decoder {
         ResnetTcArgs ra;
         ra.x = in; ra.x_ld = in_ld; ra.x_bs = in_bs;
         ra.conv1 = &w.conv1; ra.conv2 = &w.conv2; ra.res = &w.res;
-        ra.gn_g1 = w.gn1_g; ra.gn_b1 = w.gn1_b; ra.gn_g2 = w.gn2_g; ra.gn_b2 = w.gn2_b; ra.temb = temb;
+        ra.gn_g1 = w.gn1_g; ra.gn_b1 = w.gn1_b; ra.gn_g2 = w.gn2_g; ra.gn_b2 = w.gn2_b; ra.temb = temb; ra.temb_bs = temb_bs;
         ra.ln_g = m.tf[k].ln1_g; ra.ln_b = m.tf[k].ln1_b;
         ra.lens = d.ylen32; ra.len_shift = shift; ra.B = B; ra.T = Tl;
         ra.n_out = d.n;                      // conv2's operand stays in shared memory
@@ -494,7 +496,7 @@ struct Decoder {
     if (!fuse_gn()) EV_LAUNCH(ctx, s, "gn_stats", 0, RD * 4.0, group_norm_stats(d.h, B, Tl, D, 8, d.gn_partial, &chunks, s));
     GnApplyArgs g1;
     g1.x = d.h; g1.partial = part; g1.n_chunks = chunks; g1.gamma = w.gn1_g; g1.beta = w.gn1_b;
-    g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.out_act = d.a; g1.act_ld = D;
+    g1.B = B; g1.T = Tl; g1.C = D; g1.mask = mask; g1.temb = temb; g1.temb_bs = temb_bs; g1.out_act = d.a; g1.act_ld = D;
     static const int dbg_skip = []() { const char* v = getenv("EV_DEC_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
     if (temb_event) { EV_CUDA(ctx, cudaStreamWaitEvent(s, temb_event, 0)); temb_event = nullptr; }
     if (!(dbg_skip & 8)) EV_LAUNCH(ctx, s, "gn_apply", 0, RD * (4.0 + sizeof(ActT)), group_norm_apply<ActT>(g1, s));
@@ -663,9 +665,11 @@ struct Decoder {
     }
     const int F = m.cfg.n_feats;
     Epilogue e; e.mask = mask0; e.mask_pre = 1; e.alpha = dt;
-    e.res = d.xstate; e.res_ld = F; e.res_bs = (long long)T * F;
     e.out_f32 = d.xstate; e.f32_ld = F; e.f32_bs = (long long)T * F;
-    e.out_act = d.xin; e.act_ld = dec_in; e.act_bs = (long long)T * dec_in; e.mask_act = 1;
+    if (!estimator_only) {     // Euler update x += dt * v * mask, and the next step's operand
+      e.res = d.xstate; e.res_ld = F; e.res_bs = (long long)T * F;
+      e.out_act = d.xin; e.act_ld = dec_in; e.act_bs = (long long)T * dec_in; e.mask_act = 1;
+    }
     EV_TRY(run_conv<ActT>(ctx, m.final_proj, d.a, D, (long long)T * D, B, T, e, s));
     return 0;
   }
@@ -681,18 +685,22 @@ int decode_lane_count(const ev_ctx* ctx, int B) {
 template <typename ActT>
 int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const float* z, const float* spk_emb, int B,
                 int T, int n_steps, float temperature, float* decoder_out, float* mel, void* workspace, size_t ws_bytes,
-                cudaStream_t s) {
+                cudaStream_t s, const float* t_items = nullptr) {
+  // t_items != nullptr (ev_estimator): ONE evaluation of the estimator with its own time t_items[b] per item; `z` is the point
+  // it is evaluated at and decoder_out receives v * mask (decoder.py:363-443 as flow_matching.py:114 calls it)
+  const bool est = t_items != nullptr;
+  const int n_rows = est ? B : n_steps;     // rows of the time-embedding chain
   const MatchaW& m = ctx->matcha;
   const ev_matcha_cfg& c = m.cfg;
   Workspace w(workspace, ws_bytes);
-  const int n_lanes = decode_lane_count(ctx, B);
+  const int n_lanes = est ? 1 : decode_lane_count(ctx, B);
   int lane_b0[ev_ctx::kMaxLanes], lane_nb[ev_ctx::kMaxLanes];
   DecBuffers<ActT> dl[ev_ctx::kMaxLanes];
   for (int l = 0, b0 = 0; l < n_lanes; ++l) {
     lane_b0[l] = b0;
     lane_nb[l] = B / n_lanes + (l < B % n_lanes ? 1 : 0);
     b0 += lane_nb[l];
-    plan_decode<ActT>(c, lane_nb[l], T, n_steps, w, &dl[l]);
+    plan_decode<ActT>(c, lane_nb[l], T, n_rows, w, &dl[l]);
   }
   if (w.overflow || !workspace) return fail(ctx, EV_ERR_STATE, "ev_decode: workspace too small");
   ctx->prof_tag = "/dec";
@@ -710,15 +718,19 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
     EV_CUDA(ctx, cudaEventRecord(ctx->lane_fork, s));
     EV_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lane_fork, 0));
   }
-  EV_LAUNCH(ctx, st, "upload_floats", 0, 4.0 * n_steps, upload_floats(d.t_steps, ts.data(), n_steps, st));
-  ctx->launches += ceil_div(n_steps, 32) - 1;
-  EV_LAUNCH(ctx, st, "time_sinusoid", 0, 4.0 * n_steps * dec_in, time_sinusoid(d.t_steps, n_steps, dec_in, d.sinus, st));
+  if (est) {
+    EV_CUDA(ctx, cudaMemcpyAsync(d.t_steps, t_items, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    EV_LAUNCH(ctx, st, "upload_floats", 0, 4.0 * n_steps, upload_floats(d.t_steps, ts.data(), n_steps, st));
+    ctx->launches += ceil_div(n_steps, 32) - 1;
+  }
+  EV_LAUNCH(ctx, st, "time_sinusoid", 0, 4.0 * n_rows * dec_in, time_sinusoid(d.t_steps, n_rows, dec_in, d.sinus, st));
   { Epilogue e; e.act = ACT_SILU; e.out_act = d.th1; e.act_ld = 4 * D; e.act_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.time1, d.sinus, dec_in, 0, 1, n_steps, e, st)); }
+    EV_TRY(run_conv<float>(ctx, m.time1, d.sinus, dec_in, 0, 1, n_rows, e, st)); }
   { Epilogue e; e.act = ACT_MISH; e.out_act = d.th2; e.act_ld = 4 * D; e.act_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_steps, e, st)); }
+    EV_TRY(run_conv<float>(ctx, m.time2, d.th1, 4 * D, 0, 1, n_rows, e, st)); }
   { Epilogue e; e.out_f32 = d.tproj; e.f32_ld = 6 * D; e.f32_bs = 0;
-    EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_steps, e, st)); }
+    EV_TRY(run_conv<float>(ctx, m.temb_proj, d.th2, 4 * D, 0, 1, n_rows, e, st)); }
   if (temb_side) EV_CUDA(ctx, cudaEventRecord(ctx->lane_join[1], st));
   // fork: lane 0 stays on the caller's stream, the others wait for the time embeddings on their own streams
   cudaStream_t ls[ev_ctx::kMaxLanes];
@@ -742,6 +754,7 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
     dec.push_back(Decoder<ActT>{ctx, m, q, nb, T, ls[l], D, c.dec_heads * c.dec_head_dim});
     if (n_lanes == 1 && ctx->dec_side && std::is_same<ActT, bf16>::value) dec.back().side_stream = ctx->lane_stream[ev_ctx::kMaxLanes - 2];
     if (temb_side) dec.back().temb_event = ctx->lane_join[1];
+    if (est) { dec.back().temb_bs = 6LL * D; dec.back().estimator_only = true; }
     if (std::is_same<ActT, bf16>::value && nb <= kRaggedMaxB) {
       static const bool on = []() { const char* v = getenv("EV_FF_RAGGED"); return !(v && atoi(v) == 0); }();
       if (on) {
@@ -757,7 +770,8 @@ int decode_impl(ev_ctx* ctx, const float* mu_y, const int64_t* y_lengths, const 
     }
   }
   // launches interleave across lanes step by step so that eager (un-captured) calls overlap as well
-  for (int k = 0; k < n_steps; ++k)
+  if (est) EV_TRY(dec[0].step(d.tproj, 1.0f));      // item b reads row b of tproj (temb_bs)
+  for (int k = 0; k < n_steps && !est; ++k)
     for (int l = 0; l < n_lanes; ++l) EV_TRY(dec[l].step(d.tproj + (size_t)k * 6 * D, dts[k]));
   for (int l = 0; l < n_lanes; ++l) {
     const int b0 = lane_b0[l], nb = lane_nb[l];
@@ -802,6 +816,28 @@ extern "C" int ev_decode(ev_ctx* ctx, const float* mu_y, const int64_t* y_length
   if (precision == EV_PREC_BF16)
     return decode_impl<bf16>(ctx, mu_y, y_lengths, z, spk_emb, B, T_pad, n_timesteps, temperature, decoder_out, mel, workspace, workspace_bytes, s);
   return fail(ctx, EV_ERR_INVALID, "ev_decode: unknown precision");
+}
+
+extern "C" size_t ev_estimator_workspace_bytes(const ev_ctx* ctx, int B, int T_pad) {
+  return ev_decode_workspace_bytes(ctx, B, T_pad, std::max(B, 1));
+}
+
+// One evaluation of the flow-matching estimator (decoder.py:363-443) with one time per item, as the training loss calls it
+// (flow_matching.py:114): v = estimator(y, mask, mu, t, spks).  All tensors channel-first like the reference's.
+extern "C" int ev_estimator(ev_ctx* ctx, const float* y, const int64_t* y_lengths, const float* mu, const float* t, const float* spk_emb,
+                            int B, int T_pad, int precision, float* v_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ctx) return EV_ERR_INVALID;
+  if (!ctx->matcha.loaded) return fail(ctx, EV_ERR_STATE, "ev_estimator: matcha weights not loaded");
+  if (!y || !y_lengths || !mu || !t || !v_out || B <= 0 || T_pad <= 0) return fail(ctx, EV_ERR_INVALID, "ev_estimator: null argument or empty shape");
+  if (T_pad % 4) return fail(ctx, EV_ERR_INVALID, "ev_estimator: T_pad must be a multiple of 4 (the U-Net halves the length twice)");
+  if (ctx->matcha.cfg.n_spks > 1 && !spk_emb) return fail(ctx, EV_ERR_INVALID, "ev_estimator: spk_emb required");
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t s = as_stream(stream);
+  if (precision == EV_PREC_FP32)
+    return decode_impl<float>(ctx, mu, y_lengths, y, spk_emb, B, T_pad, 1, 1.0f, v_out, nullptr, workspace, workspace_bytes, s, t);
+  if (precision == EV_PREC_BF16)
+    return decode_impl<bf16>(ctx, mu, y_lengths, y, spk_emb, B, T_pad, 1, 1.0f, v_out, nullptr, workspace, workspace_bytes, s, t);
+  return fail(ctx, EV_ERR_INVALID, "ev_estimator: unknown precision");
 }
 
 // test hook: the Euler schedule as the library computes it (pure host code)

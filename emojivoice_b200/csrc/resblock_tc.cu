@@ -12,6 +12,10 @@
 //     conv1, is overwritten by lrelu(conv1 + b) for conv2, then by lrelu(x_new) for the next pair.  Taps are row
 //     offsets into it; zero margins / rows outside [0, L) implement each conv's own zero padding.
 //   * weight tiles [C x C] per (conv, tap, K-chunk) stream from L2 through a TMA ring.
+// CL = 2: two CTAs of a thread-block cluster share one window of 2 W rows: each owns W rows and, after every operand
+// phase, pushes its 32 edge rows into the neighbour's margin through distributed shared memory (st.shared::cluster +
+// a remote mbarrier arrive), so the halo is recomputed per PAIR of windows: at C = 128, k = 11 a window yields
+// (512 - 120) / 2 = 196 output rows per CTA instead of 136.  (Clusters of 2 pack all 148 SMs; clusters of 4 strand 16.)
 // Warps: 0 = TMA producer (weights), 1-2 = MMA issuers (half of the m-blocks each; warp 1 owns the TMEM allocation),
 // 3.. = 16 (or 8) "epilogue" warps that load x, convert
 // accumulators into the next operand, and write y.  Phases alternate strictly MMA -> epilogue (two mbarriers); the
@@ -20,7 +24,9 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "conv.cuh"
 #include "tc_ptx.cuh"
@@ -50,6 +56,7 @@ struct RbParams {
   int tiles_per_item, total_tiles, Wv, H;
   int w_slots;
   int resident;                        // all 6*k weight tiles stay in shared memory (C = 32): no per-tap barrier traffic
+  int debug;                           // EV_RB_DEBUG (timing experiments, wrong results): 1 = no waits on the neighbour, 2 = no edge pushes
   const int* rag;                      // ragged batch: compact (item, window) list (RaggedPlanner, conv.cuh) or nullptr = dense
 };
 
@@ -78,6 +85,28 @@ template <int C> struct RbCfg {
   static constexpr int EXTRA = ONES_BYTES + 6 * BIAS_TILE;
 };
 
+__device__ __forceinline__ uint32_t rb_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t rb_map_to_cta(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+// 16 bytes into the shared memory of a peer CTA; completes 16 bytes of transaction count on THAT CTA's mbarrier once the data
+// has landed (no fence, no release/acquire at cluster scope: those compile to MEMBAR.ALL.GPU / CCTL.IVALL, ~1.5 us per phase)
+__device__ __forceinline__ void rb_st_async16(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rbar) : "memory");
+}
+// tcgen05.commit that arrives on the barrier at the same offset in every CTA of `mask` (the peers learn that this CTA's MMAs --
+// the readers of its margins -- are complete, without a hop through a thread of this CTA)
+__device__ __forceinline__ void rb_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void rb_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // OCC = CTAs per SM: 2 (C = 32 only: 8 epilogue warps, 256 TMEM columns and <= 112 KB of shared memory per CTA) lets one
 // CTA's epilogue phases run under the other's MMA phases -- the phases of one window are short (k*8 MMAs of 40 clk
 // against ~1.5k clk of accumulator -> operand conversion) and strictly alternate, so a lone CTA leaves the tensor pipe
@@ -88,7 +117,13 @@ template <int C> struct RbCfg {
 // j convert its accumulator as soon as the MMAs of m-block j+1 have completed (they still read j's last rows through
 // their taps), and the next conv's MMAs on m-block j start once the operand rows of j-1, j, j+1 are in place.  The
 // tensor pipe then only idles when one m-block's epilogue (~400 clk) outlasts the next m-block's MMAs (k*KS*40-48 clk).
-template <int C, int OCC, bool WAVE>
+//
+// CL = CTAs per cluster (1 or 2; not combined with WAVE): see the header comment.  Protocol per operand phase: a CTA's edge warps
+// wait until the neighbour has finished the MMAs that read its margins (`nbr_done`: the neighbour's issuers commit on it by
+// multicast next to their own `mma_done`), then write their 32 edge rows locally and -- st.async, 16 bytes each completing 16
+// bytes of the neighbour's `marg_full` -- into the neighbour's margin; the MMA issuers wait for `epi_done` (own rows) and
+// `marg_full` (margin rows) before the next conv.  No cluster-scope fences or barriers inside the loop.
+template <int C, int OCC, bool WAVE, int CL>
 __global__ void __launch_bounds__(OCC == 2 ? 96 + 32 * 8 : 96 + 32 * RB_MAX_EPI_WARPS, OCC)
 resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ RbParams p) {
   using G = RbCfg<C>;
@@ -96,6 +131,19 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t w_full[RB_MAX_SLOTS], w_empty[RB_MAX_SLOTS], mma_done, epi_done;
   __shared__ __align__(8) uint64_t mma_done_mb[4], epi_done_mb[4];   // WAVE: one pair per m-block
+  __shared__ __align__(8) uint64_t nbr_done, marg_full;              // CL > 1: written by the neighbour CTA(s) of the cluster
+  static_assert(!(WAVE && CL > 1), "the wavefront schedule is not combined with clusters");
+  const uint32_t crank = CL > 1 ? rb_cluster_rank() : 0u;
+  const int n_nbr = CL > 1 ? (crank > 0 ? 1 : 0) + (crank + 1 < (uint32_t)CL ? 1 : 0) : 0;
+  const uint16_t nbr_mask = CL > 1 ? (uint16_t)((crank > 0 ? 1u << (crank - 1) : 0u) | (crank + 1 < (uint32_t)CL ? 1u << (crank + 1) : 0u)) : (uint16_t)0;
+  static_assert(CL <= 2, "one neighbour per CTA");
+  // Every CTA walks the taps of a conv upwards, like the single-window kernel: the per-row accumulation order -- and with it every
+  // output bit -- does not depend on the pairing.  Rank 0 (neighbour to the right) meets the taps that reach into the neighbour's
+  // rows in the second half of a conv and waits for the margin there; rank 1 needs its left margin from the first tap on.
+  // (Walking the taps downwards on rank 1 to hide that wait as well was measured: no gain, and the bits then depend on the rank.)
+  constexpr bool tap_desc = false;
+  const int margin_tap = (CL > 1 && crank == 0) ? (p.k - 1) / 2 + 1 : 0;     // first tap index that reads the neighbour's rows
+  const int cid = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x, n_cl = CL > 1 ? (int)gridDim.x / CL : (int)gridDim.x;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -116,6 +164,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     mbar_init(&mma_done, 2);
     mbar_init(&epi_done, (blockDim.x >> 5) - 3);
     for (int m = 0; m < 4; ++m) { mbar_init(&mma_done_mb[m], 1); mbar_init(&epi_done_mb[m], 4 * NCB); }   // one arrival per (lane quadrant, 32-column block)
+    mbar_init(&nbr_done, CL > 1 && n_nbr ? 2 * n_nbr : 1); // one multicast commit per neighbour, issuer warp and conv
+    mbar_init(&marg_full, 1);                              // expect_tx by issuer warp 1; the neighbours' st.async complete the bytes
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -141,7 +191,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   }
   fence_proxy_async();
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) rb_cluster_sync();     // the peer's barriers exist and its margins are zeroed before anything is pushed at them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   pdl_trigger();
@@ -161,10 +212,11 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           for (int j = 0; j < k; ++j)
             tma_load_3d(w_s + (uint32_t)((ci * k + j) * G::W_TILE), &maps.m[ci], &w_full[0], 0, 0, j);
       }
-      for (int tile = blockIdx.x; tile < total_tiles && !p.resident; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles && !p.resident; tile += n_cl) {
         for (int ci = 0; ci < 6; ++ci)
-          for (int kc = 0; kc < KC; ++kc)
-            for (int j = 0; j < k; ++j) {
+          for (int jj = 0; jj < k; ++jj)
+            for (int kc = 0; kc < KC; ++kc) {
+              const int j = tap_desc ? k - 1 - jj : jj;
               mbar_wait(&w_empty[sl], ph);
               mbar_expect_tx(&w_full[sl], (uint32_t)G::W_TILE);
               tma_load_3d(w_s + (uint32_t)(sl * G::W_TILE), &maps.m[ci], &w_full[sl], kc * (RB / 2), 0, j);
@@ -185,7 +237,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       mbar_wait(&w_full[0], 0);
       tcgen05_fence_after();
       uint32_t cn = 0;                      // convs issued so far: epi_done_mb[*] completion number to wait for
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles; tile += n_cl) {
 #pragma unroll 1
         for (int ci = 0; ci < 6; ++ci, ++cn) {
           const int l = ci >> 1, second = ci & 1;
@@ -236,7 +288,20 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     const uint64_t d_ones = ((uint64_t)hi_ns << 32) | (((ones_s & 0x3FFFFu) >> 4) | (8u << 16));
     const uint32_t bias_lo0 = ((bias_s & 0x3FFFFu) >> 4) | (8u << 16);
     if (resident) { mbar_wait(&w_full[0], 0); tcgen05_fence_after(); }
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // CL = 2: the warp that owns the m-block next to the neighbour (rank 0: the last one, warp 2; rank 1: the first one, warp 1)
+    // waits for the neighbour's 32 edge rows right before the first tap that reads them
+    const bool margin_warp = CL > 1 && n_nbr && warp == (crank == 0 ? 2 : 1);
+    uint32_t gph = 0;
+    auto margin_wait = [&]() {
+      if (p.debug & 3) return;
+      if (elect_one()) mbar_expect_tx(&marg_full, (uint32_t)(32 * C * 2));
+      __syncwarp();
+      mbar_wait(&marg_full, gph);
+      gph ^= 1u;
+      fence_proxy_async();
+      tcgen05_fence_after();
+    };
+    for (int tile = cid; tile < total_tiles; tile += n_cl) {
       for (int ci = 0; ci < 6; ++ci) {
         const int l = ci >> 1, second = ci & 1;
         const int d = second ? 1 : p.dil[l];
@@ -246,17 +311,22 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         tcgen05_fence_after();
         uint32_t fresh = second ? 0u : 1u;  // conv2 accumulates onto the residual stream from its first MMA on
         if (resident) {                     // KC == 1: one straight run of MMAs per conv, no barrier traffic
-          if (elect_one()) {
-            if constexpr (G::BIAS_MMA) {
+          if constexpr (G::BIAS_MMA) {
+            if (elect_one()) {
               const uint64_t d_bias = ((uint64_t)hi_ns << 32) | (bias_lo0 + (uint32_t)((ci * G::BIAS_TILE) >> 4));
 #pragma unroll
               for (int m = 0; m < MBH; ++m) umma_bf16(d_tmem + (uint32_t)((mb0 + m) * C), d_ones, d_bias, idesc, fresh ? 0u : 1u);
-              fresh = 0;
             }
-            uint32_t b_lo = w_lo0 + (uint32_t)((ci * k * G::W_TILE) >> 4);
-            uint32_t a_lo = a_lo0 + (uint32_t)(((RB_MARG - half_k * d) * RB) >> 4);
-            const uint32_t a_step = (uint32_t)((d * RB) >> 4), b_step = (uint32_t)(G::W_TILE >> 4);
-            for (int j = 0; j < k; ++j) {
+            __syncwarp();
+            fresh = 0;
+          }
+          const uint32_t b_base = w_lo0 + (uint32_t)((ci * k * G::W_TILE) >> 4);
+          for (int jj = 0; jj < k; ++jj) {
+            const int j = tap_desc ? k - 1 - jj : jj;
+            if constexpr (CL > 1) { if (margin_warp && jj == margin_tap) margin_wait(); }
+            if (elect_one()) {
+              const uint32_t a_lo = a_lo0 + (uint32_t)(((RB_MARG + (j - half_k) * d) * RB) >> 4);
+              const uint32_t b_lo = b_base + (uint32_t)((j * G::W_TILE) >> 4);
 #pragma unroll
               for (int m = 0; m < MBH; ++m) {
                 const int mb = mb0 + m;
@@ -267,11 +337,13 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
                   umma_bf16(d_tmem + (uint32_t)(mb * C), da, db, idesc, (fresh && ks == 0) ? 0u : 1u);
                 }
               }
-              fresh = 0;
-              a_lo += a_step;
-              b_lo += b_step;
             }
+            __syncwarp();
+            fresh = 0;
+          }
+          if (elect_one()) {
             umma_commit(&mma_done);
+            if constexpr (CL > 1) { if (n_nbr && !(p.debug & 4)) rb_commit_multicast(&nbr_done, nbr_mask); }
           }
           __syncwarp();
           continue;
@@ -285,8 +357,10 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           __syncwarp();
           fresh = 0;
         }
-        for (int kc = 0; kc < KC; ++kc) {
-          for (int j = 0; j < k; ++j) {
+        for (int jj = 0; jj < k; ++jj) {
+          const int j = tap_desc ? k - 1 - jj : jj;
+          if constexpr (CL > 1) { if (margin_warp && jj == margin_tap) margin_wait(); }
+          for (int kc = 0; kc < KC; ++kc) {
             mbar_wait(&w_full[sl], wph);
             tcgen05_fence_after();
             const uint32_t b_lo = w_lo0 + (uint32_t)((sl * G::W_TILE) >> 4);
@@ -309,7 +383,10 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             if (++sl == p.w_slots) { sl = 0; wph ^= 1u; }
           }
         }
-        if (elect_one()) umma_commit(&mma_done);
+        if (elect_one()) {
+          umma_commit(&mma_done);
+          if constexpr (CL > 1) { if (n_nbr && !(p.debug & 4)) rb_commit_multicast(&nbr_done, nbr_mask); }
+        }
         __syncwarp();
       }
     }
@@ -322,6 +399,28 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
     const int L = p.L, H = p.H;
     uint32_t mph = 0;
+    // CL > 1: which of this warp's blocks are edge rows of the CTA's window (first / last 32 rows) with a neighbour behind them
+    bool edge_l = false, edge_r = false;
+    if constexpr (CL > 1) {
+      for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+        const int mb = blk / NCB;
+        if (crank > 0 && q == 0 && mb == 0) edge_l = true;
+        if (crank + 1 < (uint32_t)CL && q == 3 && mb == MB - 1) edge_r = true;
+      }
+    }
+    const int n_blk = max(0, (MB * NCB - slot + n_slots - 1) / n_slots);   // this warp's (m-block, 32-column block) pairs
+    // edge blocks LAST: the neighbour's "my MMAs are done" arrival (one DSMEM hop behind our own mma_done) is then awaited behind
+    // this warp's other block instead of in front of the whole phase
+    const bool rev = CL > 1 && edge_l;
+    uint32_t sig = 0;                    // CL > 1: convs whose MMAs this CTA has reported to its neighbours
+    const uint32_t marg_full_s = smem_u32(&marg_full);
+    auto conv_done_signal = [&]() { if constexpr (CL > 1) ++sig; };   // (the issuers' multicast commits tell the neighbours)
+    // before an operand phase pushes edge rows: every neighbour has finished the MMAs of all `sig` convs so far
+    auto nbr_wait = [&]() {
+      if constexpr (CL > 1) {
+        if ((edge_l || edge_r) && sig && !(p.debug & 1)) mbar_wait(&nbr_done, (sig - 1u) & 1u);
+      }
+    };
 
     // write 32 activated channels of one row into the operand buffer (bf16, swizzled K-major layout)
     auto put_operand = [&](int wr, int cb, const float (&v)[32]) {
@@ -338,6 +437,33 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           w4[e] = *reinterpret_cast<uint32_t*>(&h2);
         }
         *reinterpret_cast<uint4*>(rp + (((c16 + i) ^ sw) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    };
+    // CL > 1: the same 32 channels of an edge row into the neighbour's margin (dir = -1: our first 32 rows -> the right margin
+    // of the left neighbour, dir = +1: our last 32 rows -> the left margin of the right neighbour); every 16 bytes complete
+    // 16 bytes of the neighbour's `marg_full` transaction count
+    auto put_remote = [&](int wr, int cb, const float (&v)[32], int dir) {
+      const int row = RB_MARG + wr - dir * W;
+      const int plane = (cb * 32) / (RB / 2), c16 = ((cb * 32) % (RB / 2)) / 8;
+      const int sw = RB == 128 ? (row & 7) : ((row >> 1) & 3);
+      const uint32_t ra = rb_map_to_cta(a_s + (uint32_t)(plane * G::A_PLANE + row * RB), crank + (uint32_t)dir);
+      const uint32_t rbar = rb_map_to_cta(marg_full_s, crank + (uint32_t)dir);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[8 * i + 2 * e], v[8 * i + 2 * e + 1]);
+          w4[e] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        rb_st_async16(ra + (uint32_t)(((c16 + i) ^ sw) << 4), w4[0], w4[1], w4[2], w4[3], rbar);
+      }
+    };
+    auto put_edges = [&](int mb, int wr, int cb, const float (&v)[32]) {
+      if constexpr (CL > 1) {
+        if (p.debug & 2) return;
+        if (edge_l && mb == 0) { nbr_wait(); put_remote(wr, cb, v, -1); }
+        if (edge_r && mb == MB - 1) { nbr_wait(); put_remote(wr, cb, v, +1); }
       }
     };
     auto phase_done = [&]() {
@@ -363,16 +489,17 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     };
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cid; tile < total_tiles; tile += n_cl) {
       int b, ti;
       if (p.rag) { const int pair = __ldg(p.rag + 1 + tile); b = pair >> 16; ti = pair & 0xffff; }
       else { b = tile / p.tiles_per_item; ti = tile - b * p.tiles_per_item; }
-      const int w0 = ti * p.Wv - H;
+      const int w0 = ti * p.Wv - H + (int)crank * W;     // CL > 1: the cluster's window is CL * W rows, this CTA owns rows [crank * W, +W)
       const bool interior = w0 >= 0 && w0 + W <= L;    // no row of this window lies outside the sequence: no zero-padding fix-ups
       const float* xb = p.x + b * p.x_bs;
       // ---- phase 0: x -> acc_x (fp32, TMEM) and lrelu(x) -> operand buffer
 #pragma unroll 1
-      for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+      for (int bi = 0; bi < n_blk; ++bi) {
+        const int blk = slot + (rev ? n_blk - 1 - bi : bi) * n_slots;
         const int mb = blk / NCB, cb = blk - mb * NCB;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {          // coalesced: 8 lanes x float4 per row, 4 rows per instruction
@@ -392,6 +519,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         }
         tmem_st32(acc_x + lane_addr + (uint32_t)(mb * C + cb * 32), raw);
         put_operand(mb * 128 + q * 32 + lane, cb, a);
+        put_edges(mb, mb * 128 + q * 32 + lane, cb, a);
         __syncwarp();
         if constexpr (WAVE) { tmem_st_wait(); block_done(mb); }
       }
@@ -405,9 +533,11 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           mbar_wait(&mma_done, mph);
           mph ^= 1u;
           tcgen05_fence_after();
+          conv_done_signal();
         }
 #pragma unroll 1
-        for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+        for (int bi = 0; bi < n_blk; ++bi) {
+          const int blk = slot + (rev ? n_blk - 1 - bi : bi) * n_slots;
           const int mb = blk / NCB, cb = blk - mb * NCB;
           const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
           const float keep = (t >= 0 && t < L) ? 1.0f : 0.0f;
@@ -433,6 +563,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) a[j] *= keep;
           }
           put_operand(wr, cb, a);
+          put_edges(mb, wr, cb, a);
           block_done(mb);
         }
         ++cn;
@@ -442,9 +573,11 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           mbar_wait(&mma_done, mph);
           mph ^= 1u;
           tcgen05_fence_after();
+          conv_done_signal();
         }
 #pragma unroll 1
-        for (int blk = slot; blk < MB * NCB; blk += n_slots) {
+        for (int bi = 0; bi < n_blk; ++bi) {
+          const int blk = slot + (rev ? n_blk - 1 - bi : bi) * n_slots;
           const int mb = blk / NCB, cb = blk - mb * NCB;
           const int wr = mb * 128 + q * 32 + lane, t = w0 + wr;
           wave_wait(mb);
@@ -471,6 +604,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
               for (int j = 0; j < 32; ++j) a[j] *= keep;
             }
             put_operand(wr, cb, a);
+            put_edges(mb, wr, cb, a);
             block_done(mb);
           } else {
             // ---- block output: transpose through the private buffer, then coalesced rows
@@ -481,7 +615,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int wr2 = mb * 128 + q * 32 + u * 4 + sub, t2 = w0 + wr2;
-              if (wr2 < H || wr2 >= W - H || t2 < 0 || t2 >= L) continue;
+              const int g2 = (int)crank * W + wr2;                   // row inside the cluster's window: its outer H rows are halo
+              if (g2 < H || g2 >= CL * W - H || t2 < 0 || t2 >= L) continue;
               float4 v = *reinterpret_cast<const float4*>(wstage + (u * 4 + sub) * RB_STAGE_LD + cl);
               const long long off = (long long)t2 * C + cb * 32 + cl;
               float* sp = p.sum + b * p.sum_bs + off;
@@ -511,7 +646,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) rb_cluster_sync();     // no CTA exits while a peer may still push rows or arrivals at it
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
@@ -521,19 +657,43 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
 int g_rb_resident = 1;   // EV_RB_RESIDENT=0: stream weights through the ring even when they would fit
 
 int g_rb_occ2 = 1;       // EV_RB_OCC2=0: one CTA per SM also at C = 32
+int g_rb_cluster = 2;    // EV_RB_CLUSTER=1: single-CTA windows (every CTA recomputes its own halo)
 int g_rb_wave = 0;       // EV_RB_WAVE=1: m-block wavefront schedule instead of phase alternation (measured equal: the kernel is
                          // bound by shared-memory bandwidth -- MMA operand fetch alone takes 32 + N/4 of every 40-48 clk)
+
+// launch with programmatic stream serialization and (cl > 1) a thread-block cluster of `cl` CTAs along x
+template <typename... KArgs, typename... Args>
+cudaError_t launch_rb_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem, int cl, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = cl; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = cl > 1 ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 template <int C>
 cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, RaggedPlanner* ragged) {
   using G = RbCfg<C>;
-  p.rag = ragged ? ragged->table(G::W - 2 * 6 * (p.k - 1), p.L, s) : nullptr;   // windows of Wv output rows
+  // CTAs per cluster window: 2 halves the recomputed halo (the wavefront schedule keeps single CTAs)
+  // Measured on B200 (profiles/r02_resblock_clusters.txt, us per ResBlock on the ragged config-2 batch, single / paired windows):
+  //   C=128: k3 797/855  k7 1658/1546  k11 2849/2194     C=64: k3 633/662  k7 1189/1172  k11 1641/1509
+  //   C=32 : k3 479/558  k7  975/1016  k11 1339/1291
+  // Launching the SAME code as clusters of two costs 2-3 % by itself (CTA placement) and the paired kernel another ~5 %, so pairs pay
+  // where the halo is a large part of a window: k >= 7 at C >= 64, k = 11 at C = 32.  EV_RB_CLUSTER=3 pairs everything, =1 nothing.
+  const bool pair_pays = (p.k >= 7 && C >= 64) || p.k >= 11;
+  const int cl = ((g_rb_cluster >= 3 || (g_rb_cluster == 2 && pair_pays)) && !g_rb_wave) ? 2 : 1;
+  { static const int dbg = []() { const char* v = getenv("EV_RB_DEBUG"); return v ? atoi(v) : 0; }(); p.debug = dbg; }
+  p.H = 6 * (p.k - 1);                    // sum over the three pairs of (k-1)/2 * (d_l + 1), d = 1, 3, 5
+  p.Wv = cl * G::W - 2 * p.H;             // output rows per (cluster) window
+  p.tiles_per_item = ceil_div(p.L, p.Wv);
+  p.total_tiles = p.tiles_per_item * B;
+  p.rag = ragged ? ragged->table(p.Wv, p.L, s) : nullptr;
   if constexpr (C == 32) {
     if (g_rb_occ2) {
-      p.H = 6 * (p.k - 1);
-      p.Wv = G::W - 2 * p.H;
-      p.tiles_per_item = ceil_div(p.L, p.Wv);
-      p.total_tiles = p.tiles_per_item * B;
       const int per_cta = (228 * 1024) / 2 - 2048;
       const int fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP + G::EXTRA;
       const int res_bytes = 6 * p.k * G::W_TILE;
@@ -547,22 +707,21 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, Ra
       if (p.w_slots >= 1 && (p.resident || p.w_slots >= 4)) {
         static DeviceOnce once2;
         cudaError_t ce2 = once2.run([&]() {
-          cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
-          if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
+          if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, per_cta);
           return ce;
         });
         if (ce2 != cudaSuccess) return ce2;
-        const int grid = std::min(p.total_tiles, 2 * tc_sm_count());
+        const int grid = cl * std::min(p.total_tiles, 2 * tc_sm_count() / cl);
         // at least a third of the SM's shared memory: a third CTA would not find TMEM columns (2 x 256 are taken)
-        if (p.resident && g_rb_wave) return launch_pdl(resblock_tc_kernel<C, 2, true>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
-        return launch_pdl(resblock_tc_kernel<C, 2, false>, dim3(grid), dim3(96 + 32 * 8), (size_t)std::max(smem, 80 * 1024), s, maps, p);
+        const size_t sm = (size_t)std::max(smem, 80 * 1024);
+        if (p.resident && g_rb_wave) return launch_rb_kernel(resblock_tc_kernel<C, 2, true, 1>, grid, 96 + 32 * 8, sm, 1, s, maps, p);
+        if (cl == 2) return launch_rb_kernel(resblock_tc_kernel<C, 2, false, 2>, grid, 96 + 32 * 8, sm, 2, s, maps, p);
+        return launch_rb_kernel(resblock_tc_kernel<C, 2, false, 1>, grid, 96 + 32 * 8, sm, 1, s, maps, p);
       }
     }
   }
-  p.H = 6 * (p.k - 1);                    // sum over the three pairs of (k-1)/2 * (d_l + 1), d = 1, 3, 5
-  p.Wv = G::W - 2 * p.H;
-  p.tiles_per_item = ceil_div(p.L, p.Wv);
-  p.total_tiles = p.tiles_per_item * B;
   const int limit = 224 * 1024;
   const int fixed16 = 1024 + G::KC * G::A_PLANE + 16 * G::STAGE_WARP + G::EXTRA, fixed8 = 1024 + G::KC * G::A_PLANE + 8 * G::STAGE_WARP + G::EXTRA;
   const int res_bytes = 6 * p.k * G::W_TILE;
@@ -579,24 +738,50 @@ cudaError_t launch_rb(const RbMaps& maps, RbParams& p, int B, cudaStream_t s, Ra
   if (p.resident) p.w_slots = 1;
   static DeviceOnce once;
   cudaError_t ce1 = once.run([&]() {
-    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
-    if (ce == cudaSuccess && G::BIAS_MMA && G::KC == 1) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaError_t ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (ce == cudaSuccess && G::BIAS_MMA && G::KC == 1) ce = cudaFuncSetAttribute(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     return ce;
   });
   if (ce1 != cudaSuccess) return ce1;
-  const int grid = std::min(p.total_tiles, tc_sm_count());
+  const int grid = cl * std::min(p.total_tiles, tc_sm_count() / cl);
+  if (p.debug & 8) {     // how many clusters the device holds at once
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(96 + 32 * n_epi); cfg.dynamicSmemBytes = (size_t)std::max(smem, 120 * 1024);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t ce = cl == 2 ? cudaOccupancyMaxActiveClusters(&n, resblock_tc_kernel<C, 1, false, 2>, &cfg) : cudaOccupancyMaxActiveClusters(&n, resblock_tc_kernel<C, 1, false, 1>, &cfg);
+    fprintf(stderr, "resblock_tc C=%d k=%d cl=%d grid=%d tiles=%d smem=%d: max active clusters %d (%s)\n", C, p.k, cl, grid, p.total_tiles, smem, n, cudaGetErrorString(ce));
+  }
   // shared memory above half an SM keeps a second CTA (and its TMEM allocation) off the SM
+  const size_t sm = (size_t)std::max(smem, 120 * 1024);
   if (G::BIAS_MMA && G::KC == 1 && p.resident && g_rb_wave)
-    return launch_pdl(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
-  return launch_pdl(resblock_tc_kernel<C, 1, false>, dim3(grid), dim3(96 + 32 * n_epi), (size_t)std::max(smem, 120 * 1024), s, maps, p);
+    return launch_rb_kernel(resblock_tc_kernel<C, 1, G::BIAS_MMA && G::KC == 1, 1>, grid, 96 + 32 * n_epi, sm, 1, s, maps, p);
+  if (cl == 2) return launch_rb_kernel(resblock_tc_kernel<C, 1, false, 2>, grid, 96 + 32 * n_epi, sm, 2, s, maps, p);
+  return launch_rb_kernel(resblock_tc_kernel<C, 1, false, 1>, (p.debug & 16) ? grid / 2 * 2 : grid, 96 + 32 * n_epi, sm, (p.debug & 16) ? 2 : 1, s, maps, p);
 }
 
 }  // namespace
 
 int g_rb_policy = -1;    // EV_RB_FUSE: 0 = never, 1 = where measured faster (default), 2 = wherever the kernel can run
 
+// EV_RB_* switches (read once)
+static void rb_read_env() {
+  static std::once_flag once;
+  std::call_once(once, []() {
+    const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0);
+    v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0);
+    v = getenv("EV_RB_WAVE"); g_rb_wave = v && atoi(v) != 0;
+    v = getenv("EV_RB_CLUSTER"); if (v) g_rb_cluster = atoi(v);
+    v = getenv("EV_RB_FUSE"); g_rb_policy = v ? atoi(v) : 1;
+  });
+}
+
 bool resblock_tc_supported(int C, int k, const int* dil) {
-  if (g_rb_policy < 0) { const char* v = getenv("EV_RB_FUSE"); g_rb_policy = v ? atoi(v) : 1; }
+  rb_read_env();
   if (g_rb_policy == 0) return false;
   if (C != 32 && C != 64 && C != 128) return false;
   if (k != 3 && k != 7 && k != 11) return false;
@@ -609,9 +794,11 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
   // The fused kernel wins wherever the layer-by-layer path is HBM/epilogue-bound (everything at C <= 64, k = 3 at C = 128); at
   // C = 128 with k >= 7 the separate convs are already MMA-bound (1.1-1.2 PFLOP/s) and the halo recompute (H = 6(k-1) rows
   // per window side, 256-row windows) costs more than the saved traffic.
+  // With paired windows (launch_rb) the halo share drops from 88 % to 31 % of the output rows at k = 11 (39 % -> 16 % at k = 7) and the
+  // fused kernel wins at C = 128 as well: k7 1546 us against 1999 layer by layer, k11 2194 against 2384 (ragged config-2 batch).
   if (C <= 64) return true;
   if (k == 3) return true;
-  return false;
+  return g_rb_cluster >= 2 && !g_rb_wave;
 }
 
 // One fused ResBlock1.  c1[l] / c2[l]: packed conv weights (bf16 K-major, as conv_tc uses); bacc[l] = cumulative conv2
@@ -619,9 +806,7 @@ bool resblock_tc_supported(int C, int k, const int* dil) {
 cudaError_t resblock_tc_launch(int C, int k, const ConvWeights* const c1[3], const ConvWeights* const c2[3], const float* const bacc[3],
                                const float* x, float* sum, bf16* act_out, int B, int L, int mode, float inv_n, float slope_out,
                                int write_f32, cudaStream_t s, std::string* err, RaggedPlanner* ragged) {
-  { static bool once = false; if (!once) { const char* v = getenv("EV_RB_RESIDENT"); g_rb_resident = !(v && atoi(v) == 0);
-                                           v = getenv("EV_RB_OCC2"); g_rb_occ2 = !(v && atoi(v) == 0);
-                                           v = getenv("EV_RB_WAVE"); g_rb_wave = v && atoi(v) != 0; once = true; } }
+  rb_read_env();
   RbMaps maps;
   RbParams p{};
   const int rb = C == 32 ? 64 : 128;

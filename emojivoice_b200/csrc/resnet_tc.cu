@@ -75,6 +75,7 @@ struct RnParams {
   int mode;
   const int* lens; int len_shift;
   const float *bias1, *bias2, *bias_r, *g1, *b1, *g2, *b2, *temb, *ln_g, *ln_b;
+  long long temb_bs;                           // item stride of temb (0: one time step for the whole batch)
   bf16* a_buf; long long a_ld, a_bs;           // mode 1: the block's output; mode 0: optional copy of conv2's operand (tests)
   float* xr; bf16* n_out;                      // (b, t, 256) dense
   float* xr_cf;                                // instead of xr: the same stream CHANNEL-FIRST (b, 256, t), for ff_tc's tail mode
@@ -441,7 +442,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     stats_pass(0u);
     exchange(0);
     if (ew == 0) RN_TR(3);
-    fold_consts(0, p.g1, p.b1, full ? p.temb : nullptr, full ? p.bias2 : nullptr);
+    fold_consts(0, p.g1, p.b1, full ? p.temb + b * p.temb_bs : nullptr, full ? p.bias2 : nullptr);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int cb = 4 * h + slot;
@@ -736,7 +737,7 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
   const int smem_bytes = plan.smem_bytes;
   p.mode = full ? 0 : 1;
   p.lens = a.lens; p.len_shift = a.len_shift;
-  p.bias1 = w1.bias; p.g1 = a.gn_g1; p.b1 = a.gn_b1; p.temb = a.temb;
+  p.bias1 = w1.bias; p.g1 = a.gn_g1; p.b1 = a.gn_b1; p.temb = a.temb; p.temb_bs = a.temb_bs;
   p.a_buf = a.a_buf; p.a_ld = a.a_ld; p.a_bs = a.a_bs;
   p.eps_gn = 1e-5f; p.eps_ln = 1e-5f;
   { static const int tr = []() { const char* v = getenv("EV_RN_TRACE"); return v ? atoi(v) : 0; }(); p.trace = tr; }

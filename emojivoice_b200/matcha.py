@@ -175,6 +175,87 @@ class MatchaTTS:
             "decoder_outputs_full": dec, "mel_full": mel,
         }
 
+    # ---- training-side forward pass: loss VALUES through the same kernels, no autograd -----------------
+    @torch.no_grad()
+    def forward(self, x, x_lengths, y, y_lengths, spks=None, out_size=None, cond=None, durations=None, *, t=None, z=None,
+                out_offset=None, dtype="fp32"):
+        """matcha_tts.py:154-245 -> (dur_loss, prior_loss, diff_loss, attn), same argument meaning.  The reference's random
+        draws can be injected: `t` (B,) ~ U[0,1) and `z` like the (cut) target (flow_matching.py:106-108), `out_offset` (B,) the
+        segment starts it draws with random.choice (matcha_tts.py:213-216); when omitted they are drawn here the same way.
+        Values only: this build has no backward pass (training itself is outside SURVEY 8)."""
+        if not self._loaded:
+            raise RuntimeError("load_state_dict() / load_from_checkpoint() first")
+        if cond is not None:
+            raise NotImplementedError("`cond` is unused by the reference estimator (decoder.py:363) and not accepted here")
+        ctx, L = self._ctx, _lib.lib()
+        dev = ctx.device
+        with torch.cuda.device(dev):
+            x = x.to(device=dev, dtype=torch.int64).contiguous()
+            x_lengths = x_lengths.to(device=dev, dtype=torch.int64).contiguous()
+            y = y.to(device=dev, dtype=torch.float32).contiguous()
+            y_lengths = y_lengths.to(device=dev, dtype=torch.int64).contiguous()
+            B, Tx = x.shape
+            F, Ty = self.n_feats, y.shape[-1]
+            if self.n_spks > 1:
+                if spks is None:
+                    raise ValueError("multi-speaker model: `spks` is required")
+                spks = spks.to(device=dev).long().contiguous()
+            else:
+                spks = None
+            enc = self._encode_eager(x, x_lengths, spks, 1.0)
+            Tc = Ty if out_size is None else int(out_size)
+            if out_size is not None and out_offset is None:     # matcha_tts.py:211-216
+                import random
+                mx = (y_lengths - Tc).clamp(0).tolist()
+                out_offset = torch.tensor([random.choice(range(0, e)) if e > 0 else 0 for e in mx], dtype=torch.int64)
+            if out_offset is not None:
+                out_offset = out_offset.to(device=dev, dtype=torch.int64).contiguous()
+            t = torch.rand(B, device=dev) if t is None else t.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+            z = torch.randn(B, F, Tc, device=dev) if z is None else z.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(z.shape) != (B, F, Tc):
+                raise ValueError(f"z must have shape {(B, F, Tc)}")
+            if self.use_precomputed_durations:
+                if durations is None:
+                    raise ValueError("use_precomputed_durations=True needs `durations`")
+                durations = durations.to(device=dev, dtype=torch.float32).reshape(B, Tx).contiguous()
+            else:
+                durations = None
+            losses = torch.empty(3, dtype=torch.float32, device=dev)
+            attn = torch.empty(B, Tx, Tc, dtype=torch.float32, device=dev)
+            ws = ctx.workspace(L.ev_train_forward_workspace_bytes(ctx.handle, B, Tx, Ty, 0 if out_size is None else Tc))
+            ctx.check(L.ev_train_forward(ctx.handle, _lib.ptr(enc["mu_x"]), _lib.ptr(enc["logw"]), _lib.ptr(x_lengths), _lib.ptr(y),
+                                         _lib.ptr(y_lengths), _lib.ptr(enc.get("spk_emb")), _lib.ptr(t), _lib.ptr(z), _lib.ptr(durations),
+                                         0 if out_size is None else Tc, _lib.ptr(out_offset), B, Tx, Ty, float(self.cfg.sigma_min),
+                                         int(bool(self.prior_loss)), _lib.PREC[dtype], _lib.ptr(losses), _lib.ptr(attn), _lib.ptr(ws),
+                                         ws.numel(), _lib.stream_ptr()), "ev_train_forward")
+        prior = losses[1] if self.prior_loss else 0
+        return losses[0], prior, losses[2], attn
+
+    __call__ = forward
+
+    def _encode_eager(self, x, x_lengths, spks, length_scale):
+        """ev_encode without the CUDA-graph cache -> dict(mu_x, logw, w_ceil, y_lengths[, spk_emb])."""
+        ctx, L = self._ctx, _lib.lib()
+        dev = ctx.device
+        B, Tx = x.shape
+        F, S = self.n_feats, (self.spk_emb_dim if self.n_spks > 1 else 0)
+        f32 = torch.float32
+        o = {"mu_x": torch.empty(B, F, Tx, dtype=f32, device=dev), "logw": torch.empty(B, 1, Tx, dtype=f32, device=dev),
+             "w_ceil": torch.empty(B, 1, Tx, dtype=f32, device=dev), "y_lengths": torch.empty(B, dtype=torch.int64, device=dev),
+             "summary": torch.empty(2, dtype=torch.int64, device=dev)}
+        if S:
+            o["spk_emb"] = torch.empty(B, S, dtype=f32, device=dev)
+        ws = ctx.workspace(L.ev_encode_workspace_bytes(ctx.handle, B, Tx))
+        ctx.check(L.ev_encode(ctx.handle, _lib.ptr(x), _lib.ptr(x_lengths), _lib.ptr(spks), B, Tx, float(length_scale), _lib.ptr(o.get("spk_emb")),
+                              _lib.ptr(o["mu_x"]), _lib.ptr(o["logw"]), _lib.ptr(o["w_ceil"]), _lib.ptr(o["y_lengths"]), _lib.ptr(o["summary"]),
+                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ev_encode")
+        return o
+
+    @property
+    def decoder(self):
+        """`model.decoder.compute_loss(...)` / `model.decoder.estimator(...)` as on the reference's CFM (flow_matching.py:87-118)."""
+        return _CFMFacade(self)
+
     def _run(self, name, key, nbytes, inputs, out_specs, call):
         """One stage (`call(inputs, outputs, workspace)` enqueues library calls only), eagerly or -- once the same shape key has
         been seen before -- as a CUDA-graph replay over static buffers: inputs are copied in, outputs cloned out, so callers
@@ -212,3 +293,46 @@ class MatchaTTS:
         if reset:
             self._replayed_launches = 0
         return n
+
+
+class _CFMFacade:
+    """The two calls of the reference's `CFM` object that the training forward uses, on an already loaded MatchaTTS."""
+
+    def __init__(self, model):
+        self._m = model
+        self.sigma_min = model.cfg.sigma_min
+        self.n_feats = model.n_feats
+
+    @torch.no_grad()
+    def estimator(self, x, mask, mu, t, spks=None, cond=None, dtype="fp32"):
+        """decoder.py:363-443: x, mu (B,n_feats,T), mask (B,1,T) a prefix mask, t (B,) or scalar, spks (B,spk_emb_dim) EMBEDDINGS."""
+        m, L = self._m, _lib.lib()
+        ctx = m._ctx
+        dev = ctx.device
+        with torch.cuda.device(dev):
+            x = x.to(device=dev, dtype=torch.float32).contiguous()
+            mu = mu.to(device=dev, dtype=torch.float32).contiguous()
+            B, F, T = x.shape
+            y_lengths = mask.to(dev).reshape(B, T).sum(-1).to(torch.int64).contiguous()      # sequence_mask prefix length
+            t = torch.as_tensor(t, dtype=torch.float32, device=dev).reshape(-1)
+            t = (t.expand(B) if t.numel() == 1 else t).contiguous()
+            spk = None if spks is None else spks.to(device=dev, dtype=torch.float32).contiguous()
+            v = torch.empty(B, F, T, dtype=torch.float32, device=dev)
+            ws = ctx.workspace(L.ev_estimator_workspace_bytes(ctx.handle, B, T))
+            ctx.check(L.ev_estimator(ctx.handle, _lib.ptr(x), _lib.ptr(y_lengths), _lib.ptr(mu), _lib.ptr(t), _lib.ptr(spk), B, T,
+                                     _lib.PREC[dtype], _lib.ptr(v), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "ev_estimator")
+        return v
+
+    @torch.no_grad()
+    def compute_loss(self, x1, mask, mu, spks=None, cond=None, *, t=None, z=None, dtype="fp32"):
+        """flow_matching.py:87-118 -> (loss, y): the conditional-flow-matching loss value and the sampled point y."""
+        dev = self._m._ctx.device
+        x1 = x1.to(device=dev, dtype=torch.float32)
+        b = x1.shape[0]
+        t = torch.rand([b, 1, 1], device=dev) if t is None else t.to(dev, torch.float32).reshape(b, 1, 1)
+        z = torch.randn_like(x1) if z is None else z.to(dev, torch.float32)
+        y = (1 - (1 - self.sigma_min) * t) * z + t * x1
+        u = x1 - (1 - self.sigma_min) * z
+        v = self.estimator(y, mask, mu.to(dev), t.reshape(b), spks, dtype=dtype)
+        loss = ((v - u).double() ** 2).sum() / (mask.to(dev).double().sum() * u.shape[1])
+        return loss.float(), y

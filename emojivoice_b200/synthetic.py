@@ -254,3 +254,22 @@ def checksum(sd: dict) -> float:
         v = sd[k].double()
         tot += float(v.sum()) + float((v * v).sum()) * 1e-3
     return tot
+
+
+def training_batch(batch: int, p_lo: int, p_hi: int, seed: int, n_feats: int = 80):
+    """Text + target mel for the training-side forward pass (MatchaTTS.forward): mel lengths exceed the text lengths (the
+    alignment search needs t_y >= t_x) and the padded length is a multiple of 4 (utils/model.py:14-20, as the reference's
+    collate pads).  -> x, x_lengths, spks, y (B, n_feats, Ty) zero beyond its length, y_lengths."""
+    x, xl, spk = phoneme_batch(batch, p_lo, p_hi, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    yl = (xl * 2 + torch.randint(0, 9, (batch,), generator=g)).long()
+    ty = int(-(-int(yl.max()) // 4) * 4)
+    y = torch.randn(batch, n_feats, ty, generator=g) * 0.8
+    y = y * (torch.arange(ty)[None, None, :] < yl[:, None, None])
+    return x, xl, spk, y, yl
+
+
+def training_draws(batch: int, n_feats: int, frames: int, seed: int):
+    """The random draws of CFM.compute_loss (flow_matching.py:106-108) from a seeded generator: t (B,), z (B, n_feats, frames)."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(batch, generator=g), torch.randn(batch, n_feats, frames, generator=g)

@@ -157,6 +157,28 @@ EV_API size_t ev_maximum_path_workspace_bytes(const ev_ctx* ctx, int B, int Tx, 
 EV_API int ev_maximum_path(ev_ctx* ctx, const float* value, const int32_t* t_xs, const int32_t* t_ys, int B, int Tx, int Ty,
                     float max_neg_val, int32_t* path, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- training-side forward pass: loss values, no backward ------------------------------------------
+ * ev_estimator replaces ONE call of the flow-matching estimator  Decoder.forward(x, mask, mu, t, spks)
+ * (Matcha-TTS/matcha/models/components/decoder.py:363-443) with a time per item, as CFM.compute_loss calls it
+ * (components/flow_matching.py:114):  y, mu, out v : (B,n_feats,T_pad) channel-first, t (B) fp32, v = estimator(...) (masked).
+ *
+ * ev_train_forward replaces MatchaTTS.forward after the text encoder (models/matcha_tts.py:177-245) together with
+ * CFM.compute_loss (flow_matching.py:87-118) and duration_loss (utils/model.py:44-46):
+ *   mu_x (B,n_feats,Tx), logw (B,1,Tx) from ev_encode; y (B,n_feats,Ty) target mel; t_rand (B) and z (B,n_feats,Tc) are the
+ *   reference's random draws (torch.rand / torch.randn_like, flow_matching.py:106-108), passed in so that runs can be compared;
+ *   durations (B,Tx) or NULL = use_precomputed_durations (matcha_tts.py:185-186), else the alignment is searched (mas.cu);
+ *   out_size > 0 cuts a segment of that many frames at out_offset[b] (int64, the reference draws it with random.choice,
+ *   matcha_tts.py:211-233); Tc = out_size or Ty must be a multiple of 4.
+ *   out: losses[3] = dur_loss, prior_loss, diff_loss (device fp32), attn (B,Tx,Tc) 0/1 fp32. */
+EV_API size_t ev_estimator_workspace_bytes(const ev_ctx* ctx, int B, int T_pad);
+EV_API int ev_estimator(ev_ctx* ctx, const float* y, const int64_t* y_lengths, const float* mu, const float* t, const float* spk_emb,
+                 int B, int T_pad, int precision, float* v_out, void* workspace, size_t workspace_bytes, void* stream);
+EV_API size_t ev_train_forward_workspace_bytes(const ev_ctx* ctx, int B, int Tx, int Ty, int out_size);
+EV_API int ev_train_forward(ev_ctx* ctx, const float* mu_x, const float* logw, const int64_t* x_lengths, const float* y,
+                     const int64_t* y_lengths, const float* spk_emb, const float* t_rand, const float* z, const float* durations,
+                     int out_size, const int64_t* out_offset, int B, int Tx, int Ty, float sigma_min, int prior_loss, int precision,
+                     float* losses, float* attn, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- bookkeeping the bench reads: kernels launched by this context since the last reset ------------------- */
 EV_API int64_t ev_launch_count(const ev_ctx* ctx, int reset);
 

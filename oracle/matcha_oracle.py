@@ -283,3 +283,62 @@ def synthesise(sd, cfg, x, x_lengths, n_timesteps, temperature=1.0, spks=None, l
     if return_steps:
         out["steps"] = steps
     return out
+
+
+# ----------------------------------------------------------------------------- matcha_tts.py: training forward
+@torch.inference_mode()
+def forward_losses(sd, cfg, x, x_lengths, y, y_lengths, spks=None, out_size=None, durations=None, *, t=None, z=None,
+                   out_offset=None, prior_loss=True, use_precomputed_durations=False, maximum_path=None):
+    """matcha_tts.py:154-245 + CFM.compute_loss (flow_matching.py:87-118) + duration_loss (utils/model.py:44-46) as loss
+    VALUES.  The reference's random draws are injectable: `t` (B,) and `z` (like the cut target) -- flow_matching.py:106-108
+    draws t = torch.rand([b,1,1]) first, then z = torch.randn_like(x1) -- and `out_offset` (B,) for the segment cut.
+    `maximum_path` defaults to the C restatement of the alignment search (oracle/mas_oracle.py).
+    -> dict(dur_loss, prior_loss, diff_loss, attn, plus the intermediates the parity tests compare)."""
+    if maximum_path is None:
+        from . import mas_oracle
+        maximum_path = mas_oracle.maximum_path
+    spk_emb = F.embedding(spks.long(), sd["spk_emb.weight"]) if cfg.n_spks > 1 else None
+    mu_x, logw, x_mask = text_encoder(sd, cfg, x, x_lengths, spk_emb)
+    y_max_length = y.shape[-1]
+    y_mask = sequence_mask(y_lengths, y_max_length).unsqueeze(1).to(x_mask.dtype)
+    attn_mask = x_mask.unsqueeze(-1) * y_mask.unsqueeze(2)
+    log_prior = None
+    if use_precomputed_durations:
+        attn = generate_path(durations.squeeze(1), attn_mask.squeeze(1))
+    else:
+        const = -0.5 * math.log(2 * math.pi) * cfg.n_feats
+        factor = -0.5 * torch.ones(mu_x.shape, dtype=mu_x.dtype)
+        y_square = torch.matmul(factor.transpose(1, 2), y ** 2)
+        y_mu_double = torch.matmul(2.0 * (factor * mu_x).transpose(1, 2), y)
+        mu_square = torch.sum(factor * (mu_x ** 2), 1).unsqueeze(-1)
+        log_prior = y_square - y_mu_double + mu_square + const
+        attn = maximum_path(log_prior, attn_mask.squeeze(1))
+    logw_ = torch.log(1e-8 + torch.sum(attn.unsqueeze(1), -1)) * x_mask
+    dur_loss = torch.sum((logw - logw_) ** 2) / torch.sum(x_lengths)
+    if out_size is not None:                                               # matcha_tts.py:211-233
+        attn_cut = torch.zeros(attn.shape[0], attn.shape[1], out_size, dtype=attn.dtype)
+        y_cut = torch.zeros(y.shape[0], cfg.n_feats, out_size, dtype=y.dtype)
+        cut_lengths = []
+        for i in range(y.shape[0]):
+            n = int(out_size + (y_lengths[i] - out_size).clamp(None, 0))
+            lo = int(out_offset[i])
+            cut_lengths.append(n)
+            y_cut[i, :, :n] = y[i, :, lo:lo + n]
+            attn_cut[i, :, :n] = attn[i, :, lo:lo + n]
+        y_cut_lengths = torch.LongTensor(cut_lengths)
+        attn, y, y_mask = attn_cut, y_cut, sequence_mask(y_cut_lengths, out_size).unsqueeze(1).to(y_mask.dtype)
+    mu_y = torch.matmul(attn.transpose(1, 2), mu_x.transpose(1, 2)).transpose(1, 2)
+    b = mu_y.shape[0]
+    t = torch.rand([b, 1, 1]) if t is None else t.reshape(b, 1, 1).to(mu_y.dtype)
+    z = torch.randn_like(y) if z is None else z
+    sigma_min = cfg.sigma_min
+    y_t = (1 - (1 - sigma_min) * t) * z + t * y
+    u = y - (1 - sigma_min) * z
+    v = estimator(sd, cfg, y_t, y_mask, mu_y, t.squeeze(), spk_emb) if b > 1 else estimator(sd, cfg, y_t, y_mask, mu_y, t.reshape(1), spk_emb)
+    diff_loss = F.mse_loss(v, u, reduction="sum") / (torch.sum(y_mask) * u.shape[1])
+    if prior_loss:
+        pl = torch.sum(0.5 * ((y - mu_y) ** 2 + math.log(2 * math.pi)) * y_mask) / (torch.sum(y_mask) * cfg.n_feats)
+    else:
+        pl = 0
+    return {"dur_loss": dur_loss, "prior_loss": pl, "diff_loss": diff_loss, "attn": attn,
+            "log_prior": log_prior, "mu_x": mu_x, "logw": logw, "mu_y": mu_y, "y_t": y_t, "u": u, "v": v, "y_mask": y_mask}

@@ -133,7 +133,7 @@ def install():
     utils = _mod("matcha.utils", get_pylogger=lambda name=__name__: logging.getLogger(name))
     utils.__path__ = [os.path.join(_MATCHA_ROOT, "matcha", "utils")]
     _mod("matcha.utils.pylogger", get_pylogger=lambda name=__name__: logging.getLogger(name))
-    _mod("matcha.utils.monotonic_align", maximum_path=None)
+    _install_monotonic_align()
     spec = importlib.util.spec_from_file_location(
         "matcha.utils.model", os.path.join(_MATCHA_ROOT, "matcha", "utils", "model.py"))
     model_mod = importlib.util.module_from_spec(spec)
@@ -141,6 +141,26 @@ def install():
     spec.loader.exec_module(model_mod)
     utils.model = model_mod
     _installed = True
+
+
+def _install_monotonic_align():
+    """MatchaTTS.forward needs the alignment search.  With the reference's own Cython kernel compiled under oracle/_ref
+    (oracle/build_oracle.py) the reference's UNMODIFIED wrapper monotonic_align/__init__.py runs on top of it; otherwise the
+    C restatement stands in (oracle/mas_oracle.py, itself pinned against the compiled reference by tests/test_mas.py)."""
+    import importlib.util
+
+    from . import build_oracle, mas_oracle
+
+    core = build_oracle.load_ref() if build_oracle.ref_module_path() else None
+    init_py = os.path.join(_MATCHA_ROOT, "matcha", "utils", "monotonic_align", "__init__.py")
+    if core is not None and os.path.exists(init_py):
+        sys.modules["matcha.utils.monotonic_align.core"] = core
+        spec = importlib.util.spec_from_file_location("matcha.utils.monotonic_align", init_py)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["matcha.utils.monotonic_align"] = mod
+        spec.loader.exec_module(mod)
+    else:
+        _mod("matcha.utils.monotonic_align", maximum_path=mas_oracle.maximum_path)
 
 
 def build_matcha(cfg, state_dict):

@@ -27,7 +27,7 @@ FILES = [
     "Matcha-TTS/matcha/models/matcha_tts.py", "Matcha-TTS/matcha/models/components/__init__.py",
     "Matcha-TTS/matcha/models/components/decoder.py", "Matcha-TTS/matcha/models/components/flow_matching.py",
     "Matcha-TTS/matcha/models/components/text_encoder.py", "Matcha-TTS/matcha/models/components/transformer.py",
-    "Matcha-TTS/matcha/utils/model.py", "Matcha-TTS/matcha/utils/rich_utils.py", "Matcha-TTS/matcha/utils/utils.py",
+    "Matcha-TTS/matcha/utils/model.py", "Matcha-TTS/matcha/utils/monotonic_align/__init__.py", "Matcha-TTS/matcha/utils/rich_utils.py", "Matcha-TTS/matcha/utils/utils.py",
 ]
 
 

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--part", default="all")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--dense-vocoder", action="store_true", help="vocode the padded frames too (bench.py's `padded_vocoder`)")
     a = ap.parse_args()
     model = ev.MatchaTTS(**VCTK.constructor_kwargs(), precision=a.precision)
     model.load_state_dict(synthetic.matcha_state_dict(VCTK, seed=1234))
@@ -36,15 +37,15 @@ def main():
         out = model.synthesise(x, xl, a.steps, 0.667, spk, 0.8)
         if a.part == "matcha":
             return out, None
-        return out, voc(out["mel"]).clamp(-1, 1)
+        return out, voc(out["mel"], lengths=None if a.dense_vocoder else out["mel_lengths"]).clamp(-1, 1)
 
     for _ in range(2):
         out, wav = step()
     torch.cuda.synchronize()
-    mel = out["mel"].clone()
+    mel, mel_len = out["mel"].clone(), out["mel_lengths"].clone()
     torch.cuda.profiler.start()
     if a.part == "vocoder":
-        voc(mel)
+        voc(mel, lengths=None if a.dense_vocoder else mel_len)
     else:
         step()
     torch.cuda.synchronize()

@@ -654,8 +654,16 @@ def test_scheduling_knobs_do_not_change_results():
     assert run(EV_RN_FUSE=0, EV_DEC_LANES=2) == unfused
     assert run(EV_RN_FUSE=0, EV_DEC_SIDE=0) == unfused
     assert run() == base                            # the fused kernel's sums have one writer each and a fixed order: reproducible
-    assert run(EV_RB_WAVE=1) == base
-    assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == base
+    # HiFi-GAN ResBlocks: windows paired in 2-CTA clusters (halo rows exchanged over DSMEM) compute every row in the same order
+    # as single windows -- with the same set of fused blocks (EV_RB_FUSE=2: all nine) the waveform does not change by a bit
+    all_fused = run(EV_RB_FUSE=2)
+    assert run(EV_RB_FUSE=2, EV_RB_CLUSTER=1) == all_fused
+    assert run(EV_RB_FUSE=2, EV_RB_CLUSTER=3) == all_fused
+    assert all_fused == base                        # the default policy fuses all nine as well
+    # the wavefront schedule and one CTA per SM keep single windows: compared with the unpaired default (C = 128, k >= 7 layer by layer)
+    single = run(EV_RB_CLUSTER=1)
+    assert run(EV_RB_WAVE=1) == single
+    assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == single
     assert run(EV_PDL=0) == base
     # skipping the padded rows of the decoder's masked per-row work (feed-forward tiles, attention query blocks, out-projection
     # tiles) must not change a single bit either: those rows never reach an output that survives the mask

@@ -47,3 +47,32 @@ def test_oracle_bit_equal_to_reference_vocoder_and_denoiser():
     bias = ho.denoiser_bias(hs, HIFIGAN_V1)
     assert torch.equal(bias, den.bias_spec)
     assert torch.equal(ho.denoise(w.clamp(-1, 1).squeeze(1), bias, 0.00025), den(w_ref.clamp(-1, 1).squeeze(), strength=0.00025))
+
+
+def _training_batch(seed, b=3):
+    return synthetic.training_batch(b, 4, 14, seed, VCTK.n_feats)
+
+
+def test_oracle_bit_equal_to_reference_training_forward(matcha_sd):
+    """MatchaTTS.forward (matcha_tts.py:154-245) of the unmodified reference -- its own monotonic_align wrapper on its own Cython
+    kernel when oracle/_ref holds the build -- against the restatement, under the same random draws."""
+    import random
+
+    ref = shim.build_matcha(VCTK, matcha_sd).eval()
+    for seed, out_size in ((31, None), (32, None), (33, 16)):
+        x, xl, spk, y, yl = _training_batch(seed)
+        torch.manual_seed(seed)
+        random.seed(seed)
+        with torch.no_grad():
+            dur, prior, diff, attn = ref(x, xl, y, yl, spks=spk, out_size=out_size)
+        torch.manual_seed(seed)
+        random.seed(seed)
+        off = None
+        if out_size is not None:           # the reference's draw, matcha_tts.py:213-216
+            mx = (yl - out_size).clamp(0).tolist()
+            off = torch.tensor([random.choice(range(0, e)) if e > 0 else 0 for e in mx])
+        t = torch.rand([x.shape[0], 1, 1])
+        z = torch.randn(x.shape[0], VCTK.n_feats, out_size or y.shape[-1])
+        o = mo.forward_losses(matcha_sd, VCTK, x, xl, y, yl, spk, out_size=out_size, t=t, z=z, out_offset=off)
+        assert torch.equal(o["attn"], attn)
+        assert torch.equal(o["dur_loss"], dur) and torch.equal(o["prior_loss"], prior) and torch.equal(o["diff_loss"], diff), (seed, o["diff_loss"], diff)
