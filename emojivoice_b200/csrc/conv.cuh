@@ -181,7 +181,11 @@ struct ResnetTcArgs {
   bf16* a_buf = nullptr; long long a_ld = 0, a_bs = 0;      // the output when conv2 == nullptr; else an optional copy of conv2's operand (tests)
   float* xr = nullptr; bf16* n_out = nullptr;               // (b, t, 256) dense outputs of the full block
   float* xr_cf = nullptr;                                   // instead of xr: the fp32 stream channel-first (b, 256, t)
+  // optional (with xr_cf): the attention's stacked q|k|v projection (Linear 256 -> 384, no bias) of n, in the same launch; n_out is
+  // then not written (nobody else reads it)
+  const ConvWeights* qkv = nullptr; bf16* qkv_out = nullptr;   // (b, t, 384) dense
 };
+bool resnet_tc_qkv_supported(const ConvWeights& qkv);
 int resnet_tc_plan(int B, int T);
 bool resnet_tc_supported(const ConvWeights& conv1, const ConvWeights* conv2, const ConvWeights* res, int B, int T);
 cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string* err);

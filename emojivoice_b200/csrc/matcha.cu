@@ -420,6 +420,7 @@ struct Decoder {
   ev_ctx* ctx; const MatchaW& m; DecBuffers<ActT>& d; int B, T; cudaStream_t s; int D, inner;
   int gn_slot = 0;   // next free [B][8][2] slot of d.gn_fused
   bool xr_is_cf = false;       // d.xr of the current block holds the residual stream channel-first (written by resnet_tc for ff_tc's tail mode)
+  bool qkv_done = false;       // the fused ResNet kernel of the current block has already written q|k|v (bf16) into d.qkv
   bool use_ff_tiles = false;   // d.ff_tiles hold this call's tile lists
   RaggedPlanner rag;           // planner state (table cache) of this call's ragged convs
   cudaStream_t side_stream = nullptr;   // side branch for res_conv (single-lane decoding), see resnet()
@@ -469,11 +470,15 @@ struct Decoder {
         ra.n_out = d.n;                      // conv2's operand stays in shared memory
         xr_is_cf = fuse_tail(k);
         if (xr_is_cf) ra.xr_cf = d.xr; else ra.xr = d.xr;
+        qkv_done = xr_is_cf && resnet_tc_qkv_supported(m.tf[k].qkv);    // the q|k|v projection of the block's attention rides along
+        if (qkv_done) { ra.qkv = &m.tf[k].qkv; ra.qkv_out = reinterpret_cast<bf16*>(d.qkv); ra.n_out = nullptr; }
         const double rows = (double)B * Tl;
-        return launch_resnet_tc(ra, 2.0 * rows * D * (4.0 * w.c_in + 3.0 * D), rows * (2.0 * w.c_in + 6.0 * D), "resnet_tc");
+        return launch_resnet_tc(ra, 2.0 * rows * D * (4.0 * w.c_in + 3.0 * D + (qkv_done ? 3.0 * inner : 0.0)),
+                                rows * (2.0 * w.c_in + 6.0 * D + (qkv_done ? 6.0 * inner - 2.0 * D : 0.0)), "resnet_tc");
       }
     }
     xr_is_cf = false;
+    qkv_done = false;
     Epilogue e1; e1.out_f32 = d.h; e1.f32_ld = D; e1.f32_bs = bsD;
     const double* part = d.gn_partial;
     if (fuse_gn()) { e1.gn_sum = next_gn_slot(); e1.gn_groups = 8; part = e1.gn_sum; }
@@ -526,8 +531,10 @@ struct Decoder {
     if constexpr (std::is_same<ActT, bf16>::value) {
       // bf16 q|k|v straight from the projection epilogue -> tcgen05 attention (attention_tc.cu)
       bf16* qkv16 = reinterpret_cast<bf16*>(d.qkv);
-      Epilogue eq; eq.out_act = qkv16; eq.act_ld = 3 * inner; eq.act_bs = (long long)Tl * 3 * inner;
-      EV_TRY(run_conv<ActT>(ctx, w.qkv, d.n, D, bsD, B, Tl, eq, s));
+      if (!qkv_done) {
+        Epilogue eq; eq.out_act = qkv16; eq.act_ld = 3 * inner; eq.act_bs = (long long)Tl * 3 * inner;
+        EV_TRY(run_conv<ActT>(ctx, w.qkv, d.n, D, bsD, B, Tl, eq, s));
+      }
       AttnTcArgs at;
       at.qkv = qkv16; at.ld = 3 * inner; at.bs = (long long)Tl * 3 * inner;
       at.B = B; at.T = Tl; at.H = Hh; at.D = hd; at.inner = inner; at.scale = 1.0f / sqrtf((float)hd);

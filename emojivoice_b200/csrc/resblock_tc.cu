@@ -489,6 +489,26 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
     };
 
+    // L2 prefetch of the NEXT window's rows of x (and of the MRF accumulator when it is read back): a lone CTA per SM otherwise sits
+    // through two rounds of DRAM latency in phase 0 and again in the output phase of every window
+    const int pf_tid = ew * 32 + lane, pf_n = n_epi * 32;
+    auto prefetch_window = [&](int tile_n) {
+      if (tile_n >= total_tiles || (p.debug & 32)) return;
+      int bn, tn;
+      if (p.rag) { const int pair = __ldg(p.rag + 1 + tile_n); bn = pair >> 16; tn = pair & 0xffff; }
+      else { bn = tile_n / p.tiles_per_item; tn = tile_n - bn * p.tiles_per_item; }
+      const int wn = tn * p.Wv - H + (int)crank * W;
+      constexpr int LPR = C * 4 / 128 > 0 ? C * 4 / 128 : 1;          // 128-byte lines per row (C = 32: one line per row)
+      const char* xn = reinterpret_cast<const char*>(p.x + bn * p.x_bs);
+      const char* sn = reinterpret_cast<const char*>(p.sum + bn * p.sum_bs);
+      for (int i = pf_tid; i < W * LPR; i += pf_n) {
+        const int t = wn + i / LPR;
+        if (t < 0 || t >= L) continue;
+        const long long off = (long long)t * C * 4 + (i % LPR) * 128;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + off));
+        if (p.mode >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + off));
+      }
+    };
     for (int tile = cid; tile < total_tiles; tile += n_cl) {
       int b, ti;
       if (p.rag) { const int pair = __ldg(p.rag + 1 + tile); b = pair >> 16; ti = pair & 0xffff; }
@@ -525,6 +545,9 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
       tmem_st_wait();
       phase_done();
+      // measured (ragged config-2 batch): k3 795 -> 756 us at C = 128, 624 -> 581 at C = 64; k7 -2 %; k11 within noise (long MMA phases),
+      // as are two CTAs per SM, which hide each other's latency already
+      if constexpr (OCC == 1) { if (p.k <= 7) prefetch_window(tile + n_cl); }
 
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {

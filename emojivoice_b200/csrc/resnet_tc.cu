@@ -26,6 +26,9 @@
 //   * with one m-block per CTA (mb = 1) conv2 accumulates into the spare 256 TMEM columns and starts on K-chunks 0-1 while the
 //     epilogue warps are still producing K-chunks 2-3 of `a`;
 //   * LayerNorm statistics are taken per row from the same TMEM tile (thread = row), combined across the four column-slot warps through shared memory (one writer per partial sum, fixed order).
+//   * optionally the block that follows starts here too: n is written into the (by then dead) operand planes instead of global
+//     memory and the attention's stacked q|k|v projection (256 -> 384, no bias) runs on it in the same launch -- issuer 0, the
+//     weight ring continues with W_qkv's 12 tiles; with two m-blocks the 768 output columns take two rounds through TMEM (q|k, then v);
 // `mode 1` stops after the first apply (final_block: conv -> GN -> Mish -> mask, decoder.py:431) and writes bf16 to global.
 //
 // Warp roles (20 warps): 0 activation-tile TMA producer, 1 weight-tile TMA producer (weights are constants: it runs free),
@@ -65,7 +68,7 @@ constexpr int RN_MAX_CLUSTER = 8;
 constexpr int RN_CONST_FLOATS = 6 * RN_C + 256 * 8 + 64 + 2 * RN_MAX_CLUSTER * 16;
 constexpr int RN_SMEM_LIMIT = 227 * 1024 - 1024; // dynamic + ~0.5 KB of static barriers must stay below 227 KB
 
-struct RnMaps { CUtensorMap x1, x3, w1, w2, wr; };
+struct RnMaps { CUtensorMap x1, x3, w1, w2, wr, wq; };
 
 struct RnParams {
   int B, T, mb, m_tiles, n_cta;
@@ -79,6 +82,7 @@ struct RnParams {
   bf16* a_buf; long long a_ld, a_bs;           // mode 1: the block's output; mode 0: optional copy of conv2's operand (tests)
   float* xr; bf16* n_out;                      // (b, t, 256) dense
   float* xr_cf;                                // instead of xr: the same stream CHANNEL-FIRST (b, 256, t), for ff_tc's tail mode
+  bf16* qkv_out;                               // != nullptr: q|k|v = n W_qkv^T (b, t, 384) computed here; n_out is not written
   float eps_gn, eps_ln;
   int trace;
 };
@@ -146,6 +150,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
   __shared__ __align__(8) uint64_t x1_full[RN_X1_SLOTS], x1_empty[RN_X1_SLOTS], x3_full[RN_X3_SLOTS], x3_empty[RN_X3_SLOTS];
   __shared__ __align__(8) uint64_t w_full[RN_MAX_W_SLOTS], w_empty[RN_MAX_W_SLOTS];
   __shared__ __align__(8) uint64_t acc_full, plane_ready[2], tm_ready[2], res_full[2], xch_bar[2];
+  __shared__ __align__(8) uint64_t qkv_ready, qkv_full[2], qkv_drained;
   __shared__ uint32_t tmem_base_smem;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -175,7 +180,9 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     mbar_init(&acc_full, 2);
     for (int h = 0; h < 2; ++h) {
       mbar_init(&plane_ready[h], RN_EPI_WARPS); mbar_init(&tm_ready[h], RN_EPI_WARPS); mbar_init(&res_full[h], 1); mbar_init(&xch_bar[h], 1);
+      mbar_init(&qkv_full[h], 1);
     }
+    mbar_init(&qkv_ready, RN_EPI_WARPS); mbar_init(&qkv_drained, RN_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -240,6 +247,9 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
             for (int h = 0; h < 2; ++h) load_w(&maps.w2, kc, h, j);
         for (int h = 0; h < 2; ++h)
           for (int kc = 0; kc < p.kc_in; ++kc) load_w(&maps.wr, kc, h, 0);
+        if (p.qkv_out)
+          for (int n3 = 0; n3 < 3; ++n3)
+            for (int kc = 0; kc < RN_C / 64; ++kc) load_w(&maps.wq, kc, n3, 0);
       }
     }
     __syncwarp();
@@ -335,6 +345,28 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
             if (++sx == RN_X3_SLOTS) { sx = 0; px ^= 1u; }
           }
           if (elect_one()) umma_commit(&res_full[hh]);
+          __syncwarp();
+        }
+        if (p.qkv_out) {
+          // q|k|v = n W_qkv^T: n sits in the operand planes (written by the LayerNorm pass), one 128-column output tile per n3.
+          // One m-block: q, k, v -> columns 0 / 128 / 256.  Two m-blocks (m at + 256): q, k first, v after the epilogue has drained them.
+          const uint32_t plane16 = (uint32_t)(R * 128) >> 4;
+          RN_WAIT(&qkv_ready, 0);
+          tcgen05_fence_after();
+          for (int n3 = 0; n3 < 3; ++n3) {
+            if (n3 == 2 && p.mb == 2) {
+              if (elect_one()) umma_commit(&qkv_full[0]);
+              __syncwarp();
+              RN_WAIT(&qkv_drained, 0);
+              tcgen05_fence_after();
+            }
+            const uint32_t d0 = tmem_base + (uint32_t)((p.mb == 2 ? (n3 & 1) : n3) * 128);
+            for (int kc = 0; kc < RN_C / 64; ++kc) {
+              tile_mmas(a_lo0 + (uint32_t)kc * plane16, d0, kc ? 1u : 0u);
+              ring_advance(1);
+            }
+          }
+          if (elect_one()) umma_commit(&qkv_full[p.mb == 2 ? 1 : 0]);
           __syncwarp();
         }
       }
@@ -609,7 +641,55 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
             pk[j >> 1] = pack_bf16(v0, v1);
             pk[(j >> 1) + 1] = pack_bf16(v2, v3);
           }
-          store_bf16_block(pk, p.n_out + ((long long)b * p.T) * RN_C + cb * 32, RN_C, m);
+          if (p.qkv_out) {
+            // operand plane (cb >> 1), row r, 128B swizzle -- the layout conv2's operand used; those planes are dead by now
+            const int r = m * 128 + rl;
+            uint8_t* prow = a_gen + (cb >> 1) * (R * 128) + r * 128;
+            const int c0 = 4 * (cb & 1), x7 = r & 7;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(prow + (((c0 + i) ^ x7) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          } else {
+            store_bf16_block(pk, p.n_out + ((long long)b * p.T) * RN_C + cb * 32, RN_C, m);
+          }
+        }
+      }
+      if (p.qkv_out) {
+        tcgen05_fence_before();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qkv_ready);
+        // drain: thread = row writes its 32 bf16 (64 contiguous bytes = two whole sectors) per 32-column block straight from registers
+        // (the transpose buffers overlap the planes the second round's MMAs still read)
+        const int n_rounds = p.mb == 2 ? 2 : 1;
+        for (int round = 0; round < n_rounds; ++round) {
+          RN_WAIT(&qkv_full[round], 0);
+          tcgen05_fence_after();
+          const int nb = (p.mb == 2 ? (round == 0 ? 8 : 4) : 12);           // 32-column blocks per m-block in this round
+          for (int m = 0; m < vmb; ++m) {
+            const int r = m * 128 + rl, t = m0 - 1 + r;
+            const bool own = r >= 1 && r <= R - 2 && t < p.T;
+            bf16* drow = p.qkv_out + ((long long)b * p.T + t) * 384 + (round == 1 ? 256 : 0);
+#pragma unroll 1
+            for (int blk = slot; blk < nb; blk += 4) {
+              uint32_t raw[32];
+              tmem_ld32(lane_addr + (uint32_t)(m * RN_C + blk * 32), raw);
+              if (own) {
+                uint4* dst = reinterpret_cast<uint4*>(drow + blk * 32);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  dst[i] = make_uint4(pack_bf16(__uint_as_float(raw[8 * i]), __uint_as_float(raw[8 * i + 1])),
+                                      pack_bf16(__uint_as_float(raw[8 * i + 2]), __uint_as_float(raw[8 * i + 3])),
+                                      pack_bf16(__uint_as_float(raw[8 * i + 4]), __uint_as_float(raw[8 * i + 5])),
+                                      pack_bf16(__uint_as_float(raw[8 * i + 6]), __uint_as_float(raw[8 * i + 7])));
+              }
+            }
+          }
+          if (round + 1 < n_rounds) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&qkv_drained);
+          }
         }
       }
       if (ew == 0) RN_TR(12);
@@ -709,6 +789,12 @@ bool resnet_tc_supported(const ConvWeights& conv1, const ConvWeights* conv2, con
   return true;
 }
 
+bool resnet_tc_qkv_supported(const ConvWeights& w) {
+  static const bool on = []() { const char* v = getenv("EV_QKV_FUSE"); return !(v && atoi(v) == 0); }();
+  return on && w.w_bf16 && !w.bias && w.taps == 1 && w.N == 384 && w.N_pad_tc == 384 && w.C_in == RN_C && w.K_pad == RN_C && w.conv_stride == 1 &&
+         !w.transposed;
+}
+
 cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string* err) {
   const ConvWeights& w1 = *a.conv1;
   const bool full = a.conv2 != nullptr;
@@ -718,7 +804,8 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if ((a.x_ld & 7) || (a.x_bs & 7) || !al16(a.x) || (a.a_buf && ((a.a_ld & 7) || (a.a_bs & 7) || !al16(a.a_buf))) || (!full && !a.a_buf) ||
-      (full && (!al16(a.xr) || !al16(a.n_out) || (!a.xr && !a.xr_cf) || !a.n_out || !a.temb || !a.ln_g || !a.ln_b))) {
+      (full && (!al16(a.xr) || !al16(a.n_out) || !al16(a.qkv_out) || (!a.xr && !a.xr_cf) || (!a.n_out && !a.qkv_out) || !a.temb || !a.ln_g || !a.ln_b)) ||
+      (a.qkv_out && (!full || !a.qkv || !resnet_tc_qkv_supported(*a.qkv)))) {
     if (err) *err = "resnet_tc: tensors must be 16-byte aligned";
     return cudaErrorInvalidValue;
   }
@@ -750,15 +837,22 @@ cudaError_t resnet_tc_launch(const ResnetTcArgs& a, cudaStream_t s, std::string*
     const ConvWeights& w2 = *a.conv2;
     const ConvWeights& wr = *a.res;
     p.bias2 = w2.bias; p.bias_r = wr.bias; p.g2 = a.gn_g2; p.b2 = a.gn_b2; p.ln_g = a.ln_g; p.ln_b = a.ln_b;
-    p.xr = a.xr; p.n_out = a.n_out; p.xr_cf = a.xr_cf;
+    p.xr = a.xr; p.n_out = a.n_out; p.xr_cf = a.xr_cf; p.qkv_out = a.qkv_out;
     ok = ok && tc_encode_bf16_map(&maps.x3, a.x, (uint64_t)w1.C_in, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.x_ld * 2, (uint64_t)a.x_bs * 2,
                                   64u, 128u, 128, err);
     ok = ok && tc_encode_bf16_map(&maps.w2, w2.w_bf16, (uint64_t)w2.K_pad, (uint64_t)w2.N_pad_tc, 3, (uint64_t)w2.K_pad * 2,
                                   (uint64_t)w2.K_pad * w2.N_pad_tc * 2, 64u, 128u, 128, err);
     ok = ok && tc_encode_bf16_map(&maps.wr, wr.w_bf16, (uint64_t)wr.K_pad, (uint64_t)wr.N_pad_tc, 1, (uint64_t)wr.K_pad * 2,
                                   (uint64_t)wr.K_pad * wr.N_pad_tc * 2, 64u, 128u, 128, err);
+    if (a.qkv_out) {
+      const ConvWeights& wq = *a.qkv;
+      ok = ok && tc_encode_bf16_map(&maps.wq, wq.w_bf16, (uint64_t)wq.K_pad, (uint64_t)wq.N_pad_tc, 1, (uint64_t)wq.K_pad * 2,
+                                    (uint64_t)wq.K_pad * wq.N_pad_tc * 2, 64u, 128u, 128, err);
+    } else {
+      maps.wq = maps.w1;
+    }
   } else {
-    maps.x3 = maps.x1; maps.w2 = maps.w1; maps.wr = maps.w1;
+    maps.x3 = maps.x1; maps.w2 = maps.w1; maps.wr = maps.w1; maps.wq = maps.w1;
   }
   if (!ok) return cudaErrorInvalidValue;
   cudaError_t ce = rn_set_attributes();

@@ -665,6 +665,9 @@ def test_scheduling_knobs_do_not_change_results():
     assert run(EV_RB_WAVE=1) == single
     assert run(EV_RB_WAVE=1, EV_RB_OCC2=0) == single
     assert run(EV_PDL=0) == base
+    # the attention's q|k|v projection inside the fused ResNet kernel multiplies the same bf16 operands in the same K order as the
+    # separate conv launch it replaces
+    assert run(EV_QKV_FUSE=0) == base
     # skipping the padded rows of the decoder's masked per-row work (feed-forward tiles, attention query blocks, out-projection
     # tiles) must not change a single bit either: those rows never reach an output that survives the mask
     assert run(EV_FF_RAGGED=0) == base
