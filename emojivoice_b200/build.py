@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("EV_NVCC_EXTRA", "").split(), "-c", s, "-o", o]   # e.g. EV_NVCC_EXTRA=-DEV_RB_TRACE
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")

@@ -145,6 +145,12 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   const int margin_tap = (CL > 1 && crank == 0) ? (p.k - 1) / 2 + 1 : 0;     // first tap index that reads the neighbour's rows
   const int cid = CL > 1 ? (int)blockIdx.x / CL : (int)blockIdx.x, n_cl = CL > 1 ? (int)gridDim.x / CL : (int)gridDim.x;
   __shared__ uint32_t tmem_base_smem;
+#ifdef EV_RB_TRACE
+  __shared__ long long rb_tr[32];          // EV_RB_DEBUG & 64: clock stamps of CTA 0's second window (printed at the end of the launch)     // nvcc -DEV_RB_TRACE + EV_RB_DEBUG=64: the device printf below costs registers, so it is not in normal builds
+#define RB_TR(i) do { if ((p.debug & 64) && blockIdx.x == 0 && lane == 0 && tr_it == 1) rb_tr[(i)] = clock64(); } while (0)
+#else
+#define RB_TR(i) do { (void)tr_it; } while (0)
+#endif
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_gen = smem_raw + (base - smem_u32(smem_raw));
@@ -301,12 +307,14 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       fence_proxy_async();
       tcgen05_fence_after();
     };
-    for (int tile = cid; tile < total_tiles; tile += n_cl) {
+    int tr_it = 0;
+    for (int tile = cid; tile < total_tiles; tile += n_cl, ++tr_it) {
       for (int ci = 0; ci < 6; ++ci) {
         const int l = ci >> 1, second = ci & 1;
         const int d = second ? 1 : p.dil[l];
         const uint32_t d_tmem = second ? acc_x : acc_mid;
         mbar_wait(&epi_done, eph);          // the operand buffer holds this conv's input
+        if (warp == 1) RB_TR(16 + 2 * ci);
         eph ^= 1u;
         tcgen05_fence_after();
         uint32_t fresh = second ? 0u : 1u;  // conv2 accumulates onto the residual stream from its first MMA on
@@ -388,6 +396,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           if constexpr (CL > 1) { if (n_nbr && !(p.debug & 4)) rb_commit_multicast(&nbr_done, nbr_mask); }
         }
         __syncwarp();
+        if (warp == 1) RB_TR(17 + 2 * ci);
       }
     }
   } else {
@@ -466,6 +475,23 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         if (edge_r && mb == MB - 1) { nbr_wait(); put_remote(wr, cb, v, +1); }
       }
     };
+    // MRF accumulator read-back (mode >= 1): the 32 x 32 block of `sum` that belongs to output block `blk` is copied global -> the
+    // warp's transpose buffer with cp.async (no registers, no stall), row-major like the accumulator rows the threads will hold.
+    // Issued for the warp's first block BEFORE the wait for the last conv's MMAs, so that DRAM latency hides behind them; the
+    // row pass then adds it from shared memory.  (Read inside the row pass, every load sat behind the previous row's store to the
+    // same array: eight DRAM latencies per block, traced as 14-25 k clk of a 60-120 k clk window.)
+    auto stage_sum = [&](int b_, int w0_, int blk) {
+      const int mb = blk / NCB, cb = blk - mb * NCB;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int wr2 = mb * 128 + q * 32 + u * 4 + sub, t2 = w0_ + wr2, g2 = (int)crank * W + wr2;
+        if (g2 < H || g2 >= CL * W - H || t2 < 0 || t2 >= L) continue;     // rows that are not stored: whatever the buffer holds
+        const float* src = p.sum + b_ * p.sum_bs + (long long)t2 * C + cb * 32 + cl;
+        const uint32_t dst = smem_u32(wstage + (u * 4 + sub) * RB_STAGE_LD + cl);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto phase_done = [&]() {
       if constexpr (WAVE) return;        // wavefront mode hands over block by block (block_done)
       tcgen05_fence_before();
@@ -509,10 +535,12 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         if (p.mode >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + off));
       }
     };
-    for (int tile = cid; tile < total_tiles; tile += n_cl) {
+    int tr_it = 0;
+    for (int tile = cid; tile < total_tiles; tile += n_cl, ++tr_it) {
       int b, ti;
       if (p.rag) { const int pair = __ldg(p.rag + 1 + tile); b = pair >> 16; ti = pair & 0xffff; }
       else { b = tile / p.tiles_per_item; ti = tile - b * p.tiles_per_item; }
+      if (ew == 0) RB_TR(0);
       const int w0 = ti * p.Wv - H + (int)crank * W;     // CL > 1: the cluster's window is CL * W rows, this CTA owns rows [crank * W, +W)
       const bool interior = w0 >= 0 && w0 + W <= L;    // no row of this window lies outside the sequence: no zero-padding fix-ups
       const float* xb = p.x + b * p.x_bs;
@@ -545,9 +573,10 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
       }
       tmem_st_wait();
       phase_done();
-      // measured (ragged config-2 batch): k3 795 -> 756 us at C = 128, 624 -> 581 at C = 64; k7 -2 %; k11 within noise (long MMA phases),
-      // as are two CTAs per SM, which hide each other's latency already
-      if constexpr (OCC == 1) { if (p.k <= 7) prefetch_window(tile + n_cl); }
+      if (ew == 0) RB_TR(1);
+      // measured (ragged config-2 batch, vocoder total): no prefetch 13.58 ms, everywhere 13.49 ms (k3 at C = 128: 831 -> 761 us, C = 64:
+      // 640 -> 580, C = 32: 497 -> 454); EV_RB_DEBUG=128 switches it off
+      if (!(p.debug & 128)) prefetch_window(tile + n_cl);
 
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
@@ -557,6 +586,7 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
           mph ^= 1u;
           tcgen05_fence_after();
           conv_done_signal();
+          if (ew == 0) RB_TR(2 + 4 * l);
         }
 #pragma unroll 1
         for (int bi = 0; bi < n_blk; ++bi) {
@@ -591,12 +621,15 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
         }
         ++cn;
         phase_done();
+        if (ew == 0) RB_TR(3 + 4 * l);
         // ---- after conv2_l: acc_x now holds x_new - (accumulated conv2 biases)
+        if (l == 2 && p.mode >= 1 && n_blk > 0) stage_sum(b, w0, slot + (rev ? n_blk - 1 : 0) * n_slots);
         if constexpr (!WAVE) {
           mbar_wait(&mma_done, mph);
           mph ^= 1u;
           tcgen05_fence_after();
           conv_done_signal();
+          if (ew == 0) RB_TR(4 + 4 * l);
         }
 #pragma unroll 1
         for (int bi = 0; bi < n_blk; ++bi) {
@@ -630,7 +663,17 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
             put_edges(mb, wr, cb, a);
             block_done(mb);
           } else {
-            // ---- block output: transpose through the private buffer, then coalesced rows
+            // ---- block output: (+ the staged MRF accumulator) -> transpose through the private buffer -> coalesced rows
+            if (p.mode >= 1) {
+              asm volatile("cp.async.wait_group 0;" ::: "memory");
+              __syncwarp();                                            // every lane's copies have landed
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 s4 = *reinterpret_cast<const float4*>(wstage + lane * RB_STAGE_LD + j);
+                a[j] += s4.x; a[j + 1] += s4.y; a[j + 2] += s4.z; a[j + 3] += s4.w;
+              }
+              __syncwarp();                                            // all rows read before the buffer is rewritten
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(wstage + lane * RB_STAGE_LD + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
@@ -642,13 +685,8 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
               if (g2 < H || g2 >= CL * W - H || t2 < 0 || t2 >= L) continue;
               float4 v = *reinterpret_cast<const float4*>(wstage + (u * 4 + sub) * RB_STAGE_LD + cl);
               const long long off = (long long)t2 * C + cb * 32 + cl;
-              float* sp = p.sum + b * p.sum_bs + off;
-              if (p.mode >= 1) {
-                const float4 s4 = *reinterpret_cast<const float4*>(sp);
-                v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
-              }
               if (p.mode == 2) { v.x *= p.inv_n; v.y *= p.inv_n; v.z *= p.inv_n; v.w *= p.inv_n; }
-              if (p.mode < 2 || p.write_f32) *reinterpret_cast<float4*>(sp) = v;
+              if (p.mode < 2 || p.write_f32) *reinterpret_cast<float4*>(p.sum + b * p.sum_bs + off) = v;
               if (p.mode == 2 && p.act_out) {
                 const float s = p.slope_out;
                 __nv_bfloat162 lo = __floats2bfloat162_rn(fmaxf(v.x, s * v.x), fmaxf(v.y, s * v.y));
@@ -659,11 +697,13 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
                 *reinterpret_cast<uint2*>(p.act_out + b * p.act_bs + off) = pk;
               }
             }
-            __syncwarp();
+            __syncwarp();                                              // the row pass has read the buffer
+            if (p.mode >= 1 && bi + 1 < n_blk) stage_sum(b, w0, slot + (rev ? n_blk - 2 - bi : bi + 1) * n_slots);
           }
         }
         ++cn;
         if (l < 2) phase_done();
+        if (ew == 0) RB_TR(5 + 4 * l);
       }
       tcgen05_fence_before();   // acc_x is rewritten by the next tile's phase 0
     }
@@ -671,6 +711,16 @@ resblock_tc_kernel(const __grid_constant__ RbMaps maps, const __grid_constant__ 
   tcgen05_fence_before();
   if constexpr (CL > 1) rb_cluster_sync();     // no CTA exits while a peer may still push rows or arrivals at it
   else __syncthreads();
+#ifdef EV_RB_TRACE
+  if ((p.debug & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = rb_tr[0];
+    printf("RBTR C=%d k=%d cl=%d occ=%d | epi: ph0 %lld |", C, p.k, CL, OCC, rb_tr[1] - t0);
+    for (int l = 0; l < 3; ++l) printf(" c1 mma_done %lld op %lld c2 mma_done %lld op %lld |", rb_tr[2 + 4 * l] - t0, rb_tr[3 + 4 * l] - t0, rb_tr[4 + 4 * l] - t0, rb_tr[5 + 4 * l] - t0);
+    printf(" issuer (epi_done seen, issued):");
+    for (int ci = 0; ci < 6; ++ci) printf(" %lld %lld", rb_tr[16 + 2 * ci] - t0, rb_tr[17 + 2 * ci] - t0);
+    printf("\n");
+  }
+#endif
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
