@@ -501,13 +501,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r0 = m0 + mb * BM + q * 32 + sub;
         const int t0 = up_s * r0 + phase - up_p, dt = up_s * 4;
         float4 rr[U];
-        if (p.vec_ok && has_res) {   // residual loads fly while the accumulator is fetched and staged
-          const float* res_p = e.res + b * e.res_bs + co;
+        if (p.vec_ok && (has_res || has_res2)) {   // residual loads fly while the accumulator is fetched and staged
+          const float* res_p = has_res ? e.res + b * e.res_bs + co : nullptr;
+          // the second residual (MRF partial sum) is fetched here too and folded into rr: read inside the row loop below it would sit
+          // behind the previous row's store to the same array (out_f32 == res2) -- one DRAM latency per row instead of one per block
+          const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int t = t0 + u * dt;
             const bool ok = n_ok && (r0 + 4 * u) < M && (unsigned)t < (unsigned)T_out;
-            rr[u] = ok ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rr[u] = (ok && has_res) ? *reinterpret_cast<const float4*>(res_p + (long long)t * e.res_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && has_res2) {
+              const float4 r2 = *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld);
+              rr[u].x += r2.x; rr[u].y += r2.y; rr[u].z += r2.z; rr[u].w += r2.w;
+            }
           }
         }
         if (n_grp > 1) {
@@ -560,7 +567,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             sa4 = __ldg(reinterpret_cast<const float4*>(e.snake_a + co));
             sb4 = __ldg(reinterpret_cast<const float4*>(e.snake_invb + co));
           }
-          const float* res2_p = has_res2 ? e.res2 + b * e.res2_bs + co : nullptr;
           float* f32_p = has_f32 ? e.out_f32 + b * e.f32_bs + co : nullptr;
           bf16* act_p = has_act ? out_act + b * e.act_bs + co : nullptr;
           float gs = 0.0f, gq = 0.0f;
@@ -574,11 +580,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float mv = ((t << e.mask.shift) < len_b) ? 1.0f : 0.0f;
             if (mask_pre && mv == 0.0f) { v0 = v1 = v2 = v3 = 0.0f; }   // a select, not a multiply: a padded row may hold anything
             if (use_alpha) { v0 *= alpha; v1 *= alpha; v2 *= alpha; v3 *= alpha; }
-            if (has_res) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
-            if (has_res2) {
-              const float4 r2 = *reinterpret_cast<const float4*>(res2_p + (long long)t * e.res2_ld);
-              v0 += r2.x; v1 += r2.y; v2 += r2.z; v3 += r2.w;
-            }
+            if (has_res || has_res2) { v0 += rr[u].x; v1 += rr[u].y; v2 += rr[u].z; v3 += rr[u].w; }
             if (use_div) { v0 *= inv_div; v1 *= inv_div; v2 *= inv_div; v3 *= inv_div; }
             if (has_f32 && !f32_act) *reinterpret_cast<float4*>(f32_p + (long long)t * e.f32_ld) = make_float4(v0, v1, v2, v3);
             if (e.gn_sum) { gs += (v0 + v1) + (v2 + v3); gq += (v0 * v0 + v1 * v1) + (v2 * v2 + v3 * v3); }

@@ -461,10 +461,14 @@ __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict_
   }
   for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
   const float* xb = x + (long long)b * L * C;
-  for (int i = threadIdx.x; i < (256 + 6) * C; i += 256) {
-    const int r = i / C, c = i - r * C, t = t0 + r - 3;
-    float v = (t >= 0 && t < L) ? xb[(long long)t * C + c] : 0.0f;
-    xs[r * (C + 1) + c] = v > 0.0f ? v : v * 0.01f;
+  constexpr int C4 = C / 4;                                    // 16-byte loads: the kernel is a pure HBM stream (132 B per sample)
+  for (int i = threadIdx.x; i < (256 + 6) * C4; i += 256) {
+    const int r = i / C4, c = (i - r * C4) * 4, t = t0 + r - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < L) v = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * C + c));
+    float* d = xs + r * (C + 1) + c;
+    d[0] = v.x > 0.0f ? v.x : v.x * 0.01f; d[1] = v.y > 0.0f ? v.y : v.y * 0.01f;
+    d[2] = v.z > 0.0f ? v.z : v.z * 0.01f; d[3] = v.w > 0.0f ? v.w : v.w * 0.01f;
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;

@@ -293,6 +293,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
       for (int kc = 0; kc < p.kc_in; ++kc) {
         RN_WAIT(&x1_full[sx], px);
         tcgen05_fence_after();
+        if (h == 0 && kc == 0) RN_TR(15);
         const uint32_t a_lo = a_lo0 + (uint32_t)(sx * p.x1_slot_bytes >> 4);
         for (int j = 0; j < 3; ++j) {
           tile_mmas(a_lo + (uint32_t)j * row16, tmem_base + (uint32_t)(h * 128), (kc | j) ? 1u : 0u);
@@ -475,28 +476,39 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
     exchange(0);
     if (ew == 0) RN_TR(3);
     fold_consts(0, p.g1, p.b1, full ? p.temb + b * p.temb_bs : nullptr, full ? p.bias2 : nullptr);
+    if (ew == 0) RN_TR(13);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
       const int cb = 4 * h + slot;
+      if (ew == 0 && h == 1) RN_TR(14);
 #pragma unroll 1
       for (int m = 0; m < p.mb; ++m) {
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
         const int r = m * 128 + rl, t = m0 - 1 + r;
         const bool valid = t >= 0 && t < p.T && (t << p.len_shift) < len_b;   // (Mish * m + temb) * m; rows outside [0, T) are conv2's zero padding
         uint32_t pk[16];
+        // the pass is MUFU-bound (ex2 + rcp per element: ~2.4 k clk per 32 x 32 block with 16 warps): a warp whose 32 frames are all
+        // padding -- a third of the rows of a config-2 batch -- writes its zeros without the arithmetic (warp-uniform branch)
+        if (__any_sync(0xffffffffu, valid)) {
+          uint32_t raw[32];
+          tmem_ld32(lane_addr + (uint32_t)(m * RN_C + cb * 32), raw);
+          if (ew == 0 && h == 0 && m == 0) RN_TR(16);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = cb * 32 + j;
-          const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
-          const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
-          const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
-          const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
-          const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
-          const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
-          pk[j >> 1] = valid ? pack_bf16(v0, v1) : 0u;                 // a select: the row may hold anything
-          pk[(j >> 1) + 1] = valid ? pack_bf16(v2, v3) : 0u;
+          for (int j = 0; j < 32; j += 4) {
+            const int c = cb * 32 + j;
+            const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
+            const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
+            const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
+            const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
+            const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
+            const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
+            pk[j >> 1] = valid ? pack_bf16(v0, v1) : 0u;                 // a select: the row may hold anything
+            pk[(j >> 1) + 1] = valid ? pack_bf16(v2, v3) : 0u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
         }
+        if (ew == 0 && h == 0 && m == 0) { asm volatile("" ::"r"(pk[0]), "r"(pk[15])); RN_TR(17); }
         if (full) {
           // K-major operand plane (cb >> 1), row r, 16-byte chunks 4 (cb & 1) + i, 128B swizzle: chunk ^= r & 7
           uint8_t* prow = a_gen + (cb >> 1) * (R * 128) + r * 128;
@@ -513,6 +525,7 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
           store_bf16_block(pk, p.a_buf + b * p.a_bs + cb * 32, p.a_ld, m);
         }
       }
+      if (ew == 0 && h == 0) RN_TR(18);
       if (full) {
         tcgen05_fence_before();
         fence_proxy_async();                                           // generic-proxy smem stores -> the MMAs' async-proxy reads
@@ -537,20 +550,28 @@ resnet_tc_kernel(const __grid_constant__ RnMaps maps, const __grid_constant__ Rn
         for (int m = 0; m < vmb; ++m) {
           uint32_t raw[32];
           const uint32_t taddr = lane_addr + acc2_col + (uint32_t)(m * RN_C + cb * 32);
-          tmem_ld32(taddr, raw);
           const int t = m0 - 1 + m * 128 + rl;
           const bool valid = t >= 0 && t < p.T && (t << p.len_shift) < len_b;
+          if (__any_sync(0xffffffffu, valid)) {
+            tmem_ld32(taddr, raw);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int c = cb * 32 + j;
-            const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
-            const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
-            const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
-            const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
-            const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
-            const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
-            raw[j] = __float_as_uint(valid ? v0 : ex.x); raw[j + 1] = __float_as_uint(valid ? v1 : ex.y);
-            raw[j + 2] = __float_as_uint(valid ? v2 : ex.z); raw[j + 3] = __float_as_uint(valid ? v3 : ex.w);
+            for (int j = 0; j < 32; j += 4) {
+              const int c = cb * 32 + j;
+              const float4 sc = *reinterpret_cast<const float4*>(c_scale + c), sh = *reinterpret_cast<const float4*>(c_shift + c);
+              const float4 ex = *reinterpret_cast<const float4*>(c_extra + c);
+              const float v0 = mish_add(fmaf(__uint_as_float(raw[j]), sc.x, sh.x), ex.x);
+              const float v1 = mish_add(fmaf(__uint_as_float(raw[j + 1]), sc.y, sh.y), ex.y);
+              const float v2 = mish_add(fmaf(__uint_as_float(raw[j + 2]), sc.z, sh.z), ex.z);
+              const float v3 = mish_add(fmaf(__uint_as_float(raw[j + 3]), sc.w, sh.w), ex.w);
+              raw[j] = __float_as_uint(valid ? v0 : ex.x); raw[j + 1] = __float_as_uint(valid ? v1 : ex.y);
+              raw[j + 2] = __float_as_uint(valid ? v2 : ex.z); raw[j + 3] = __float_as_uint(valid ? v3 : ex.w);
+            }
+          } else {           // 32 padded frames: the masked block output is the res_conv bias alone
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ex = *reinterpret_cast<const float4*>(c_extra + cb * 32 + j);
+              raw[j] = __float_as_uint(ex.x); raw[j + 1] = __float_as_uint(ex.y); raw[j + 2] = __float_as_uint(ex.z); raw[j + 3] = __float_as_uint(ex.w);
+            }
           }
           tmem_st32(taddr, raw);
         }

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from emojivoice_b200 import _lib  # noqa: E402
 
-NAMES = {0: "entry", 1: "conv1 issued", 2: "acc1 seen", 3: "barrier 1 passed", 4: "apply 1 done", 7: "conv2 issued", 8: "acc2 seen",
+NAMES = {0: "entry", 15: "first input tile landed", 13: "constants folded", 16: "apply 1: first tmem_ld done", 17: "math done", 18: "stored", 14: "apply 1 half 0 done", 1: "conv1 issued", 2: "acc1 seen", 3: "barrier 1 passed", 4: "apply 1 done", 7: "conv2 issued", 8: "acc2 seen",
          5: "barrier 2 passed", 9: "apply 2 -> TMEM done", 10: "res issued", 11: "res half 0 seen", 6: "xr stored", 12: "exit of epilogue"}
 
 
@@ -39,7 +39,7 @@ def main():
             buf = (C.c_uint64 * 32)()
             ctx.check(L.ev_test_resnet_trace(ctx.handle, buf, 32), "trace")
             t0 = buf[0]
-            print("   trace (clk from entry, CTA 0): " + ", ".join(f"{NAMES[i]} {buf[i] - t0}" for i in (1, 2, 3, 4, 7, 8, 5, 9, 10, 11, 6, 12) if buf[i] >= t0 and buf[i] != 0))
+            print("   trace (clk from entry, CTA 0): " + ", ".join(f"{NAMES[i]} {buf[i] - t0}" for i in (15, 1, 2, 3, 13, 16, 17, 18, 14, 4, 7, 8, 5, 9, 10, 11, 6, 12) if buf[i] >= t0 and buf[i] != 0))
 
 
 if __name__ == "__main__":
