@@ -2,7 +2,8 @@
 """Timeline of ONE tensor-core conv launch (EV_TC_TRACE=1): clock64 stamps written by each CTA at the pipeline's milestones
 (include/emojivoice_b200.h: ev_test_conv_trace).  Prints medians over CTAs, in clocks relative to CTA entry.
 
-    EV_TC_TRACE=1 python scripts/conv_trace.py [B Cin T Cout K]      (default: a decoder conv, 32 256 334 256 3)
+    EV_TC_TRACE=1 python scripts/conv_trace.py [B Cin T Cout K [precision]]      (default: a decoder conv, 32 256 334 256 3;
+    precision 1 = bf16, 2 = the text encoder's 3xTF32 path)
 """
 import ctypes as C
 import os
@@ -26,6 +27,7 @@ NAMES = ["entry", "prologue done", "after pdl wait", "first TMA issued", "first 
 def main():
     a = [int(v) for v in sys.argv[1:6]] if len(sys.argv) >= 6 else [32, 256, 334, 256, 3]
     B, Cin, T, Cout, K = a
+    prec = int(sys.argv[6]) if len(sys.argv) >= 7 else 1
     ctx = _lib.Context()
     x = torch.randn(B, Cin, T, device="cuda")
     w = torch.randn(Cout, Cin, K, device="cuda") / (Cin * K) ** 0.5
@@ -33,14 +35,14 @@ def main():
     y = torch.empty(B, Cout, T, device="cuda")
     L = _lib.lib()
     for rep in range(3):
-        ctx.check(L.ev_test_conv1d(ctx.handle, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), B, Cin, T, Cout, K, 1, K // 2, 1, 0, 1,
+        ctx.check(L.ev_test_conv1d(ctx.handle, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), B, Cin, T, Cout, K, 1, K // 2, 1, 0, prec,
                                    _lib.ptr(y), _lib.stream_ptr()), "ev_test_conv1d")
     buf = np.zeros(512 * 24, dtype=np.uint64)
     ctx.check(L.ev_test_conv_trace(ctx.handle, buf.ctypes.data_as(C.c_void_p), buf.size), "ev_test_conv_trace")
     t = buf.reshape(512, 24).astype(np.int64)
     live = t[:, 0] != 0
     t = t[live]
-    print(f"conv B={B} Cin={Cin} T={T} Cout={Cout} K={K}: {t.shape[0]} CTAs traced")
+    print(f"conv B={B} Cin={Cin} T={T} Cout={Cout} K={K} precision={prec}: {t.shape[0]} CTAs traced")
     rel = t[:, :20] - t[:, :1]
     rel[:, 16:20] = t[:, 16:20]          # accumulated waits, not time stamps
     for i, n in enumerate(NAMES):
