@@ -85,6 +85,10 @@ struct ConvWeights {
   float* w_f32 = nullptr;   // [taps][C_in][N_pad]      (N contiguous; SIMT B-operand)
   bf16* w_bf16 = nullptr;   // [taps][N_pad128][K_pad]  (C_in contiguous, K-major; TMA/UMMA B-operand)
   float* w_tf32 = nullptr;  // [taps][N_pad128][3*K32]  split fp32 for the 3xTF32 path: [hi | lo | hi], K32 = C_in padded to 32
+  // 3xFP16 split (the faster fp32-accurate path): w * 2^e as [hi | lo | hi] halves, [taps][N_pad128][3*C_in] (C_in % 64 == 0);
+  // e is chosen per layer so that max |w| 2^e lies in [2^13, 2^14): both halves of every weight of ordinary size are normal fp16
+  // numbers.  f16_scale[0] = 2^e, f16_scale[1] = 2^-e / kF16ActScale (what the epilogue multiplies the accumulator with).
+  void* w_f16x3 = nullptr; float* f16_scale = nullptr;
   int K32 = 0;
   float* bias = nullptr;    // [C_out] or nullptr
   int taps = 0, C_in = 0, N = 0, N_pad = 0, N_pad_tc = 0, K_pad = 0;
@@ -129,6 +133,8 @@ cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, 
                              const Epilogue& e, cudaStream_t stream);
 // conv_tc.cu
 // x: bf16 activations, or (tf32x3 != 0) the split fp32 pair [hi | lo] of width 2*C_in per row (x_ld, x_bs in elements)
+constexpr float kF16ActScale = 8.0f;   // activations are split as halves of x * 8: lo stays a normal fp16 number down to |x| ~ 0.016
+// split: 0 = bf16 operands; 1 = 3xTF32 (x: the fp32 pair [hi | lo], 2*C_in floats per row); 2 = 3xFP16 (x: [hi | lo] halves, 2*C_in per row)
 cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err,
                            RaggedPlanner* ragged = nullptr);

@@ -61,12 +61,15 @@ struct TcParams {
   int bk, row_bytes, ksteps;    // K-chunk channels, bytes per smem row (= swizzle width), UMMA K-steps per chunk
   int b_tile_bytes;
   int resident;                 // all weight tiles stay in smem for the CTA's lifetime (narrow layers)
-  int tf32;                     // operands are 32-bit (3xTF32 split path): K-chunks walk the sections [hi | hi | lo] of A
+  int tf32;                     // split-operand path (3xTF32 or 3xFP16): K-chunks walk the sections [hi | hi | lo] of A
+  int mma_tf32;                 // the MMAs are kind::tf32 (3xTF32); 0: kind::f16 (bf16 operands, or the fp16 halves of the 3xFP16 split)
+  const float* descale;         // 3xFP16: descale[1] multiplies every partial sum when it is flushed (undoes the power-of-two pre-scaling)
   int kch1;                     // K-chunks per section (== kchunks unless tf32)
   int tf32_share;               // 3xTF32 with operand sharing: per 32-channel chunk c the steps (x_hi, w_lo) (x_hi, w_hi) (x_lo, w_hi)
                                 // run back to back, the activation tile of step 0 is reused by step 1 and the weight tiles of
                                 // step 1 by step 2: 2 + 2*taps tile loads per chunk instead of 3 + 3*taps (the path is L2->SM bound)
   int sec_off[3];               // column offset of each A section
+  int idle_arrive;              // see `idle_issuer` in the kernel (EV_TC_IDLE_ARRIVE=0 switches it off)
   int debug_nob;                // EV_TC_DEBUG_NOB bit 0 / 1 / 2: skip weight loads / activation loads / lean-path stores.  Timing
                                 // experiments only (results are wrong): they showed the MMA-bound layers are issue-bound, not memory-bound
   int trace;                    // EV_TC_TRACE=1: per-CTA clock64 stamps of the pipeline's milestones (scripts/conv_trace.py)
@@ -228,7 +231,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int sh_c = kc / 3, sh_s = kc - 3 * sh_c;       // operand-sharing walk (tf32_share): chunk, step
             if (p.tf32_share) {
               if (sh_s != 1) {     // step 1 reuses step 0's activation tile
-                mbar_wait(&a_empty[sa], pa);
+                { EV_TW_BEGIN(); mbar_wait(&a_empty[sa], pa); EV_TW_END(tw_a); }
                 mbar_expect_tx(&a_full[sa], a_bytes);
                 const uint32_t dst = a_base + (uint32_t)(sa * p.a_slot_bytes);
                 const int col = p.grp_col0[0] + (sh_s == 2 ? p.sec_off[2] : 0) + sh_c * p.bk, row = m0 + p.grp_row0[0];
@@ -239,7 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (sh_s != 2) {     // step 2 reuses step 1's weight tiles; sections of the packed weights are [hi | lo | hi]
                 const int wcol = (sh_s == 0 ? p.kch1 * p.bk : 0) + sh_c * p.bk;
                 for (int j = 0; j < grp_taps; ++j) {
-                  mbar_wait(&b_empty[sb], pb);
+                  { EV_TW_BEGIN(); mbar_wait(&b_empty[sb], pb); EV_TW_END(tw_b); }
                   mbar_expect_tx(&b_full[sb], (uint32_t)p.b_tile_bytes);
                   tma_load_3d(b_base + (uint32_t)(sb * p.b_tile_bytes), &tmB, &b_full[sb], wcol, n0, j);
                   if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
@@ -286,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // instructions per weight tile: ring slots / phases advance incrementally and descriptors by adds (a single
     // warp issues ~1 dependent instruction per 5-8 clk, so 200 instructions per tap would cap the tensor pipe).
     const uint32_t idesc = p.idesc;
-    const bool tf32 = p.tf32 != 0;
+    const bool tf32 = p.mma_tf32 != 0;
     const uint32_t hi = desc_hi_word(p.desc_sbo, p.desc_layout);
     const uint32_t mb_step16 = (uint32_t)(BM * p.row_bytes) >> 4, tap_step16 = p.tap_step16;
     const uint32_t b_step16 = (uint32_t)p.b_tile_bytes >> 4, a_step16 = (uint32_t)p.a_slot_bytes >> 4;
@@ -296,7 +299,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t acc_stride = (uint32_t)(p.mb * BN);
     const int my_mb = warp - 1, mb_stride = p.n_issuers;   // this issuer owns m-blocks my_mb, my_mb + mb_stride, ...
     int sa = 0, sb = 0, vt = 0;     // vt counts accumulator-set uses: one per tile, or one per flush group (3xTF32)
-    long long tw_a = 0, tw_b = 0;
+    // An issuer warp that owns no valid m-block of the tile (the second issuer of a one-m-block tile) has nothing in flight: it keeps
+    // the barrier protocol with plain arrivals instead of tcgen05.commit, which would queue behind the other warp's MMAs
+    bool idle_issuer = false;
+    auto signal = [&](uint64_t* bar) { if (idle_issuer) mbar_arrive(bar); else umma_commit(bar); };
+    long long tw_a = 0, tw_b = 0, tw_acc = 0;
     uint32_t pa = 0, pb = 0;        // parity to wait for on the "full" barriers
     int sh_sb = 0; uint32_t sh_pb = 0;   // tf32_share: ring position of the weight tiles that step 2 reuses
     const int flush_kc = p.flush_kc;
@@ -305,6 +312,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int mt = first_mt;
       if (tile != (int)blockIdx.x) { int b_, nt_; decode_tile(p, tile, b_, mt, nt_); }
       const int vmb = min(p.mb, (p.g.M - mt * tile_rows + BM - 1) / BM);     // m-blocks that hold valid rows
+      idle_issuer = p.idle_arrive && my_mb >= vmb && !(mb_stride == 1 && vmb > 1);
       int buf = 0, in_group = 0;
       uint32_t d_tmem = 0;
       uint32_t acc = 0;
@@ -312,7 +320,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kc = 0; kc < kchunks; ++kc) {
         if (in_group == 0) {        // open an accumulation group on the next accumulator set
           buf = vt & 1;
-          mbar_wait(&acc_empty[buf], ((uint32_t)(vt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator set
+          { EV_TW_BEGIN(); mbar_wait(&acc_empty[buf], ((uint32_t)(vt >> 1) & 1u) ^ 1u); EV_TW_END(tw_acc); }   // epilogue has drained this accumulator set
           tcgen05_fence_after();
           d_tmem = tmem_base + (uint32_t)buf * acc_stride;
           acc = 0;
@@ -320,17 +328,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.tf32_share) {
           // operand-sharing walk (one issuer, one m-block, one tap group): see TcParams::tf32_share
           const int sh_s = kc % 3;
-          if (sh_s != 1) { mbar_wait(&a_full[sa], pa); tcgen05_fence_after(); }     // step 1 reads step 0's tile again
+          if (sh_s != 1) { EV_TW_BEGIN(); mbar_wait(&a_full[sa], pa); EV_TW_END(tw_a); tcgen05_fence_after(); }     // step 1 reads step 0's tile again
           const uint32_t a_lo_s = a_lo0 + (uint32_t)sa * a_step16 + p.tap_first16;
           if (sh_s == 1) { sh_sb = sb; sh_pb = pb; }                                  // step 2 walks step 1's weight slots again
           if (sh_s == 2) { sb = sh_sb; pb = sh_pb; }
           uint32_t a_lo = a_lo_s;
           for (int j = 0; j < grp_taps; ++j) {
-            if (sh_s != 2) { mbar_wait(&b_full[sb], pb); tcgen05_fence_after(); }
+            if (sh_s != 2) { EV_TW_BEGIN(); mbar_wait(&b_full[sb], pb); EV_TW_END(tw_b); tcgen05_fence_after(); }
             const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_step16;
             if (elect_one()) {     // both issuer warps keep the barrier protocol; only the one that owns a valid m-block issues
-              if (my_mb < vmb) issue_tap<4, true>(d_tmem + (uint32_t)(my_mb * BN), hi, a_lo + (uint32_t)my_mb * mb_step16, b_lo, idesc, acc);
-              if (sh_s != 1) umma_commit(&b_empty[sb]);                              // step 1's weight tiles stay for step 2
+              if (my_mb < vmb) {
+                if (tf32) issue_tap<4, true>(d_tmem + (uint32_t)(my_mb * BN), hi, a_lo + (uint32_t)my_mb * mb_step16, b_lo, idesc, acc);
+                else issue_tap<4, false>(d_tmem + (uint32_t)(my_mb * BN), hi, a_lo + (uint32_t)my_mb * mb_step16, b_lo, idesc, acc);
+              }
+              if (sh_s != 1) signal(&b_empty[sb]);                              // step 1's weight tiles stay for step 2
             }
             __syncwarp();
             acc = 1;
@@ -338,7 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; }
           }
           if (sh_s != 0) {                                                            // step 0's activation tile stays for step 1
-            if (elect_one()) umma_commit(&a_empty[sa]);
+            if (elect_one()) signal(&a_empty[sa]);
             __syncwarp();
             if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
           }
@@ -373,19 +384,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (my_mb < vmb) issue_tap<2, false>(dm, hi, am, b_lo, idesc, acc);
                 if (second) issue_tap<2, false>(dm + (uint32_t)BN, hi, am + mb_step16, b_lo, idesc, acc);
               }
-              if (!resident) umma_commit(&b_empty[sb]);   // weight slot is free once both issuers' MMAs have read it
+              if (!resident) signal(&b_empty[sb]);   // weight slot is free once both issuers' MMAs have read it
             }
             __syncwarp();
             acc = 1;
             a_lo += tap_step16;
             if (!resident) { if (++sb == B_SLOTS) { sb = 0; pb ^= 1u; } }
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
+          if (elect_one()) signal(&a_empty[sa]);     // activation tile is free once every tap of the group has read it
           __syncwarp();
           if (++sa == A_SLOTS) { sa = 0; pa ^= 1u; }
         }
         if (++in_group == flush_kc || kc == kchunks - 1) {   // group complete -> epilogue (output pass or partial-sum flush)
-          if (elect_one()) umma_commit(&acc_full[buf]);
+          if (elect_one()) signal(&acc_full[buf]);
           __syncwarp();
           if (warp == 1) { if (tile == (int)blockIdx.x) EV_TR(5); EV_TR(6); }
           in_group = 0;
@@ -393,7 +404,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (warp == 1) { EV_TW_STORE(16, tw_b); EV_TW_STORE(17, tw_a); }
+    if (warp == 1) { EV_TW_STORE(16, tw_b); EV_TW_STORE(17, tw_a); EV_TW_STORE(20, tw_acc); }
   } else {
     // ---------------- epilogue (warps 2..9).  Warp (q, half) owns TMEM lanes [32q, 32q+32) and every second 32-column
     // block of them; the eight warps run free of each other (no CTA barrier):
@@ -518,8 +529,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         if (n_grp > 1) {
-          // two-level accumulation (3xTF32): this warp owns exactly one block; every group's TMEM partial sum is added
-          // with rounded fp32 adds into the master accumulator kept in the warp's transpose buffer
+          // two-level accumulation (3xTF32 / 3xFP16): this warp owns exactly one block; every group's TMEM partial sum is added
+          // with rounded fp32 adds into the master accumulator kept in the warp's transpose buffer (3xFP16: times the power of
+          // two that undoes the operands' pre-scaling -- exact, so still one rounding per add)
+          const float ds = p.descale ? __ldg(p.descale + 1) : 1.0f;
 #pragma unroll 1
           for (int grp = 0; grp < n_grp; ++grp) {
             const int v = ti + grp, vb = v & 1;
@@ -534,7 +547,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; j += 4) {
               float4 m4 = make_float4(0.f, 0.f, 0.f, 0.f);
               if (grp > 0) m4 = *reinterpret_cast<const float4*>(srow_w + j);
-              m4.x += __uint_as_float(raw[j]); m4.y += __uint_as_float(raw[j + 1]); m4.z += __uint_as_float(raw[j + 2]); m4.w += __uint_as_float(raw[j + 3]);
+              m4.x = fmaf(__uint_as_float(raw[j]), ds, m4.x); m4.y = fmaf(__uint_as_float(raw[j + 1]), ds, m4.y);
+              m4.z = fmaf(__uint_as_float(raw[j + 2]), ds, m4.z); m4.w = fmaf(__uint_as_float(raw[j + 3]), ds, m4.w);
               *reinterpret_cast<float4*>(srow_w + j) = m4;
             }
           }
@@ -700,6 +714,7 @@ bool plan_smem(TcParams& p, int k, int epi_warps, int* smem_out) {
     b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes;
     if (b_slots < 4 && a_slots == 3) { a_slots = 2; b_slots = (budget - a_slots * p.a_slot_bytes) / p.b_tile_bytes; }
     if (b_slots > MAX_B_SLOTS) b_slots = MAX_B_SLOTS;
+    { static const int cap = []() { const char* v = getenv("EV_TC_MAXB"); return v ? atoi(v) : 0; }(); if (cap > 0 && b_slots > cap) b_slots = cap; }   // timing experiments
     if (b_slots < (k > 1 ? g_min_b2 : 3)) return false;
   }
   if (a_slots < 2) return false;
@@ -787,7 +802,7 @@ bool conv_tc_init(std::string* err) {
 cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err, RaggedPlanner* ragged) {
   if (!g_encode && !conv_tc_init(err)) return cudaErrorNotSupported;
-  const int esz = tf32x3 ? 4 : 2;
+  const int esz = tf32x3 == 1 ? 4 : 2;
   if ((x_ld * esz & 15) || (x_bs * esz & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) {
     if (err) *err = "conv_tc: activation tensor is not 16-byte aligned / strided";
     return cudaErrorInvalidValue;
@@ -812,7 +827,22 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
   p.e = e;
   // K-chunk width: 64 channels under the 128-byte swizzle, or 32 under the 64-byte swizzle when that avoids padded K
   p.tf32 = tf32x3 ? 1 : 0;
-  if (tf32x3) {      // 32 fp32 channels per 128-byte row, UMMA K = 8; K-chunks walk [x_hi | x_hi | x_lo] x [w_hi | w_lo | w_hi]
+  p.mma_tf32 = tf32x3 == 1 ? 1 : 0;
+  p.descale = nullptr;
+  if (tf32x3 == 2) {      // 3xFP16: 64 halves per 128-byte row, UMMA K = 16; the same walk over [x_hi | x_hi | x_lo] x [w_hi | w_lo | w_hi]
+    if (g.conv_stride != 1 || !w.w_f16x3 || !w.f16_scale || g.C_in % 64) { if (err) *err = "conv_tc: the 3xFP16 path needs stride 1, C_in % 64 == 0 and split weights"; return cudaErrorInvalidValue; }
+    p.bk = 64;
+    p.row_bytes = 128;
+    p.ksteps = 4;
+    p.kch1 = g.C_in / 64;
+    p.kchunks = 3 * p.kch1;
+    p.sec_off[0] = 0; p.sec_off[1] = 0; p.sec_off[2] = g.C_in;
+    p.idesc = make_idesc(BM, BN) & ~((7u << 7) | (7u << 10));      // kind::f16 with F16 (format 0) operands instead of BF16
+    p.flush_kc = std::max(1, 16 / (g.taps * p.ksteps));
+    if (g_tf32_flush == 0) p.flush_kc = p.kchunks;
+    p.tf32_share = g_tf32_share;
+    p.descale = w.f16_scale;
+  } else if (tf32x3) {      // 32 fp32 channels per 128-byte row, UMMA K = 8; K-chunks walk [x_hi | x_hi | x_lo] x [w_hi | w_lo | w_hi]
     if (g.conv_stride != 1 || !w.w_tf32) { if (err) *err = "conv_tc: the 3xTF32 path needs stride 1 and split weights"; return cudaErrorInvalidValue; }
     p.bk = 32;
     p.row_bytes = 128;
@@ -899,9 +929,13 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
   p.a_boxes = a_rows > 256 ? 2 : 1;
   p.a_box_rows = (int)align_up((size_t)ceil_div(a_rows, p.a_boxes), 8);
   p.a_slot_bytes = (int)align_up((size_t)p.a_boxes * p.a_box_rows * p.row_bytes, 1024);
-  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * esz, (uint32_t)p.bk, (uint32_t)p.a_box_rows, err, p.row_bytes, tf32x3 != 0);
+  bool ok = encode_map(&tmA, x, d0, d1, (uint64_t)g.B, s1, (uint64_t)x_bs * esz, (uint32_t)p.bk, (uint32_t)p.a_box_rows, err, p.row_bytes, tf32x3 == 1);
   if (!ok) return cudaErrorInvalidValue;
-  if (tf32x3) {
+  if (tf32x3 == 2) {
+    if (w.N_pad_tc % BN != 0) { if (err) *err = "conv_tc: split weight padding does not match the tile shape"; return cudaErrorInvalidValue; }
+    const uint64_t k3 = 3ull * (uint64_t)g.C_in;
+    ok = encode_map(&tmB, w.w_f16x3, k3, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, k3 * 2, k3 * w.N_pad_tc * 2, 64u, (uint32_t)BN, err, 128, false);
+  } else if (tf32x3) {
     if (w.N_pad_tc % BN != 0 || w.K32 % 32 != 0) { if (err) *err = "conv_tc: split weight padding does not match the tile shape"; return cudaErrorInvalidValue; }
     const uint64_t k3 = 3ull * w.K32;
     ok = encode_map(&tmB, w.w_tf32, k3, (uint64_t)w.N_pad_tc, (uint64_t)w.taps, k3 * 4, k3 * w.N_pad_tc * 4, 32u, (uint32_t)BN, err, 128, true);
@@ -914,7 +948,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
                     (uint64_t)w.K_pad * w.N_pad_tc * 2, (uint32_t)p.bk, (uint32_t)BN, err, p.row_bytes);
   }
   if (!ok) return cudaErrorInvalidValue;
-  if (tf32x3 && e.out_act) { if (err) *err = "conv_tc: the 3xTF32 path writes fp32 outputs only"; return cudaErrorInvalidValue; }
+  if (tf32x3 && e.out_act) { if (err) *err = "conv_tc: the split-operand paths write fp32 outputs only"; return cudaErrorInvalidValue; }
   if (e.act != ACT_NONE && e.act != ACT_RELU && e.act != ACT_LRELU && e.act != ACT_SNAKE) {
     if (err) *err = "conv_tc: the tensor-core epilogue implements identity / (leaky) ReLU / SnakeBeta only";
     return cudaErrorInvalidValue;
@@ -933,6 +967,7 @@ cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, lon
     return cudaErrorInvalidValue;
   }
   { static const int nob = []() { const char* v = getenv("EV_TC_DEBUG_NOB"); return v ? atoi(v) : 0; }(); p.debug_nob = nob; }
+  { static const int ia = []() { const char* v = getenv("EV_TC_IDLE_ARRIVE"); return v ? atoi(v) : 1; }(); p.idle_arrive = ia; }
   { static const int tr = []() { const char* v = getenv("EV_TC_TRACE"); return v ? atoi(v) : 0; }(); p.trace = tr; }
   switch (BN) {
     case 32: return launch_bn<32>(tmA, tmB, p, stream, ragged);

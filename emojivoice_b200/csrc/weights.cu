@@ -1,4 +1,6 @@
 // Weight packing (reference state_dict layouts -> kernel layouts, fp32 + bf16 twins) and the conv dispatch.
+#include <cuda_fp16.h>
+
 #include "ctx.cuh"
 
 namespace ev {
@@ -111,6 +113,61 @@ __global__ void pack_conv_tf32_kernel(const float* __restrict__ src, int C_out, 
   }
 }
 
+// ---- 3xFP16 split: v = hi + lo with hi = fp16(v), lo = fp16(v - hi): 22 mantissa bits, products x_hi w_hi + x_hi w_lo + x_lo w_hi on
+// kind::f16 MMAs (K = 16, half the operand bytes and less than half the tensor time of the tf32 products), fp32 accumulation.
+// Values are pre-scaled by powers of two (exact) so that the lo halves are normal fp16 numbers; the epilogue undoes it.
+__global__ void absmax_kernel(const float* __restrict__ src, long long n, unsigned int* __restrict__ cell) {
+  unsigned int m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(fabsf(src[i])));          // non-negative floats order like their bit patterns
+  for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(cell, m);
+}
+__global__ void f16_scale_kernel(const unsigned int* __restrict__ cell, float* __restrict__ scale) {
+  const float mx = __uint_as_float(*cell);
+  int e = 0;
+  if (mx > 0.0f && isfinite(mx)) { int ex; frexpf(mx, &ex); e = 14 - ex; }   // mx = f * 2^ex, f in [0.5, 1): mx * 2^e in [2^13, 2^14)
+  e = max(-100, min(100, e));
+  scale[0] = ldexpf(1.0f, e);
+  scale[1] = ldexpf(1.0f, -e) / kF16ActScale;
+}
+__global__ void pack_conv_f16x3_kernel(const float* __restrict__ src, int C_out, int C_in, int K, int taps, int n_local, int n_off,
+                                       __half* __restrict__ dst, int N_pad_tc, const float* __restrict__ scale) {
+  const long long total = (long long)taps * C_in * n_local;
+  const float sc = scale[0];
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx % n_local);
+    const int ci = (int)((idx / n_local) % C_in);
+    const int tap = (int)(idx / ((long long)n_local * C_in));
+    const float v = src[((long long)n * C_in + ci) * K + tap] * sc;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    __half* row = dst + ((long long)tap * N_pad_tc + n_off + n) * (3LL * C_in);
+    row[ci] = hi;
+    row[C_in + ci] = lo;
+    row[2 * C_in + ci] = hi;
+  }
+}
+// x (rows x C fp32, row stride ld) -> [x_hi | x_lo] halves of x * kF16ActScale (rows x 2C): the A operand of the 3xFP16 path
+__global__ void split_f16_kernel(const float* __restrict__ x, long long ld, int C, long long rows, __half* __restrict__ out) {
+  const long long n4 = rows * (C >> 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C >> 2);
+    const int c = (int)(i - r * (C >> 2)) << 2;
+    float4 v = *reinterpret_cast<const float4*>(x + r * ld + c);
+    v.x *= kF16ActScale; v.y *= kF16ActScale; v.z *= kF16ActScale; v.w *= kF16ActScale;
+    const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+    const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+    const __half2 la = __floats2half2_rn(v.x - __half2float(h0), v.y - __half2float(h1));
+    const __half2 lb = __floats2half2_rn(v.z - __half2float(h2), v.w - __half2float(h3));
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&ha); hv.y = *reinterpret_cast<const uint32_t*>(&hb);
+    lv.x = *reinterpret_cast<const uint32_t*>(&la); lv.y = *reinterpret_cast<const uint32_t*>(&lb);
+    *reinterpret_cast<uint2*>(out + r * 2 * C + c) = hv;
+    *reinterpret_cast<uint2*>(out + r * 2 * C + C + c) = lv;
+  }
+}
+
 // x (rows x C fp32, row stride ld) -> [x_hi | x_lo] (rows x 2C): the A operand of the 3xTF32 path
 __global__ void split_tf32_kernel(const float* __restrict__ x, long long ld, int C, long long rows, float* __restrict__ out) {
   const long long n4 = rows * (C >> 2);
@@ -171,6 +228,23 @@ int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weig
     EV_TRY(device_alloc(ctx, (size_t)w.taps * w.N_pad_tc * 3 * w.K32 * sizeof(float), &p, true, ws.stream));
     w.w_tf32 = reinterpret_cast<float*>(p);
   }
+  unsigned int* absmax_cell = nullptr;
+  if (want_tf32 && c_in % 64 == 0) {        // the 3xFP16 operand set of the same layer
+    EV_TRY(device_alloc(ctx, (size_t)w.taps * w.N_pad_tc * 3 * c_in * sizeof(__half), &p, true, ws.stream));
+    w.w_f16x3 = p;
+    EV_TRY(device_alloc(ctx, 4 * sizeof(float), &p, true, ws.stream));
+    w.f16_scale = reinterpret_cast<float*>(p);
+    absmax_cell = reinterpret_cast<unsigned int*>(w.f16_scale + 2);
+    for (int i = 0; i < parts; ++i) {
+      const ev_tensor* t = ws.get(weight_names[i], {(long long)c_out_each, (long long)c_in, (long long)ksize});
+      if (!t) return ctx->err.rfind("missing", 0) == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
+      const long long n = (long long)c_out_each * c_in * ksize;
+      absmax_kernel<<<(int)std::min<long long>(1024, ceil_div_ll(n, 256)), 256, 0, ws.stream>>>(t->data, n, absmax_cell);
+      EV_CUDA(ctx, cudaGetLastError());
+    }
+    f16_scale_kernel<<<1, 1, 0, ws.stream>>>(absmax_cell, w.f16_scale);
+    EV_CUDA(ctx, cudaGetLastError());
+  }
   for (int i = 0; i < parts; ++i) {
     const ev_tensor* t = ws.get(weight_names[i], {(long long)c_out_each, (long long)c_in, (long long)ksize});
     if (!t) return ctx->err.rfind("missing", 0) == 0 ? EV_ERR_MISSING : EV_ERR_INVALID;
@@ -182,6 +256,11 @@ int make_conv(ev_ctx* ctx, WeightStore& ws, const std::vector<std::string>& weig
     if (w.w_tf32) {
       pack_conv_tf32_kernel<<<blocks, 256, 0, ws.stream>>>(t->data, c_out_each, c_in, ksize, w.taps, n_local, i * n_local, w.w_tf32,
                                                            w.N_pad_tc, w.K32);
+      EV_CUDA(ctx, cudaGetLastError());
+    }
+    if (w.w_f16x3) {
+      pack_conv_f16x3_kernel<<<blocks, 256, 0, ws.stream>>>(t->data, c_out_each, c_in, ksize, w.taps, n_local, i * n_local,
+                                                            reinterpret_cast<__half*>(w.w_f16x3), w.N_pad_tc, w.f16_scale);
       EV_CUDA(ctx, cudaGetLastError());
     }
   }
@@ -286,21 +365,30 @@ int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x
   const long long rows = (long long)B * T_in;
   const double flops = 2.0 * B * (double)T_out * w.C_out * w.taps * w.C_in;
   const double bytes = 4.0 * (rows * w.C_in + (double)w.taps * w.N * w.C_in + (double)B * T_out * w.C_out * (e.res ? 2 : 1));
+  // EV_ENC_SPLIT=tf32: the 3xTF32 products (round 1); default: 3xFP16 where the layer has that operand set
+  static const bool use_f16 = []() { const char* v = getenv("EV_ENC_SPLIT"); return !(v && std::string(v) == "tf32"); }();
+  const int split = (use_f16 && w.w_f16x3) ? 2 : 1;
   {
     const int blocks = (int)std::min<long long>(2048, ceil_div_ll(rows * (w.C_in / 4), 256));
     cudaError_t ce;
-    { LaunchScope ls(ctx, s, "split_tf32", 0, 12.0 * rows * w.C_in); split_tf32_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w.C_in, rows, scratch); ce = cudaGetLastError(); }
-    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "split_tf32");
+    if (split == 2) {
+      LaunchScope ls(ctx, s, "split_f16", 0, 8.0 * rows * w.C_in);
+      split_f16_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w.C_in, rows, reinterpret_cast<__half*>(scratch));
+      ce = cudaGetLastError();
+    } else {
+      LaunchScope ls(ctx, s, "split_tf32", 0, 12.0 * rows * w.C_in); split_tf32_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w.C_in, rows, scratch); ce = cudaGetLastError();
+    }
+    if (ce != cudaSuccess) return cuda_fail(ctx, ce, "split");
   }
   std::string msg;
   cudaError_t ce;
-  std::string nm = std::string("conv_tc_tf32x3") + ctx->prof_tag;
+  std::string nm = std::string(split == 2 ? "conv_tc_f16x3" : "conv_tc_tf32x3") + ctx->prof_tag;
   if (ctx->profiling && ctx->prof_detail) {   // EV_PROF_DETAIL=1: one class per layer shape
     char buf[64];
     snprintf(buf, sizeof buf, " c%d n%d k%d m%d", w.C_in, w.N, w.taps, g.M);
     nm += buf;
   }
-  { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, scratch, 2LL * w.C_in, (long long)T_in * 2 * w.C_in, 1, w, e, s, &msg); }
+  { LaunchScope ls(ctx, s, nm.c_str(), flops, bytes); ce = conv_tc_launch(g, scratch, 2LL * w.C_in, (long long)T_in * 2 * w.C_in, split, w, e, s, &msg); }
   if (ce != cudaSuccess) return fail(ctx, EV_ERR_CUDA, "conv_tc_launch(tf32x3): " + (msg.empty() ? std::string(cudaGetErrorString(ce)) : msg));
   return 0;
 }

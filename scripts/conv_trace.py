@@ -21,7 +21,7 @@ NAMES = ["entry", "prologue done", "after pdl wait", "first TMA issued", "first 
          "last commit", "first accumulator seen (epilogue)", "first tile stored", "last tile stored", "exit", "(globaltimer)",
          "producer: tile loop entered", "producer: first tile decoded", "producer: first slot free", "epilogue warp 0: first block done",
          "MMA warp: clk waiting for weight tiles", "MMA warp: clk waiting for activation tiles", "producer: clk waiting for a free weight slot",
-         "producer: clk waiting for a free activation slot"]
+         "producer: clk waiting for a free activation slot", "MMA warp: clk waiting for a drained accumulator"]
 
 
 def main():
@@ -43,8 +43,8 @@ def main():
     live = t[:, 0] != 0
     t = t[live]
     print(f"conv B={B} Cin={Cin} T={T} Cout={Cout} K={K} precision={prec}: {t.shape[0]} CTAs traced")
-    rel = t[:, :20] - t[:, :1]
-    rel[:, 16:20] = t[:, 16:20]          # accumulated waits, not time stamps
+    rel = t[:, :21] - t[:, :1]
+    rel[:, 16:21] = t[:, 16:21]          # accumulated waits, not time stamps
     for i, n in enumerate(NAMES):
         if i == 11:
             continue

@@ -11,7 +11,7 @@
 
 using namespace ev::tc;
 
-struct Cfg { int N, layout, n_acc, n_iter, row_step, n_issuers, ks_per_tap, n_spin; };
+struct Cfg { int N, layout, n_acc, n_iter, row_step, n_issuers, ks_per_tap, n_spin, tf32, fill, commit_each; };
 
 __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -20,9 +20,10 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out)
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 160 * 1024 / 16; i += blockDim.x)
-    reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)))[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem_raw + (base - smem_u32(smem_raw)))[i] =
+        c.fill ? make_uint4(0x3f8ccccdu + 7919u * i, 0xbf19999au + 104729u * i, 0x3e4ccccdu + 31u * i, 0xbdcccccdu + 17u * i) : make_uint4(0, 0, 0, 0);   // |x| ~ 0.1 .. 2
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&done[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&done[i], i == 2 ? 1 << 20 : 1);     // done[2]: a sink for per-tap commits
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out)
   const uint32_t b_lo0 = (((base + 96 * 1024) & 0x3FFFFu) >> 4) | (1u << 16);
   long long t0 = 0, t1 = 0;
   if (warp < c.n_issuers) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = c.tf32 ? make_idesc_tf32(128, c.N) : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(c.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
     __syncwarp();
     t0 = clock64();
     if (elect_one()) {
@@ -58,9 +59,11 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out)
             if (ks >= c.ks_per_tap) break;
             const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((m * 128 * RB) >> 4) + 2u * ks);
             const uint64_t db = ((uint64_t)hi << 32) | (b_lo0 + 2u * ks);
-            umma_bf16(d0 + (uint32_t)(m * c.N), da, db, idesc, 1u);
+            if (c.tf32) umma_tf32(d0 + (uint32_t)(m * c.N), da, db, idesc, 1u);      // kind::tf32: K = 8 fp32 elements = the same 32 bytes per row
+            else umma_bf16(d0 + (uint32_t)(m * c.N), da, db, idesc, 1u);
           }
         }
+        if (c.commit_each) umma_commit(&done[2]);      // like the conv kernels: one commit per (tap, weight tile)
         a_lo += a_step;
         if (++wrap == 25) { wrap = 0; a_lo = a_lo0; }
       }
@@ -92,6 +95,21 @@ int main(int argc, char** argv) {
   printf("grid %d CTAs, 128x Nx16 bf16 MMAs, clk per MMA (max over CTAs / issuers)\n", grid);
   printf("%5s %7s %6s %9s %9s %8s | %10s %12s\n", "N", "swizzle", "mblk", "row_step", "issuers", "ks/tap", "clk/MMA", "floor(N/2)");
   printf("(mblk = m-blocks per tap, each with ks k-steps; spin = warps waiting on an mbarrier meanwhile)\n");
+  if (argc > 2 && atoi(argv[2]) == 1) {       // kind::tf32 (the text encoder's 3xTF32 path): N = 128, 128B swizzle
+    printf("kind::tf32, 128 x 128 x 8 MMAs:\n");
+    for (int issuers = 1; issuers <= 2; ++issuers)
+      for (int n_acc = 1; n_acc <= 2; ++n_acc) {
+        Cfg c{128, 2, n_acc, 4096 / (4 * n_acc), 1, issuers, 4, 0, 1, argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 0};
+        cudaMemset(out, 0, sizeof(long long) * 4 * grid);
+        mma_rate_kernel<<<grid, 640, 200 * 1024>>>(c, out);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
+        cudaMemcpy(h.data(), out, sizeof(long long) * 4 * grid, cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (long long v : h) mx = v > mx ? v : mx;
+        printf("  issuers %d m-blocks %d: %.1f clk per MMA\n", issuers, n_acc, (double)mx / (double)(c.n_iter * 4 * n_acc * issuers));
+      }
+    return 0;
+  }
   const int Ns[] = {32, 64, 128};
   for (int N : Ns)
     for (int layout : {2, 4})
@@ -102,7 +120,7 @@ int main(int argc, char** argv) {
               for (int n_spin : {0, 16}) {
                 if (issuers * n_acc * N > 512) continue;
                 const int ks = layout == 2 ? (half ? 2 : 4) : 2;
-                Cfg c{N, layout, n_acc, 4096 / (ks * n_acc), row_step, issuers, ks, n_spin};
+                Cfg c{N, layout, n_acc, 4096 / (ks * n_acc), row_step, issuers, ks, n_spin, 0, 0, 0};
                 cudaMemset(out, 0, sizeof(long long) * 4 * grid);
                 mma_rate_kernel<<<grid, 640, 200 * 1024>>>(c, out);
                 cudaError_t ce = cudaDeviceSynchronize();
