@@ -11,7 +11,7 @@
 
 using namespace ev::tc;
 
-struct Cfg { int N, layout, n_acc, n_iter, row_step, n_issuers, ks_per_tap, n_spin, tf32, fill, commit_each; };
+struct Cfg { int N, layout, n_acc, n_iter, row_step, n_issuers, ks_per_tap, n_spin, tf32, fill, commit_each, b_tiles; };
 
 __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out) {
   extern __shared__ uint8_t smem_raw[];
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(640, 1) mma_rate_kernel(Cfg c, long long* out)
           for (int ks = 0; ks < 4; ++ks) {
             if (ks >= c.ks_per_tap) break;
             const uint64_t da = ((uint64_t)hi << 32) | (a_lo + (uint32_t)((m * 128 * RB) >> 4) + 2u * ks);
-            const uint64_t db = ((uint64_t)hi << 32) | (b_lo0 + 2u * ks);
+            const uint64_t db = ((uint64_t)hi << 32) | (b_lo0 + (uint32_t)((it % c.b_tiles) * ((c.N * RB) >> 4)) + 2u * ks);   // b_tiles > 1: a new weight tile per tap
             if (c.tf32) umma_tf32(d0 + (uint32_t)(m * c.N), da, db, idesc, 1u);      // kind::tf32: K = 8 fp32 elements = the same 32 bytes per row
             else umma_bf16(d0 + (uint32_t)(m * c.N), da, db, idesc, 1u);
           }
@@ -96,10 +96,10 @@ int main(int argc, char** argv) {
   printf("%5s %7s %6s %9s %9s %8s | %10s %12s\n", "N", "swizzle", "mblk", "row_step", "issuers", "ks/tap", "clk/MMA", "floor(N/2)");
   printf("(mblk = m-blocks per tap, each with ks k-steps; spin = warps waiting on an mbarrier meanwhile)\n");
   if (argc > 2 && atoi(argv[2]) == 1) {       // kind::tf32 (the text encoder's 3xTF32 path): N = 128, 128B swizzle
-    printf("kind::tf32, 128 x 128 x 8 MMAs:\n");
+    printf("%s, 128 x 128 MMAs, %d weight tile(s) cycled:\n", (argc > 5 ? atoi(argv[5]) : 1) ? "kind::tf32 (K = 8)" : "kind::f16 (K = 16)", argc > 6 ? atoi(argv[6]) : 1);
     for (int issuers = 1; issuers <= 2; ++issuers)
       for (int n_acc = 1; n_acc <= 2; ++n_acc) {
-        Cfg c{128, 2, n_acc, 4096 / (4 * n_acc), 1, issuers, 4, 0, 1, argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 0};
+        Cfg c{128, 2, n_acc, 4096 / (4 * n_acc), 1, issuers, 4, 0, argc > 5 ? atoi(argv[5]) : 1, argc > 3 ? atoi(argv[3]) : 0, argc > 4 ? atoi(argv[4]) : 0, argc > 6 ? atoi(argv[6]) : 1};
         cudaMemset(out, 0, sizeof(long long) * 4 * grid);
         mma_rate_kernel<<<grid, 640, 200 * 1024>>>(c, out);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
@@ -120,7 +120,7 @@ int main(int argc, char** argv) {
               for (int n_spin : {0, 16}) {
                 if (issuers * n_acc * N > 512) continue;
                 const int ks = layout == 2 ? (half ? 2 : 4) : 2;
-                Cfg c{N, layout, n_acc, 4096 / (ks * n_acc), row_step, issuers, ks, n_spin, 0, 0, 0};
+                Cfg c{N, layout, n_acc, 4096 / (ks * n_acc), row_step, issuers, ks, n_spin, 0, 0, 0, 1};
                 cudaMemset(out, 0, sizeof(long long) * 4 * grid);
                 mma_rate_kernel<<<grid, 640, 200 * 1024>>>(c, out);
                 cudaError_t ce = cudaDeviceSynchronize();
