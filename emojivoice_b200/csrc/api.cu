@@ -244,6 +244,55 @@ extern "C" int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y
   return EV_OK;
 }
 
+// Text-encoder attention alone (text_encoder.py:223-246, head width 128, RoPE on the first 64 features): qkv (B, T, 3*H*128)
+// CHANNEL-LAST fp32 [q | k | v], x_lengths (B) int64 or NULL, out (B, T, H*128).  impl 0: fp32 CUDA cores (attention.cu),
+// 1: tcgen05 with 3xFP16 split operands (attention_enc_tc.cu).  repeat / avg_us_host as ev_test_ff_block.
+extern "C" int ev_test_encoder_attention(ev_ctx* ctx, const float* qkv, const int64_t* x_lengths, int B, int T, int H, int impl,
+                                         float* out, int repeat, float* avg_us_host, void* stream) {
+  if (!ctx || !qkv || !out || B <= 0 || T <= 0 || H <= 0) return EV_ERR_INVALID;
+  cudaStream_t s = as_stream(stream);
+  EV_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int hd = 128, inner = H * hd, rope_dim = hd / 2;
+  const size_t mark = ctx->owned.size();
+  auto release = [&]() {
+    cudaStreamSynchronize(s);
+    for (size_t i = mark; i < ctx->owned.size(); ++i) cudaFree(ctx->owned[i]);
+    ctx->owned.resize(mark);
+  };
+  void *li = nullptr, *rc = nullptr, *rs = nullptr;
+  int rcode;
+  if ((rcode = device_alloc(ctx, (size_t)B * 4, &li, false, s)) || (rcode = device_alloc(ctx, (size_t)T * (rope_dim / 2) * 4, &rc, false, s)) ||
+      (rcode = device_alloc(ctx, (size_t)T * (rope_dim / 2) * 4, &rs, false, s))) { release(); return rcode; }
+  int* lens = nullptr;
+  cudaError_t ce = cudaSuccess;
+  if (x_lengths) { lens = reinterpret_cast<int*>(li); ce = i64_to_i32(reinterpret_cast<const long long*>(x_lengths), lens, B, s); }
+  if (ce == cudaSuccess) ce = rope_tables(reinterpret_cast<float*>(rc), reinterpret_cast<float*>(rs), T, rope_dim, 10000.0f, s);
+  AttnArgs at;
+  at.q = qkv; at.k = qkv + inner; at.v = qkv + 2 * inner; at.ld = 3 * inner; at.bs = (long long)T * 3 * inner;
+  at.B = B; at.T = T; at.H = H; at.D = hd; at.scale = 1.0f / sqrtf((float)hd); at.lens = lens; at.len_shift = 0; at.mode = 0;
+  at.rope_cos = reinterpret_cast<float*>(rc); at.rope_sin = reinterpret_cast<float*>(rs); at.rope_dim = rope_dim;
+  at.out = out; at.out_ld = inner; at.out_bs = (long long)T * inner;
+  if (impl == 1 && !attention_enc_tc_supported(at)) { release(); return fail(ctx, EV_ERR_INVALID, "ev_test_encoder_attention: shape not supported by the tcgen05 kernel"); }
+  auto run = [&]() { return impl == 1 ? attention_enc_tc(at, s) : attention_rows<float>(at, s); };
+  if (ce == cudaSuccess) ce = run();
+  if (ce == cudaSuccess && repeat > 0 && avg_us_host) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < repeat && ce == cudaSuccess; ++i) ce = run();
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us_host = 1e3f * ms / (float)repeat;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+  release();
+  if (ce != cudaSuccess) return cuda_fail(ctx, ce, "ev_test_encoder_attention");
+  return EV_OK;
+}
+
 // Fused transformer feed-forward alone (ff_tc.cu): x (B, T, 256) CHANNEL-LAST fp32; w1 (inner, 256), w2 (256, inner) as
 // nn.Linear stores them; snake_a = exp(alpha), snake_invb = 1 / (exp(beta) + 1e-9); out (B, T, 256) fp32 (the kernel's
 // bf16 result widened).  y_lengths (B) int64 or NULL: rows with (t << len_shift) >= y_lengths[b] come out as zero.

@@ -58,6 +58,10 @@ struct AttnArgs {
   void* out = nullptr; long long out_ld = 0, out_bs = 0;   // (b, t, h*D + d)
 };
 template <typename ActT> cudaError_t attention_rows(const AttnArgs& a, cudaStream_t s);
+// Text-encoder attention (mode 0, head width 128, T <= 384) on tcgen05 with 3xFP16 split operands, fp32 output
+// (attention_enc_tc.cu); any other shape stays on attention_rows<float>.
+bool attention_enc_tc_supported(const AttnArgs& a);
+cudaError_t attention_enc_tc(const AttnArgs& a, cudaStream_t s);
 // Decoder attention (mode 1 semantics) on tcgen05 tensor cores: bf16 q|k|v packed per row, head_dim 64 (attention_tc.cu)
 struct AttnTcArgs {
   const bf16* qkv = nullptr; long long ld = 0, bs = 0;   // (b, t, [q | k | v]), each section `inner` wide, head h at h*64

@@ -269,7 +269,13 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     at.lens = e.xlen32; at.len_shift = 0; at.mode = 0;
     at.rope_cos = m.rope_cos; at.rope_sin = m.rope_sin; at.rope_dim = hd / 2;
     at.out = e.att; at.out_ld = H; at.out_bs = bsH;
-    EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
+    // tcgen05 with split fp16 operands where the shape allows (head width 128, Tx <= 384; EV_ENC_ATTN=f32 keeps the CUDA-core
+    // kernel); both are fp32-accurate
+    static const bool enc_attn_tc = []() { const char* v = getenv("EV_ENC_ATTN"); return !(v && std::string(v) == "f32"); }();
+    if (enc_attn_tc && attention_enc_tc_supported(at))   // 3 products per contraction
+      EV_LAUNCH(ctx, s, "attention_enc_tc", 3.0 * 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_enc_tc(at, s));
+    else
+      EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
     Epilogue eo;  // x + y
     eo.res = e.X; eo.res_ld = H; eo.res_bs = bsH; eo.out_f32 = e.tmp; eo.f32_ld = H; eo.f32_bs = bsH;
     EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH * B, 1, B * Tx, eo, e.split, s));

@@ -206,6 +206,12 @@ EV_API int ev_test_conv1d(ev_ctx* ctx, const float* x, const float* w, const flo
  * t is "valid" (+1) while (t << len_shift) < y_lengths[b].  out (B, H*64, T).  precision: fp32 CUDA cores / bf16 tcgen05. */
 EV_API int ev_test_attention(ev_ctx* ctx, const float* qkv, const int64_t* y_lengths, int B, int T, int H, int len_shift,
                       int precision, float* out, void* stream);
+/* Text-encoder self-attention alone (MultiHeadAttention.attention, text_encoder.py:223-246: RoPE on the first half of each
+ * 128-wide head, scores / sqrt(128), -1e4 where the query OR the key is padded).  qkv (B, T, 3*H*128) CHANNEL-LAST [q | k | v],
+ * x_lengths (B) int64 or NULL, out (B, T, H*128).  impl 0: fp32 CUDA cores; 1: tcgen05 with 3xFP16 split operands (T <= 384).
+ * repeat / avg_us_host as ev_test_ff_block. */
+EV_API int ev_test_encoder_attention(ev_ctx* ctx, const float* qkv, const int64_t* x_lengths, int B, int T, int H, int impl,
+                              float* out, int repeat, float* avg_us_host, void* stream);
 /* The float32 Euler times/steps of flow_matching.py:52,68-83 as the library computes them (pure host code). */
 /* Fused LayerNorm + feed-forward of one decoder transformer block (transformer.py:296-316): x (B,T,256) CHANNEL-LAST,
  * w1 (inner,256), w2 (256,inner), snake_a = exp(alpha), snake_invb = 1/(exp(beta)+1e-9); out (B,T,256) channel-last,

@@ -3,8 +3,11 @@ oracle on the same seeded inputs and against the fixtures the reference itself p
 
 Tolerances (BASELINE.json north_star): durations / alignment bit-exact; mel / waveform rel-L2 <= 1e-4 in fp32 mode and
 <= 1e-2 in bf16 mode (tcgen05 operands, fp32 accumulation)."""
+import math
+
 import numpy as np
 import pytest
+
 import torch
 import torch.nn.functional as F
 
@@ -132,6 +135,38 @@ def test_decoder_attention_matches_torch_sdpa(ctx, case, prec):
     ctx.check(_lib.lib().ev_test_attention(ctx.handle, _lib.ptr(qd), _lib.ptr(ld), B, T, H, shift, _lib.PREC[prec],
                                            _lib.ptr(out), _lib.stream_ptr()), "ev_test_attention")
     assert rel_l2(out.cpu(), ref) < (2e-6 if prec == "fp32" else 6e-3)    # bf16: P and the output are rounded to bf16
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("case", [(3, 177, 2), (2, 64, 2), (1, 1, 2), (2, 129, 1), (2, 300, 2), (1, 384, 2), (2, 65, 2)])
+def test_encoder_attention_matches_reference_semantics(ctx, case, impl):
+    """text_encoder.py:223-246 in float64: RoPE on the first half of each 128-wide head, scores / sqrt(128), -1e4 where the
+    query OR the key is padded, softmax over all Tx keys.  impl 0 = fp32 CUDA cores, 1 = tcgen05 with 3xFP16 split operands:
+    both must be fp32-accurate (durations downstream are compared bit for bit)."""
+    B, T, H = case
+    g = torch.Generator().manual_seed(7 * B + T)
+    qkv = torch.randn(B, T, 3 * H * 128, generator=g) * 1.7
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    if B > 2:
+        lens[1] = 1
+    q, k, v = (z.reshape(B, T, H, 128).transpose(1, 2).double() for z in qkv.chunk(3, dim=2))      # b h t c
+    q, k = mo._rope(q, 64).double(), mo._rope(k, 64).double()
+    m = (torch.arange(T)[None, :] < lens[:, None]).double()
+    attn_mask = (m[:, None, :, None] * m[:, None, None, :])
+    scores = (q @ k.transpose(-2, -1)) / math.sqrt(128)
+    scores = scores.masked_fill(attn_mask == 0, -1e4)
+    ref = (torch.softmax(scores, dim=-1) @ v).transpose(1, 2).reshape(B, T, H * 128)
+    out = torch.full((B, T, H * 128), float("nan"), device="cuda")
+    qd, ld = qkv.cuda(), lens.cuda()
+    ctx.check(_lib.lib().ev_test_encoder_attention(ctx.handle, _lib.ptr(qd), _lib.ptr(ld), B, T, H, impl, _lib.ptr(out), 0, None,
+                                                   _lib.stream_ptr()), "ev_test_encoder_attention")
+    valid = m.bool()[:, :, None].expand_as(ref)
+    err = rel_l2(out.cpu()[valid], ref[valid])
+    assert err < 2e-6, err
+    # padded query rows: every in-range key gets -1e4, i.e. a uniform softmax -> the mean of v
+    assert torch.isfinite(out).all()
+    assert rel_l2(out.cpu(), ref) < 2e-6
 
 
 @pytest.mark.parametrize("case", [(2, 200, 0), (3, 129, 1), (1, 1, 0), (32, 334, 1), (5, 668, 0), (40, 1100, 0)])   # the last: several tiles per CTA
