@@ -9,6 +9,12 @@ configs[1] (batch 32 emoji-tagged utterances of ~5 s, bf16, random-init VCTK Mat
 For N > 1 the driver launches one rank per GPU with torch.distributed.run; utterances shard by batch, every
 rank synthesises the same 32-utterance batch (weak scaling: identical work per GPU), no collective on the data path.
 
+Throughput is measured with `--in-flight` (default 3) batches in flight per GPU: step i runs on lane i % 3, a lane being
+its own model / vocoder instance and CUDA stream (emojivoice_b200.Lanes, what synthesise_corpus does with a corpus) --
+a step is a chain of ~70 dependent launches, many latency-bound, and the other lanes' kernels fill its gaps.  K steps are
+still timed as one bracket (barrier + synchronize, CUDA events, max over ranks); `one_step_at_a_time` is the same loop
+without the overlap (the figure every earlier bench line of this repo reports).
+
 One JSON line is printed by rank 0 (see the task contract): `value` is measured with the inputs resident in HBM,
 `e2e` through the same public API with pinned HOST inputs and the waveform read back, `roofline` for the dominant
 kernel class (plus `rooflines` per stage) from a CUDA-event-instrumented step, `cpu_baseline` = the reference's own CPU
@@ -231,6 +237,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the config3 / config5 / denoiser blocks (headline numbers only)")
+    ap.add_argument("--in-flight", type=int, default=3,
+                    help="batches in flight on one GPU (lanes = model/vocoder instances on their own streams, ev.Lanes); 1 = one step at a time")
     ap.add_argument("--dense-vocoder", action="store_true",
                     help="vocode the padded frames of every utterance too (the default skips the time tiles past each utterance's "
                          "own length: identical waveform on [: length*256], zero beyond -- what cli.py:307-311 crops away)")
@@ -286,29 +294,58 @@ def main():
     x_dev, xl_dev, spk_dev = x.to(dev), xl.to(dev), spks.to(dev)
 
     ragged = [not args.dense_vocoder]
+    # batches in flight: step i runs on lane i % n (its own model / vocoder instance and stream, emojivoice_b200/batch.py Lanes);
+    # `serial[0]` pins every step to lane 0, i.e. one step at a time
+    lanes = ev.lanes_for(model, voc, max(1, args.in_flight))
+    n_lanes = len(lanes)
+    caller = torch.cuda.current_stream(dev)
+    serial = [False]
+    counter = [0]
 
-    def vocode(out):
+    def next_lane():
+        i = counter[0]
+        counter[0] += 1
+        lane = 0 if serial[0] else i % n_lanes
+        return lane, lanes.models[lane], lanes.vocoders[lane], lanes.streams[lane] or caller
+
+    def vocode(v, out):
         # to_waveform (feel_me.py:183).  Ragged: item b is vocoded up to mel_lengths[b] (+ receptive field) only
-        return voc(out["mel"], lengths=out["mel_lengths"] if ragged[0] else None).clamp(-1, 1)
+        return v(out["mel"], lengths=out["mel_lengths"] if ragged[0] else None).clamp(-1, 1)
+
+    lane_done = [None] * n_lanes
 
     def step_resident():
-        out = model.synthesise(x_dev, xl_dev, N_TIMESTEPS, TEMPERATURE, spk_dev, LENGTH_SCALE)
-        return out, vocode(out)
+        lane, m, v, st = next_lane()
+        if lane_done[lane] is not None and n_lanes > 1 and not serial[0]:
+            lane_done[lane].synchronize()                        # one step per lane in flight: the host does not run further ahead
+        with torch.cuda.stream(st):
+            out = m.synthesise(x_dev, xl_dev, N_TIMESTEPS, TEMPERATURE, spk_dev, LENGTH_SCALE)
+            wav = vocode(v, out)
+            lane_done[lane] = torch.cuda.Event()
+            lane_done[lane].record()
+        return out, wav
 
-    wav_host = [None]
-    len_host = torch.empty(BATCH, dtype=torch.int64).pin_memory()
+    host = [dict(wav=None, len=torch.empty(BATCH, dtype=torch.int64).pin_memory(), done=None) for _ in range(n_lanes)]
 
     def step_e2e():
-        xd = x_pin.to(dev, non_blocking=True)
-        ld = xl_pin.to(dev, non_blocking=True)
-        sd_ = spk_pin.to(dev, non_blocking=True)
-        out = model.synthesise(xd, ld, N_TIMESTEPS, TEMPERATURE, sd_, LENGTH_SCALE)
-        wav = vocode(out)
-        if wav_host[0] is None or wav_host[0].shape != wav.shape:
-            wav_host[0] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
-        wav_host[0].copy_(wav, non_blocking=True)               # .cpu() of to_waveform (feel_me.py:187)
-        len_host.copy_(out["mel_lengths"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        lane, m, v, st = next_lane()
+        h = host[lane]
+        if h["done"] is not None:
+            h["done"].synchronize()                              # the host has this lane's previous result before the slot is reused
+        with torch.cuda.stream(st):
+            xd = x_pin.to(dev, non_blocking=True)
+            ld = xl_pin.to(dev, non_blocking=True)
+            sd_ = spk_pin.to(dev, non_blocking=True)
+            out = m.synthesise(xd, ld, N_TIMESTEPS, TEMPERATURE, sd_, LENGTH_SCALE)
+            wav = vocode(v, out)
+            if h["wav"] is None or h["wav"].shape != wav.shape:
+                h["wav"] = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
+            h["wav"].copy_(wav, non_blocking=True)               # .cpu() of to_waveform (feel_me.py:187)
+            h["len"].copy_(out["mel_lengths"], non_blocking=True)
+            h["done"] = torch.cuda.Event()
+            h["done"].record()
+        if n_lanes == 1 or serial[0]:
+            h["done"].synchronize()                              # one step at a time: the result is on the host before the next step starts
         return out, wav
 
     def settle(fn, floor, window, cap_s=15.0, cap_n=60):
@@ -326,18 +363,25 @@ def main():
                 return res, len(recent)
 
     def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream -> ms (this rank)."""
+        """K steps bracketed by barrier + synchronize, CUDA events on the launching stream -> ms (this rank).  The lanes'
+        streams fork from the start event and join before the end event, so the events span every step's last kernel."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        for st in lanes.streams:
+            if st is not None:
+                st.wait_event(e0)
         for _ in range(steps):
             fn()
+        for st in lanes.streams:
+            if st is not None:
+                caller.wait_stream(st)
         e1.record()
         barrier()
         return e0.elapsed_time(e1)
 
     # warm-up: W steps at least (graphs are captured on the second sight of a shape), then until the step time has settled
-    (out, wav), n_warm = settle(step_resident, max(n_warm_min, 4), 6)
+    (out, wav), n_warm = settle(step_resident, max(n_warm_min, 2 * n_lanes + 2), 6)     # every lane captures its graphs on its second step
     secs_per_step = audio_seconds(out["mel_lengths"].cpu())
     frames = int(out["mel_lengths"].sum())
     t_pad = int(out["t_pad"])
@@ -345,6 +389,7 @@ def main():
                 _lib_mod.lib().ev_decode_workspace_bytes(model._ctx.handle, BATCH, t_pad, N_TIMESTEPS))
 
     if args.profile_one_step:
+        serial[0] = True
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
         step_resident()
@@ -356,29 +401,47 @@ def main():
     # ---------------- timed region: K steps, inputs resident in HBM
     sampler = ClockSampler(local_rank)
     sampler.start()
-    model.launch_count(reset=True); voc.launch_count(reset=True)
+    def count_launches(reset=False):
+        return sum(m.launch_count(reset) + v.launch_count(reset) for m, v in zip(lanes.models, lanes.vocoders))
+
+    if n_lanes > 1:
+        timed(step_resident, 2 * n_lanes)                        # untimed: brings the lanes into their steady overlap
+    count_launches(reset=True)
     ms = timed(step_resident, args.steps)
-    launches = model.launch_count() + voc.launch_count()
+    launches = count_launches()
     clocks = sampler.stop()
+    # one step at a time (every step on lane 0): the loop rounds 1 and 2 reported until in-flight lanes existed
+    ms_serial = None
+    if n_lanes > 1:
+        serial[0] = True
+        timed(step_resident, 3)
+        ms_serial = timed(step_resident, args.steps)
+        serial[0] = False
 
     # ---------------- e2e: same steps through the public API with pinned host inputs and the waveform read back
-    settle(step_e2e, 4, 4, cap_n=40)
+    settle(step_e2e, 2 * n_lanes + 2, 4, cap_n=40)
     ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_serial = None
+    if n_lanes > 1:
+        serial[0] = True
+        timed(step_e2e, 3)
+        ms_e2e_serial = timed(step_e2e, args.steps)
+        serial[0] = False
 
     # ---------------- the same with the padded frames vocoded too: the reference's literal work list (vocoder(mel), no kwarg)
     ms_dense = ms_e2e_dense = None
     if ragged[0]:
         ragged[0] = False
-        for _ in range(3):
-            step_resident()
+        settle(step_resident, 2 * n_lanes + 1, 3, cap_n=20)
         ms_dense = timed(step_resident, args.steps)
-        settle(step_e2e, 3, 3, cap_n=20)
+        settle(step_e2e, 2 * n_lanes + 1, 3, cap_n=20)
         ms_e2e_dense = timed(step_e2e, args.steps)
         ragged[0] = True
 
-    red = reduce([ms, ms_e2e, ms_dense or 0.0, ms_e2e_dense or 0.0], MAX)        # the slowest rank bounds the job
+    red = reduce([ms, ms_e2e, ms_dense or 0.0, ms_e2e_dense or 0.0, ms_serial or 0.0, ms_e2e_serial or 0.0], MAX)        # the slowest rank bounds the job
     ms, ms_e2e = red[0], red[1]
     ms_dense, ms_e2e_dense = (red[2], red[3]) if ms_dense is not None else (None, None)
+    ms_serial, ms_e2e_serial = (red[4], red[5]) if ms_serial is not None else (None, None)
     total_secs, launches = reduce([secs_per_step, float(launches)], SUM)
     launches = int(launches)
     per_s = lambda t_ms: total_secs * args.steps / (t_ms / 1e3)
@@ -404,10 +467,13 @@ def main():
 
     # ---------------- roofline: one more step with CUDA events around every launch
     model.cuda_graphs = voc.cuda_graphs = False                  # per-launch events need eager launches, not a graph replay
+    serial[0] = True                                             # lane 0 = `model` / `voc`, alone on the GPU
     model._ctx.profile_begin(); voc._ctx.profile_begin()
     step_resident()
+    torch.cuda.synchronize()
     stats = model._ctx.profile_end() + voc._ctx.profile_end()
     model.cuda_graphs = voc.cuda_graphs = True
+    serial[0] = False
     agg = {}
     for s in stats:
         a = agg.setdefault(s["name"], dict(name=s["name"], launches=0, total_ms=0.0, flops=0.0, bytes=0.0))
@@ -450,7 +516,7 @@ def main():
             barrier()
             t0 = time.perf_counter()
             res, st = ev.synthesise_corpus(model, voc, utts, batch_size=32, n_timesteps=N_TIMESTEPS, temperature=TEMPERATURE,
-                                           length_scale=LENGTH_SCALE, rank=rank, world_size=world)
+                                           length_scale=LENGTH_SCALE, rank=rank, world_size=world, lanes=lanes)
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
             wall_max, dev_max = reduce([wall, st.seconds], MAX)
@@ -460,7 +526,8 @@ def main():
             del res
         config3 = {"workload": "BASELINE.json configs[2]: 1024 mixed-length utterances (P~U[20,150]), 11 emoji voices, micro-batches of 32 "
                                "sorted by length, dealt to the ranks by estimated FLOPs (sharding.shard), synthesise_corpus: "
-                               "collate -> synthesise -> ragged vocoder -> pinned D2H on a copy stream -> per-utterance crop",
+                               "collate -> synthesise -> ragged vocoder -> pinned D2H on a copy stream -> per-utterance crop, "
+                               "%d micro-batches in flight per GPU" % n_lanes,
                    "scaling": "strong", "utterances": int(n3), "audio_seconds": round(secs3, 1), "n_gpus": world,
                    "timing": "host wall clock around the whole call incl. D2H + crop, max over ranks (pass 0 = shapes never seen before)",
                    "passes": passes, "value_first_pass": passes[0]["audio_s_per_s_wall"], "value_warm": passes[-1]["audio_s_per_s_wall"]}
@@ -481,12 +548,15 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
         "data": "synthetic",
-        "config": workload_config(),
+        "config": dict(workload_config(), in_flight=n_lanes,
+                       steps_in_flight="%d batches in flight per GPU (step i on lane i %% %d: own model / vocoder instance + stream, ev.Lanes); "
+                                       "`one_step_at_a_time` is the same loop with a step starting only when the previous one is done" % (n_lanes, n_lanes)
+                       if n_lanes > 1 else "one step at a time"),
         "details": dict(audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames, t_pad=t_pad,
                         warmup_steps_run=n_warm, per_rank_batch="identical on every rank (seed 2000)",
                         l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
                         "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
-                        launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up)",
+                        launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up, per lane)",
                         vocoder=("ragged: time tiles past each utterance's own length (+ the receptive field behind each layer: 13 frames at conv_pre ... 2 at the last stage) are "
                                  "not computed; waveform bit-identical to the dense generator on [: mel_length*256] and zero beyond "
                                  "-- the part the reference's batched caller crops away (cli.py:307-311); `padded_vocoder` is the "
@@ -496,6 +566,12 @@ def main():
         "e2e": {"value": round(value_e2e, 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches),
+        "in_flight": n_lanes,
+        "one_step_at_a_time": ({"value": round(per_s(ms_serial), 2), "unit": "audio-s/s", "ms_per_step": round(ms_serial / args.steps, 3),
+                                "e2e": {"value": round(per_s(ms_e2e_serial), 2), "unit": "audio-s/s", "ms_per_step": round(ms_e2e_serial / args.steps, 3)},
+                                "what": "the same K steps issued one after another on one stream (a step starts when the previous one has "
+                                        "finished; e2e: host sync per step) -- the loop every earlier bench line of this repo reports"}
+                               if ms_serial else None),
         "padded_vocoder": ({"value": round(per_s(ms_dense), 2), "unit": "audio-s/s", "ms_per_step": round(ms_dense / args.steps, 3),
                             "e2e": {"value": round(per_s(ms_e2e_dense), 2), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                                     "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e_dense / args.steps, 3)},

@@ -6,6 +6,6 @@ from .hifigan import Denoiser, Generator, to_waveform  # noqa: F401
 from .matcha import MatchaTTS  # noqa: F401
 from . import audio_io, batch, monotonic_align, sharding, text_cleaners, text_frontend  # noqa: F401
 from .monotonic_align import maximum_path  # noqa: F401
-from .batch import synthesise_corpus, synthesise_file  # noqa: F401
+from .batch import Lanes, lanes_for, synthesise_corpus, synthesise_file  # noqa: F401
 
 __version__ = "0.1.0"

@@ -32,7 +32,7 @@ constexpr int Q_BYTES = 4 * TILE_Q;                 // [hi c0 | hi c1 | lo c0 | 
 constexpr int BLK_BYTES = 4 * TILE_K;               // a K or V block [hi c0 | hi c1 | lo c0 | lo c1], and the P block [hi | lo]
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + 3 * BLK_BYTES;
 constexpr uint32_t TMEM_COLS = 256, S_A = 0, S_B = 64, O_COL = 128;
-constexpr float kOpScale = 8.0f;                    // q, k, v are split as halves of x * 8 (as the conv activations are)
+constexpr float kOpScale = kF16ActScale;            // q, k, v are split as halves of x * 8 (as the conv activations are)
 constexpr float kPScale = 4096.0f;                  // p in [0, 1] is split as halves of p * 4096
 
 // One thread's share of a 64-row x 128-feature q / k tile: one ROTATED item (features [8i, 8i+8) and their partners
@@ -143,6 +143,7 @@ struct Params {
   const int* lens; int len_shift;
   const float* rope_cos; const float* rope_sin;
   float* out; long long out_ld, out_bs;
+  __half* split; int split_ld;     // optional pre-split copy of the output for the out-projection conv (AttnArgs::split)
   int trace;                       // EV_ENC_ATTN_TRACE=1: CTA (0,0,0) prints clock stamps of its milestones (timing experiments)
 };
 
@@ -338,7 +339,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_enc_tc_kernel(const Params p)
 #pragma unroll 4
     for (int r = warp; r < BQ; r += THREADS / 32) {
       const int tr = q0 + r;
-      if (tr < p.T) *reinterpret_cast<float4*>(ob + (long long)tr * p.out_ld + 4 * lane) = stage[r * 32 + (lane ^ (r & 31))];
+      if (tr < p.T) {
+        const float4 y = stage[r * 32 + (lane ^ (r & 31))];
+        *reinterpret_cast<float4*>(ob + (long long)tr * p.out_ld + 4 * lane) = y;
+        if (p.split) {   // [hi | lo] halves of y * 8, exactly what split_f16_kernel would make of the stored row
+          const float v0 = y.x * kF16ActScale, v1 = y.y * kF16ActScale, v2 = y.z * kF16ActScale, v3 = y.w * kF16ActScale;
+          const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1), h2 = __float2half_rn(v2), h3 = __float2half_rn(v3);
+          const __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+          const __half2 la = __floats2half2_rn(v0 - __half2float(h0), v1 - __half2float(h1));
+          const __half2 lb = __floats2half2_rn(v2 - __half2float(h2), v3 - __half2float(h3));
+          __half* sp = p.split + ((long long)b * p.T + tr) * 2 * p.split_ld + h * HD + 4 * lane;
+          *reinterpret_cast<uint2*>(sp) = make_uint2(*reinterpret_cast<const uint32_t*>(&ha), *reinterpret_cast<const uint32_t*>(&hb));
+          *reinterpret_cast<uint2*>(sp + p.split_ld) = make_uint2(*reinterpret_cast<const uint32_t*>(&la), *reinterpret_cast<const uint32_t*>(&lb));
+        }
+      }
     }
   }
   EV_STAMP();
@@ -375,6 +389,7 @@ cudaError_t attention_enc_tc(const AttnArgs& a, cudaStream_t s) {
   p.lens = a.lens; p.len_shift = a.len_shift;
   p.rope_cos = a.rope_cos; p.rope_sin = a.rope_sin;
   p.out = reinterpret_cast<float*>(a.out); p.out_ld = a.out_ld; p.out_bs = a.out_bs;
+  p.split = reinterpret_cast<__half*>(a.split); p.split_ld = a.H * HD;
   static const int trace = []() { const char* v = getenv("EV_ENC_ATTN_TRACE"); return (v && v[0] == '1') ? 1 : 0; }();
   p.trace = trace;
   dim3 grid(ceil_div(a.T, BQ), a.H, a.B);

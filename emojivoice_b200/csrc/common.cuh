@@ -1,6 +1,7 @@
 // Shared definitions of the emojivoice_b200 CUDA library (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -13,6 +14,10 @@
 #endif
 
 namespace ev {
+
+// 3xFP16 split operands (weights.cu, attention_enc_tc.cu): activations are split as fp16 halves of x * 8, so that lo stays a normal
+// fp16 number down to |x| ~ 0.016
+constexpr float kF16ActScale = 8.0f;
 
 typedef __nv_bfloat16 bf16;
 

@@ -133,7 +133,6 @@ cudaError_t conv_simt_launch(const ConvGeom& g, const float* x, long long x_ld, 
                              const Epilogue& e, cudaStream_t stream);
 // conv_tc.cu
 // x: bf16 activations, or (tf32x3 != 0) the split fp32 pair [hi | lo] of width 2*C_in per row (x_ld, x_bs in elements)
-constexpr float kF16ActScale = 8.0f;   // activations are split as halves of x * 8: lo stays a normal fp16 number down to |x| ~ 0.016
 // split: 0 = bf16 operands; 1 = 3xTF32 (x: the fp32 pair [hi | lo], 2*C_in floats per row); 2 = 3xFP16 (x: [hi | lo] halves, 2*C_in per row)
 cudaError_t conv_tc_launch(const ConvGeom& g, const void* x, long long x_ld, long long x_bs, int tf32x3,
                            const ConvWeights& w, const Epilogue& e, cudaStream_t stream, std::string* err,

@@ -181,8 +181,11 @@ int conv_geometry(const ConvWeights& w, int B, int T_in, ConvGeom* g);
 
 // Launch `w` on x (ActT = float -> CUDA-core fp32, bf16 -> tcgen05); e carries the fused epilogue.
 // fp32-accurate tensor-core convolution (3xTF32 split); `scratch` holds B*T_in*2*C_in floats
+// presplit: `scratch` already holds the 3xFP16 [hi | lo] operand of x (written by the producer: LnArgs::split / AttnArgs::split);
+// honoured only when the 3xFP16 path runs (enc_split_f16()), otherwise x is split here as usual
 int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x_ld, long long x_bs, int B, int T_in, Epilogue e,
-                  float* scratch, cudaStream_t s);
+                  float* scratch, cudaStream_t s, bool presplit = false);
+bool enc_split_f16();   // EV_ENC_SPLIT=tf32 selects the round-1 3xTF32 products (their operand has another layout)
 
 template <typename ActT>
 int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, long long x_bs, int B, int T_in,

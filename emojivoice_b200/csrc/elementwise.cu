@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(LnArgs a) {
   const float m = a.mask.at(b, t);
   ActT* oa = a.out_act ? reinterpret_cast<ActT*>(a.out_act) + (long long)warp * a.act_ld : nullptr;
   float* of = a.out_f32 ? a.out_f32 + (long long)warp * a.f32_ld : nullptr;
+  __half* sp = a.split ? reinterpret_cast<__half*>(a.split) + (long long)warp * 2 * a.C : nullptr;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int c = lane + 32 * i;
@@ -125,6 +126,12 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(LnArgs a) {
       y *= m;
       if (of) of[c] = y;
       if (oa) oa[c] = from_float<ActT>(y);
+      if (sp) {   // exactly what split_f16_kernel computes from the stored value
+        const float ys = y * kF16ActScale;
+        const __half hi = __float2half_rn(ys);
+        sp[c] = hi;
+        sp[a.C + c] = __float2half_rn(ys - __half2float(hi));
+      }
     }
   }
 }

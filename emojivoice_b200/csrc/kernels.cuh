@@ -41,6 +41,8 @@ struct LnArgs {
   RowMask mask = {nullptr, 0};
   float* out_f32 = nullptr; long long f32_ld = 0;
   void* out_act = nullptr; long long act_ld = 0;
+  void* split = nullptr;     // optional [rows][2C] fp16: the [hi | lo] halves of y * kF16ActScale, i.e. the pre-split operand of a
+                             // following 3xFP16 conv (what split_f16_kernel would make of out_f32; saves that launch)
   int B = 0, T = 0, C = 0;   // rows are (b, t); row stride applies to b*T + t
 };
 template <typename ActT> cudaError_t layer_norm_rows(const LnArgs& a, cudaStream_t s);
@@ -56,6 +58,7 @@ struct AttnArgs {
                            // 1: decoder (additive +1 on valid keys, diffusers float attn_mask)
   const float* rope_cos = nullptr; const float* rope_sin = nullptr; int rope_dim = 0;  // tables [t][rope_dim/2]
   void* out = nullptr; long long out_ld = 0, out_bs = 0;   // (b, t, h*D + d)
+  void* split = nullptr;   // attention_enc_tc only: optional [B*T][2*H*D] fp16 [hi | lo] halves of out * kF16ActScale (see LnArgs::split)
 };
 template <typename ActT> cudaError_t attention_rows(const AttnArgs& a, cudaStream_t s);
 // Text-encoder attention (mode 0, head width 128, T <= 384) on tcgen05 with 3xFP16 split operands, fp32 output

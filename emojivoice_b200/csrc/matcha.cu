@@ -228,6 +228,8 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
               embed_speakers(reinterpret_cast<const long long*>(spks), m.spk_table, B, c.spk_emb_dim, c.n_spks, spk_emb, summ ? summ + 1 : nullptr, s));
   EV_LAUNCH(ctx, s, "embed_tokens", 0, R * (8 + 8.0 * C),
             embed_tokens(reinterpret_cast<const long long*>(x), m.tok_emb, B, Tx, C, c.n_vocab, sqrtf((float)C), mask, e.h0, C, summ ? summ + 1 : nullptr, s));
+  // Producers write the next 3xFP16 conv's [hi | lo] operand themselves (LayerNorm, the tcgen05 attention): 25 split launches less
+  const bool ps = enc_split_f16() && ctx->enc_tc;
   if (c.enc_prenet) {
     // ConvReluNorm (text_encoder.py:60-67): 3 x [conv5(x*mask) -> LN -> ReLU], 1x1 proj, + x_org, * mask
     const float* cur = e.h0;
@@ -235,17 +237,17 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     for (int i = 0; i < 3; ++i) {
       Epilogue ep;
       ep.out_f32 = e.tmp; ep.f32_ld = C; ep.f32_bs = bsC;
-      EV_TRY(run_conv_tf32(ctx, m.pre_conv[i], cur, C, bsC, B, Tx, ep, e.split, s));
+      EV_TRY(run_conv_tf32(ctx, m.pre_conv[i], cur, C, bsC, B, Tx, ep, e.split, s, ps && i > 0));
       LnArgs ln;
       ln.x = e.tmp; ln.x_ld = C; ln.gamma = m.pre_g[i]; ln.beta = m.pre_b[i]; ln.eps = 1e-4f; ln.post_relu = 1; ln.mask = mask;
-      ln.out_f32 = pp[i & 1]; ln.f32_ld = C; ln.B = B; ln.T = Tx; ln.C = C;
+      ln.out_f32 = pp[i & 1]; ln.f32_ld = C; ln.B = B; ln.T = Tx; ln.C = C; ln.split = ps ? e.split : nullptr;
       EV_LAUNCH(ctx, s, "layer_norm", 0, R * C * 8.0, layer_norm_rows<float>(ln, s));
       cur = pp[i & 1];
     }
     Epilogue ep;
     ep.res = e.h0; ep.res_ld = C; ep.res_bs = bsC;
     ep.out_act = e.X; ep.act_ld = H; ep.act_bs = bsH; ep.mask = mask; ep.mask_act = 1;
-    EV_TRY(run_conv_tf32(ctx, m.pre_proj, cur, C, bsC, B, Tx, ep, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, m.pre_proj, cur, C, bsC, B, Tx, ep, e.split, s, ps));
   } else {
     EV_CUDA(ctx, cudaMemcpy2DAsync(e.X, (size_t)H * 4, e.h0, (size_t)C * 4, (size_t)C * 4, (size_t)B * Tx, cudaMemcpyDeviceToDevice, s));
   }
@@ -262,7 +264,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     // 1x1 convs without a mask in the epilogue see the batch as ONE sequence of B*Tx rows (the tensors are dense): 128-row
     // tiles then straddle utterances instead of leaving every utterance's last tile mostly empty (Tx = 177: 45 m-tiles, not 64).
     // Row-wise the arithmetic is unchanged, so the results are bit-identical.
-    EV_TRY(run_conv_tf32(ctx, L.qkv, e.X, H, bsH * B, 1, B * Tx, ep, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, L.qkv, e.X, H, bsH * B, 1, B * Tx, ep, e.split, s, ps && i > 0));
     AttnArgs at;
     at.q = e.qkv; at.k = e.qkv + H; at.v = e.qkv + 2 * H; at.ld = 3 * H; at.bs = (long long)Tx * 3 * H;
     at.B = B; at.T = Tx; at.H = c.enc_heads; at.D = hd; at.scale = 1.0f / sqrtf((float)hd);
@@ -272,21 +274,23 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     // tcgen05 with split fp16 operands where the shape allows (head width 128, Tx <= 384; EV_ENC_ATTN=f32 keeps the CUDA-core
     // kernel); both are fp32-accurate
     static const bool enc_attn_tc = []() { const char* v = getenv("EV_ENC_ATTN"); return !(v && std::string(v) == "f32"); }();
-    if (enc_attn_tc && attention_enc_tc_supported(at))   // 3 products per contraction
+    const bool att_tc = enc_attn_tc && attention_enc_tc_supported(at);
+    if (att_tc) at.split = ps ? e.split : nullptr;
+    if (att_tc)   // 3 products per contraction
       EV_LAUNCH(ctx, s, "attention_enc_tc", 3.0 * 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_enc_tc(at, s));
     else
       EV_LAUNCH(ctx, s, "attention_enc_f32", 4.0 * B * c.enc_heads * (double)Tx * Tx * hd, R * H * 16.0, attention_rows<float>(at, s));
     Epilogue eo;  // x + y
     eo.res = e.X; eo.res_ld = H; eo.res_bs = bsH; eo.out_f32 = e.tmp; eo.f32_ld = H; eo.f32_bs = bsH;
-    EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH * B, 1, B * Tx, eo, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, L.o, e.att, H, bsH * B, 1, B * Tx, eo, e.split, s, ps && att_tc));
     LnArgs l1;
     l1.x = e.tmp; l1.x_ld = H; l1.gamma = L.ln1_g; l1.beta = L.ln1_b; l1.eps = 1e-4f; l1.mask = mask;
-    l1.out_f32 = e.X1; l1.f32_ld = H; l1.B = B; l1.T = Tx; l1.C = H;
+    l1.out_f32 = e.X1; l1.f32_ld = H; l1.B = B; l1.T = Tx; l1.C = H; l1.split = ps ? e.split : nullptr;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * H * 8.0, layer_norm_rows<float>(l1, s));
     Epilogue e1;  // relu(conv_1(x*mask)) * mask
     e1.act = ACT_RELU; e1.mask = mask; e1.mask_act = 1;
     e1.out_act = e.F; e1.act_ld = c.enc_filter_channels; e1.act_bs = (long long)Tx * c.enc_filter_channels;
-    EV_TRY(run_conv_tf32(ctx, L.ffn1, e.X1, H, bsH, B, Tx, e1, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, L.ffn1, e.X1, H, bsH, B, Tx, e1, e.split, s, ps));
     Epilogue e2;  // x + conv_2(..)*mask
     e2.mask = mask; e2.mask_pre = 1; e2.res = e.X1; e2.res_ld = H; e2.res_bs = bsH;
     e2.out_f32 = e.tmp; e2.f32_ld = H; e2.f32_bs = bsH;
@@ -298,7 +302,7 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
   {  // mu = proj_m(x) * mask  (text_encoder.py:405) -> channel-first output
     Epilogue ep;
     ep.mask = mask; ep.mask_pre = 1; ep.out_f32 = e.mu_cl; ep.f32_ld = c.n_feats; ep.f32_bs = (long long)Tx * c.n_feats;
-    EV_TRY(run_conv_tf32(ctx, m.proj_m, e.X, H, bsH, B, Tx, ep, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, m.proj_m, e.X, H, bsH, B, Tx, ep, e.split, s, ps && c.enc_layers > 0));
     EV_LAUNCH(ctx, s, "cl_to_cf", 0, R * c.n_feats * 8.0, cl_to_cf(e.mu_cl, c.n_feats, (long long)Tx * c.n_feats, B, c.n_feats, Tx, mu_x, 1.0f, 0.0f, s));
   }
   {  // DurationPredictor (text_encoder.py:84-94): conv -> relu -> LN (x2), 1x1 proj, masks in between
@@ -306,13 +310,13 @@ extern "C" int ev_encode(ev_ctx* ctx, const int64_t* x, const int64_t* x_lengths
     const long long bsF = (long long)Tx * Fd;
     Epilogue ep;
     ep.out_f32 = e.tmp; ep.f32_ld = Fd; ep.f32_bs = bsF;
-    EV_TRY(run_conv_tf32(ctx, m.dp_conv1, e.X, H, bsH, B, Tx, ep, e.split, s));
+    EV_TRY(run_conv_tf32(ctx, m.dp_conv1, e.X, H, bsH, B, Tx, ep, e.split, s, ps && c.enc_layers > 0));   // the operand proj_m used
     LnArgs ln;
     ln.x = e.tmp; ln.x_ld = Fd; ln.pre_relu = 1; ln.gamma = m.dp_g1; ln.beta = m.dp_b1; ln.eps = 1e-4f; ln.mask = mask;
-    ln.out_f32 = e.D1; ln.f32_ld = Fd; ln.B = B; ln.T = Tx; ln.C = Fd;
+    ln.out_f32 = e.D1; ln.f32_ld = Fd; ln.B = B; ln.T = Tx; ln.C = Fd; ln.split = ps ? e.split : nullptr;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
-    EV_TRY(run_conv_tf32(ctx, m.dp_conv2, e.D1, Fd, bsF, B, Tx, ep, e.split, s));
-    ln.gamma = m.dp_g2; ln.beta = m.dp_b2; ln.out_f32 = e.D2;
+    EV_TRY(run_conv_tf32(ctx, m.dp_conv2, e.D1, Fd, bsF, B, Tx, ep, e.split, s, ps));
+    ln.gamma = m.dp_g2; ln.beta = m.dp_b2; ln.out_f32 = e.D2; ln.split = nullptr;
     EV_LAUNCH(ctx, s, "layer_norm", 0, R * Fd * 8.0, layer_norm_rows<float>(ln, s));
     Epilogue el;
     el.mask = mask; el.mask_pre = 1; el.out_f32 = logw; el.f32_ld = 1; el.f32_bs = Tx;

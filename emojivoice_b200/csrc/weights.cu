@@ -344,8 +344,13 @@ int run_conv(ev_ctx* ctx, const ConvWeights& w, const ActT* x, long long x_ld, l
 // fp32-accurate convolution on the tensor cores (3xTF32): x is split into [hi | lo] in `scratch` (B*T_in*2*C_in floats),
 // then one tcgen05 GEMM over the concatenated K does x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with fp32 accumulation.
 // Falls back to the CUDA-core kernel when the layer has no split weights or the tile path cannot serve the epilogue.
+bool enc_split_f16() {
+  static const bool use_f16 = []() { const char* v = getenv("EV_ENC_SPLIT"); return !(v && std::string(v) == "tf32"); }();
+  return use_f16;
+}
+
 int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x_ld, long long x_bs, int B, int T_in, Epilogue e,
-                  float* scratch, cudaStream_t s) {
+                  float* scratch, cudaStream_t s, bool presplit) {
   const bool aligned = (e.f32_ld % 4 == 0) && (e.f32_bs % 4 == 0) && (e.act_ld % 4 == 0) && (e.res_ld % 4 == 0) && w.N % 4 == 0;
   const bool act_ok = e.act == ACT_NONE || e.act == ACT_RELU || e.act == ACT_LRELU;
   if (!w.w_tf32 || !scratch || x_bs != (long long)T_in * x_ld || !aligned || !act_ok || (e.out_act && e.out_f32) || !ctx->enc_tc ||
@@ -366,9 +371,8 @@ int run_conv_tf32(ev_ctx* ctx, const ConvWeights& w, const float* x, long long x
   const double flops = 2.0 * B * (double)T_out * w.C_out * w.taps * w.C_in;
   const double bytes = 4.0 * (rows * w.C_in + (double)w.taps * w.N * w.C_in + (double)B * T_out * w.C_out * (e.res ? 2 : 1));
   // EV_ENC_SPLIT=tf32: the 3xTF32 products (round 1); default: 3xFP16 where the layer has that operand set
-  static const bool use_f16 = []() { const char* v = getenv("EV_ENC_SPLIT"); return !(v && std::string(v) == "tf32"); }();
-  const int split = (use_f16 && w.w_f16x3) ? 2 : 1;
-  {
+  const int split = (enc_split_f16() && w.w_f16x3) ? 2 : 1;
+  if (!(presplit && split == 2)) {
     const int blocks = (int)std::min<long long>(2048, ceil_div_ll(rows * (w.C_in / 4), 256));
     cudaError_t ce;
     if (split == 2) {

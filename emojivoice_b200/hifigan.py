@@ -54,6 +54,15 @@ class Generator:
     def remove_weight_norm(self):
         self._materialise()
 
+    def replica(self):
+        """Another generator on the same device with its own context (weights, workspace, graph cache): see MatchaTTS.replica."""
+        if self._sd is None:
+            raise RuntimeError("load_state_dict() first")
+        g = Generator(self.h, device=self.device, precision=self.precision, cuda_graphs=self.cuda_graphs)
+        g.load_state_dict(self._sd)
+        g._materialise()
+        return g
+
     def _materialise(self):
         if self._ctx is not None:
             return

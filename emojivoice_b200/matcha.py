@@ -82,7 +82,16 @@ class MatchaTTS:
         self._ctx.check(rc, "ev_load_matcha")
         del keep
         self._loaded = True
+        self._sd = state_dict                     # kept by reference for replica()
         return self
+
+    def replica(self):
+        """Another instance of this model on the same device with its own context -- packed weights (35 MB), workspace and
+        graph cache -- so that a second batch can be in flight on another stream (`batch.Lanes`)."""
+        if not self._loaded:
+            raise RuntimeError("load_state_dict() / load_from_checkpoint() first")
+        m = MatchaTTS(**self.hparams, device=self.device, precision=self.precision, cuda_graphs=self.cuda_graphs)
+        return m.load_state_dict(self._sd)
 
     @staticmethod
     def fix_len_compatibility(length: int, num_downsamplings_in_unet: int = 2) -> int:

@@ -550,6 +550,30 @@ def test_ragged_vocoder_full_size_batch(matcha, matcha_sd, vocoders):
         assert torch.equal(r0[i]["waveform"], r1[i]["waveform"])
 
 
+def test_corpus_lanes_do_not_change_results(matcha, matcha_sd, vocoders):
+    """Several micro-batches in flight (ev.Lanes: model / vocoder replicas on their own streams) give the waveforms of the
+    one-at-a-time loop bit for bit, with and without the denoiser; stats count every utterance once."""
+    gen, _ = vocoders["hifigan_gain1"]
+    x, xl, spks = synthetic.phoneme_batch(10, 5, 30, seed=21)
+    utts = [(x[i, : int(xl[i])].tolist(), int(spks[i])) for i in range(10)]
+    zs = {}
+
+    def z_fn(mb, model, x_, xl_, spks_):
+        probe = model.synthesise(x_, xl_, 1, 0.667, spks_, 1.0)
+        return zs.setdefault(tuple(mb.items), synthetic.prior_noise(len(mb.items), 80, probe["t_pad"], seed=5))
+
+    den = ev.Denoiser(gen)
+    for denoiser in (None, den):
+        r1, s1 = ev.synthesise_corpus(matcha, gen, utts, batch_size=2, n_timesteps=2, z_fn=z_fn, denoiser=denoiser)
+        r3, s3 = ev.synthesise_corpus(matcha, gen, utts, batch_size=2, n_timesteps=2, z_fn=z_fn, denoiser=denoiser, in_flight=3)
+        assert sorted(r1) == sorted(r3) == list(range(10))
+        assert s1.utterances == s3.utterances == 10 and s3.extra["in_flight"] == 3 and s3.seconds > 0
+        for i in r1:
+            assert r1[i]["mel_length"] == r3[i]["mel_length"]
+            assert torch.equal(r1[i]["waveform"], r3[i]["waveform"])
+    assert len(ev.lanes_for(matcha, gen, 3)) == 3 and ev.lanes_for(matcha, gen, 3) is ev.lanes_for(matcha, gen, 3)
+
+
 def test_end_to_end_emoji_text_to_waveform(matcha, matcha_sd, vocoders):
     gen, hsd = vocoders["hifigan_gain1"]
     text, spk = ev.emoji_to_spk("that is wonderful \U0001F60D")
