@@ -452,41 +452,63 @@ __global__ void __launch_bounds__(256, MODE == 1 ? 3 : 4) gn_apply256_kernel(GnA
 }
 
 // ---------------------------------------------------------------------------------------------- vocoder tail
+// LeakyReLU(0.01) -> conv_post (C -> 1, k = 7, padding 3) -> tanh -> clamp (hifigan/models.py:191-195).
+// thread = input row: it holds the row's C values in registers and forms the SEVEN tap products w[j] . x[row] (7 C FMAs on
+// register operands; the weights come as broadcast 16-byte shared loads); out[t] = bias + sum_j partial_j[t + j] then costs seven
+// shared loads.  A block owns kPostOut = 250 outputs = 256 rows with the +-3 halo.  The first version read every x value from
+// shared memory once per tap (448 LDS per output) and was bound by the shared-memory pipe at 2.0 TB/s; this one is an HBM stream.
+constexpr int kPostOut = 250;
 template <int C>
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ x, int L, const float* __restrict__ w,
                                                         const float* __restrict__ bias, float* __restrict__ wav,
                                                         const int* __restrict__ lens, int hop) {
-  // 256 output samples per block; the (256+6) x C input window is staged in shared memory with LeakyReLU(0.01) applied
-  __shared__ float xs[(256 + 6) * (C + 1)];
-  __shared__ float ws[7 * C];
-  const int b = blockIdx.y, t0 = blockIdx.x * 256;
+  constexpr int C4 = C / 4, PITCH = C + 4;                     // row pitch in floats: 16-byte aligned, conflict-free for 16-byte accesses
+  __shared__ __align__(16) float xs[256 * PITCH];
+  __shared__ __align__(16) float ws[7 * C];
+  __shared__ float ps[7][256 + 8];
+  const int b = blockIdx.y, t0 = blockIdx.x * kPostOut;
   // ragged batch: samples beyond the utterance's own length were never computed upstream -> the waveform is zero there
   const long long valid = lens ? min((long long)L, (long long)max(lens[b], 0) * hop) : (long long)L;
   if (t0 >= valid) {
-    if (t0 + (int)threadIdx.x < L) wav[(long long)b * L + t0 + threadIdx.x] = 0.0f;
+    if ((int)threadIdx.x < kPostOut && t0 + (int)threadIdx.x < L) wav[(long long)b * L + t0 + threadIdx.x] = 0.0f;
     return;
   }
   for (int i = threadIdx.x; i < 7 * C; i += 256) ws[i] = w[i];
   const float* xb = x + (long long)b * L * C;
-  constexpr int C4 = C / 4;                                    // 16-byte loads: the kernel is a pure HBM stream (132 B per sample)
-  for (int i = threadIdx.x; i < (256 + 6) * C4; i += 256) {
-    const int r = i / C4, c = (i - r * C4) * 4, t = t0 + r - 3;
+  // coalesced 16-byte loads of the 256 x C window (rows t0 - 3 .. t0 + 252), LeakyReLU applied on the way in
+#pragma unroll
+  for (int it = 0; it < C4; ++it) {
+    const int i = threadIdx.x + it * 256, r = i / C4, c = (i - r * C4) * 4, t = t0 + r - 3;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t >= 0 && t < L) v = __ldcs(reinterpret_cast<const float4*>(xb + (long long)t * C + c));
-    float* d = xs + r * (C + 1) + c;
-    d[0] = v.x > 0.0f ? v.x : v.x * 0.01f; d[1] = v.y > 0.0f ? v.y : v.y * 0.01f;
-    d[2] = v.z > 0.0f ? v.z : v.z * 0.01f; d[3] = v.w > 0.0f ? v.w : v.w * 0.01f;
+    v.x = v.x > 0.0f ? v.x : v.x * 0.01f; v.y = v.y > 0.0f ? v.y : v.y * 0.01f;
+    v.z = v.z > 0.0f ? v.z : v.z * 0.01f; v.w = v.w > 0.0f ? v.w : v.w * 0.01f;
+    *reinterpret_cast<float4*>(xs + r * PITCH + c) = v;
+  }
+  __syncthreads();
+  float xr[C];
+#pragma unroll
+  for (int c4 = 0; c4 < C4; ++c4) {
+    const float4 v = *reinterpret_cast<const float4*>(xs + threadIdx.x * PITCH + 4 * c4);
+    xr[4 * c4] = v.x; xr[4 * c4 + 1] = v.y; xr[4 * c4 + 2] = v.z; xr[4 * c4 + 3] = v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int c4 = 0; c4 < C4; ++c4) {
+      const float4 wv = *reinterpret_cast<const float4*>(ws + j * C + 4 * c4);
+      acc = fmaf(wv.x, xr[4 * c4], acc); acc = fmaf(wv.y, xr[4 * c4 + 1], acc);
+      acc = fmaf(wv.z, xr[4 * c4 + 2], acc); acc = fmaf(wv.w, xr[4 * c4 + 3], acc);
+    }
+    ps[j][threadIdx.x] = acc;                                  // tap j of output (row - j): row = tid, output = tid - j
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
-  if (t >= L) return;
+  if ((int)threadIdx.x >= kPostOut || t >= L) return;
   float acc = bias[0];
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const float* xr = xs + (threadIdx.x + j) * (C + 1);
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc = fmaf(ws[j * C + c], xr[c], acc);
-  }
+  for (int j = 0; j < 7; ++j) acc += ps[j][threadIdx.x + j];    // output tid reads rows tid .. tid + 6 (= samples t - 3 .. t + 3)
   float y = tanhf(acc);
   y = fminf(fmaxf(y, -1.0f), 1.0f);
   wav[(long long)b * L + t] = t < valid ? y : 0.0f;
@@ -610,7 +632,7 @@ template cudaError_t group_norm_apply<bf16>(const GnApplyArgs&, cudaStream_t);
 
 cudaError_t conv_post_tanh(const float* x, int B, int L, int C, const float* w, const float* bias, float* wav, const int* lens,
                            int hop, cudaStream_t s) {
-  dim3 grid(ceil_div(L, 256), B);
+  dim3 grid(ceil_div(L, kPostOut), B);
   if (C == 32) conv_post_kernel<32><<<grid, 256, 0, s>>>(x, L, w, bias, wav, lens, hop);
   else if (C == 16) conv_post_kernel<16><<<grid, 256, 0, s>>>(x, L, w, bias, wav, lens, hop);
   else return cudaErrorInvalidValue;
