@@ -46,12 +46,13 @@ class Lanes:
 
 
 def lanes_for(model, vocoder, n: int) -> Lanes:
-    """The (cached) lanes of a model / vocoder pair."""
-    cache = model.__dict__.setdefault("_lanes", {})
-    key = (id(vocoder), int(n))
-    if key not in cache:
-        cache[key] = Lanes(model, vocoder, int(n))
-    return cache[key]
+    """The (cached) lanes of a model / vocoder pair: replicas are built once per (vocoder, n) and kept on the model."""
+    cache = model.__dict__.setdefault("_lanes", [])
+    for lanes in cache:
+        if lanes.vocoders[0] is vocoder and len(lanes) == int(n):
+            return lanes
+    cache.append(Lanes(model, vocoder, int(n)))
+    return cache[-1]
 
 
 @torch.inference_mode()
@@ -94,67 +95,73 @@ def synthesise_corpus(model, vocoder, utterances, batch_size=32, n_timesteps=10,
             results[i] = rec
 
     saved_graphs = [(m.cuda_graphs, v.cuda_graphs) for m, v in zip(lanes.models, lanes.vocoders)]
+
+    def restore_graphs():
+        for (mg, vg), m, v in zip(saved_graphs, lanes.models, lanes.vocoders):
+            m.cuda_graphs, v.cuda_graphs = mg, vg
+
     if not cuda_graphs:
         for m, v in zip(lanes.models, lanes.vocoders):
             m.cuda_graphs = v.cuda_graphs = False
-    caller = torch.cuda.current_stream(dev)
-    for st in lanes.streams:
-        if st is not None:
-            st.wait_stream(caller)
-    # largest micro-batch first: the workspace and the caching allocator's blocks are sized once, every later batch fits
-    plan = sorted(plan, key=lambda m: -m.cost)
-    for k, mb in enumerate(plan):
-        lane = k % n_lanes
-        m, v, st = lanes.models[lane], lanes.vocoders[lane], lanes.streams[lane] or caller
-        x, xl, spks = collate(utterances, mb.items)
-        with torch.cuda.stream(st):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            kw = {}
-            if z_fn is not None:
-                kw["z"] = z_fn(mb, m, x, xl, spks)
-            out = m.synthesise(x, xl, n_timesteps, temperature, spks if m.n_spks > 1 else None, length_scale, **kw)
-            use_ragged = ragged and denoiser is None
-            wav = v(out["mel"], lengths=out["mel_lengths"] if use_ragged else None).clamp(-1, 1)   # to_waveform, cli.py:121-126
-            if denoiser is not None:
-                wav = lanes.denoiser(lane, denoiser)(wav.squeeze(1), strength=denoiser_strength).unsqueeze(1)
-            e1.record()
-            # read-back on a copy stream into pinned memory (the `.cpu()` of to_waveform): the host crops an EARLIER micro-batch
-            # while this one's copy -- and the next ones' kernels -- are in flight
-            slot = pinned.setdefault(k % (n_lanes + 1), {})
-            if "wav" not in slot or slot["wav"].numel() < wav.numel():
-                slot["wav"] = torch.empty(wav.numel(), dtype=wav.dtype).pin_memory()
-            if "len" not in slot or slot["len"].numel() < len(mb.items):
-                slot["len"] = torch.empty(len(mb.items), dtype=torch.int64).pin_memory()
-            wav_host = slot["wav"][: wav.numel()].view(wav.shape)
-            len_host = slot["len"][: len(mb.items)]
-            copy_stream.wait_stream(st)
-            with torch.cuda.stream(copy_stream):
-                wav_host.copy_(wav, non_blocking=True)
-                len_host.copy_(out["mel_lengths"], non_blocking=True)
-                done = torch.cuda.Event()
-                done.record()
-            wav.record_stream(copy_stream)                        # both sources are read by the copy stream after this iteration
-            out["mel_lengths"].record_stream(copy_stream)         # rebinds `out`: the allocator must not recycle them early
-        if not span:
-            span.append(e0)
-        span.append(e1)
-        pending.append(dict(done=done, e0=e0, e1=e1, wav_host=wav_host, len_host=len_host, xl=xl.tolist(), items=mb.items,
-                            mel=out["mel"] if keep_mel else None))
-        if len(pending) > n_lanes:
+    try:
+        caller = torch.cuda.current_stream(dev)
+        for st in lanes.streams:
+            if st is not None:
+                st.wait_stream(caller)
+        # largest micro-batch first: the workspace and the caching allocator's blocks are sized once, every later batch fits
+        plan = sorted(plan, key=lambda m: -m.cost)
+        for k, mb in enumerate(plan):
+            lane = k % n_lanes
+            m, v, st = lanes.models[lane], lanes.vocoders[lane], lanes.streams[lane] or caller
+            x, xl, spks = collate(utterances, mb.items)
+            with torch.cuda.stream(st):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                kw = {}
+                if z_fn is not None:
+                    kw["z"] = z_fn(mb, m, x, xl, spks)
+                out = m.synthesise(x, xl, n_timesteps, temperature, spks if m.n_spks > 1 else None, length_scale, **kw)
+                use_ragged = ragged and denoiser is None
+                wav = v(out["mel"], lengths=out["mel_lengths"] if use_ragged else None).clamp(-1, 1)   # to_waveform, cli.py:121-126
+                if denoiser is not None:
+                    wav = lanes.denoiser(lane, denoiser)(wav.squeeze(1), strength=denoiser_strength).unsqueeze(1)
+                e1.record()
+                # read-back on a copy stream into pinned memory (the `.cpu()` of to_waveform): the host crops an EARLIER micro-batch
+                # while this one's copy -- and the next ones' kernels -- are in flight
+                slot = pinned.setdefault(k % (n_lanes + 1), {})
+                if "wav" not in slot or slot["wav"].numel() < wav.numel():
+                    slot["wav"] = torch.empty(wav.numel(), dtype=wav.dtype).pin_memory()
+                if "len" not in slot or slot["len"].numel() < len(mb.items):
+                    slot["len"] = torch.empty(len(mb.items), dtype=torch.int64).pin_memory()
+                wav_host = slot["wav"][: wav.numel()].view(wav.shape)
+                len_host = slot["len"][: len(mb.items)]
+                copy_stream.wait_stream(st)
+                with torch.cuda.stream(copy_stream):
+                    wav_host.copy_(wav, non_blocking=True)
+                    len_host.copy_(out["mel_lengths"], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record()
+                wav.record_stream(copy_stream)                        # both sources are read by the copy stream after this iteration
+                out["mel_lengths"].record_stream(copy_stream)         # rebinds `out`: the allocator must not recycle them early
+            if not span:
+                span.append(e0)
+            span.append(e1)
+            pending.append(dict(done=done, e0=e0, e1=e1, wav_host=wav_host, len_host=len_host, xl=xl.tolist(), items=mb.items,
+                                mel=out["mel"] if keep_mel else None))
+            if len(pending) > n_lanes:
+                finish(pending.pop(0))
+        while pending:
             finish(pending.pop(0))
-    while pending:
-        finish(pending.pop(0))
-    for st in lanes.streams:
-        if st is not None:
-            caller.wait_stream(st)
-    if n_lanes > 1 and len(span) > 1:
-        for e in span[1:]:
-            e.synchronize()
-        stats.seconds += max(span[0].elapsed_time(e) for e in span[1:]) / 1e3
-    stats.extra["in_flight"] = n_lanes
-    for (mg, vg), m, v in zip(saved_graphs, lanes.models, lanes.vocoders):
-        m.cuda_graphs, v.cuda_graphs = mg, vg
+        for st in lanes.streams:
+            if st is not None:
+                caller.wait_stream(st)
+        if n_lanes > 1 and len(span) > 1:
+            for e in span[1:]:
+                e.synchronize()
+            stats.seconds += max(span[0].elapsed_time(e) for e in span[1:]) / 1e3
+        stats.extra["in_flight"] = n_lanes
+    finally:
+        restore_graphs()
     return results, stats
 
 

@@ -144,3 +144,21 @@ def test_ragged_vocoder_margins_cover_the_generators_look_ahead():
     assert 5 < look_ahead_frames - 3 <= pre.value - 1, look_ahead_frames
     # stage by stage the margins shrink with the remaining depth of the generator and never drop below one spare frame
     assert all(stage[i] >= stage[i + 1] >= 2 for i in range(n - 1)) and all(up[i] >= stage[i] for i in range(n))
+
+
+def test_lanes_host_logic():
+    """ev.Lanes / lanes_for without a GPU: argument check, lane 0 is the caller's own pair, the cache is keyed by the vocoder OBJECT."""
+    import emojivoice_b200 as ev
+
+    class Fake:
+        pass
+
+    m, v1, v2 = Fake(), Fake(), Fake()
+    with pytest.raises(ValueError):
+        ev.Lanes(m, v1, 0)
+    one = ev.lanes_for(m, v1, 1)
+    assert len(one) == 1 and one.models[0] is m and one.vocoders[0] is v1 and one.streams == [None]
+    assert ev.lanes_for(m, v1, 1) is one
+    assert ev.lanes_for(m, v2, 1) is not one and ev.lanes_for(m, v2, 1).vocoders[0] is v2
+    d = object()
+    assert one.denoiser(0, d) is d and one.denoiser(0, None) is None
