@@ -548,12 +548,12 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
         "data": "synthetic",
-        "config": dict(workload_config(), in_flight=n_lanes,
-                       steps_in_flight="%d batches in flight per GPU (step i on lane i %% %d: own model / vocoder instance + stream, ev.Lanes); "
-                                       "`one_step_at_a_time` is the same loop with a step starting only when the previous one is done" % (n_lanes, n_lanes)
-                       if n_lanes > 1 else "one step at a time"),
+        "config": workload_config(),
         "details": dict(audio_seconds_per_step_per_gpu=round(secs_per_step, 2), mel_frames_per_step_per_gpu=frames, t_pad=t_pad,
                         warmup_steps_run=n_warm, per_rank_batch="identical on every rank (seed 2000)",
+                        steps_in_flight=("%d batches in flight per GPU (step i on lane i %% %d: own model / vocoder instance + stream, ev.Lanes; a lane "
+                                         "takes its next step when its previous one is done); `one_step_at_a_time` is the same loop with a step "
+                                         "starting only when the previous one has finished" % (n_lanes, n_lanes)) if n_lanes > 1 else "one step at a time",
                         l2="no flush: each step streams a %.1f GB activation workspace (>> 126 MB L2); weights "
                         "(35 MB bf16) stay L2-resident as they would in service" % (ws_bytes / 1e9),
                         launch="encoder, alignment + decoder and vocoder replayed as CUDA graphs (captured during warm-up, per lane)",
